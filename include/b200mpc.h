@@ -1,0 +1,143 @@
+/*
+ * b200mpc.h -- C ABI of the B200-native batched MPC solve engine.
+ *
+ * The reference (nicolapiccinelli/libmpc, libmpc++ v0.7.1) has no FFI: the seam this library sits behind is the
+ * C++ virtual interface mpc::IOptimizer<sizer> (include/mpc/IOptimizer.hpp:24-58) together with the setters of
+ * mpc::LMPC<> that feed mpc::ProblemBuilder / mpc::LOptimizer.  Each entry point below names the reference
+ * member it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - extern "C", opaque handle, plain pointers and sizes, int return code (0 = ok, <0 = B200MPC_E*), no
+ *     exceptions cross the boundary.
+ *   - All matrices are FP64.  A/B/C/Bd/Dd are ROW-major [rows x cols].  Every horizon matrix is STAGE-major:
+ *     [ph][dim] (== the memory image of the reference's column-major Eigen mat<dim,ph>).
+ *   - `per_instance` = 0: one copy shared by the whole batch; 1: `batch` consecutive copies.
+ *   - `dev` = 0: pointer is host memory (copied with cudaMemcpyAsync on the handle's stream);
+ *     `dev` = 1: pointer is device memory on the handle's device (copied device-to-device, no host involvement).
+ *   - The engine solves `batch` independent LMPC problems per call.  mpc::LMPC<>::optimize() is batch == 1.
+ */
+#ifndef B200MPC_H
+#define B200MPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MPC_OK 0
+#define B200MPC_EINVAL (-1)  /* bad argument / dimension                                                     */
+#define B200MPC_ECUDA (-2)   /* CUDA runtime error (b200mpc_last_error() holds the string)                   */
+#define B200MPC_ENOGPU (-3)  /* no CUDA device: the engine has no CPU fallback                               */
+#define B200MPC_ESTATE (-4)  /* call order violation (e.g. solve before set_model)                           */
+
+typedef struct b200mpc_lmpc* b200mpc_lmpc_t;
+
+/* mpc::MPCSize for LMPC<Tnx,Tnu,Tndu,Tny,Tph,Tch>   (include/mpc/LMPC.hpp:23-26, include/mpc/Dim.hpp:107-132) */
+typedef struct b200mpc_lmpc_dims {
+    int nx, nu, ndu, ny, ph, ch;
+} b200mpc_lmpc_dims;
+
+/* mpc::LParameters (include/mpc/Types.hpp:142-160) + the OSQP v0.6.3 defaults LOptimizer::run inherits through
+ * osqp_set_default_settings (include/mpc/LMPC/LOptimizer.hpp:244-257).  b200mpc_lmpc_default_params fills the
+ * reference defaults. */
+typedef struct b200mpc_lmpc_params {
+    int maximum_iteration;        /* Parameters::maximum_iteration = 100                                     */
+    int enable_warm_start;        /* Parameters::enable_warm_start = false                                   */
+    double alpha;                 /* 1.6                                                                     */
+    double rho;                   /* 1e-6                                                                    */
+    double eps_rel, eps_abs;      /* 1e-4                                                                    */
+    double eps_prim_inf, eps_dual_inf; /* 1e-3                                                               */
+    int adaptive_rho;             /* true                                                                    */
+    int polish;                   /* true                                                                    */
+    /* OSQP defaults libmpc does not override */
+    double sigma;                 /* 1e-6                                                                    */
+    double delta;                 /* 1e-6                                                                    */
+    double adaptive_rho_tolerance;/* 5                                                                       */
+    int scaling;                  /* 10                                                                      */
+    int check_termination;        /* 25                                                                      */
+    int adaptive_rho_interval;    /* 25: v0.6.3 derives it from wall-clock time; pinned      */
+    int polish_refine_iter;       /* 3                                                                       */
+} b200mpc_lmpc_params;
+
+/* mpc::ResultStatus (include/mpc/Types.hpp:84-91) */
+enum { B200MPC_SUCCESS = 0, B200MPC_MAX_ITERATION = 1, B200MPC_INFEASIBLE = 2, B200MPC_ERROR = 3, B200MPC_UNKNOWN = 4 };
+
+const char* b200mpc_last_error(void);
+int b200mpc_device_count(void);
+
+void b200mpc_lmpc_default_params(b200mpc_lmpc_params* p);
+
+/* LMPC::LMPC()/onSetup -> ProblemBuilder::onInit + LOptimizer::onInit (LMPC.hpp:51-61,728-735;
+ * ProblemBuilder.hpp:88-172; LOptimizer.hpp:59-82): allocates device state for `batch` controllers with the
+ * reference defaults (zero model/weights, infinite bounds, zero references). */
+int b200mpc_lmpc_create(const b200mpc_lmpc_dims* dims, int batch, int device, b200mpc_lmpc_t* out);
+int b200mpc_lmpc_destroy(b200mpc_lmpc_t h);
+/* cudaStream_t to run on (0 = legacy default stream); passed as void* to keep cuda headers out of this file. */
+int b200mpc_lmpc_set_stream(b200mpc_lmpc_t h, void* stream);
+
+/* LMPC::setOptimizerParameters (LMPC.hpp:79-82) -> LOptimizer::setParameters (LOptimizer.hpp:100-108) */
+int b200mpc_lmpc_set_params(b200mpc_lmpc_t h, const b200mpc_lmpc_params* p);
+
+/* LMPC::setStateSpaceModel(A,B,C) (LMPC.hpp:493-500) -> ProblemBuilder::setStateModel (ProblemBuilder.hpp:184-211)
+ * A[nx*nx], B[nx*nu], C[ny*nx] row-major. */
+int b200mpc_lmpc_set_model(b200mpc_lmpc_t h, const double* A, const double* B, const double* C,
+                           int per_instance, int dev);
+/* LMPC::setDisturbances(Bd,Dd) (LMPC.hpp:518-525) -> ProblemBuilder::setExogenousInput (:222-236) */
+int b200mpc_lmpc_set_disturbances(b200mpc_lmpc_t h, const double* Bd, const double* Dd, int per_instance, int dev);
+/* LMPC::setObjectiveWeights(OWeightMat,UWeightMat,DeltaUWeightMat) (LMPC.hpp:306-313) -> setObjective (:247-263)
+ * OW[ph*ny], UW[ph*nu], DUW[ph*nu] stage-major. */
+int b200mpc_lmpc_set_weights(b200mpc_lmpc_t h, const double* OW, const double* UW, const double* DUW,
+                             int per_instance, int dev);
+/* LMPC::setStateBounds / setInputBounds / setOutputBounds matrix forms (LMPC.hpp:111-141) -> ProblemBuilder
+ * (:378-432).  XMin/XMax[ph*nx], UMin/UMax[ch*nu] (the tail ph-ch is replicated as in :406-410), YMin/YMax[ph*ny].
+ * Infinite bounds are IEEE +-inf exactly like mpc::inf (Types.hpp:228). */
+int b200mpc_lmpc_set_state_bounds(b200mpc_lmpc_t h, const double* XMin, const double* XMax, int per_instance, int dev);
+int b200mpc_lmpc_set_input_bounds(b200mpc_lmpc_t h, const double* UMin, const double* UMax, int per_instance, int dev);
+int b200mpc_lmpc_set_output_bounds(b200mpc_lmpc_t h, const double* YMin, const double* YMax, int per_instance, int dev);
+/* LMPC::setScalarConstraint(min,max,X,U,slice all) (LMPC.hpp:355-407) -> ProblemBuilder::setScalarConstraint
+ * (:347-365).  SMin/SMax[ph], X[nx], U[nu].  As in the reference the multiplier applies to every stage. */
+int b200mpc_lmpc_set_scalar_constraint(b200mpc_lmpc_t h, const double* SMin, const double* SMax, const double* X,
+                                       const double* U, int per_instance, int dev);
+/* LMPC::setReferences(outRefMat,cmdRefMat,deltaCmdRefMat) (LMPC.hpp:596-602) -> LOptimizer::setReferences
+ * (LOptimizer.hpp:119-129).  yRef[ph*ny], uRef[ph*nu], duRef[ph*nu]. */
+int b200mpc_lmpc_set_references(b200mpc_lmpc_t h, const double* yRef, const double* uRef, const double* duRef,
+                                int per_instance, int dev);
+/* LMPC::setExogenousInputs(uMeasMat) (LMPC.hpp:534-538) -> LOptimizer::setExogenousInputs (:161-165). uMeas[ph*ndu] */
+int b200mpc_lmpc_set_exogenous_inputs(b200mpc_lmpc_t h, const double* uMeas, int per_instance, int dev);
+
+/* LMPC::setSolverWarmStart / getSolverWarmStartPrimal/Dual (LMPC.hpp:677-722): primal[batch*n], dual[batch*m] in the
+ * reference's variable/row order.  n = (ph+1)(nx+nu)+ph*nu, m = 2(ph+1)(nx+nu)+(ph+1)ny+ph*nu+(ph+1). */
+int b200mpc_lmpc_set_warm_start(b200mpc_lmpc_t h, const double* primal, const double* dual, int dev);
+int b200mpc_lmpc_get_warm_start(b200mpc_lmpc_t h, double* primal, double* dual, int dev);
+
+/* IOptimizer::run(x0,u0) (IOptimizer.hpp:50, LOptimizer.hpp:189-368) for `batch` instances:
+ * x0[batch*nx], u0[batch*nu].  Enqueues the copies + ONE kernel on the handle's stream; does not synchronise.
+ * Results stay on the device until fetched. */
+int b200mpc_lmpc_solve(b200mpc_lmpc_t h, const double* x0, const double* u0, int dev);
+
+/* mpc::Result<nu> fields (Types.hpp:168-182), one entry per instance.  Any pointer may be NULL.
+ *   cmd[batch*nu], cost[batch], status[batch] (ResultStatus), solver_status[batch] (OSQP status_val),
+ *   is_feasible[batch] (0/1), iterations[batch], rho_updates[batch], status_polish[batch]
+ * `dev`=0 copies to host and synchronises the stream; `dev`=1 copies device-to-device asynchronously. */
+int b200mpc_lmpc_get_result(b200mpc_lmpc_t h, double* cmd, double* cost, int32_t* status, int32_t* solver_status,
+                            int32_t* is_feasible, int32_t* iterations, int32_t* rho_updates,
+                            int32_t* status_polish, int dev);
+/* mpc::OptSequence (Types.hpp:184-199) as filled by LOptimizer::run (:305-338): state[batch*(ph+1)*nx],
+ * input[batch*(ph+1)*nu], output[batch*(ph+1)*ny], row-major [(ph+1) x dim] per instance. */
+int b200mpc_lmpc_get_sequence(b200mpc_lmpc_t h, double* state, double* input, double* output, int dev);
+/* Device pointer of the command block cmd[batch*nu] (for a fused NCCL all-gather on the same stream). */
+int b200mpc_lmpc_cmd_device_ptr(b200mpc_lmpc_t h, double** cmd_dev);
+
+/* Engine introspection used by bench.py / profiles: resident warp slots, workspace bytes per slot, kernel
+ * launches issued so far, algorithmic FP64 flop estimate of the last solve (sum over instances). */
+int b200mpc_lmpc_info(b200mpc_lmpc_t h, int* warp_slots, size_t* workspace_bytes_per_slot, long long* launches);
+/* Override launch geometry (0 = auto): warps per CTA and CTAs per SM of the persistent solve kernel. */
+int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm);
+int b200mpc_sync(b200mpc_lmpc_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MPC_H */

@@ -1,0 +1,455 @@
+"""libmpc_b200 -- B200-native batched MPC solve engine behind the libmpc++ (mpc::LMPC<>) API.
+
+Python host-side mirror of the reference's controller interface over the C ABI in include/b200mpc.h
+(libmpc_b200/libb200mpc.so, hand-written sm_100a CUDA).  The C++20 mirror of the same interface is
+include/mpc_b200/LMPC.hpp.  There is NO CPU fallback: constructing a controller without the CUDA extension or
+without a GPU raises.
+
+Reference anchors (paths relative to the libmpc++ repository):
+  mpc::LMPC<Tnx,Tnu,Tndu,Tny,Tph,Tch>   include/mpc/LMPC.hpp:23-749
+  mpc::IMPC::optimize                    include/mpc/IMPC.hpp:149-166
+  mpc::LParameters / Result / OptSequence include/mpc/Types.hpp:142-199
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200mpc.so")
+
+inf = float("inf")
+
+# mpc::ResultStatus (Types.hpp:84-91)
+SUCCESS, MAX_ITERATION, INFEASIBLE, ERROR, UNKNOWN = range(5)
+
+
+class _Dims(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("nx", "nu", "ndu", "ny", "ph", "ch")]
+
+
+class _Params(C.Structure):
+    _fields_ = [("maximum_iteration", C.c_int), ("enable_warm_start", C.c_int), ("alpha", C.c_double),
+                ("rho", C.c_double), ("eps_rel", C.c_double), ("eps_abs", C.c_double), ("eps_prim_inf", C.c_double),
+                ("eps_dual_inf", C.c_double), ("adaptive_rho", C.c_int), ("polish", C.c_int), ("sigma", C.c_double),
+                ("delta", C.c_double), ("adaptive_rho_tolerance", C.c_double), ("scaling", C.c_int),
+                ("check_termination", C.c_int), ("adaptive_rho_interval", C.c_int), ("polish_refine_iter", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA extension; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(libmpc_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    dp = C.POINTER(C.c_double)
+    ip = C.POINTER(C.c_int32)
+    H = C.c_void_p
+    lib.b200mpc_last_error.restype = C.c_char_p
+    lib.b200mpc_device_count.restype = C.c_int
+    lib.b200mpc_lmpc_default_params.argtypes = [C.POINTER(_Params)]
+    lib.b200mpc_lmpc_create.argtypes = [C.POINTER(_Dims), C.c_int, C.c_int, C.POINTER(H)]
+    lib.b200mpc_lmpc_destroy.argtypes = [H]
+    lib.b200mpc_lmpc_set_stream.argtypes = [H, C.c_void_p]
+    lib.b200mpc_lmpc_set_params.argtypes = [H, C.POINTER(_Params)]
+    for name, nptr in (("set_model", 3), ("set_disturbances", 2), ("set_weights", 3), ("set_state_bounds", 2),
+                       ("set_input_bounds", 2), ("set_output_bounds", 2), ("set_scalar_constraint", 4),
+                       ("set_references", 3), ("set_exogenous_inputs", 1)):
+        getattr(lib, "b200mpc_lmpc_" + name).argtypes = [H] + [C.c_void_p] * nptr + [C.c_int, C.c_int]
+    lib.b200mpc_lmpc_set_warm_start.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int]
+    lib.b200mpc_lmpc_get_warm_start.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int]
+    lib.b200mpc_lmpc_solve.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int]
+    lib.b200mpc_lmpc_get_result.argtypes = [H] + [C.c_void_p] * 8 + [C.c_int]
+    lib.b200mpc_lmpc_get_sequence.argtypes = [H] + [C.c_void_p] * 3 + [C.c_int]
+    lib.b200mpc_lmpc_cmd_device_ptr.argtypes = [H, C.POINTER(C.c_void_p)]
+    lib.b200mpc_lmpc_info.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_longlong)]
+    lib.b200mpc_lmpc_set_launch.argtypes = [H, C.c_int, C.c_int]
+    lib.b200mpc_sync.argtypes = [H]
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "b200mpc_last_error", "b200mpc_device_count", "b200mpc_lmpc_default_params", "b200mpc_lmpc_create",
+    "b200mpc_lmpc_destroy", "b200mpc_lmpc_set_stream", "b200mpc_lmpc_set_params", "b200mpc_lmpc_set_model",
+    "b200mpc_lmpc_set_disturbances", "b200mpc_lmpc_set_weights", "b200mpc_lmpc_set_state_bounds",
+    "b200mpc_lmpc_set_input_bounds", "b200mpc_lmpc_set_output_bounds", "b200mpc_lmpc_set_scalar_constraint",
+    "b200mpc_lmpc_set_references", "b200mpc_lmpc_set_exogenous_inputs", "b200mpc_lmpc_set_warm_start",
+    "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
+    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_sync",
+]
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"b200mpc error {rc}: {load_library().b200mpc_last_error().decode()}")
+
+
+@dataclass
+class LParameters:
+    """mpc::LParameters (Types.hpp:99-160)."""
+    maximum_iteration: int = 100
+    time_limit: float = 0.0
+    enable_warm_start: bool = False
+    alpha: float = 1.6
+    rho: float = 1e-6
+    eps_rel: float = 1e-4
+    eps_abs: float = 1e-4
+    eps_prim_inf: float = 1e-3
+    eps_dual_inf: float = 1e-3
+    verbose: bool = False
+    adaptive_rho: bool = True
+    polish: bool = True
+
+
+@dataclass
+class HorizonSlice:
+    """mpc::HorizonSlice (Types.hpp:57-79): [start, end), all() == {-1,-1}."""
+    start: int = -1
+    end: int = -1
+
+    @staticmethod
+    def all():
+        return HorizonSlice(-1, -1)
+
+
+class Result:
+    """mpc::Result<nu> for a batch (Types.hpp:168-182): arrays with a leading batch axis."""
+
+    def __init__(self, cmd, cost, status, solver_status, is_feasible, iterations, rho_updates, status_polish):
+        self.cmd, self.cost, self.status, self.solver_status = cmd, cost, status, solver_status
+        self.is_feasible, self.iterations, self.rho_updates, self.status_polish = is_feasible, iterations, rho_updates, status_polish
+
+
+class OptSequence:
+    def __init__(self, state, input, output):
+        self.state, self.input, self.output = state, input, output
+
+
+def _slice(s):
+    if s is None:
+        return HorizonSlice.all()
+    if isinstance(s, HorizonSlice):
+        return s
+    a, b = s
+    return HorizonSlice(int(a), int(b))
+
+
+class LMPC:
+    """Batched mpc::LMPC<Tnx,Tnu,Tndu,Tny,Tph,Tch>.  With batch=1 it is a drop-in for one reference controller; every
+    setter accepts either the reference's shape (shared by the batch) or the same with a leading batch axis."""
+
+    def __init__(self, nx, nu, ndu, ny, ph, ch, batch=1, device=0):
+        self.lib = load_library()
+        self.nx, self.nu, self.ndu, self.ny, self.ph, self.ch, self.batch = nx, nu, ndu, ny, ph, ch, batch
+        self.n = (ph + 1) * (nx + nu) + ph * nu
+        self.m = 2 * (ph + 1) * (nx + nu) + (ph + 1) * ny + ph * nu + (ph + 1)
+        self._h = C.c_void_p()
+        dims = _Dims(nx, nu, ndu, ny, ph, ch)
+        _check(self.lib.b200mpc_lmpc_create(C.byref(dims), batch, device, C.byref(self._h)))
+        # host mirror of the builder state (API-level matrices, [.., dim, ph])
+        z = np.zeros
+        self._st = dict(
+            OW=z((ny, ph)), UW=z((nu, ph)), DUW=z((nu, ph)),
+            XMin=np.full((nx, ph), -inf), XMax=np.full((nx, ph), inf),
+            YMin=np.full((ny, ph), -inf), YMax=np.full((ny, ph), inf),
+            UMin=np.full((nu, ph), -inf), UMax=np.full((nu, ph), inf),   # internal minU/maxU: nu x ph
+            SMin=np.full((ph,), -inf), SMax=np.full((ph,), inf), SX=z((nx,)), SU=z((nu,)),
+            yRef=z((ny, ph)), uRef=z((nu, ph)), duRef=z((nu, ph)), uMeas=z((ndu, ph)))
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.lib.b200mpc_lmpc_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _hz(self, a, tail):
+        """[.., dim, ph] -> contiguous stage-major [.., ph, dim]; returns (array, per_instance)."""
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim == len(tail):
+            pi = 0
+        elif a.ndim == len(tail) + 1 and a.shape[0] == self.batch:
+            pi = 1
+        else:
+            raise ValueError(f"expected shape {tail} or {(self.batch,) + tuple(tail)}, got {a.shape}")
+        if tuple(a.shape[-len(tail):]) != tuple(tail):
+            raise ValueError(f"expected trailing shape {tail}, got {a.shape}")
+        if len(tail) == 2:
+            a = np.swapaxes(a, -1, -2)
+        return np.ascontiguousarray(a), pi
+
+    def _mat(self, a, shape):
+        a = np.asarray(a, dtype=np.float64)
+        if a.shape == tuple(shape):
+            return np.ascontiguousarray(a), 0
+        if a.shape == (self.batch,) + tuple(shape):
+            return np.ascontiguousarray(a), 1
+        raise ValueError(f"expected shape {shape} or {(self.batch,) + tuple(shape)}, got {a.shape}")
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def _bcast_pi(self, arrs_pi):
+        """The C setters take one per_instance flag for the whole group: broadcast shared members if needed."""
+        pi = max(p for _, p in arrs_pi)
+        out = []
+        for a, p in arrs_pi:
+            if pi and not p:
+                a = np.ascontiguousarray(np.broadcast_to(a, (self.batch,) + a.shape))
+            out.append(a)
+        return out, pi
+
+    # ---- unsupported in LMPC, as in the reference (LMPC.hpp:68-100) -----------------------------
+    def setDiscretizationSamplingTime(self, ts):
+        raise RuntimeError("Linear MPC supports only discrete time systems")
+
+    def setInputScale(self, scaling):
+        raise RuntimeError("Linear MPC does not support input scaling")
+
+    def setStateScale(self, scaling):
+        raise RuntimeError("Linear MPC does not support state scaling")
+
+    # ---- setters ---------------------------------------------------------------------------------
+    def setOptimizerParameters(self, p: LParameters):
+        q = _Params()
+        self.lib.b200mpc_lmpc_default_params(C.byref(q))
+        q.maximum_iteration = int(p.maximum_iteration)
+        q.enable_warm_start = int(bool(p.enable_warm_start))
+        q.alpha, q.rho, q.eps_rel, q.eps_abs = p.alpha, p.rho, p.eps_rel, p.eps_abs
+        q.eps_prim_inf, q.eps_dual_inf = p.eps_prim_inf, p.eps_dual_inf
+        q.adaptive_rho, q.polish = int(bool(p.adaptive_rho)), int(bool(p.polish))
+        _check(self.lib.b200mpc_lmpc_set_params(self._h, C.byref(q)))
+
+    def setStateSpaceModel(self, A, B, Cm):
+        (A, B, Cm), pi = self._bcast_pi([self._mat(A, (self.nx, self.nx)), self._mat(B, (self.nx, self.nu)),
+                                         self._mat(Cm, (self.ny, self.nx))])
+        _check(self.lib.b200mpc_lmpc_set_model(self._h, self._p(A), self._p(B), self._p(Cm), pi, 0))
+        _check(self.lib.b200mpc_sync(self._h))
+        return True
+
+    def setDisturbances(self, Bd, Dd):
+        (Bd, Dd), pi = self._bcast_pi([self._mat(Bd, (self.nx, self.ndu)), self._mat(Dd, (self.ny, self.ndu))])
+        _check(self.lib.b200mpc_lmpc_set_disturbances(self._h, self._p(Bd), self._p(Dd), pi, 0))
+        _check(self.lib.b200mpc_sync(self._h))
+        return True
+
+    def _group(self, names, values, slice_, dims, horizon, validate_ctrl=False):
+        """Shared implementation of the matrix / vector+slice setter pairs of LMPC.hpp."""
+        st = self._st
+        sl = _slice(slice_)
+        vals = [np.asarray(v, dtype=np.float64) for v in values]
+        is_matrix = vals[0].ndim >= 2 and vals[0].shape[-1] == horizon and vals[0].shape[-2] == dims[0] and slice_ is None
+        if is_matrix:
+            for nme, v in zip(names, vals):
+                st[nme] = v.copy()
+            return True
+        # vector form
+        lim = self.ch if validate_ctrl else self.ph
+        if sl.start == -1 and sl.end == -1:
+            rng = range(horizon)
+        else:
+            if sl.start >= sl.end or sl.start > lim or sl.end > lim:   # IMPC.hpp:252-272
+                return False
+            rng = range(sl.start, sl.end)
+        for nme, v, dim in zip(names, vals, dims):
+            cur = st[nme]
+            if v.ndim == 2 and cur.ndim == 2:     # per-instance vectors: promote the host mirror
+                cur = np.broadcast_to(cur, (self.batch,) + cur.shape).copy()
+            if v.shape[-1] != dim:
+                raise ValueError(f"{nme}: expected vector of length {dim}")
+            for i in rng:
+                cur[..., :, i] = v
+            st[nme] = cur
+        return True
+
+    def setObjectiveWeights(self, OWeight, UWeight, DeltaUWeight, slice=None):
+        ok = self._group(("OW", "UW", "DUW"), (OWeight, UWeight, DeltaUWeight), slice, (self.ny, self.nu, self.nu), self.ph)
+        if ok:
+            self._push_weights()
+        return ok
+
+    def setStateBounds(self, XMin, XMax, slice=None):
+        ok = self._group(("XMin", "XMax"), (XMin, XMax), slice, (self.nx, self.nx), self.ph)
+        if ok:
+            self._push2("b200mpc_lmpc_set_state_bounds", "XMin", "XMax", (self.nx, self.ph))
+        return ok
+
+    def setOutputBounds(self, YMin, YMax, slice=None):
+        ok = self._group(("YMin", "YMax"), (YMin, YMax), slice, (self.ny, self.ny), self.ph)
+        if ok:
+            self._push2("b200mpc_lmpc_set_output_bounds", "YMin", "YMax", (self.ny, self.ph))
+        return ok
+
+    def setInputBounds(self, UMin, UMax, slice=None):
+        """Matrix form is [nu x ch] with the tail replicated (ProblemBuilder.hpp:397-413); vector+slice form indexes
+        the control horizon (LMPC.hpp:197-241) and touches only the named columns (ProblemBuilder.hpp:469-477)."""
+        a = np.asarray(UMin, dtype=np.float64)
+        if slice is None and a.ndim >= 2 and a.shape[-1] == self.ch and a.shape[-2] == self.nu:
+            for nme, v in (("UMin", UMin), ("UMax", UMax)):
+                v = np.asarray(v, dtype=np.float64)
+                full = np.concatenate([v, np.repeat(v[..., :, -1:], self.ph - self.ch, axis=-1)], axis=-1)
+                self._st[nme] = full
+        else:
+            sl = _slice(slice)
+            if sl.start == -1 and sl.end == -1:
+                # LMPC.hpp:200-216 builds a [nu x ch] matrix and calls the matrix setter
+                v0, v1 = np.asarray(UMin, float), np.asarray(UMax, float)
+                return self.setInputBounds(np.repeat(v0[..., :, None], self.ch, axis=-1),
+                                           np.repeat(v1[..., :, None], self.ch, axis=-1))
+            if not self._group(("UMin", "UMax"), (UMin, UMax), sl, (self.nu, self.nu), self.ph, validate_ctrl=True):
+                return False
+        # the C setter takes the [ch] columns and replicates the tail itself; pass internal columns directly by using ch=ph view
+        self._push_input_bounds()
+        return True
+
+    def setScalarConstraint(self, smin, smax, X, U, slice=None):
+        """LMPC.hpp:355-422.  The multiplier [X;U] applies to every stage (ProblemBuilder.hpp:329-332)."""
+        st = self._st
+        sl = _slice(slice)
+        if sl.start == -1 and sl.end == -1:
+            for key, v in (("SMin", smin), ("SMax", smax)):
+                v = np.asarray(v, dtype=np.float64)
+                if v.ndim == 0:
+                    v = np.full((self.ph,), float(v))
+                elif v.shape not in ((self.ph,), (self.batch, self.ph)):
+                    raise ValueError("scalar-constraint bounds: expected scalar, [ph] or [batch, ph]")
+                st[key] = v.copy()
+        else:
+            if sl.start >= sl.end or sl.start > self.ph or sl.end > self.ph:
+                return False
+            for i in range(sl.start, sl.end):
+                st["SMin"][..., i] = smin
+                st["SMax"][..., i] = smax
+        st["SX"], st["SU"] = np.asarray(X, float).copy(), np.asarray(U, float).copy()
+        arrs = [self._hz(st["SMin"], (self.ph,)), self._hz(st["SMax"], (self.ph,)), self._hz(st["SX"], (self.nx,)),
+                self._hz(st["SU"], (self.nu,))]
+        (a, b, c, d), pi = self._bcast_pi(arrs)
+        _check(self.lib.b200mpc_lmpc_set_scalar_constraint(self._h, self._p(a), self._p(b), self._p(c), self._p(d), pi, 0))
+        _check(self.lib.b200mpc_sync(self._h))
+        return True
+
+    def setReferences(self, outRef, cmdRef, deltaCmdRef, slice=None):
+        ok = self._group(("yRef", "uRef", "duRef"), (outRef, cmdRef, deltaCmdRef), slice, (self.ny, self.nu, self.nu), self.ph)
+        if ok:
+            arrs = [self._hz(self._st[k], s) for k, s in (("yRef", (self.ny, self.ph)), ("uRef", (self.nu, self.ph)),
+                                                           ("duRef", (self.nu, self.ph)))]
+            (a, b, c), pi = self._bcast_pi(arrs)
+            _check(self.lib.b200mpc_lmpc_set_references(self._h, self._p(a), self._p(b), self._p(c), pi, 0))
+            _check(self.lib.b200mpc_sync(self._h))
+        return ok
+
+    def setExogenousInputs(self, uMeas, slice=None):
+        ok = self._group(("uMeas",), (uMeas,), slice, (self.ndu,), self.ph, validate_ctrl=slice is not None)
+        if ok:
+            a, pi = self._hz(self._st["uMeas"], (self.ndu, self.ph))
+            _check(self.lib.b200mpc_lmpc_set_exogenous_inputs(self._h, self._p(a), pi, 0))
+            _check(self.lib.b200mpc_sync(self._h))
+        return ok
+
+    def _push_weights(self):
+        arrs = [self._hz(self._st[k], s) for k, s in (("OW", (self.ny, self.ph)), ("UW", (self.nu, self.ph)),
+                                                       ("DUW", (self.nu, self.ph)))]
+        (a, b, c), pi = self._bcast_pi(arrs)
+        _check(self.lib.b200mpc_lmpc_set_weights(self._h, self._p(a), self._p(b), self._p(c), pi, 0))
+        _check(self.lib.b200mpc_sync(self._h))
+
+    def _push2(self, fn, k0, k1, shape):
+        (a, b), pi = self._bcast_pi([self._hz(self._st[k0], shape), self._hz(self._st[k1], shape)])
+        _check(getattr(self.lib, fn)(self._h, self._p(a), self._p(b), pi, 0))
+        _check(self.lib.b200mpc_sync(self._h))
+
+    def _push_input_bounds(self):
+        # host mirror holds the internal [nu x ph] matrices; the C entry point wants [ch] columns + tail rule.  The
+        # internal columns beyond ch can differ from column ch-1 only through per-index setters, which the reference
+        # restricts to index < ch, so sending the first ch columns reproduces the internal state exactly.
+        lo, hi = self._st["UMin"][..., :, :self.ch], self._st["UMax"][..., :, :self.ch]
+        (a, b), pi = self._bcast_pi([self._hz(lo, (self.nu, self.ch)), self._hz(hi, (self.nu, self.ch))])
+        _check(self.lib.b200mpc_lmpc_set_input_bounds(self._h, self._p(a), self._p(b), pi, 0))
+        _check(self.lib.b200mpc_sync(self._h))
+
+    # ---- warm start accessors (LMPC.hpp:677-722) -------------------------------------------------
+    def getSolverWarmStartPrimal(self):
+        x = np.empty((self.batch, self.n))
+        _check(self.lib.b200mpc_lmpc_get_warm_start(self._h, self._p(x), None, 0))
+        return x
+
+    def getSolverWarmStartDual(self):
+        y = np.empty((self.batch, self.m))
+        _check(self.lib.b200mpc_lmpc_get_warm_start(self._h, None, self._p(y), 0))
+        return y
+
+    def setSolverWarmStart(self, primal, dual):
+        x = np.ascontiguousarray(np.broadcast_to(np.asarray(primal, float), (self.batch, self.n)))
+        y = np.ascontiguousarray(np.broadcast_to(np.asarray(dual, float), (self.batch, self.m)))
+        _check(self.lib.b200mpc_lmpc_set_warm_start(self._h, self._p(x), self._p(y), 0))
+        _check(self.lib.b200mpc_sync(self._h))
+
+    # ---- solve -------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.lib.b200mpc_lmpc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_launch(self, warps_per_cta=0, ctas_per_sm=0):
+        _check(self.lib.b200mpc_lmpc_set_launch(self._h, warps_per_cta, ctas_per_sm))
+
+    def info(self):
+        a, b, c = C.c_int(), C.c_size_t(), C.c_longlong()
+        _check(self.lib.b200mpc_lmpc_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(warp_slots=a.value, workspace_bytes_per_slot=b.value, launches=c.value)
+
+    def solve_async(self, x0, u0, dev=False):
+        """Enqueue one batched IOptimizer::run.  x0/u0: host arrays, or raw device pointers (ints) when dev=True."""
+        if dev:
+            _check(self.lib.b200mpc_lmpc_solve(self._h, C.c_void_p(int(x0)), C.c_void_p(int(u0)), 1))
+            return
+        x0 = np.ascontiguousarray(np.broadcast_to(np.asarray(x0, float), (self.batch, self.nx)))
+        u0 = np.ascontiguousarray(np.broadcast_to(np.asarray(u0, float), (self.batch, self.nu)))
+        self._keep = [x0, u0]
+        _check(self.lib.b200mpc_lmpc_solve(self._h, self._p(x0), self._p(u0), 0))
+
+    def fetch_result(self):
+        B = self.batch
+        cmd, cost = np.empty((B, self.nu)), np.empty(B)
+        ints = [np.empty(B, dtype=np.int32) for _ in range(6)]
+        _check(self.lib.b200mpc_lmpc_get_result(self._h, self._p(cmd), self._p(cost), *[self._p(a) for a in ints], 0))
+        return Result(cmd, cost, ints[0], ints[1], ints[2].astype(bool), ints[3], ints[4], ints[5])
+
+    def optimize(self, x0, lastU):
+        """IMPC::optimize(x0,lastU) (IMPC.hpp:149-166) for the whole batch."""
+        self.solve_async(x0, lastU)
+        self._last = self.fetch_result()
+        return self._last
+
+    step = optimize   # pre-0.5.0 name of the same call (CHANGELOG.md:64-65)
+
+    def getLastResult(self):
+        return self._last
+
+    def getOptimalSequence(self):
+        B, ph = self.batch, self.ph
+        s, i, o = np.empty((B, ph + 1, self.nx)), np.empty((B, ph + 1, self.nu)), np.empty((B, ph + 1, self.ny))
+        _check(self.lib.b200mpc_lmpc_get_sequence(self._h, self._p(s), self._p(i), self._p(o), 0))
+        return OptSequence(s, i, o)
+
+    def cmd_device_ptr(self):
+        p = C.c_void_p()
+        _check(self.lib.b200mpc_lmpc_cmd_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def get_result_into(self, cmd_ptr=None, status_ptr=None, iters_ptr=None):
+        """Device-to-device copy of results into caller-owned device buffers (async on the handle's stream)."""
+        v = lambda p: C.c_void_p(int(p)) if p else None
+        _check(self.lib.b200mpc_lmpc_get_result(self._h, v(cmd_ptr), None, v(status_ptr), None, None, v(iters_ptr), None, None, 1))

@@ -1,0 +1,434 @@
+// b200mpc_capi.cu -- host side of the C ABI declared in include/b200mpc.h.
+// Owns the device-resident controller state of a batch of LMPC instances (what ProblemBuilder + LOptimizer hold per
+// object in the reference: include/mpc/LMPC/ProblemBuilder.hpp:827-857, include/mpc/LMPC/LOptimizer.hpp:518-527) and
+// launches the single persistent solve kernel.  There is no CPU fallback: without a CUDA device every entry point
+// that would compute returns B200MPC_ENOGPU.
+#include "../../include/b200mpc.h"
+#include "lmpc_kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace b200mpc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(B200MPC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DevBuf {
+    double* p = nullptr;
+    size_t count = 0;       // doubles per instance
+    bool per_instance = false;
+};
+
+struct b200mpc_lmpc {
+    Dm d;
+    int batch = 0, device = 0;
+    cudaStream_t stream = 0;
+    Params p;
+    int enable_warm_start = 0;
+    bool has_prev = false, model_set = false;
+    DevBuf A, B, C, Bd, Dd, OW, UW, DUW, XMin, XMax, YMin, YMax, UMin, UMax, SMin, SMax, SX, SU, yRef, uRef, duRef, uMeas;
+    double *x0 = nullptr, *u0 = nullptr;
+    // results
+    double *cmd = nullptr, *prev_cmd = nullptr, *cost = nullptr, *seq_state = nullptr, *seq_input = nullptr, *seq_output = nullptr;
+    double *sol_x = nullptr, *sol_y = nullptr;
+    int *status = nullptr, *solver_status = nullptr, *feasible = nullptr, *iters = nullptr, *rho_updates = nullptr, *polish = nullptr;
+    // engine
+    double* workspace = nullptr;
+    size_t ws_stride = 0;
+    int* counter = nullptr;
+    int warps_per_cta = 0, ctas_per_sm = 0, grid = 0, num_sms = 0;
+    int req_wpc = 0, req_cps = 0;
+    long long launches = 0;
+    std::vector<double> stage;   // host staging
+};
+
+extern "C" const char* b200mpc_last_error(void) { return g_err.c_str(); }
+
+extern "C" int b200mpc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void b200mpc_lmpc_default_params(b200mpc_lmpc_params* p) {
+    if (!p) return;
+    p->maximum_iteration = 100; p->enable_warm_start = 0;
+    p->alpha = 1.6; p->rho = 1e-6; p->eps_rel = 1e-4; p->eps_abs = 1e-4; p->eps_prim_inf = 1e-3; p->eps_dual_inf = 1e-3;
+    p->adaptive_rho = 1; p->polish = 1;
+    p->sigma = 1e-6; p->delta = 1e-6; p->adaptive_rho_tolerance = 5.0; p->scaling = 10; p->check_termination = 25;
+    p->adaptive_rho_interval = 25; p->polish_refine_iter = 3;
+}
+
+static int fill_const(b200mpc_lmpc* h, DevBuf& b, size_t count, double v) {
+    b.count = count; b.per_instance = false;
+    size_t bytes = (count ? count : 1) * sizeof(double);
+    CK(cudaMalloc(&b.p, bytes));
+    std::vector<double> tmp(count ? count : 1, v);
+    CK(cudaMemcpy(b.p, tmp.data(), bytes, cudaMemcpyHostToDevice));
+    (void)h;
+    return B200MPC_OK;
+}
+
+static int upload(b200mpc_lmpc* h, DevBuf& b, const double* src, int per_instance, int dev) {
+    if (!src && b.count) return fail(B200MPC_EINVAL, "null pointer");
+    bool pi = per_instance != 0;
+    size_t total = b.count * (pi ? (size_t)h->batch : 1);
+    if (pi != b.per_instance) {
+        double* np = nullptr;
+        CK(cudaMalloc(&np, (total ? total : 1) * sizeof(double)));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(b.p);
+        b.p = np; b.per_instance = pi;
+    }
+    if (total) CK(cudaMemcpyAsync(b.p, src, total * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    return B200MPC_OK;
+}
+
+template <class T>
+static int dalloc(T** p, size_t n) {
+    CK(cudaMalloc(p, (n ? n : 1) * sizeof(T)));
+    CK(cudaMemset(*p, 0, (n ? n : 1) * sizeof(T)));
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_lmpc_create(const b200mpc_lmpc_dims* dims, int batch, int device, b200mpc_lmpc_t* out) {
+    if (!dims || !out || batch <= 0) return fail(B200MPC_EINVAL, "bad arguments");
+    if (dims->nx < 0 || dims->nu < 0 || dims->ndu < 0 || dims->ny < 0 || dims->ph < 1 || dims->ch < 1 || dims->ch > dims->ph ||
+        dims->nx + dims->nu <= 0)
+        return fail(B200MPC_EINVAL, "bad dimensions");
+    int ndev = b200mpc_device_count();
+    if (ndev <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(B200MPC_EINVAL, "bad device index");
+    CK(cudaSetDevice(device));
+    b200mpc_lmpc* h = new (std::nothrow) b200mpc_lmpc();
+    if (!h) return fail(B200MPC_EINVAL, "out of host memory");
+    h->d.nx = dims->nx; h->d.nu = dims->nu; h->d.ndu = dims->ndu; h->d.ny = dims->ny; h->d.ph = dims->ph; h->d.ch = dims->ch;
+    h->d.derive();
+    h->batch = batch; h->device = device;
+    b200mpc_lmpc_params dp; b200mpc_lmpc_default_params(&dp);
+    const Dm& d = h->d;
+    const double inf = std::numeric_limits<double>::infinity();
+    int rc;
+#define F(buf, cnt, val) if ((rc = fill_const(h, h->buf, (size_t)(cnt), (val))) != 0) return rc
+    F(A, d.nx * d.nx, 0.0); F(B, d.nx * d.nu, 0.0); F(C, d.ny * d.nx, 0.0); F(Bd, d.nx * d.ndu, 0.0); F(Dd, d.ny * d.ndu, 0.0);
+    F(OW, d.ph * d.ny, 0.0); F(UW, d.ph * d.nu, 0.0); F(DUW, d.ph * d.nu, 0.0);
+    F(XMin, d.ph * d.nx, -inf); F(XMax, d.ph * d.nx, inf); F(YMin, d.ph * d.ny, -inf); F(YMax, d.ph * d.ny, inf);
+    F(UMin, d.ph * d.nu, -inf); F(UMax, d.ph * d.nu, inf); F(SMin, d.ph, -inf); F(SMax, d.ph, inf);
+    F(SX, d.nx, 0.0); F(SU, d.nu, 0.0);
+    F(yRef, d.ph * d.ny, 0.0); F(uRef, d.ph * d.nu, 0.0); F(duRef, d.ph * d.nu, 0.0); F(uMeas, d.ph * d.ndu, 0.0);
+#undef F
+    size_t Bn = (size_t)batch;
+    if ((rc = dalloc(&h->x0, Bn * d.nx))) return rc;
+    if ((rc = dalloc(&h->u0, Bn * d.nu))) return rc;
+    if ((rc = dalloc(&h->cmd, Bn * d.nu))) return rc;
+    if ((rc = dalloc(&h->prev_cmd, Bn * d.nu))) return rc;
+    if ((rc = dalloc(&h->cost, Bn))) return rc;
+    if ((rc = dalloc(&h->seq_state, Bn * (d.ph + 1) * d.nx))) return rc;
+    if ((rc = dalloc(&h->seq_input, Bn * (d.ph + 1) * d.nu))) return rc;
+    if ((rc = dalloc(&h->seq_output, Bn * (d.ph + 1) * d.ny))) return rc;
+    if ((rc = dalloc(&h->sol_x, Bn * d.n))) return rc;
+    if ((rc = dalloc(&h->sol_y, Bn * d.m))) return rc;
+    if ((rc = dalloc(&h->status, Bn))) return rc;
+    if ((rc = dalloc(&h->solver_status, Bn))) return rc;
+    if ((rc = dalloc(&h->feasible, Bn))) return rc;
+    if ((rc = dalloc(&h->iters, Bn))) return rc;
+    if ((rc = dalloc(&h->rho_updates, Bn))) return rc;
+    if ((rc = dalloc(&h->polish, Bn))) return rc;
+    if ((rc = dalloc(&h->counter, 1))) return rc;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    *out = h;
+    return b200mpc_lmpc_set_params(h, &dp);
+}
+
+static void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; }
+
+extern "C" int b200mpc_lmpc_destroy(b200mpc_lmpc_t h) {
+    if (!h) return B200MPC_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->A, &h->B, &h->C, &h->Bd, &h->Dd, &h->OW, &h->UW, &h->DUW, &h->XMin, &h->XMax, &h->YMin, &h->YMax,
+                      &h->UMin, &h->UMax, &h->SMin, &h->SMax, &h->SX, &h->SU, &h->yRef, &h->uRef, &h->duRef, &h->uMeas};
+    for (DevBuf* b : bufs) free_buf(*b);
+    void* ptrs[] = {h->x0, h->u0, h->cmd, h->prev_cmd, h->cost, h->seq_state, h->seq_input, h->seq_output, h->sol_x, h->sol_y,
+                    h->status, h->solver_status, h->feasible, h->iters, h->rho_updates, h->polish, h->counter, h->workspace};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete h;
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_lmpc_set_stream(b200mpc_lmpc_t h, void* stream) {
+    if (!h) return fail(B200MPC_EINVAL, "null handle");
+    h->stream = (cudaStream_t)stream;
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_lmpc_set_params(b200mpc_lmpc_t h, const b200mpc_lmpc_params* q) {
+    if (!h || !q) return fail(B200MPC_EINVAL, "null argument");
+    if (q->check_termination < 0 || q->scaling < 0 || q->adaptive_rho_interval < 0) return fail(B200MPC_EINVAL, "bad parameter");
+    Params& p = h->p;
+    p.max_iter = q->maximum_iteration; p.adaptive_rho = q->adaptive_rho; p.polish = q->polish; p.scaling = q->scaling;
+    p.check_termination = q->check_termination; p.adaptive_rho_interval = q->adaptive_rho_interval;
+    p.polish_refine_iter = q->polish_refine_iter;
+    p.alpha = q->alpha; p.rho = q->rho; p.sigma = q->sigma; p.delta = q->delta; p.eps_abs = q->eps_abs; p.eps_rel = q->eps_rel;
+    p.eps_prim_inf = q->eps_prim_inf; p.eps_dual_inf = q->eps_dual_inf; p.adaptive_rho_tolerance = q->adaptive_rho_tolerance;
+    h->enable_warm_start = q->enable_warm_start;
+    return B200MPC_OK;
+}
+
+#define HCHECK() do { if (!h) return fail(B200MPC_EINVAL, "null handle"); CK(cudaSetDevice(h->device)); } while (0)
+
+extern "C" int b200mpc_lmpc_set_model(b200mpc_lmpc_t h, const double* A, const double* B, const double* C, int pi, int dev) {
+    HCHECK();
+    int rc;
+    if ((rc = upload(h, h->A, A, pi, dev))) return rc;
+    if ((rc = upload(h, h->B, B, pi, dev))) return rc;
+    if ((rc = upload(h, h->C, C, pi, dev))) return rc;
+    h->model_set = true;
+    return B200MPC_OK;
+}
+extern "C" int b200mpc_lmpc_set_disturbances(b200mpc_lmpc_t h, const double* Bd, const double* Dd, int pi, int dev) {
+    HCHECK();
+    int rc;
+    if ((rc = upload(h, h->Bd, Bd, pi, dev))) return rc;
+    return upload(h, h->Dd, Dd, pi, dev);
+}
+extern "C" int b200mpc_lmpc_set_weights(b200mpc_lmpc_t h, const double* OW, const double* UW, const double* DUW, int pi, int dev) {
+    HCHECK();
+    int rc;
+    if ((rc = upload(h, h->OW, OW, pi, dev))) return rc;
+    if ((rc = upload(h, h->UW, UW, pi, dev))) return rc;
+    return upload(h, h->DUW, DUW, pi, dev);
+}
+extern "C" int b200mpc_lmpc_set_state_bounds(b200mpc_lmpc_t h, const double* lo, const double* hi, int pi, int dev) {
+    HCHECK();
+    int rc;
+    if ((rc = upload(h, h->XMin, lo, pi, dev))) return rc;
+    return upload(h, h->XMax, hi, pi, dev);
+}
+extern "C" int b200mpc_lmpc_set_output_bounds(b200mpc_lmpc_t h, const double* lo, const double* hi, int pi, int dev) {
+    HCHECK();
+    int rc;
+    if ((rc = upload(h, h->YMin, lo, pi, dev))) return rc;
+    return upload(h, h->YMax, hi, pi, dev);
+}
+
+__global__ void expand_tail_kernel(double* dst, const double* src, int nu, int ch, int ph, long long copies) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = copies * ph * nu;
+    if (idx >= total) return;
+    long long inst = idx / ((long long)ph * nu);
+    int rem = (int)(idx - inst * ph * nu);
+    int col = rem / nu, r = rem - col * nu;
+    int sc = col < ch ? col : ch - 1;       // ProblemBuilder.hpp:402-410
+    dst[idx] = src[inst * ch * nu + (long long)sc * nu + r];
+}
+
+static int upload_input_bounds(b200mpc_lmpc* h, DevBuf& b, const double* src, int per_instance, int dev) {
+    const Dm& d = h->d;
+    if (!src && b.count) return fail(B200MPC_EINVAL, "null pointer");
+    size_t copies = per_instance ? (size_t)h->batch : 1;
+    if (!dev) {
+        h->stage.resize(copies * d.ph * d.nu);
+        for (size_t i = 0; i < copies; ++i)
+            for (int col = 0; col < d.ph; ++col) {
+                int sc = col < d.ch ? col : d.ch - 1;
+                for (int r = 0; r < d.nu; ++r) h->stage[(i * d.ph + col) * d.nu + r] = src[(i * d.ch + sc) * d.nu + r];
+            }
+        int rc = upload(h, b, h->stage.data(), per_instance, 0);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(h->stream));   // staging buffer is reused
+        return B200MPC_OK;
+    }
+    // device source: make sure the destination has the right shape, then expand on the device
+    bool pi = per_instance != 0;
+    if (pi != b.per_instance) {
+        double* np = nullptr;
+        CK(cudaMalloc(&np, (copies * b.count ? copies * b.count : 1) * sizeof(double)));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(b.p); b.p = np; b.per_instance = pi;
+    }
+    long long total = (long long)copies * d.ph * d.nu;
+    if (total) expand_tail_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(b.p, src, d.nu, d.ch, d.ph, (long long)copies);
+    CK(cudaGetLastError());
+    return B200MPC_OK;
+}
+extern "C" int b200mpc_lmpc_set_input_bounds(b200mpc_lmpc_t h, const double* lo, const double* hi, int pi, int dev) {
+    HCHECK();
+    int rc;
+    if ((rc = upload_input_bounds(h, h->UMin, lo, pi, dev))) return rc;
+    return upload_input_bounds(h, h->UMax, hi, pi, dev);
+}
+extern "C" int b200mpc_lmpc_set_scalar_constraint(b200mpc_lmpc_t h, const double* SMin, const double* SMax, const double* X,
+                                                  const double* U, int pi, int dev) {
+    HCHECK();
+    int rc;
+    if ((rc = upload(h, h->SMin, SMin, pi, dev))) return rc;
+    if ((rc = upload(h, h->SMax, SMax, pi, dev))) return rc;
+    if ((rc = upload(h, h->SX, X, pi, dev))) return rc;
+    return upload(h, h->SU, U, pi, dev);
+}
+extern "C" int b200mpc_lmpc_set_references(b200mpc_lmpc_t h, const double* yRef, const double* uRef, const double* duRef, int pi, int dev) {
+    HCHECK();
+    int rc;
+    if ((rc = upload(h, h->yRef, yRef, pi, dev))) return rc;
+    if ((rc = upload(h, h->uRef, uRef, pi, dev))) return rc;
+    return upload(h, h->duRef, duRef, pi, dev);
+}
+extern "C" int b200mpc_lmpc_set_exogenous_inputs(b200mpc_lmpc_t h, const double* uMeas, int pi, int dev) {
+    HCHECK();
+    return upload(h, h->uMeas, uMeas, pi, dev);
+}
+
+extern "C" int b200mpc_lmpc_set_warm_start(b200mpc_lmpc_t h, const double* primal, const double* dual, int dev) {
+    HCHECK();
+    if (!primal || !dual) return fail(B200MPC_EINVAL, "null pointer");
+    cudaMemcpyKind k = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CK(cudaMemcpyAsync(h->sol_x, primal, (size_t)h->batch * h->d.n * sizeof(double), k, h->stream));
+    CK(cudaMemcpyAsync(h->sol_y, dual, (size_t)h->batch * h->d.m * sizeof(double), k, h->stream));
+    h->has_prev = true;
+    return B200MPC_OK;
+}
+extern "C" int b200mpc_lmpc_get_warm_start(b200mpc_lmpc_t h, double* primal, double* dual, int dev) {
+    HCHECK();
+    cudaMemcpyKind k = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (primal) CK(cudaMemcpyAsync(primal, h->sol_x, (size_t)h->batch * h->d.n * sizeof(double), k, h->stream));
+    if (dual) CK(cudaMemcpyAsync(dual, h->sol_y, (size_t)h->batch * h->d.m * sizeof(double), k, h->stream));
+    if (!dev) CK(cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+static int configure_launch(b200mpc_lmpc* h) {
+    if (h->workspace) return B200MPC_OK;
+    const Dm& d = h->d;
+    size_t smem_warp = (size_t)d.smem_doubles() * sizeof(double);
+    int dev_max_smem = 0;
+    CK(cudaDeviceGetAttribute(&dev_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    int wpc = h->req_wpc > 0 ? h->req_wpc : 4;
+    while (wpc > 1 && smem_warp * wpc > (size_t)dev_max_smem) --wpc;
+    if (smem_warp * wpc > (size_t)dev_max_smem) return fail(B200MPC_EINVAL, "problem dimensions exceed shared memory of one warp");
+    size_t smem_cta = smem_warp * wpc;
+    CK(cudaFuncSetAttribute(lmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lmpc_solve_kernel, wpc * 32, smem_cta));
+    if (occ < 1) return fail(B200MPC_ECUDA, "kernel does not fit on an SM");
+    int cps = h->req_cps > 0 ? (h->req_cps < occ ? h->req_cps : occ) : occ;
+    int grid = h->num_sms * cps;
+    int need = (h->batch + wpc - 1) / wpc;
+    if (grid > need) grid = need;
+    h->warps_per_cta = wpc; h->ctas_per_sm = cps; h->grid = grid;
+    size_t wsd = (d.ws_doubles() + 31) & ~(size_t)31;
+    h->ws_stride = wsd;
+    size_t slots = (size_t)grid * wpc;
+    CK(cudaMalloc(&h->workspace, slots * wsd * sizeof(double)));
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm) {
+    HCHECK();
+    if (warps_per_cta < 0 || warps_per_cta > 8 || ctas_per_sm < 0) return fail(B200MPC_EINVAL, "bad launch geometry");
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->workspace) { cudaFree(h->workspace); h->workspace = nullptr; }
+    h->req_wpc = warps_per_cta; h->req_cps = ctas_per_sm;
+    return configure_launch(h);
+}
+
+extern "C" int b200mpc_lmpc_solve(b200mpc_lmpc_t h, const double* x0, const double* u0, int dev) {
+    HCHECK();
+    if (!x0 || (!u0 && h->d.nu)) return fail(B200MPC_EINVAL, "null pointer");
+    int rc = configure_launch(h);
+    if (rc) return rc;
+    const Dm& d = h->d;
+    cudaMemcpyKind k = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (d.nx) CK(cudaMemcpyAsync(h->x0, x0, (size_t)h->batch * d.nx * sizeof(double), k, h->stream));
+    if (d.nu) CK(cudaMemcpyAsync(h->u0, u0, (size_t)h->batch * d.nu * sizeof(double), k, h->stream));
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(int), h->stream));
+    Prob pr;
+#define A_(name) pr.name.p = h->name.p; pr.name.stride = h->name.per_instance ? (long long)h->name.count : 0
+    A_(A); A_(B); A_(C); A_(Bd); A_(Dd); A_(OW); A_(UW); A_(DUW); A_(XMin); A_(XMax); A_(YMin); A_(YMax); A_(UMin); A_(UMax);
+    A_(SMin); A_(SMax); A_(SX); A_(SU); A_(yRef); A_(uRef); A_(duRef); A_(uMeas);
+#undef A_
+    pr.x0 = h->x0; pr.u0 = h->u0;
+    pr.warm_x = h->sol_x; pr.warm_y = h->sol_y;
+    pr.warm = (h->enable_warm_start && h->has_prev) ? 1 : 0;   // LOptimizer.hpp:268-281
+    Out o;
+    o.cmd = h->cmd; o.cost = h->cost; o.status = h->status; o.solver_status = h->solver_status; o.feasible = h->feasible;
+    o.iters = h->iters; o.rho_updates = h->rho_updates; o.polish = h->polish;
+    o.seq_state = h->seq_state; o.seq_input = h->seq_input; o.seq_output = h->seq_output;
+    o.sol_x = h->sol_x; o.sol_y = h->sol_y; o.prev_cmd = h->prev_cmd;
+    size_t smem_cta = (size_t)d.smem_doubles() * sizeof(double) * h->warps_per_cta;
+    lmpc_solve_kernel<<<h->grid, h->warps_per_cta * 32, smem_cta, h->stream>>>(h->d, h->p, pr, o, h->batch, h->workspace,
+                                                                              h->ws_stride, h->counter);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    h->has_prev = true;   // optimal_prev_x / optimal_prev_y now hold a solution (LOptimizer.hpp:295-296)
+    return B200MPC_OK;
+}
+
+template <class T>
+static int fetch(b200mpc_lmpc* h, T* dst, const T* src, size_t n, int dev) {
+    if (!dst || !n) return B200MPC_OK;
+    CK(cudaMemcpyAsync(dst, src, n * sizeof(T), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_lmpc_get_result(b200mpc_lmpc_t h, double* cmd, double* cost, int32_t* status, int32_t* solver_status,
+                                       int32_t* is_feasible, int32_t* iterations, int32_t* rho_updates, int32_t* status_polish, int dev) {
+    HCHECK();
+    size_t Bn = (size_t)h->batch;
+    int rc;
+    if ((rc = fetch(h, cmd, h->cmd, Bn * h->d.nu, dev))) return rc;
+    if ((rc = fetch(h, cost, h->cost, Bn, dev))) return rc;
+    if ((rc = fetch(h, status, h->status, Bn, dev))) return rc;
+    if ((rc = fetch(h, solver_status, h->solver_status, Bn, dev))) return rc;
+    if ((rc = fetch(h, is_feasible, h->feasible, Bn, dev))) return rc;
+    if ((rc = fetch(h, iterations, h->iters, Bn, dev))) return rc;
+    if ((rc = fetch(h, rho_updates, h->rho_updates, Bn, dev))) return rc;
+    if ((rc = fetch(h, status_polish, h->polish, Bn, dev))) return rc;
+    if (!dev) CK(cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_lmpc_get_sequence(b200mpc_lmpc_t h, double* state, double* input, double* output, int dev) {
+    HCHECK();
+    size_t Bn = (size_t)h->batch * (h->d.ph + 1);
+    int rc;
+    if ((rc = fetch(h, state, h->seq_state, Bn * h->d.nx, dev))) return rc;
+    if ((rc = fetch(h, input, h->seq_input, Bn * h->d.nu, dev))) return rc;
+    if ((rc = fetch(h, output, h->seq_output, Bn * h->d.ny, dev))) return rc;
+    if (!dev) CK(cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_lmpc_cmd_device_ptr(b200mpc_lmpc_t h, double** cmd_dev) {
+    if (!h || !cmd_dev) return fail(B200MPC_EINVAL, "null argument");
+    *cmd_dev = h->cmd;
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_lmpc_info(b200mpc_lmpc_t h, int* warp_slots, size_t* ws_bytes, long long* launches) {
+    HCHECK();
+    int rc = configure_launch(h);
+    if (rc) return rc;
+    if (warp_slots) *warp_slots = h->grid * h->warps_per_cta;
+    if (ws_bytes) *ws_bytes = h->ws_stride * sizeof(double);
+    if (launches) *launches = h->launches;
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_sync(b200mpc_lmpc_t h) {
+    HCHECK();
+    CK(cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
