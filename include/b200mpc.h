@@ -135,6 +135,9 @@ int b200mpc_lmpc_cmd_device_ptr(b200mpc_lmpc_t h, double** cmd_dev);
 int b200mpc_lmpc_info(b200mpc_lmpc_t h, int* warp_slots, size_t* workspace_bytes_per_slot, long long* launches);
 /* Override launch geometry (0 = auto): warps per CTA and CTAs per SM of the persistent solve kernel. */
 int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm);
+/* Profiling aid: first call (out_host ignored) enables per-instance phase cycle counters; later calls copy
+ * batch*8 counters [setup, factorize, admm sweeps, info, polish prep, polish factor, polish solve, unpack] to the host. */
+int b200mpc_lmpc_profile(b200mpc_lmpc_t h, long long* out_host);
 int b200mpc_sync(b200mpc_lmpc_t h);
 
 #ifdef __cplusplus

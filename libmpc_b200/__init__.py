@@ -73,6 +73,7 @@ def load_library():
     lib.b200mpc_lmpc_cmd_device_ptr.argtypes = [H, C.POINTER(C.c_void_p)]
     lib.b200mpc_lmpc_info.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_longlong)]
     lib.b200mpc_lmpc_set_launch.argtypes = [H, C.c_int, C.c_int]
+    lib.b200mpc_lmpc_profile.argtypes = [H, C.c_void_p]
     lib.b200mpc_sync.argtypes = [H]
     _lib = lib
     return lib
@@ -85,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_set_input_bounds", "b200mpc_lmpc_set_output_bounds", "b200mpc_lmpc_set_scalar_constraint",
     "b200mpc_lmpc_set_references", "b200mpc_lmpc_set_exogenous_inputs", "b200mpc_lmpc_set_warm_start",
     "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
-    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_sync",
+    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_profile", "b200mpc_sync",
 ]
 
 
@@ -409,6 +410,15 @@ class LMPC:
         a, b, c = C.c_int(), C.c_size_t(), C.c_longlong()
         _check(self.lib.b200mpc_lmpc_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(warp_slots=a.value, workspace_bytes_per_slot=b.value, launches=c.value)
+
+    def profile(self, fetch=False):
+        """Enable (first call) or fetch the per-instance phase cycle counters [batch, 8]."""
+        if not fetch:
+            _check(self.lib.b200mpc_lmpc_profile(self._h, None))
+            return None
+        out = np.zeros((self.batch, 16), dtype=np.int64)
+        _check(self.lib.b200mpc_lmpc_profile(self._h, self._p(out)))
+        return out
 
     def solve_async(self, x0, u0, dev=False):
         """Enqueue one batched IOptimizer::run.  x0/u0: host arrays, or raw device pointers (ints) when dev=True."""

@@ -41,6 +41,7 @@ struct b200mpc_lmpc {
     // results
     double *cmd = nullptr, *prev_cmd = nullptr, *cost = nullptr, *seq_state = nullptr, *seq_input = nullptr, *seq_output = nullptr;
     double *sol_x = nullptr, *sol_y = nullptr;
+    long long* prof = nullptr;
     int *status = nullptr, *solver_status = nullptr, *feasible = nullptr, *iters = nullptr, *rho_updates = nullptr, *polish = nullptr;
     // engine
     double* workspace = nullptr;
@@ -48,6 +49,8 @@ struct b200mpc_lmpc {
     int* counter = nullptr;
     int warps_per_cta = 0, ctas_per_sm = 0, grid = 0, num_sms = 0;
     int req_wpc = 0, req_cps = 0;
+    size_t smem_cta = 0;
+    bool force_generic = false;
     long long launches = 0;
     std::vector<double> stage;   // host staging
 };
@@ -162,7 +165,7 @@ extern "C" int b200mpc_lmpc_destroy(b200mpc_lmpc_t h) {
                       &h->UMin, &h->UMax, &h->SMin, &h->SMax, &h->SX, &h->SU, &h->yRef, &h->uRef, &h->duRef, &h->uMeas};
     for (DevBuf* b : bufs) free_buf(*b);
     void* ptrs[] = {h->x0, h->u0, h->cmd, h->prev_cmd, h->cost, h->seq_state, h->seq_input, h->seq_output, h->sol_x, h->sol_y,
-                    h->status, h->solver_status, h->feasible, h->iters, h->rho_updates, h->polish, h->counter, h->workspace};
+                    h->status, h->solver_status, h->feasible, h->iters, h->rho_updates, h->polish, h->counter, h->workspace, h->prof};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
     return B200MPC_OK;
@@ -309,35 +312,60 @@ extern "C" int b200mpc_lmpc_get_warm_start(b200mpc_lmpc_t h, double* primal, dou
     return B200MPC_OK;
 }
 
-static int configure_launch(b200mpc_lmpc* h) {
-    if (h->workspace) return B200MPC_OK;
-    const Dm& d = h->d;
-    size_t smem_warp = (size_t)d.smem_doubles() * sizeof(double);
+// ---- kernel instantiations: compile-time dimensions for the named workloads, runtime dimensions otherwise --------
+typedef SDm<12, 4, 4, 12> DmQuad;    // quadrotor_ex / BASELINE configs[1],[4]
+
+template <class DM>
+static int configure_t(b200mpc_lmpc* h) {
+    DM dm; dm.from(h->d);
+    size_t smem_warp = (size_t)dm.smem_doubles() * sizeof(double);
     int dev_max_smem = 0;
     CK(cudaDeviceGetAttribute(&dev_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     int wpc = h->req_wpc > 0 ? h->req_wpc : 4;
     while (wpc > 1 && smem_warp * wpc > (size_t)dev_max_smem) --wpc;
     if (smem_warp * wpc > (size_t)dev_max_smem) return fail(B200MPC_EINVAL, "problem dimensions exceed shared memory of one warp");
     size_t smem_cta = smem_warp * wpc;
-    CK(cudaFuncSetAttribute(lmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CK(cudaFuncSetAttribute(lmpc_solve_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lmpc_solve_kernel, wpc * 32, smem_cta));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lmpc_solve_kernel<DM>, wpc * 32, smem_cta));
     if (occ < 1) return fail(B200MPC_ECUDA, "kernel does not fit on an SM");
     int cps = h->req_cps > 0 ? (h->req_cps < occ ? h->req_cps : occ) : occ;
     int grid = h->num_sms * cps;
     int need = (h->batch + wpc - 1) / wpc;
     if (grid > need) grid = need;
     h->warps_per_cta = wpc; h->ctas_per_sm = cps; h->grid = grid;
-    size_t wsd = (d.ws_doubles() + 31) & ~(size_t)31;
+    h->smem_cta = smem_cta;
+    size_t wsd = (dm.ws_doubles() + 31) & ~(size_t)31;
     h->ws_stride = wsd;
     size_t slots = (size_t)grid * wpc;
     CK(cudaMalloc(&h->workspace, slots * wsd * sizeof(double)));
     return B200MPC_OK;
 }
+template <class DM>
+static int launch_t(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
+    DM dm; dm.from(h->d);
+    lmpc_solve_kernel<DM><<<h->grid, h->warps_per_cta * 32, h->smem_cta, h->stream>>>(dm, h->p, pr, o, h->batch, h->workspace,
+                                                                                      h->ws_stride, h->counter);
+    CK(cudaGetLastError());
+    return B200MPC_OK;
+}
+static bool is_quad(const Dm& d) { return d.nx == 12 && d.nu == 4 && d.ndu == 4 && d.ny == 12; }
+
+static int configure_launch(b200mpc_lmpc* h) {
+    if (h->workspace) return B200MPC_OK;
+    if (!h->force_generic && is_quad(h->d)) return configure_t<DmQuad>(h);
+    return configure_t<Dm>(h);
+}
+static int launch(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
+    if (!h->force_generic && is_quad(h->d)) return launch_t<DmQuad>(h, pr, o);
+    return launch_t<Dm>(h, pr, o);
+}
 
 extern "C" int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm) {
     HCHECK();
-    if (warps_per_cta < 0 || warps_per_cta > 8 || ctas_per_sm < 0) return fail(B200MPC_EINVAL, "bad launch geometry");
+    if (warps_per_cta < -4 || warps_per_cta > 4 || ctas_per_sm < 0) return fail(B200MPC_EINVAL, "bad launch geometry");
+    h->force_generic = warps_per_cta < 0;   // negative: use the runtime-dimension kernel (parity testing of both instantiations)
+    if (warps_per_cta < 0) warps_per_cta = -warps_per_cta;
     CK(cudaStreamSynchronize(h->stream));
     if (h->workspace) { cudaFree(h->workspace); h->workspace = nullptr; }
     h->req_wpc = warps_per_cta; h->req_cps = ctas_per_sm;
@@ -366,11 +394,8 @@ extern "C" int b200mpc_lmpc_solve(b200mpc_lmpc_t h, const double* x0, const doub
     o.cmd = h->cmd; o.cost = h->cost; o.status = h->status; o.solver_status = h->solver_status; o.feasible = h->feasible;
     o.iters = h->iters; o.rho_updates = h->rho_updates; o.polish = h->polish;
     o.seq_state = h->seq_state; o.seq_input = h->seq_input; o.seq_output = h->seq_output;
-    o.sol_x = h->sol_x; o.sol_y = h->sol_y; o.prev_cmd = h->prev_cmd;
-    size_t smem_cta = (size_t)d.smem_doubles() * sizeof(double) * h->warps_per_cta;
-    lmpc_solve_kernel<<<h->grid, h->warps_per_cta * 32, smem_cta, h->stream>>>(h->d, h->p, pr, o, h->batch, h->workspace,
-                                                                              h->ws_stride, h->counter);
-    CK(cudaGetLastError());
+    o.sol_x = h->sol_x; o.sol_y = h->sol_y; o.prev_cmd = h->prev_cmd; o.prof = h->prof;
+    if ((rc = launch(h, pr, o))) return rc;
     h->launches += 1;
     h->has_prev = true;   // optimal_prev_x / optimal_prev_y now hold a solution (LOptimizer.hpp:295-296)
     return B200MPC_OK;
@@ -424,6 +449,16 @@ extern "C" int b200mpc_lmpc_info(b200mpc_lmpc_t h, int* warp_slots, size_t* ws_b
     if (warp_slots) *warp_slots = h->grid * h->warps_per_cta;
     if (ws_bytes) *ws_bytes = h->ws_stride * sizeof(double);
     if (launches) *launches = h->launches;
+    return B200MPC_OK;
+}
+
+// Debug/profiling aid: per-instance cycle counters of the phases of the solve kernel
+// [setup+scale, factorize, admm sweeps, info/termination, polish prep, polish factor, polish solve, unpack].
+extern "C" int b200mpc_lmpc_profile(b200mpc_lmpc_t h, long long* out_host) {
+    HCHECK();
+    size_t n = (size_t)h->batch * 16;
+    if (!h->prof) { CK(cudaMalloc(&h->prof, n * sizeof(long long))); CK(cudaMemset(h->prof, 0, n * sizeof(long long))); return B200MPC_OK; }
+    if (out_host) { CK(cudaStreamSynchronize(h->stream)); CK(cudaMemcpy(out_host, h->prof, n * sizeof(long long), cudaMemcpyDeviceToHost)); }
     return B200MPC_OK;
 }
 

@@ -8,16 +8,20 @@
 //     driven by LOptimizer::run                                        include/mpc/LMPC/LOptimizer.hpp:241-284
 //   * the unpack / status map of LOptimizer::run                       include/mpc/LMPC/LOptimizer.hpp:292-361,386-415
 //
-// Data layout.  Variables are kept stage-major: w_i = [x_i ; xu_i ; du_i] (b = nx+2nu doubles, the last stage has no
-// du).  Constraint rows are kept stage-major too: stage i owns [box(i) ; out(i) ; sc(i) ; eq(i+1) ; du(i)], and the ne
-// rows eq(0) sit in front.  With that ownership one ADMM iteration is exactly one forward sweep (rhs assembly fused
-// with the block forward substitution) and one backward sweep (back substitution fused with z~ = A x~, the relaxation,
-// the projection and the dual update); nothing of size m x n is ever stored.
+// Data layout.  Variables are stage-major: w_i = [x_i ; xu_i ; du_i] (b = nx+2nu doubles, the last stage has no du).
+// Constraint rows are stage-major too: stage i owns [box(i) ; out(i) ; sc(i) ; eq(i+1) ; du(i)]; the ne rows eq(0)
+// are kept apart.  With that ownership one ADMM iteration is exactly one forward sweep (rhs assembly fused with the
+// block forward substitution) and one backward sweep (back substitution fused with z~ = A x~, the relaxation, the
+// projection and the dual update); nothing of size m x n is ever stored.
 //
 // The reduced KKT matrix  H = Pbar + sigma I + Abar' diag(rho) Abar  is block tridiagonal over the stages; it is
 // factorised by a block Cholesky (diagonal blocks inverted explicitly, so the sweeps are mat-vecs, not substitutions).
-// Per-instance state lives in a per-warp-slot workspace in global memory that is sized by the number of RESIDENT warps
-// (not by the batch), so it stays L2 resident; stage factor blocks are staged through shared memory.
+//
+// Memory.  Per-instance state lives in a per-warp-slot workspace in global memory sized by the number of RESIDENT
+// warps (not by the batch).  Everything a sweep needs of stage i is packed in two contiguous records -- a static one
+// (factor blocks, D, q, E, row types, bounds) and a dynamic one (x, z, y) -- which one elected lane pulls into a
+// 3-slot shared-memory ring with cp.async.bulk (TMA) + mbarrier two stages ahead of the arithmetic, so no global
+// load sits on the dependent chain of a sweep.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,6 +31,7 @@ namespace b200mpc {
 
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3, kRhoTol = 1e-4;
 constexpr double kOsqpInfty = 1e30, kMinScaling = 1e-4, kMaxScaling = 1e4;
+constexpr int kRing = 3;
 
 // OSQP status_val (constants.h of v0.6.3)
 enum { OSQP_DUAL_INFEASIBLE_INACCURATE = 4, OSQP_PRIMAL_INFEASIBLE_INACCURATE = 3, OSQP_SOLVED_INACCURATE = 2,
@@ -35,16 +40,57 @@ enum { OSQP_DUAL_INFEASIBLE_INACCURATE = 4, OSQP_PRIMAL_INFEASIBLE_INACCURATE = 
 // mpc::ResultStatus
 enum { RS_SUCCESS = 0, RS_MAX_ITERATION = 1, RS_INFEASIBLE = 2, RS_ERROR = 3, RS_UNKNOWN = 4 };
 
+
+// Shared-memory (per warp) and workspace (per slot) layouts, as offsets in doubles.  Kept as plain functions of the
+// dimensions so that device code can rebuild every pointer from two bases (the extern __shared__ symbol + warp offset,
+// and the slot's workspace pointer): pointers derived that way stay in registers and shared accesses compile to LDS.
+#define B200_LAYOUT_HOST_DEVICE                                                                                    \
+    __host__ __device__ int sBARS() const { return ring_doubles(); }                                                \
+    __host__ __device__ int sG() const { return sBARS() + kRing + 1; }                                              \
+    __host__ __device__ int sC() const { return sG() + ne * ldG; }                                                  \
+    __host__ __device__ int sS() const { return sC() + ny * ldC; }                                                  \
+    __host__ __device__ int sUXC() const { return sS() + ne; }                                                      \
+    __host__ __device__ int sUXN() const { return sUXC() + b; }                                                     \
+    __host__ __device__ int sVTMP() const { return sUXN() + b; }                                                    \
+    __host__ __device__ int sTCUR() const { return sVTMP() + b; }                                                   \
+    __host__ __device__ int sXCUR() const { return sTCUR() + b; }                                                   \
+    __host__ __device__ int sXN() const { return sXCUR() + b; }                                                     \
+    __host__ __device__ int sVEQP() const { return sXN() + ne; }                                                    \
+    __host__ __device__ int sCARRY() const { return sVEQP() + ne; }                                                 \
+    __host__ __device__ int sVROW() const { return sCARRY() + ne; }                                                 \
+    __host__ __device__ int sYV() const { return sVROW() + RS; }                                                    \
+    __host__ __device__ int smem_doubles() const { return (sYV() + ny + 3) & ~1; }                                  \
+    __host__ __device__ size_t wDREC() const { return (size_t)(ph + 1) * SRS; }                                      \
+    __host__ __device__ size_t wE0() const { return wDREC() + (size_t)(ph + 1) * DRS; }                              \
+    __host__ __device__ size_t wT0() const { return wE0() + 5 * (size_t)ne; }                                        \
+    __host__ __device__ size_t wT() const { return wT0() + (ne + 7) / 8 + 1; }                                       \
+    __host__ __device__ size_t wVA() const { return wT() + n; }                                                      \
+    __host__ __device__ size_t wPX() const { return wVA() + n; }                                                     \
+    __host__ __device__ size_t wRA() const { return wPX() + n; }                                                     \
+    __host__ __device__ size_t wRB() const { return wRA() + m; }                                                     \
+    __host__ __device__ size_t wRC() const { return wRB() + m; }                                                     \
+    __host__ __device__ size_t wRUIZ() const { return wRC() + m; }                                                   \
+    __host__ __device__ size_t ws_doubles() const { return wRUIZ() + ruiz_doubles() + 32; }
+
+#define B200_DERIVED_HOST_DEVICE                                                                                   \
+    __host__ __device__ int roff(int i) const { return ne + i * RS; }                                              \
+    __host__ __device__ int rcount(int i) const { return i < ph ? RS : RSL; }                                      \
+    __host__ __device__ int bcount(int i) const { return i < ph ? b : ne; }                                        \
+    __host__ __device__ size_t ruiz_doubles() const { return 2 * (size_t)n + (size_t)m + 8; }                        \
+    __host__ __device__ int fac_doubles() const { return nx * nx + 2 * b * ldb + 2 * ne * ldb; }                    \
+    __host__ __device__ int ring_doubles() const { int r = kRing * SLOT, f = fac_doubles(); return ((r > f ? r : f) + 1) & ~1; } \
+    B200_LAYOUT_HOST_DEVICE
+
+// Runtime dimensions (any shape).
 struct Dm {
     int nx, nu, ndu, ny, ph, ch;
-    int ne, b, n, m;        // ne=nx+nu, b=ne+nu
-    int RS, RSL;            // rows owned by a stage (<ph) / by the last stage
-    int oBOX, oOUT, oSC, oEQ, oDU;   // offsets inside a stage's row segment
-    int ldG, ldC, ldb;      // odd leading dimensions (bank-conflict free column walks)
-    int FS;                 // doubles per stage factor block: packed Linv (b(b+1)/2) + Lc (ne x ldb), even
-    int oLc;                // offset of Lc inside a factor block
-    // reference row offsets (ProblemBuilder.hpp:70-76)
-    int M0, M1, M2, M3;
+    int ne, b, n, m;
+    int RS, RSL, oBOX, oOUT, oSC, oEQ, oDU;      // rows owned by a stage and the offsets of its groups
+    int ldG, ldC, ldb;                           // odd leading dimensions (conflict-free column walks)
+    int oLc, FS;                                 // factor block: packed Linv (b(b+1)/2) + Lc (ne x ldb)
+    int oD, oQ, oE, oT, RT, oLO, oUP, SRS;       // static record
+    int oZ, oY, DRS, SLOT;                       // dynamic record ([x | z | y]) and ring slot size
+    int M0, M1, M2, M3;                          // reference row offsets (ProblemBuilder.hpp:70-76)
     __host__ __device__ void derive() {
         ne = nx + nu; b = ne + nu;
         n = (ph + 1) * ne + ph * nu;
@@ -54,23 +100,32 @@ struct Dm {
         ldG = b | 1; ldC = nx | 1; ldb = b | 1;
         oLc = (b * (b + 1) / 2 + 1) & ~1;
         FS = (oLc + ne * ldb + 1) & ~1;
+        oD = FS; oQ = oD + b; oE = oQ + b; oT = oE + RS; RT = (RS + 7) / 8; oLO = oT + RT; oUP = oLO + RS;
+        SRS = (oUP + RS + 1) & ~1;
+        oZ = b; oY = b + RS; DRS = (b + 2 * RS + 1) & ~1; SLOT = SRS + DRS;
         M0 = (ph + 1) * ne; M1 = 2 * (ph + 1) * ne; M2 = M1 + (ph + 1) * ny; M3 = M2 + ph * nu;
     }
-    __host__ __device__ int roff(int i) const { return ne + i * RS; }
-    __host__ __device__ int rcount(int i) const { return i < ph ? RS : RSL; }
-    __host__ __device__ int bcount(int i) const { return i < ph ? b : ne; }
-    // workspace sizes (doubles)
-    __host__ __device__ size_t ws_doubles() const {
-        return (size_t)6 * n + (size_t)8 * m + (size_t)(ph + 1) * FS + ((m + 7) / 8) + 16;
-    }
-    // shared memory per warp (doubles)
-    __host__ __device__ int smem_doubles() const {
-        int model = ne * ldG + ny * ldC + ne;
-        int vec = 5 * b + 2 * ne + RS + ny + 4;
-        int fac = 2 * b * ldb + 2 * ne * ldb + nx * nx;
-        int ring = 2 * FS;
-        return (model + vec + (fac > ring ? fac : ring) + 3) & ~1;
-    }
+    __host__ __device__ void from(const Dm& d) { *this = d; }
+    B200_DERIVED_HOST_DEVICE
+};
+
+// Compile-time dimensions: identical member names, so the same device code instantiates with every inner loop bound
+// known (full unrolling, constant-folded index arithmetic).  ph/ch stay runtime.
+template <int NX_, int NU_, int NDU_, int NY_>
+struct SDm {
+    static constexpr int nx = NX_, nu = NU_, ndu = NDU_, ny = NY_;
+    static constexpr int ne = NX_ + NU_, b = NX_ + 2 * NU_;
+    static constexpr int oBOX = 0, oOUT = ne, oSC = ne + ny, oEQ = ne + ny + 1, oDU = oEQ + ne;
+    static constexpr int RS = oDU + nu, RSL = oEQ;
+    static constexpr int ldG = b | 1, ldC = nx | 1, ldb = b | 1;
+    static constexpr int oLc = (b * (b + 1) / 2 + 1) & ~1;
+    static constexpr int FS = (oLc + ne * ldb + 1) & ~1;
+    static constexpr int oD = FS, oQ = oD + b, oE = oQ + b, oT = oE + RS, RT = (RS + 7) / 8, oLO = oT + RT, oUP = oLO + RS;
+    static constexpr int SRS = (oUP + RS + 1) & ~1;
+    static constexpr int oZ = b, oY = b + RS, DRS = (b + 2 * RS + 1) & ~1, SLOT = SRS + DRS;
+    int ph, ch, n, m, M0, M1, M2, M3;
+    __host__ __device__ void from(const Dm& d) { ph = d.ph; ch = d.ch; n = d.n; m = d.m; M0 = d.M0; M1 = d.M1; M2 = d.M2; M3 = d.M3; }
+    B200_DERIVED_HOST_DEVICE
 };
 
 struct Arr { const double* p; long long stride; };
@@ -92,9 +147,10 @@ struct Out {
     double* seq_state; double* seq_input; double* seq_output;   // may be null
     double* sol_x; double* sol_y;                               // reference order [batch*n],[batch*m]; may be null
     double* prev_cmd;                                           // [batch*nu] last command (failure semantics)
+    long long* prof;                                            // optional [batch*8] cycle counters per phase (null = off)
 };
 
-// ------------------------------------------------------------------------------------------------------------
+// ---- warp helpers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double wmax(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -112,6 +168,29 @@ __device__ __forceinline__ double lim_scaling(double v) {
 }
 __device__ __forceinline__ double ldp(const Arr& a, int inst, int idx) { return __ldg(a.p + (long long)inst * a.stride + idx); }
 
+// ---- TMA (cp.async.bulk) + mbarrier -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
 struct InfoNorms {
     double pri, dua;                 // unscaled residual norms (termination)
     double nz, nAx, nq, nAty, nPx;   // unscaled normalisers
@@ -119,22 +198,21 @@ struct InfoNorms {
     double xPx, qx;
 };
 
-// Per-warp context ------------------------------------------------------------------------------------------
+// Per-warp context: only scalars + two bases.  Device functions rebuild their pointers locally with B200_LOCALS so that
+// they live in registers (a pointer read back from this struct would be an LDL + a generic LD).
+extern __shared__ __align__(16) double smem[];
+
+template <class DM>
 struct Ctx {
-    const Dm& d; const Params& p; const Prob& pr; int inst; int lane;
-    __device__ Ctx(const Dm& d_, const Params& p_, const Prob& pr_) : d(d_), p(p_), pr(pr_) {}
-    // shared memory
-    double *G, *Cm, *s;
-    double *uxc, *uxn, *xn, *vrowA, *veqp, *tA, *tB, *vtmp, *yv;
-    double *fb0, *fb1;               // factor ring (aliases the factor scratch)
-    double *S, *Li, *Hc, *Lc, *Pblk; // factor scratch
-    // workspace (global)
-    double *D, *qs, *x, *t, *va, *px;            // variables (n each)
-    double *E, *lo, *up, *z, *y, *ra, *rb, *rc;   // rows (m each)
-    double *fac; int8_t* rtype;
-    double c;                       // cost scaling
-    double rsel[3], rinv[3];        // rho by row type
-    // per-stage unscaled problem data helpers
+    const DM& d; const Params& p; const Prob& pr; int inst; int lane;
+    __device__ Ctx(const DM& d_, const Params& p_, const Prob& pr_) : d(d_), p(p_), pr(pr_) {}
+    int sb;                          // this warp's offset (doubles) into the dynamic shared memory
+    double* ws;                      // this slot's workspace
+    double *wD, *wq, *wE;            // Ruiz working arrays (shared memory when they fit, workspace otherwise)
+    uint32_t rres, rflags;           // ring state: 3 x 10-bit resident stage+1 | pending bits [0..2], parity bits [4..6]
+    double c;                        // cost scaling
+    double rsel[3], rinv[3];         // rho by row type
+    long long sp[8];                 // sweep-phase cycle counters (profiling aid)
     __device__ __forceinline__ int jcol(int i) const { return i > 0 ? i - 1 : 0; }
     __device__ __forceinline__ double wO(int i, int r) const { return ldp(pr.OW, inst, jcol(i) * d.ny + r); }
     __device__ __forceinline__ double wU(int i, int r) const { return ldp(pr.UW, inst, jcol(i) * d.nu + r); }
@@ -142,10 +220,104 @@ struct Ctx {
     __device__ __forceinline__ int voff(int i) const { return i * d.b; }
 };
 
+#define B200_LOCALS(c)                                                                                             \
+    const DM& d = (c).d;                                                                                           \
+    const int lane = (c).lane;                                                                                     \
+    double* const sm_ = smem + (c).sb;                                                                             \
+    double* const ring = sm_;                                                                                      \
+    double* const Pblk = sm_;                                                                                      \
+    double* const Sf = Pblk + d.nx * d.nx;                                                                         \
+    double* const Li = Sf + d.b * d.ldb;                                                                           \
+    double* const Hc = Li + d.b * d.ldb;                                                                           \
+    double* const Lcs = Hc + d.ne * d.ldb;                                                                         \
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(sm_ + d.sBARS());                                           \
+    double* const G = sm_ + d.sG();                                                                                \
+    double* const Cm = sm_ + d.sC();                                                                               \
+    double* const sv = sm_ + d.sS();                                                                               \
+    double* uxc = sm_ + d.sUXC();                                                                                  \
+    double* uxn = sm_ + d.sUXN();                                                                                  \
+    double* const vtmp = sm_ + d.sVTMP();                                                                          \
+    double* const tcur = sm_ + d.sTCUR();                                                                          \
+    double* const xcur = sm_ + d.sXCUR();                                                                          \
+    double* const xn = sm_ + d.sXN();                                                                              \
+    double* const veqp = sm_ + d.sVEQP();                                                                          \
+    double* const carry = sm_ + d.sCARRY();                                                                        \
+    double* const vrow = sm_ + d.sVROW();                                                                          \
+    double* const yv = sm_ + d.sYV();                                                                              \
+    double* const ws_ = (c).ws;                                                                                    \
+    double* const srec = ws_;                                                                                      \
+    double* const drec = ws_ + d.wDREC();                                                                          \
+    double* const e0E = ws_ + d.wE0();                                                                             \
+    double* const e0lo = e0E + d.ne;                                                                               \
+    double* const e0up = e0lo + d.ne;                                                                              \
+    double* const e0z = e0up + d.ne;                                                                               \
+    double* const e0y = e0z + d.ne;                                                                                \
+    int8_t* const e0t = reinterpret_cast<int8_t*>(ws_ + d.wT0());                                                  \
+    double* const tg = ws_ + d.wT();                                                                               \
+    double* const va = ws_ + d.wVA();                                                                              \
+    double* const px = ws_ + d.wPX();                                                                              \
+    double* const ra = ws_ + d.wRA();                                                                              \
+    double* const rb = ws_ + d.wRB();                                                                              \
+    double* const rc = ws_ + d.wRC();                                                                              \
+    const double rs0 = (c).rsel[0], rs1 = (c).rsel[1], rs2 = (c).rsel[2];                                          \
+    const double ri0 = (c).rinv[0], ri1 = (c).rinv[1], ri2 = (c).rinv[2];                                          \
+    const double csc = (c).c;                                                                                      \
+    (void)ring; (void)Pblk; (void)Sf; (void)Li; (void)Hc; (void)Lcs; (void)bars; (void)G; (void)Cm; (void)sv; (void)uxc; \
+    (void)uxn; (void)vtmp; (void)tcur; (void)xcur; (void)xn; (void)veqp; (void)carry; (void)vrow; (void)yv; (void)srec;  \
+    (void)drec; (void)e0E; (void)e0lo; (void)e0up; (void)e0z; (void)e0y; (void)e0t; (void)tg; (void)va; (void)px;       \
+    (void)ra; (void)rb; (void)rc; (void)rs0; (void)rs1; (void)rs2; (void)ri0; (void)ri1; (void)ri2; (void)csc; (void)lane
+#define SRP(i) (srec + (size_t)(i) * d.SRS)
+#define DRP(i) (drec + (size_t)(i) * d.DRS)
+#define RHO_OF(ty) ((ty) == 0 ? rs0 : ((ty) == 1 ? rs1 : rs2))
+#define RINV_OF(ty) ((ty) == 0 ? ri0 : ((ty) == 1 ? ri1 : ri2))
+
+// ---- ring management (state packed in two registers of the context) -----------------------------------------------
+__device__ __forceinline__ int ring_res(uint32_t rres, int slot) { return (int)((rres >> (10 * slot)) & 1023u) - 1; }
+template <class DM>
+__device__ __forceinline__ void ring_reset(Ctx<DM>& c) {
+    // called after generic-proxy stores changed records: make them visible to the async proxy, drop residency
+    fence_proxy_async();
+    __syncwarp();
+    c.rres = 0; c.rflags &= 0x70u;   // keep the parities, clear pending
+}
+template <class DM>
+__device__ __forceinline__ void ring_issue(Ctx<DM>& c, int i) {
+    const DM& d = c.d;
+    if (i < 0 || i > d.ph) return;
+    int slot = i % kRing;
+    if (ring_res(c.rres, slot) == i) return;
+    c.rres = (c.rres & ~(1023u << (10 * slot))) | ((uint32_t)(i + 1) << (10 * slot));
+    c.rflags |= (1u << slot);
+    if (c.lane == 0) {
+        double* const sm_ = smem + c.sb;
+        uint64_t* const bars = reinterpret_cast<uint64_t*>(sm_ + d.sBARS());
+        double* dst = sm_ + slot * d.SLOT;
+        const double* srec = c.ws;
+        const double* drec = c.ws + d.wDREC();
+        mbar_expect_tx(&bars[slot], (uint32_t)(d.SLOT * sizeof(double)));
+        tma_load_1d(dst, srec + (size_t)i * d.SRS, (uint32_t)(d.SRS * sizeof(double)), &bars[slot]);
+        tma_load_1d(dst + d.SRS, drec + (size_t)i * d.DRS, (uint32_t)(d.DRS * sizeof(double)), &bars[slot]);
+    }
+}
+template <class DM>
+__device__ __forceinline__ double* ring_acquire(Ctx<DM>& c, int i) {
+    const DM& d = c.d;
+    int slot = i % kRing;
+    if (ring_res(c.rres, slot) != i) ring_issue(c, i);
+    double* const sm_ = smem + c.sb;
+    if (c.rflags & (1u << slot)) {
+        uint64_t* const bars = reinterpret_cast<uint64_t*>(sm_ + d.sBARS());
+        mbar_wait(&bars[slot], (c.rflags >> (4 + slot)) & 1u);
+        c.rflags = (c.rflags ^ (1u << (4 + slot))) & ~(1u << slot);
+    }
+    return sm_ + slot * d.SLOT;
+}
+
 // ---- model to shared memory ---------------------------------------------------------------------------------
-__device__ void load_model(Ctx& c) {
-    const Dm& d = c.d;
-    for (int e = c.lane; e < d.ne * d.b; e += 32) {
+template <class DM>
+__device__ void load_model(Ctx<DM>& c) {
+    B200_LOCALS(c);
+    for (int e = lane; e < d.ne * d.b; e += 32) {
         int r = e / d.b, k = e - r * d.b;
         double v;
         if (r < d.nx) {
@@ -156,34 +328,36 @@ __device__ void load_model(Ctx& c) {
             int j = r - d.nx;
             v = ((k >= d.nx && k < d.ne && k - d.nx == j) || (k >= d.ne && k - d.ne == j)) ? 1.0 : 0.0;
         }
-        c.G[r * d.ldG + k] = v;
+        G[r * d.ldG + k] = v;
     }
-    for (int e = c.lane; e < d.ny * d.nx; e += 32) {
+    for (int e = lane; e < d.ny * d.nx; e += 32) {
         int r = e / d.nx, k = e - r * d.nx;
-        c.Cm[r * d.ldC + k] = ldp(c.pr.C, c.inst, e);
+        Cm[r * d.ldC + k] = ldp(c.pr.C, c.inst, e);
     }
-    for (int k = c.lane; k < d.ne; k += 32)
-        c.s[k] = k < d.nx ? ldp(c.pr.SX, c.inst, k) : ldp(c.pr.SU, c.inst, k - d.nx);
+    for (int k = lane; k < d.ne; k += 32)
+        sv[k] = k < d.nx ? ldp(c.pr.SX, c.inst, k) : ldp(c.pr.SU, c.inst, k - d.nx);
     __syncwarp();
 }
 
 // ---- unscaled q of stage i, variable k (ProblemBuilder.hpp:586-595); needs yv = wO*(-yRef + Dd d) in smem ------
-__device__ void stage_q_prepare(Ctx& c, int i) {
-    const Dm& d = c.d;
+template <class DM>
+__device__ void stage_q_prepare(Ctx<DM>& c, int i) {
+    B200_LOCALS(c);
     int j = c.jcol(i);
-    for (int r = c.lane; r < d.ny; r += 32) {
+    for (int r = lane; r < d.ny; r += 32) {
         double acc = -ldp(c.pr.yRef, c.inst, j * d.ny + r);
         for (int q = 0; q < d.ndu; ++q) acc += ldp(c.pr.Dd, c.inst, r * d.ndu + q) * ldp(c.pr.uMeas, c.inst, j * d.ndu + q);
-        c.yv[r] = c.wO(i, r) * acc;
+        yv[r] = c.wO(i, r) * acc;
     }
     __syncwarp();
 }
-__device__ __forceinline__ double stage_q(Ctx& c, int i, int k) {
-    const Dm& d = c.d;
+template <class DM>
+__device__ __forceinline__ double stage_q(Ctx<DM>& c, int i, int k) {
+    B200_LOCALS(c);
     int j = c.jcol(i);
     if (k < d.nx) {
         double acc = 0;
-        for (int r = 0; r < d.ny; ++r) acc += c.Cm[r * d.ldC + k] * c.yv[r];
+        for (int r = 0; r < d.ny; ++r) acc += Cm[r * d.ldC + k] * yv[r];
         return acc;
     } else if (k < d.ne) {
         int q = k - d.nx;
@@ -194,8 +368,9 @@ __device__ __forceinline__ double stage_q(Ctx& c, int i, int k) {
     }
 }
 // unscaled bounds of row r of stage i (ProblemBuilder.hpp:597-630,727-809); eq0 handled by caller
-__device__ __forceinline__ void stage_bounds(Ctx& c, int i, int r, double& l, double& u) {
-    const Dm& d = c.d;
+template <class DM>
+__device__ __forceinline__ void stage_bounds(Ctx<DM>& c, int i, int r, double& l, double& u) {
+    B200_LOCALS(c);
     int j = c.jcol(i);
     const double inf = INFINITY;
     if (r < d.oOUT) {            // box(i): [minX(i); minU(min(i,ph-1))]
@@ -221,63 +396,66 @@ __device__ __forceinline__ void stage_bounds(Ctx& c, int i, int r, double& l, do
 }
 
 // ---- Pblk = C' diag(wO_i) C (nx x nx), cached across stages with identical weights -----------------------------
-__device__ void stage_Pblk(Ctx& c, int i, bool& valid) {
-    const Dm& d = c.d;
+template <class DM>
+__device__ void stage_Pblk(Ctx<DM>& c, int i, bool& valid) {
+    B200_LOCALS(c);
     bool same = valid && i > 0;
     if (same) {
         bool diff = false;
-        for (int r = c.lane; r < d.ny; r += 32) diff |= (c.wO(i, r) != c.wO(i - 1, r));
+        for (int r = lane; r < d.ny; r += 32) diff |= (c.wO(i, r) != c.wO(i - 1, r));
         same = !wany(diff);
     }
     if (same) return;
-    for (int r = c.lane; r < d.ny; r += 32) c.yv[r] = c.wO(i, r);
+    for (int r = lane; r < d.ny; r += 32) yv[r] = c.wO(i, r);
     __syncwarp();
-    for (int e = c.lane; e < d.nx * d.nx; e += 32) {
+    for (int e = lane; e < d.nx * d.nx; e += 32) {
         int a = e / d.nx, k = e - a * d.nx;
         double acc = 0;
-        for (int r = 0; r < d.ny; ++r) acc += c.Cm[r * d.ldC + a] * c.yv[r] * c.Cm[r * d.ldC + k];
-        c.Pblk[e] = acc;
+        for (int r = 0; r < d.ny; ++r) acc += Cm[r * d.ldC + a] * yv[r] * Cm[r * d.ldC + k];
+        Pblk[e] = acc;
     }
     __syncwarp();
     valid = true;
 }
 // column inf-norm of the (D-scaled, not yet c-scaled) P column k of stage i: max_j D_j |P_jk| D_k
-__device__ __forceinline__ double Pcol_norm(Ctx& c, int i, int k, const double* dcur) {
-    const Dm& d = c.d;
+template <class DM>
+__device__ __forceinline__ double Pcol_norm(Ctx<DM>& c, int i, int k, const double* dcur) {
+    B200_LOCALS(c);
     if (k < d.nx) {
         double mx = 0;
-        for (int j = 0; j < d.nx; ++j) mx = fmax(mx, dcur[j] * fabs(c.Pblk[j * d.nx + k]));
+        for (int j = 0; j < d.nx; ++j) mx = fmax(mx, dcur[j] * fabs(Pblk[j * d.nx + k]));
         return mx * dcur[k];
     } else if (k < d.ne) return dcur[k] * dcur[k] * fabs(c.wU(i, k - d.nx));
     return dcur[k] * dcur[k] * fabs(c.wDU(i, k - d.ne));
 }
 
 // ---- setup: q, Ruiz equilibration (scaling.c scale_data), scaled bounds, row types ------------------------------
-__device__ bool setup_and_scale(Ctx& c) {
-    const Dm& d = c.d;
-    const int lane = c.lane;
-    // unscaled q into qs, D=1, E=1
+// Works on flat stage-major arrays wD[n], wq[n], wE[m] (shared memory when they fit beside Pblk, global otherwise) and
+// scatters the result into the stage records.
+template <class DM>
+__device__ bool setup_and_scale(Ctx<DM>& c) {
+    B200_LOCALS(c);
+    double* wD = c.wD; double* wq = c.wq; double* wE = c.wE;
     for (int i = 0; i <= d.ph; ++i) {
         stage_q_prepare(c, i);
         int bi = d.bcount(i);
-        for (int k = lane; k < bi; k += 32) { c.qs[c.voff(i) + k] = stage_q(c, i, k); c.D[c.voff(i) + k] = 1.0; }
+        for (int k = lane; k < bi; k += 32) { wq[c.voff(i) + k] = stage_q(c, i, k); wD[c.voff(i) + k] = 1.0; }
         __syncwarp();
     }
-    for (int g = lane; g < d.m; g += 32) c.E[g] = 1.0;
+    for (int g = lane; g < d.m; g += 32) wE[g] = 1.0;
     __syncwarp();
     c.c = 1.0;
     double pending_c = 1.0;
-    double* Dt = c.va; double* Et = c.ra;
-    double* dcur = c.uxc; double* dnxt = c.uxn; double* erow = c.vrowA; double* eprev = c.veqp;
+    double* Dt = va; double* Et = ra;
+    double* dcur = uxc; double* dnxt = uxn; double* erow = vrow; double* eprev = veqp;
     for (int it = 0; it < c.p.scaling; ++it) {
-        // pass A: norms with the current D,E
         bool pv = false;
         for (int i = 0; i <= d.ph; ++i) {
             int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
-            for (int k = lane; k < bi; k += 32) dcur[k] = c.D[vo + k];
-            if (i < d.ph) for (int k = lane; k < d.ne; k += 32) dnxt[k] = c.D[vo + d.b + k];
-            for (int r = lane; r < rs; r += 32) erow[r] = c.E[ro + r];
-            if (i == 0) for (int r = lane; r < d.ne; r += 32) eprev[r] = c.E[r];
+            for (int k = lane; k < bi; k += 32) dcur[k] = wD[vo + k];
+            if (i < d.ph) for (int k = lane; k < d.ne; k += 32) dnxt[k] = wD[vo + d.b + k];
+            for (int r = lane; r < rs; r += 32) erow[r] = wE[ro + r];
+            if (i == 0) for (int r = lane; r < d.ne; r += 32) eprev[r] = wE[r];
             __syncwarp();
             stage_Pblk(c, i, pv);
             for (int k = lane; k < bi; k += 32) {
@@ -286,18 +464,18 @@ __device__ bool setup_and_scale(Ctx& c) {
                 if (k < d.ne) {
                     cn = fmax(cn, eprev[k] * dk);
                     cn = fmax(cn, erow[d.oBOX + k] * dk);
-                    if (k < d.nx) for (int r = 0; r < d.ny; ++r) cn = fmax(cn, erow[d.oOUT + r] * fabs(c.Cm[r * d.ldC + k]) * dk);
-                    cn = fmax(cn, erow[d.oSC] * fabs(c.s[k]) * dk);
+                    if (k < d.nx) for (int r = 0; r < d.ny; ++r) cn = fmax(cn, erow[d.oOUT + r] * fabs(Cm[r * d.ldC + k]) * dk);
+                    cn = fmax(cn, erow[d.oSC] * fabs(sv[k]) * dk);
                 } else cn = fmax(cn, erow[d.oDU + k - d.ne] * dk);
-                if (i < d.ph) for (int r = 0; r < d.ne; ++r) cn = fmax(cn, erow[d.oEQ + r] * fabs(c.G[r * d.ldG + k]) * dk);
+                if (i < d.ph) for (int r = 0; r < d.ne; ++r) cn = fmax(cn, erow[d.oEQ + r] * fabs(G[r * d.ldG + k]) * dk);
                 Dt[vo + k] = 1.0 / sqrt(lim_scaling(cn));
             }
             for (int r = lane; r < rs; r += 32) {
                 double e = erow[r], rn;
                 if (r < d.oOUT) rn = e * dcur[r];
-                else if (r < d.oSC) { rn = 0; int q = r - d.oOUT; for (int k = 0; k < d.nx; ++k) rn = fmax(rn, e * fabs(c.Cm[q * d.ldC + k]) * dcur[k]); }
-                else if (r < d.oEQ) { rn = 0; for (int k = 0; k < d.ne; ++k) rn = fmax(rn, e * fabs(c.s[k]) * dcur[k]); }
-                else if (r < d.oDU) { int q = r - d.oEQ; rn = e * dnxt[q]; for (int k = 0; k < d.b; ++k) rn = fmax(rn, e * fabs(c.G[q * d.ldG + k]) * dcur[k]); }
+                else if (r < d.oSC) { rn = 0; int q = r - d.oOUT; for (int k = 0; k < d.nx; ++k) rn = fmax(rn, e * fabs(Cm[q * d.ldC + k]) * dcur[k]); }
+                else if (r < d.oEQ) { rn = 0; for (int k = 0; k < d.ne; ++k) rn = fmax(rn, e * fabs(sv[k]) * dcur[k]); }
+                else if (r < d.oDU) { int q = r - d.oEQ; rn = e * dnxt[q]; for (int k = 0; k < d.b; ++k) rn = fmax(rn, e * fabs(G[q * d.ldG + k]) * dcur[k]); }
                 else rn = e * dcur[d.ne + r - d.oDU];
                 Et[ro + r] = 1.0 / sqrt(lim_scaling(rn));
             }
@@ -306,17 +484,16 @@ __device__ bool setup_and_scale(Ctx& c) {
             if (i < d.ph) for (int r = lane; r < d.ne; r += 32) eprev[r] = erow[d.oEQ + r];
             __syncwarp();
         }
-        // pass B: apply, accumulate cost-normalisation terms
         double psum = 0, qmax = 0;
         pv = false;
-        for (int g = lane; g < d.m; g += 32) c.E[g] *= Et[g];
+        for (int g = lane; g < d.m; g += 32) wE[g] *= Et[g];
         for (int i = 0; i <= d.ph; ++i) {
             int bi = d.bcount(i), vo = c.voff(i);
             for (int k = lane; k < bi; k += 32) {
-                double dn = c.D[vo + k] * Dt[vo + k];
-                c.D[vo + k] = dn; dcur[k] = dn;
-                double qv = (c.qs[vo + k] * pending_c) * Dt[vo + k];
-                c.qs[vo + k] = qv; qmax = fmax(qmax, fabs(qv));
+                double dn = wD[vo + k] * Dt[vo + k];
+                wD[vo + k] = dn; dcur[k] = dn;
+                double qv = (wq[vo + k] * pending_c) * Dt[vo + k];
+                wq[vo + k] = qv; qmax = fmax(qmax, fabs(qv));
             }
             __syncwarp();
             stage_Pblk(c, i, pv);
@@ -330,70 +507,77 @@ __device__ bool setup_and_scale(Ctx& c) {
         ct = 1.0 / lim_scaling(ct);
         c.c *= ct; pending_c = ct;
     }
-    // finalise: pending q scaling, scaled bounds, row types, validate l<=u
+    // scatter into the records: D, scaled q, E, scaled bounds, row types; validate l<=u
     bool bad = false;
-    for (int k = lane; k < d.n; k += 32) c.qs[k] *= pending_c;
     for (int i = 0; i <= d.ph; ++i) {
-        int rs = d.rcount(i), ro = d.roff(i);
+        int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
+        double* S = SRP(i);
+        int8_t* rt = reinterpret_cast<int8_t*>(S + d.oT);
+        for (int k = lane; k < bi; k += 32) { S[d.oD + k] = wD[vo + k]; S[d.oQ + k] = wq[vo + k] * pending_c; }
         for (int r = lane; r < rs; r += 32) {
             double l, u; stage_bounds(c, i, r, l, u);
             bad |= (l > u);
-            double e = c.E[ro + r];
+            double e = wE[ro + r];
             l *= e; u *= e;
-            c.lo[ro + r] = l; c.up[ro + r] = u;
-            int8_t ty = ((l < -kOsqpInfty * kMinScaling) && (u > kOsqpInfty * kMinScaling)) ? 0 : ((u - l < kRhoTol) ? 2 : 1);
-            c.rtype[ro + r] = ty;
+            S[d.oE + r] = e; S[d.oLO + r] = l; S[d.oUP + r] = u;
+            rt[r] = ((l < -kOsqpInfty * kMinScaling) && (u > kOsqpInfty * kMinScaling)) ? 0 : ((u - l < kRhoTol) ? 2 : 1);
         }
     }
     for (int r = lane; r < d.ne; r += 32) {   // eq(0) = -[x0;u0]
         double v = r < d.nx ? -__ldg(c.pr.x0 + (long long)c.inst * d.nx + r) : -__ldg(c.pr.u0 + (long long)c.inst * d.nu + (r - d.nx));
-        v *= c.E[r];
-        c.lo[r] = v; c.up[r] = v; c.rtype[r] = 2;
+        double e = wE[r];
+        v *= e;
+        e0E[r] = e; e0lo[r] = v; e0up[r] = v; e0t[r] = 2;
     }
     __syncwarp();
     return !wany(bad);
 }
 
-__device__ __forceinline__ void set_rho(Ctx& c, double rho) {
+template <class DM>
+__device__ __forceinline__ void set_rho(Ctx<DM>& c, double rho) {
     c.rsel[0] = kRhoMin; c.rsel[1] = rho; c.rsel[2] = kRhoEqOverIneq * rho;
     for (int k = 0; k < 3; ++k) c.rinv[k] = 1.0 / c.rsel[k];
 }
 
+__device__ __forceinline__ void unrank_pair(int pidx, int& r, int& k) {
+    r = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= pidx) ++r;
+    while (r * (r + 1) / 2 > pidx) --r;
+    k = pidx - r * (r + 1) / 2;
+}
+
 // ---- block tridiagonal Cholesky of H = D (c P + A' R' A) D + sigma I ---------------------------------------------
-// rsel[rtype] gives the row weight; polish passes {0, 1/delta, -} with rtype = activity.  Returns false on a
-// non-positive pivot.
-__device__ bool factorize(Ctx& c, double sigma) {
-    const Dm& d = c.d;
-    const int lane = c.lane, ldb = d.ldb;
-    double* rw = c.vrowA;      // rho' = rho E^2 of this stage's rows
-    double* rwp = c.veqp;      // rho' of eq(i) rows (owned by the previous stage)
-    double* dw = c.uxc;        // D of this stage
-    double* dn = c.uxn;        // D of e_{i+1}
+// rho_of(rtype) gives the row weight; polish passes {0, 1/delta, -} with rtype = activity.  Returns false on a
+// non-positive pivot.  Uses the ring area as scratch, so the ring is reset on exit.
+template <class DM>
+__device__ bool factorize(Ctx<DM>& c, double sigma) {
+    B200_LOCALS(c);
+    const int ldb = d.ldb;
+    double* rw = vrow;       // rho' = rho E^2 of this stage's rows
+    double* rwp = veqp;      // rho' of eq(i) rows (owned by the previous stage)
+    double* dw = uxc;        // D of this stage
+    double* dn = uxn;        // D of e_{i+1}
     bool ok = true;
     for (int i = 0; i <= d.ph; ++i) {
-        int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
-        int bprev = d.b;
-        for (int r = lane; r < rs; r += 32) { double e = c.E[ro + r]; rw[r] = c.rsel[c.rtype[ro + r]] * e * e; }
-        if (i == 0) for (int r = lane; r < d.ne; r += 32) { double e = c.E[r]; rwp[r] = c.rsel[c.rtype[r]] * e * e; }
-        for (int k = lane; k < bi; k += 32) dw[k] = c.D[vo + k];
-        if (i < d.ph) for (int k = lane; k < d.ne; k += 32) dn[k] = c.D[vo + d.b + k];
-        for (int r = lane; r < d.ny; r += 32) c.yv[r] = 0.0;
+        int bi = d.bcount(i), rs = d.rcount(i);
+        const int bprev = d.b;
+        double* Sg = SRP(i);
+        const int8_t* rt = reinterpret_cast<const int8_t*>(Sg + d.oT);
+        for (int r = lane; r < rs; r += 32) { double e = Sg[d.oE + r]; rw[r] = RHO_OF(rt[r]) * e * e; }
+        if (i == 0) for (int r = lane; r < d.ne; r += 32) { double e = e0E[r]; rwp[r] = RHO_OF(e0t[r]) * e * e; }
+        for (int k = lane; k < bi; k += 32) dw[k] = Sg[d.oD + k];
+        if (i < d.ph) { const double* Sn = SRP(i + 1); for (int k = lane; k < d.ne; k += 32) dn[k] = Sn[d.oD + k]; }
         __syncwarp();
-        for (int r = lane; r < d.ny; r += 32) c.yv[r] = c.c * c.wO(i, r) + rw[d.oOUT + r];
+        for (int r = lane; r < d.ny; r += 32) yv[r] = c.c * c.wO(i, r) + rw[d.oOUT + r];
         __syncwarp();
-        // lower triangle of S
         int npairs = bi * (bi + 1) / 2;
         for (int pidx = lane; pidx < npairs; pidx += 32) {
-            // unrank (r,k), k<=r
-            int r = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
-            while ((r + 1) * (r + 2) / 2 <= pidx) ++r;
-            while (r * (r + 1) / 2 > pidx) --r;
-            int k = pidx - r * (r + 1) / 2;
+            int r, k; unrank_pair(pidx, r, k);
             double v = 0;
-            if (i < d.ph) for (int j = 0; j < d.ne; ++j) v += c.G[j * d.ldG + r] * rw[d.oEQ + j] * c.G[j * d.ldG + k];
+            if (i < d.ph) for (int j = 0; j < d.ne; ++j) v += G[j * d.ldG + r] * rw[d.oEQ + j] * G[j * d.ldG + k];
             if (r < d.ne) {
-                v += rw[d.oSC] * c.s[r] * c.s[k];
-                if (r < d.nx) for (int j = 0; j < d.ny; ++j) v += c.Cm[j * d.ldC + r] * c.yv[j] * c.Cm[j * d.ldC + k];
+                v += rw[d.oSC] * sv[r] * sv[k];
+                if (r < d.nx) for (int j = 0; j < d.ny; ++j) v += Cm[j * d.ldC + r] * yv[j] * Cm[j * d.ldC + k];
                 if (r == k) {
                     v += rwp[k] + rw[d.oBOX + k];
                     if (k >= d.nx) v += c.c * c.wU(i, k - d.nx);
@@ -403,312 +587,337 @@ __device__ bool factorize(Ctx& c, double sigma) {
             if (r == k) v += sigma;
             if (i > 0 && r < d.ne) {   // Schur complement of the previous stage: Lc_{i-1} Lc_{i-1}'
                 double acc = 0;
-                for (int q = 0; q < bprev; ++q) acc += c.Lc[r * ldb + q] * c.Lc[k * ldb + q];
+                for (int q = 0; q < bprev; ++q) acc += Lcs[r * ldb + q] * Lcs[k * ldb + q];
                 v -= acc;
             }
-            c.S[r * ldb + k] = v;
+            Sf[r * ldb + k] = v;
         }
         __syncwarp();
-        // Cholesky (right-looking), in place
-        for (int k = 0; k < bi; ++k) {
-            double dkk = c.S[k * ldb + k];
+        for (int k = 0; k < bi; ++k) {       // right-looking Cholesky, in place
+            double dkk = Sf[k * ldb + k];
             if (!(dkk > 0.0)) ok = false;
             double piv = sqrt(dkk), inv = 1.0 / piv;
             __syncwarp();
-            for (int r = k + lane; r < bi; r += 32) c.S[r * ldb + k] = (r == k) ? piv : c.S[r * ldb + k] * inv;
+            for (int r = k + lane; r < bi; r += 32) Sf[r * ldb + k] = (r == k) ? piv : Sf[r * ldb + k] * inv;
             __syncwarp();
             for (int r = k + 1 + lane; r < bi; r += 32) {
-                double lrk = c.S[r * ldb + k];
-                for (int q = k + 1; q <= r; ++q) c.S[r * ldb + q] -= lrk * c.S[q * ldb + k];
+                double lrk = Sf[r * ldb + k];
+                for (int q = k + 1; q <= r; ++q) Sf[r * ldb + q] -= lrk * Sf[q * ldb + k];
             }
             __syncwarp();
         }
-        // inverse of L: lane = column
-        for (int col = lane; col < bi; col += 32) {
+        for (int col = lane; col < bi; col += 32) {     // inverse of L: lane = column
             for (int r = 0; r < bi; ++r) {
                 double v;
                 if (r < col) v = 0.0;
-                else if (r == col) v = 1.0 / c.S[r * ldb + r];
+                else if (r == col) v = 1.0 / Sf[r * ldb + r];
                 else {
                     double acc = 0;
-                    for (int q = col; q < r; ++q) acc += c.S[r * ldb + q] * c.Li[q * ldb + col];
-                    v = -acc / c.S[r * ldb + r];
+                    for (int q = col; q < r; ++q) acc += Sf[r * ldb + q] * Li[q * ldb + col];
+                    v = -acc / Sf[r * ldb + r];
                 }
-                c.Li[r * ldb + col] = v;
+                Li[r * ldb + col] = v;
             }
         }
         __syncwarp();
-        double* fblk = c.fac + (size_t)i * d.FS;
         for (int pidx = lane; pidx < npairs; pidx += 32) {
-            int r = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
-            while ((r + 1) * (r + 2) / 2 <= pidx) ++r;
-            while (r * (r + 1) / 2 > pidx) --r;
-            int k = pidx - r * (r + 1) / 2;
-            fblk[pidx] = c.Li[r * ldb + k];
+            int r, k; unrank_pair(pidx, r, k);
+            Sg[pidx] = Li[r * ldb + k];
         }
         if (i < d.ph) {
             // Hc = -(D_e(i+1) rho'_eq(i+1)) G Dw ;  Lc = Hc Li'
             for (int e = lane; e < d.ne * bi; e += 32) {
                 int r = e / bi, k = e - r * bi;
-                c.Hc[r * ldb + k] = -(dn[r] * rw[d.oEQ + r]) * c.G[r * d.ldG + k] * dw[k];
+                Hc[r * ldb + k] = -(dn[r] * rw[d.oEQ + r]) * G[r * d.ldG + k] * dw[k];
             }
             __syncwarp();
             for (int e = lane; e < d.ne * bi; e += 32) {
                 int r = e / bi, k = e - r * bi;
                 double acc = 0;
-                for (int q = 0; q <= k; ++q) acc += c.Hc[r * ldb + q] * c.Li[k * ldb + q];
-                c.Lc[r * ldb + k] = acc;
-                fblk[d.oLc + r * ldb + k] = acc;
+                for (int q = 0; q <= k; ++q) acc += Hc[r * ldb + q] * Li[k * ldb + q];
+                Lcs[r * ldb + k] = acc;
+                Sg[d.oLc + r * ldb + k] = acc;
             }
             __syncwarp();
             for (int r = lane; r < d.ne; r += 32) rwp[r] = rw[d.oEQ + r];
         }
         __syncwarp();
     }
+    ring_reset(c);
     return !wany(!ok);
 }
 
-// ---- factor block i -> shared memory ring slot ------------------------------------------------------------------
-__device__ __forceinline__ void load_fblk(Ctx& c, int i, double* dst) {
-    const double* src = c.fac + (size_t)i * c.d.FS;
-    const double2* s2 = reinterpret_cast<const double2*>(src);
-    double2* d2 = reinterpret_cast<double2*>(dst);
-    int n2 = c.d.FS >> 1;
-    for (int e = c.lane; e < n2; e += 32) d2[e] = s2[e];
+// dot product of a strided shared-memory vector with a contiguous one, two independent accumulators
+__device__ __forceinline__ double sdot(const double* a, int sa, const double* x, int nn) {
+    double a0 = 0, a1 = 0;
+    int q = 0;
+    for (; q + 1 < nn; q += 2) { a0 = fma(a[q * sa], x[q], a0); a1 = fma(a[(q + 1) * sa], x[q + 1], a1); }
+    if (q < nn) a0 = fma(a[q * sa], x[q], a0);
+    return a0 + a1;
 }
 
 // ---- one reduced-KKT solve fused with the ADMM updates (MODE 0) or with the polish bookkeeping (MODE 1) -----------
 //  MODE 0: rhs = sigma x - q + A'(rho z - y);  x~ = H^-1 rhs;  then x,z,y updates of osqp.c (update_x/z/y)
 //  MODE 1: rhs = r1 + A'(w r2) (w = act/delta); dx = H^-1 rhs; px += dx; pnu += w (A dx - r2)      [r1=va, r2=rc, pnu=rb]
-template <int MODE>
-__device__ void kkt_sweeps(Ctx& c, bool store_delta, bool first) {
-    const Dm& d = c.d;
-    const int lane = c.lane, ldb = d.ldb;
+// Every stage's data comes from the TMA ring; t (forward result) goes through global memory lane-to-same-lane.
+template <class DM, int MODE>
+__device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
+    B200_LOCALS(c);
+    const int ldb = d.ldb;
     const double sigma = c.p.sigma, alpha = c.p.alpha;
-    double* vrow = c.vrowA; double* veqp = c.veqp;
-    double* tprev = c.tA; double* tcur = c.tB;
+    long long q0 = clock64(), q1;
+#define SPROF(slot) do { q1 = clock64(); c.sp[slot] += q1 - q0; q0 = q1; } while (0)
     // ---------------- forward ----------------
+    ring_issue(c, 0); ring_issue(c, 1); ring_issue(c, 2);
     for (int r = lane; r < d.ne; r += 32) {
-        int ty = c.rtype[r];
-        veqp[r] = MODE == 0 ? c.E[r] * (c.rsel[ty] * c.z[r] - c.y[r]) : c.E[r] * (c.rsel[ty] * c.rc[r]);
+        int ty = e0t[r];
+        veqp[r] = MODE == 0 ? e0E[r] * (RHO_OF(ty) * e0z[r] - e0y[r]) : e0E[r] * (RHO_OF(ty) * rc[r]);
     }
     for (int i = 0; i <= d.ph; ++i) {
-        int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
-        double* fcur = (i & 1) ? c.fb1 : c.fb0;
-        double* fprv = (i & 1) ? c.fb0 : c.fb1;
-        load_fblk(c, i, fcur);
+        const int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
+        const double* S = ring_acquire(c, i);
+        SPROF(0);
+        const double* Dy = S + d.SRS;
+        const int8_t* rt = reinterpret_cast<const int8_t*>(S + d.oT);
         for (int r = lane; r < rs; r += 32) {
-            int g = ro + r; int ty = c.rtype[g];
-            vrow[r] = MODE == 0 ? c.E[g] * (c.rsel[ty] * c.z[g] - c.y[g]) : c.E[g] * (c.rsel[ty] * c.rc[g]);
+            int ty = rt[r];
+            vrow[r] = MODE == 0 ? S[d.oE + r] * (RHO_OF(ty) * Dy[d.oZ + r] - Dy[d.oY + r]) : S[d.oE + r] * (RHO_OF(ty) * rc[ro + r]);
         }
         __syncwarp();
         for (int k = lane; k < bi; k += 32) {
             double au;
             if (k < d.ne) {
-                au = vrow[d.oBOX + k] - veqp[k] + c.s[k] * vrow[d.oSC];
-                if (k < d.nx) for (int j = 0; j < d.ny; ++j) au += c.Cm[j * d.ldC + k] * vrow[d.oOUT + j];
+                au = vrow[d.oBOX + k] - veqp[k] + sv[k] * vrow[d.oSC];
+                if (k < d.nx) au += sdot(Cm + k, d.ldC, vrow + d.oOUT, d.ny);
             } else au = vrow[d.oDU + k - d.ne];
-            if (i < d.ph) for (int j = 0; j < d.ne; ++j) au += c.G[j * d.ldG + k] * vrow[d.oEQ + j];
-            double rhs = MODE == 0 ? (sigma * c.x[vo + k] - c.qs[vo + k] + c.D[vo + k] * au) : (c.va[vo + k] + c.D[vo + k] * au);
-            if (i > 0 && k < d.ne) {
-                const double* Lcp = fprv + d.oLc + k * ldb;
-                double acc = 0;
-                for (int q = 0; q < d.b; ++q) acc += Lcp[q] * tprev[q];
-                rhs -= acc;
-            }
-            c.vtmp[k] = rhs;
+            if (i < d.ph) au += sdot(G + k, d.ldG, vrow + d.oEQ, d.ne);
+            double rhs;
+            if (MODE == 0) rhs = sigma * Dy[k] - S[d.oQ + k] + S[d.oD + k] * au;
+            else rhs = va[vo + k] + S[d.oD + k] * au;
+            if (i > 0 && k < d.ne) rhs -= carry[k];
+            vtmp[k] = rhs;
         }
         __syncwarp();
+        SPROF(1);
         for (int k = lane; k < bi; k += 32) {
-            const double* Lr = fcur + k * (k + 1) / 2;
-            double acc = 0;
-            for (int q = 0; q <= k; ++q) acc += Lr[q] * c.vtmp[q];
-            tcur[k] = acc; c.t[vo + k] = acc;
+            double acc = sdot(S + k * (k + 1) / 2, 1, vtmp, k + 1);
+            tcur[k] = acc; tg[vo + k] = acc;
         }
-        if (i < d.ph) for (int r = lane; r < d.ne; r += 32) veqp[r] = vrow[d.oEQ + r];
         __syncwarp();
-        double* tt = tprev; tprev = tcur; tcur = tt;
+        SPROF(2);
+        if (i < d.ph) {
+            for (int k = lane; k < d.ne; k += 32) {
+                carry[k] = sdot(S + d.oLc + k * ldb, 1, tcur, d.b);
+                veqp[k] = vrow[d.oEQ + k];
+            }
+        }
+        __syncwarp();
+        ring_issue(c, i + kRing);
+        SPROF(3);
     }
     // ---------------- backward ----------------
-    double* uxc = c.uxc; double* uxn = c.uxn; double* xn = c.xn;
+    double tnext = 0;
+    if (lane < d.bcount(d.ph)) tnext = tg[c.voff(d.ph) + lane];
     for (int i = d.ph; i >= 0; --i) {
-        int bi = d.bcount(i), ro = d.roff(i), vo = c.voff(i);
-        double* fcur = (i & 1) ? c.fb1 : c.fb0;
-        if (i != d.ph) load_fblk(c, i, fcur);   // block ph is still resident from the forward sweep
-        __syncwarp();
+        const int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
+        double* S = ring_acquire(c, i);
+        SPROF(4);
+        double* Dy = S + d.SRS;
+        double* Dg = DRP(i);
+        const int8_t* rt = reinterpret_cast<const int8_t*>(S + d.oT);
+        double tk = tnext;
+        if (i > 0 && lane < d.b) tnext = tg[c.voff(i - 1) + lane];     // prefetch for the next step
         for (int k = lane; k < bi; k += 32) {
-            double w = c.t[vo + k];
-            if (i < d.ph) {
-                const double* Lcc = fcur + d.oLc + k;
-                double acc = 0;
-                for (int r = 0; r < d.ne; ++r) acc += Lcc[r * ldb] * xn[r];
-                w -= acc;
-            }
-            c.vtmp[k] = w;
+            double w = (k == lane) ? tk : tg[vo + k];
+            if (i < d.ph) w -= sdot(S + d.oLc + k, ldb, xn, d.ne);
+            vtmp[k] = w;
         }
         __syncwarp();
         for (int k = lane; k < bi; k += 32) {
-            double acc = 0;
-            for (int r = k; r < bi; ++r) acc += fcur[r * (r + 1) / 2 + k] * c.vtmp[r];
-            double xt = acc;
+            double a0 = 0, a1 = 0;
+            int r = k;
+            for (; r + 1 < bi; r += 2) { a0 = fma(S[r * (r + 1) / 2 + k], vtmp[r], a0); a1 = fma(S[(r + 1) * (r + 2) / 2 + k], vtmp[r + 1], a1); }
+            if (r < bi) a0 = fma(S[r * (r + 1) / 2 + k], vtmp[r], a0);
+            double xt = a0 + a1;
             if (MODE == 0) {
-                double xo = c.x[vo + k];
+                double xo = Dy[k];
                 double xnew = alpha * xt + (1.0 - alpha) * xo;
-                c.x[vo + k] = xnew;
-                if (store_delta) c.va[vo + k] = xnew - xo;
+                Dy[k] = xnew; Dg[k] = xnew;
+                if (store_delta) va[vo + k] = xnew - xo;
             } else {
-                c.px[vo + k] = first ? xt : c.px[vo + k] + xt;
+                px[vo + k] = first ? xt : (px[vo + k] + xt);
             }
-            uxc[k] = c.D[vo + k] * xt;
-            c.tA[k] = xt;     // scaled x~ of this stage (tA/tB are free during the backward sweep)
+            uxc[k] = S[d.oD + k] * xt;
+            xcur[k] = xt;
         }
         __syncwarp();
+        SPROF(5);
         // rows owned by stage i
-        auto row_update = [&](int g, double a) {
-            int ty = c.rtype[g];
+        for (int r = lane; r < rs; r += 32) {
+            double a;
+            if (r < d.oOUT) a = uxc[r];
+            else if (r < d.oSC) a = sdot(Cm + (r - d.oOUT) * d.ldC, 1, uxc, d.nx);
+            else if (r < d.oEQ) a = sdot(sv, 1, uxc, d.ne);
+            else if (r < d.oDU) a = sdot(G + (r - d.oEQ) * d.ldG, 1, uxc, d.b) - uxn[r - d.oEQ];
+            else a = uxc[d.ne + r - d.oDU];
+            int ty = rt[r];
             if (MODE == 0) {
-                double zt = c.E[g] * a;
-                double zo = c.z[g];
+                double zt = S[d.oE + r] * a;
+                double zo = Dy[d.oZ + r];
                 double zr = alpha * zt + (1.0 - alpha) * zo;
-                double yo = c.y[g];
-                double zn = fmin(fmax(zr + c.rinv[ty] * yo, c.lo[g]), c.up[g]);
-                double dy = c.rsel[ty] * (zr - zn);
-                c.y[g] = yo + dy; c.z[g] = zn;
-                if (store_delta) c.ra[g] = dy;
+                double yo = Dy[d.oY + r];
+                double zn = fmin(fmax(zr + RINV_OF(ty) * yo, S[d.oLO + r]), S[d.oUP + r]);
+                double dy = RHO_OF(ty) * (zr - zn);
+                double yn = yo + dy;
+                Dy[d.oY + r] = yn; Dy[d.oZ + r] = zn; Dg[d.oY + r] = yn; Dg[d.oZ + r] = zn;
+                if (store_delta) ra[ro + r] = dy;
             } else {
-                double dnu = c.rsel[ty] * (c.E[g] * a - c.rc[g]);
-                c.rb[g] = first ? dnu : c.rb[g] + dnu;
+                double dnu = RHO_OF(ty) * (S[d.oE + r] * a - rc[ro + r]);
+                rb[ro + r] = first ? dnu : rb[ro + r] + dnu;
             }
-        };
-        for (int r = lane; r < d.ne; r += 32) row_update(ro + d.oBOX + r, uxc[r]);
-        for (int r = lane; r < d.ny; r += 32) {
-            double a = 0;
-            for (int k = 0; k < d.nx; ++k) a += c.Cm[r * d.ldC + k] * uxc[k];
-            row_update(ro + d.oOUT + r, a);
         }
-        if (lane == 0) {
-            double a = 0;
-            for (int k = 0; k < d.ne; ++k) a += c.s[k] * uxc[k];
-            row_update(ro + d.oSC, a);
-        }
-        if (i < d.ph) {
+        if (i == 0) {
             for (int r = lane; r < d.ne; r += 32) {
-                double a = -uxn[r];
-                for (int k = 0; k < d.b; ++k) a += c.G[r * d.ldG + k] * uxc[k];
-                row_update(ro + d.oEQ + r, a);
+                int ty = e0t[r];
+                double a = -uxc[r];
+                if (MODE == 0) {
+                    double zt = e0E[r] * a, zo = e0z[r];
+                    double zr = alpha * zt + (1.0 - alpha) * zo;
+                    double yo = e0y[r];
+                    double zn = fmin(fmax(zr + RINV_OF(ty) * yo, e0lo[r]), e0up[r]);
+                    double dy = RHO_OF(ty) * (zr - zn);
+                    e0y[r] = yo + dy; e0z[r] = zn;
+                    if (store_delta) ra[r] = dy;
+                } else {
+                    double dnu = RHO_OF(ty) * (e0E[r] * a - rc[r]);
+                    rb[r] = first ? dnu : rb[r] + dnu;
+                }
             }
-            for (int r = lane; r < d.nu; r += 32) row_update(ro + d.oDU + r, uxc[d.ne + r]);
         }
-        if (i == 0) for (int r = lane; r < d.ne; r += 32) row_update(r, -uxc[r]);
         __syncwarp();
-        for (int r = lane; r < d.ne; r += 32) { uxn[r] = uxc[r]; xn[r] = c.tA[r]; }
+        for (int r = lane; r < d.ne; r += 32) { uxn[r] = uxc[r]; xn[r] = xcur[r]; }
         __syncwarp();
+        if (i >= kRing) ring_issue(c, i - kRing);
+        SPROF(6);
     }
+#undef SPROF
+    // global x,z,y were rewritten by generic stores: order them before the TMA reads of the next sweep
+    fence_proxy_async();
+    __syncwarp();
 }
 
-// ---- generic structured products --------------------------------------------------------------------------------
-// rows_pass: for every row g:  rowfn(g, a_g . ux)  with ux = D*xsrc (unscaled variable values)
-template <class RowFn>
-__device__ void rows_pass(Ctx& c, const double* xsrc, RowFn rowfn) {
-    const Dm& d = c.d;
-    const int lane = c.lane;
-    double* uxc = c.uxc; double* uxn = c.uxn;
-    for (int k = lane; k < d.bcount(0); k += 32) uxc[k] = c.D[k] * xsrc[k];
+// ---- generic structured products (record data through the ring) --------------------------------------------------
+// rows_pass: for every row:  rowfn(i, r, g, S, Dy, a_g . ux)  with ux = D*xfn(i,k,Dy) (unscaled variable values);
+// i = -1 marks the eq(0) rows (S, Dy null).
+template <class DM, class XFn, class RowFn>
+__device__ void rows_pass(Ctx<DM>& c, XFn xfn, RowFn rowfn) {
+    B200_LOCALS(c);
+    ring_issue(c, 0); ring_issue(c, 1); ring_issue(c, 2);
+    {
+        const double* S0 = ring_acquire(c, 0);
+        for (int k = lane; k < d.bcount(0); k += 32) uxc[k] = S0[d.oD + k] * xfn(0, k, S0 + d.SRS);
+    }
     __syncwarp();
     for (int i = 0; i <= d.ph; ++i) {
-        int ro = d.roff(i), vo = c.voff(i);
-        if (i < d.ph) for (int k = lane; k < d.bcount(i + 1); k += 32) uxn[k] = c.D[vo + d.b + k] * xsrc[vo + d.b + k];
-        __syncwarp();
-        for (int r = lane; r < d.ne; r += 32) rowfn(ro + d.oBOX + r, uxc[r]);
-        for (int r = lane; r < d.ny; r += 32) {
-            double a = 0;
-            for (int k = 0; k < d.nx; ++k) a += c.Cm[r * d.ldC + k] * uxc[k];
-            rowfn(ro + d.oOUT + r, a);
-        }
-        if (lane == 0) {
-            double a = 0;
-            for (int k = 0; k < d.ne; ++k) a += c.s[k] * uxc[k];
-            rowfn(ro + d.oSC, a);
-        }
+        const int rs = d.rcount(i), ro = d.roff(i);
+        double* S = ring_acquire(c, i);
+        double* Dy = S + d.SRS;
         if (i < d.ph) {
-            for (int r = lane; r < d.ne; r += 32) {
-                double a = -uxn[r];
-                for (int k = 0; k < d.b; ++k) a += c.G[r * d.ldG + k] * uxc[k];
-                rowfn(ro + d.oEQ + r, a);
-            }
-            for (int r = lane; r < d.nu; r += 32) rowfn(ro + d.oDU + r, uxc[d.ne + r]);
+            const double* Sn = ring_acquire(c, i + 1);
+            for (int k = lane; k < d.bcount(i + 1); k += 32) uxn[k] = Sn[d.oD + k] * xfn(i + 1, k, Sn + d.SRS);
         }
-        if (i == 0) for (int r = lane; r < d.ne; r += 32) rowfn(r, -uxc[r]);
         __syncwarp();
+        for (int r = lane; r < rs; r += 32) {
+            double a;
+            if (r < d.oOUT) a = uxc[r];
+            else if (r < d.oSC) a = sdot(Cm + (r - d.oOUT) * d.ldC, 1, uxc, d.nx);
+            else if (r < d.oEQ) a = sdot(sv, 1, uxc, d.ne);
+            else if (r < d.oDU) a = sdot(G + (r - d.oEQ) * d.ldG, 1, uxc, d.b) - uxn[r - d.oEQ];
+            else a = uxc[d.ne + r - d.oDU];
+            rowfn(i, r, ro + r, S, Dy, a);
+        }
+        if (i == 0) for (int r = lane; r < d.ne; r += 32) rowfn(-1, r, r, (double*)nullptr, (double*)nullptr, -uxc[r]);
+        __syncwarp();
+        ring_issue(c, i + kRing);
         double* tt = uxc; uxc = uxn; uxn = tt;
     }
 }
-// cols_pass: for every variable kg: colfn(kg, D_k * sum_r a_r[k] v_r, c*D_k*(P ux)_k) with v_r = rowval(g) (already
-// E-weighted) and ux = D*xsrc (xsrc may be null when WITHP is false)
-template <bool WITHP, class RowVal, class ColFn>
-__device__ void cols_pass(Ctx& c, const double* xsrc, RowVal rowval, ColFn colfn) {
-    const Dm& d = c.d;
-    const int lane = c.lane;
-    double* vrow = c.vrowA; double* veqp = c.veqp; double* uxc = c.uxc;
-    for (int r = lane; r < d.ne; r += 32) veqp[r] = rowval(r);
+// cols_pass: for every variable: colfn(i, k, vo+k, S, Dy, D_k * sum_r a_r[k] v_r, c*D_k*(P ux)_k) with
+// v_r = rowval(i, r, g, S, Dy) (already E-weighted) and ux = D*xfn(...) (only when WITHP)
+template <class DM, bool WITHP, class XFn, class RowVal, class ColFn>
+__device__ void cols_pass(Ctx<DM>& c, XFn xfn, RowVal rowval, ColFn colfn) {
+    B200_LOCALS(c);
+    ring_issue(c, 0); ring_issue(c, 1); ring_issue(c, 2);
+    for (int r = lane; r < d.ne; r += 32) veqp[r] = rowval(-1, r, r, (double*)nullptr, (double*)nullptr);
     for (int i = 0; i <= d.ph; ++i) {
-        int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
-        for (int r = lane; r < rs; r += 32) vrow[r] = rowval(ro + r);
-        if (WITHP) for (int k = lane; k < bi; k += 32) uxc[k] = c.D[vo + k] * xsrc[vo + k];
+        const int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
+        double* S = ring_acquire(c, i);
+        double* Dy = S + d.SRS;
+        for (int r = lane; r < rs; r += 32) vrow[r] = rowval(i, r, ro + r, S, Dy);
+        if (WITHP) for (int k = lane; k < bi; k += 32) uxc[k] = S[d.oD + k] * xfn(i, k, Dy);
         __syncwarp();
         if (WITHP) {
-            for (int r = lane; r < d.ny; r += 32) {
-                double a = 0;
-                for (int k = 0; k < d.nx; ++k) a += c.Cm[r * d.ldC + k] * uxc[k];
-                c.yv[r] = c.wO(i, r) * a;
-            }
+            for (int r = lane; r < d.ny; r += 32) yv[r] = c.wO(i, r) * sdot(Cm + r * d.ldC, 1, uxc, d.nx);
             __syncwarp();
         }
         for (int k = lane; k < bi; k += 32) {
             double au, pu = 0;
             if (k < d.ne) {
-                au = vrow[d.oBOX + k] - veqp[k] + c.s[k] * vrow[d.oSC];
-                if (k < d.nx) for (int j = 0; j < d.ny; ++j) au += c.Cm[j * d.ldC + k] * vrow[d.oOUT + j];
+                au = vrow[d.oBOX + k] - veqp[k] + sv[k] * vrow[d.oSC];
+                if (k < d.nx) au += sdot(Cm + k, d.ldC, vrow + d.oOUT, d.ny);
             } else au = vrow[d.oDU + k - d.ne];
-            if (i < d.ph) for (int j = 0; j < d.ne; ++j) au += c.G[j * d.ldG + k] * vrow[d.oEQ + j];
+            if (i < d.ph) au += sdot(G + k, d.ldG, vrow + d.oEQ, d.ne);
             if (WITHP) {
-                if (k < d.nx) for (int j = 0; j < d.ny; ++j) pu += c.Cm[j * d.ldC + k] * c.yv[j];
+                if (k < d.nx) pu = sdot(Cm + k, d.ldC, yv, d.ny);
                 else if (k < d.ne) pu = c.wU(i, k - d.nx) * uxc[k];
                 else pu = c.wDU(i, k - d.ne) * uxc[k];
-                pu *= c.c * c.D[vo + k];
+                pu *= c.c * S[d.oD + k];
             }
-            colfn(vo + k, c.D[vo + k] * au, pu);
+            colfn(i, k, vo + k, S, Dy, S[d.oD + k] * au, pu);
         }
         __syncwarp();
         if (i < d.ph) for (int r = lane; r < d.ne; r += 32) veqp[r] = vrow[d.oEQ + r];
         __syncwarp();
+        ring_issue(c, i + kRing);
     }
 }
 
+// accessors usable with i == -1 (eq0 rows); e0 = base of the eq0 block [E | lo | up | z | y] in the workspace
+template <class DM> __device__ __forceinline__ double rowE(Ctx<DM>& c, int i, int r, const double* S) { return i < 0 ? (c.ws + c.d.wE0())[r] : S[c.d.oE + r]; }
+template <class DM> __device__ __forceinline__ double rowLO(Ctx<DM>& c, int i, int r, const double* S) { return i < 0 ? (c.ws + c.d.wE0() + c.d.ne)[r] : S[c.d.oLO + r]; }
+template <class DM> __device__ __forceinline__ double rowUP(Ctx<DM>& c, int i, int r, const double* S) { return i < 0 ? (c.ws + c.d.wE0() + 2 * c.d.ne)[r] : S[c.d.oUP + r]; }
+template <class DM> __device__ __forceinline__ double rowZ(Ctx<DM>& c, int i, int r, const double* Dy) { return i < 0 ? (c.ws + c.d.wE0() + 3 * c.d.ne)[r] : Dy[c.d.oZ + r]; }
+template <class DM> __device__ __forceinline__ double rowY(Ctx<DM>& c, int i, int r, const double* Dy) { return i < 0 ? (c.ws + c.d.wE0() + 4 * c.d.ne)[r] : Dy[c.d.oY + r]; }
+template <class DM> __device__ __forceinline__ int rowT(Ctx<DM>& c, int i, int r, const double* S) {
+    return i < 0 ? reinterpret_cast<const int8_t*>(c.ws + c.d.wT0())[r] : reinterpret_cast<const int8_t*>(S + c.d.oT)[r];
+}
+
 // update_info (auxil.c): residuals + every norm the termination test and the rho estimate need.
-// zy(g, Ax, z, y) supplies the (z,y) pair of row g (ADMM iterate or the polished pair).
-template <class ZY>
-__device__ InfoNorms info_pass(Ctx& c, const double* xsrc, ZY zy) {
+// xfn supplies the scaled x; zy(i, r, g, S, Dy, Ax, z, y) supplies the (z,y) pair of a row.
+template <class DM, class XFn, class ZY>
+__device__ InfoNorms info_pass(Ctx<DM>& c, XFn xfn, ZY zy) {
+    B200_LOCALS(c);
     InfoNorms I;
     double pri = 0, nz = 0, nAx = 0, spri = 0, snz = 0, snAx = 0;
-    rows_pass(c, xsrc, [&](int g, double a) {
-        double e = c.E[g], einv = 1.0 / e;
+    rows_pass(c, xfn, [&](int i, int r, int g, double* S, double* Dy, double a) {
+        double e = rowE(c, i, r, S), einv = 1.0 / e;
         double Ax = e * a, z, y;
-        zy(g, Ax, z, y);
-        c.rc[g] = e * y;            // E-weighted dual for the column pass
+        zy(i, r, g, S, Dy, Ax, z, y);
+        rc[g] = e * y;            // E-weighted dual for the column pass
         double pv = Ax - z;
         spri = fmax(spri, fabs(pv)); snz = fmax(snz, fabs(z)); snAx = fmax(snAx, fabs(Ax));
         pri = fmax(pri, fabs(einv * pv)); nz = fmax(nz, fabs(einv * z)); nAx = fmax(nAx, fabs(einv * Ax));
     });
     __syncwarp();
     double dua = 0, nq = 0, nAty = 0, nPx = 0, sdua = 0, snq = 0, snAty = 0, snPx = 0, xPx = 0, qx = 0;
-    cols_pass<true>(c, xsrc, [&](int g) { return c.rc[g]; }, [&](int kg, double aty, double px) {
-        double dinv = 1.0 / c.D[kg];
-        double q = c.qs[kg];
+    cols_pass<DM, true>(c, xfn, [&](int, int, int g, double*, double*) { return rc[g]; },
+                        [&](int i, int k, int, double* S, double* Dy, double aty, double px) {
+        double dinv = 1.0 / S[c.d.oD + k];
+        double q = S[c.d.oQ + k];
         double dv = q + px + aty;
         sdua = fmax(sdua, fabs(dv)); snq = fmax(snq, fabs(q)); snAty = fmax(snAty, fabs(aty)); snPx = fmax(snPx, fabs(px));
         dua = fmax(dua, fabs(dinv * dv)); nq = fmax(nq, fabs(dinv * q)); nAty = fmax(nAty, fabs(dinv * aty)); nPx = fmax(nPx, fabs(dinv * px));
-        double xv = xsrc[kg];
+        double xv = xfn(i, k, Dy);
         xPx += xv * px; qx += q * xv;
     });
     double cinv = 1.0 / c.c;
@@ -720,25 +929,33 @@ __device__ InfoNorms info_pass(Ctx& c, const double* xsrc, ZY zy) {
 }
 
 // is_primal_infeasible (auxil.c); delta_y lives in ra
-__device__ bool primal_infeasible(Ctx& c, double eps) {
-    const Dm& d = c.d;
+template <class DM>
+__device__ bool primal_infeasible(Ctx<DM>& c, double eps) {
+    B200_LOCALS(c);
     double nd = 0, lhs = 0;
-    for (int g = c.lane; g < d.m; g += 32) {
-        double l = c.lo[g], u = c.up[g], dy = c.ra[g];
+    auto one = [&](int g, double l, double u, double e) {
+        double dy = ra[g];
         if (u > kOsqpInfty * kMinScaling) {
             if (l < -kOsqpInfty * kMinScaling) dy = 0.0; else dy = fmin(dy, 0.0);
         } else if (l < -kOsqpInfty * kMinScaling) dy = fmax(dy, 0.0);
-        c.ra[g] = dy;
-        nd = fmax(nd, fabs(c.E[g] * dy));
+        ra[g] = dy;
+        nd = fmax(nd, fabs(e * dy));
         lhs += u * fmax(dy, 0.0) + l * fmin(dy, 0.0);   // IEEE: inf*0 = NaN, exactly as in the reference build
+    };
+    for (int r = lane; r < d.ne; r += 32) one(r, e0lo[r], e0up[r], e0E[r]);
+    for (int i = 0; i <= d.ph; ++i) {
+        const double* S = SRP(i);
+        int ro = d.roff(i);
+        for (int r = lane; r < d.rcount(i); r += 32) one(ro + r, S[d.oLO + r], S[d.oUP + r], S[d.oE + r]);
     }
     nd = wmax(nd); lhs = wsum(lhs);
     __syncwarp();
     if (nd > eps) {
         if (lhs < -eps * nd) {
             double mx = 0;
-            cols_pass<false>(c, nullptr, [&](int g) { return c.E[g] * c.ra[g]; },
-                             [&](int kg, double aty, double) { mx = fmax(mx, fabs(aty / c.D[kg])); });
+            cols_pass<DM, false>(c, [&](int, int, const double*) { return 0.0; },
+                                 [&](int i, int r, int g, double* S, double*) { return rowE(c, i, r, S) * ra[g]; },
+                                 [&](int, int k, int, double* S, double*, double aty, double) { mx = fmax(mx, fabs(aty / S[c.d.oD + k])); });
             mx = wmax(mx);
             return mx < eps * nd;
         }
@@ -746,24 +963,30 @@ __device__ bool primal_infeasible(Ctx& c, double eps) {
     return false;
 }
 // is_dual_infeasible (auxil.c); delta_x lives in va
-__device__ bool dual_infeasible(Ctx& c, double eps) {
-    const Dm& d = c.d;
+template <class DM>
+__device__ bool dual_infeasible(Ctx<DM>& c, double eps) {
+    B200_LOCALS(c);
     double nd = 0, qd = 0;
-    for (int k = c.lane; k < d.n; k += 32) { double dx = c.va[k]; nd = fmax(nd, fabs(c.D[k] * dx)); qd += c.qs[k] * dx; }
+    for (int i = 0; i <= d.ph; ++i) {
+        const double* S = SRP(i);
+        int vo = c.voff(i);
+        for (int k = lane; k < d.bcount(i); k += 32) { double dx = va[vo + k]; nd = fmax(nd, fabs(S[d.oD + k] * dx)); qd += S[d.oQ + k] * dx; }
+    }
     nd = wmax(nd); qd = wsum(qd);
     double cs = c.c;
+    auto dxfn = [&](int i, int k, const double*) { return va[c.voff(i) + k]; };
     if (nd > eps) {
         if (qd < -cs * eps * nd) {
             double mx = 0;
-            cols_pass<true>(c, c.va, [&](int) { return 0.0; },
-                            [&](int kg, double, double px) { mx = fmax(mx, fabs(px / c.D[kg])); });
+            cols_pass<DM, true>(c, dxfn, [&](int, int, int, double*, double*) { return 0.0; },
+                                [&](int, int k, int, double* S, double*, double, double px) { mx = fmax(mx, fabs(px / S[c.d.oD + k])); });
             mx = wmax(mx);
             if (mx < cs * eps * nd) {
                 bool bad = false;
-                rows_pass(c, c.va, [&](int g, double a) {
+                rows_pass(c, dxfn, [&](int i, int r, int, double* S, double*, double a) {
                     double adx = a;   // Einv * (E a) = a
-                    if (((c.up[g] < kOsqpInfty * kMinScaling) && (adx > eps * nd)) ||
-                        ((c.lo[g] > -kOsqpInfty * kMinScaling) && (adx < -eps * nd))) bad = true;
+                    if (((rowUP(c, i, r, S) < kOsqpInfty * kMinScaling) && (adx > eps * nd)) ||
+                        ((rowLO(c, i, r, S) > -kOsqpInfty * kMinScaling) && (adx < -eps * nd))) bad = true;
                 });
                 return !wany(bad);
             }
@@ -773,7 +996,8 @@ __device__ bool dual_infeasible(Ctx& c, double eps) {
 }
 
 // check_termination (auxil.c).  Returns true when the loop must stop; status/obj updated.
-__device__ bool check_termination(Ctx& c, const InfoNorms& I, bool approximate, int& status, double& obj) {
+template <class DM>
+__device__ bool check_termination(Ctx<DM>& c, const InfoNorms& I, bool approximate, int& status, double& obj) {
     double eps_abs = c.p.eps_abs, eps_rel = c.p.eps_rel, epi = c.p.eps_prim_inf, edi = c.p.eps_dual_inf;
     if (I.pri > kOsqpInfty || I.dua > kOsqpInfty) { status = OSQP_NON_CVX; obj = NAN; return true; }
     if (approximate) { eps_abs *= 10; eps_rel *= 10; epi *= 10; edi *= 10; }
@@ -799,64 +1023,86 @@ __device__ __forceinline__ int to_result_status(int st) {   // LOptimizer.hpp:38
     }
 }
 
-// reference row index of internal row g / reference variable index of internal variable kg
-__device__ __forceinline__ int ref_row(const Dm& d, int g) {
-    if (g < d.ne) return g;
-    int i = (g - d.ne) / d.RS, r = (g - d.ne) - i * d.RS;
+// reference row index of a row (i,r) (i=-1: eq0) / reference variable index of (i,k)
+template <class DM>
+__device__ __forceinline__ int ref_row(const DM& d, int i, int r) {
+    if (i < 0) return r;
     if (r < d.oOUT) return d.M0 + i * d.ne + r;
     if (r < d.oSC) return d.M1 + i * d.ny + (r - d.oOUT);
     if (r < d.oEQ) return d.M3 + i;
     if (r < d.oDU) return (i + 1) * d.ne + (r - d.oEQ);
     return d.M2 + i * d.nu + (r - d.oDU);
 }
-__device__ __forceinline__ int ref_var(const Dm& d, int kg) {
-    int i = kg / d.b, k = kg - i * d.b;
+template <class DM>
+__device__ __forceinline__ int ref_var(const DM& d, int i, int k) {
     return k < d.ne ? i * d.ne + k : (d.ph + 1) * d.ne + i * d.nu + (k - d.ne);
 }
-__device__ __forceinline__ int int_var_e(const Dm& d, int i, int k) { return i * d.b + k; }
 
 // ---- the whole LOptimizer::run for one instance -----------------------------------------------------------------
-__device__ void solve_instance(Ctx& c, const Out& o) {
-    const Dm& d = c.d;
-    const int lane = c.lane, inst = c.inst;
+template <class DM>
+__device__ void solve_instance(Ctx<DM>& c, const Out& o) {
+    B200_LOCALS(c);
+    const int inst = c.inst;
+    const long long ib = inst;
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 8; ++k) c.sp[k] = 0;
+    long long t0 = clock64(), t1;
+#define PROF(slot) do { t1 = clock64(); pt[slot] += t1 - t0; t0 = t1; } while (0)
     load_model(c);
     bool valid = setup_and_scale(c);
+    PROF(0);
     int status = OSQP_UNSOLVED; double obj = 0; int iters = 0, rho_updates = 0, status_polish = 0;
     double rho = fmin(fmax(c.p.rho, kRhoMin), kRhoMax);
     set_rho(c, rho);
     if (valid) valid = factorize(c, c.p.sigma);
+    PROF(1);
     if (!valid) {
         // osqp_setup would have failed (validate_data / factorisation): LOptimizer.hpp:348-361 failure semantics
-        for (int k = lane; k < d.nu; k += 32) o.cmd[(long long)inst * d.nu + k] = o.prev_cmd[(long long)inst * d.nu + k];
+        ring_reset(c);
+        for (int k = lane; k < d.nu; k += 32) o.cmd[ib * d.nu + k] = o.prev_cmd[ib * d.nu + k];
         if (lane == 0) { o.cost[inst] = INFINITY; o.status[inst] = RS_ERROR; o.solver_status[inst] = B200_SETUP_ERROR;
                          o.feasible[inst] = 0; o.iters[inst] = 0; o.rho_updates[inst] = 0; o.polish[inst] = 0; }
-        if (o.seq_state) for (int e = lane; e < (d.ph + 1) * d.nx; e += 32) o.seq_state[(long long)inst * (d.ph + 1) * d.nx + e] = 0;
-        if (o.seq_input) for (int e = lane; e < (d.ph + 1) * d.nu; e += 32) o.seq_input[(long long)inst * (d.ph + 1) * d.nu + e] = 0;
-        if (o.seq_output) for (int e = lane; e < (d.ph + 1) * d.ny; e += 32) o.seq_output[(long long)inst * (d.ph + 1) * d.ny + e] = 0;
+        if (o.seq_state) for (int e = lane; e < (d.ph + 1) * d.nx; e += 32) o.seq_state[ib * (d.ph + 1) * d.nx + e] = 0;
+        if (o.seq_input) for (int e = lane; e < (d.ph + 1) * d.nu; e += 32) o.seq_input[ib * (d.ph + 1) * d.nu + e] = 0;
+        if (o.seq_output) for (int e = lane; e < (d.ph + 1) * d.ny; e += 32) o.seq_output[ib * (d.ph + 1) * d.ny + e] = 0;
         return;
     }
+    auto xrec = [&](int, int k, const double* Dy) { return Dy[k]; };
     // cold / warm start (osqp_warm_start: x <- Dinv x, y <- c Einv y, z <- A x)
     if (c.pr.warm) {
-        for (int kg = lane; kg < d.n; kg += 32) c.x[kg] = __ldg(c.pr.warm_x + (long long)inst * d.n + ref_var(d, kg)) / c.D[kg];
-        for (int g = lane; g < d.m; g += 32) c.y[g] = c.c * (__ldg(c.pr.warm_y + (long long)inst * d.m + ref_row(d, g)) / c.E[g]);
-        __syncwarp();
-        rows_pass(c, c.x, [&](int g, double a) { c.z[g] = c.E[g] * a; });
+        for (int i = 0; i <= d.ph; ++i) {
+            double* S = SRP(i); double* Dg = DRP(i);
+            for (int k = lane; k < d.bcount(i); k += 32) Dg[k] = __ldg(c.pr.warm_x + ib * d.n + ref_var(d, i, k)) / S[d.oD + k];
+            for (int r = lane; r < d.rcount(i); r += 32) Dg[d.oY + r] = c.c * (__ldg(c.pr.warm_y + ib * d.m + ref_row(d, i, r)) / S[d.oE + r]);
+        }
+        for (int r = lane; r < d.ne; r += 32) e0y[r] = c.c * (__ldg(c.pr.warm_y + ib * d.m + r) / e0E[r]);
+        ring_reset(c);
+        rows_pass(c, xrec, [&](int i, int r, int, double* S, double*, double a) {
+            if (i < 0) e0z[r] = e0E[r] * a; else DRP(i)[d.oZ + r] = S[d.oE + r] * a;
+        });
+        ring_reset(c);
     } else {
-        for (int k = lane; k < d.n; k += 32) c.x[k] = 0.0;
-        for (int g = lane; g < d.m; g += 32) { c.z[g] = 0.0; c.y[g] = 0.0; }
+        for (int i = 0; i <= d.ph; ++i) {
+            double* Dg = DRP(i);
+            for (int e = lane; e < d.DRS; e += 32) Dg[e] = 0.0;
+        }
+        for (int r = lane; r < d.ne; r += 32) { e0z[r] = 0.0; e0y[r] = 0.0; }
+        ring_reset(c);
     }
-    __syncwarp();
     InfoNorms I; I.pri = I.dua = 0;
     bool can_check = false, done = false;
-    auto admm_zy = [&](int g, double, double& z, double& y) { z = c.z[g]; y = c.y[g]; };
+    auto admm_zy = [&](int i, int r, int, double*, double* Dy, double, double& z, double& y) { z = rowZ(c, i, r, Dy); y = rowY(c, i, r, Dy); };
     int it = 1;
     for (; it <= c.p.max_iter; ++it) {
         can_check = c.p.check_termination && (it % c.p.check_termination == 0);
         bool can_adapt = c.p.adaptive_rho && c.p.adaptive_rho_interval && (it % c.p.adaptive_rho_interval == 0);
-        kkt_sweeps<0>(c, can_check || it == c.p.max_iter, false);
+        kkt_sweeps<DM, 0>(c, can_check || it == c.p.max_iter, false);
+        PROF(2);
         if (can_check || can_adapt) {
-            I = info_pass(c, c.x, admm_zy);
-            if (can_check && check_termination(c, I, false, status, obj)) { done = true; break; }
+            I = info_pass(c, xrec, admm_zy);
+            bool stop = can_check && check_termination(c, I, false, status, obj);
+            PROF(3);
+            if (stop) { done = true; break; }
         }
         if (can_adapt) {
             // compute_rho_estimate (auxil.c) on the SCALED residuals
@@ -867,98 +1113,125 @@ __device__ void solve_instance(Ctx& c, const Out& o) {
             if (est > rho * c.p.adaptive_rho_tolerance || est < rho / c.p.adaptive_rho_tolerance) {
                 rho = est; set_rho(c, rho);
                 factorize(c, c.p.sigma);
+                PROF(1);
                 ++rho_updates;
             }
         }
     }
     iters = done ? it : c.p.max_iter;
     if (!done && !can_check) {
-        I = info_pass(c, c.x, admm_zy);
+        I = info_pass(c, xrec, admm_zy);
         check_termination(c, I, false, status, obj);
     }
     bool has_solution = !(status == OSQP_PRIMAL_INFEASIBLE || status == OSQP_PRIMAL_INFEASIBLE_INACCURATE ||
                           status == OSQP_DUAL_INFEASIBLE || status == OSQP_DUAL_INFEASIBLE_INACCURATE || status == OSQP_NON_CVX);
-    if (has_solution) {
-        obj = (0.5 * I.xPx + I.qx) / c.c;
-    }
+    if (has_solution) obj = (0.5 * I.xPx + I.qx) / c.c;
     if (status == OSQP_UNSOLVED) {
         if (!check_termination(c, I, true, status, obj)) status = OSQP_MAX_ITER_REACHED;
     }
+    bool use_px = false;
+    PROF(3);
     // ---------------- polish (polish.c) ----------------
     if (c.p.polish && status == OSQP_SOLVED) {
         const double dinv = 1.0 / c.p.delta;
-        for (int g = lane; g < d.m; g += 32) {
-            double z = c.z[g], y = c.y[g], l = c.lo[g], u = c.up[g];
+        auto mark = [&](double z, double y, double l, double u, int8_t& ty, double& bact) {
             bool low = (z - l) < -y;
             bool upp = !low && ((u - z) < y);
-            c.rtype[g] = (low || upp) ? 1 : 0;
-            c.ra[g] = low ? l : (upp ? u : 0.0);     // b_act
+            ty = (low || upp) ? 1 : 0;
+            bact = low ? l : (upp ? u : 0.0);
+        };
+        for (int i = 0; i <= d.ph; ++i) {
+            double* S = SRP(i); const double* Dg = DRP(i);
+            int8_t* rt = reinterpret_cast<int8_t*>(S + d.oT);
+            int ro = d.roff(i);
+            for (int r = lane; r < d.rcount(i); r += 32) {
+                int8_t ty; double ba;
+                mark(Dg[d.oZ + r], Dg[d.oY + r], S[d.oLO + r], S[d.oUP + r], ty, ba);
+                rt[r] = ty; ra[ro + r] = ba; rc[ro + r] = ba;
+            }
+            for (int k = lane; k < d.bcount(i); k += 32) va[c.voff(i) + k] = -S[d.oQ + k];
+        }
+        for (int r = lane; r < d.ne; r += 32) {
+            int8_t ty; double ba;
+            mark(e0z[r], e0y[r], e0lo[r], e0up[r], ty, ba);
+            e0t[r] = ty; ra[r] = ba; rc[r] = ba;
         }
         c.rsel[0] = 0.0; c.rsel[1] = dinv; c.rsel[2] = 0.0;
         __syncwarp();
-        if (factorize(c, c.p.delta)) {
-            for (int k = lane; k < d.n; k += 32) c.va[k] = -c.qs[k];
-            for (int g = lane; g < d.m; g += 32) c.rc[g] = c.ra[g];
-            __syncwarp();
-            kkt_sweeps<1>(c, false, true);
+        PROF(4);
+        bool fok = factorize(c, c.p.delta);
+        PROF(5);
+        if (fok) {
+            auto pxfn = [&](int i, int k, const double*) { return px[c.voff(i) + k]; };
+            kkt_sweeps<DM, 1>(c, false, true);
             for (int rf = 0; rf < c.p.polish_refine_iter; ++rf) {
                 // r1 = -q - P px - A' pnu ; r2 = act (b - A px)
-                cols_pass<true>(c, c.px, [&](int g) { return c.E[g] * c.rb[g]; },
-                                [&](int kg, double aty, double pxv) { c.va[kg] = -c.qs[kg] - pxv - aty; });
-                rows_pass(c, c.px, [&](int g, double a) { c.rc[g] = c.rtype[g] ? (c.ra[g] - c.E[g] * a) : 0.0; });
+                cols_pass<DM, true>(c, pxfn, [&](int i, int r, int g, double* S, double*) { return rowE(c, i, r, S) * rb[g]; },
+                                    [&](int, int k, int kg, double* S, double*, double aty, double pxv) { va[kg] = -S[c.d.oQ + k] - pxv - aty; });
+                rows_pass(c, pxfn, [&](int i, int r, int g, double* S, double*, double a) {
+                    rc[g] = rowT(c, i, r, S) ? (ra[g] - rowE(c, i, r, S) * a) : 0.0;
+                });
                 __syncwarp();
-                kkt_sweeps<1>(c, false, false);
+                kkt_sweeps<DM, 1>(c, false, false);
             }
             // polished (z,y): z = A px, project_normalcone
-            auto pol_zy = [&](int g, double Ax, double& z, double& y) {
-                double t = Ax + c.rb[g];
-                z = fmin(fmax(t, c.lo[g]), c.up[g]);
+            auto pol_zy = [&](int i, int r, int g, double* S, double*, double Ax, double& z, double& y) {
+                double t = Ax + rb[g];
+                z = fmin(fmax(t, rowLO(c, i, r, S)), rowUP(c, i, r, S));
                 y = t - z;
             };
-            // info_pass overwrites rc (free now); keep pnu in rb
-            InfoNorms P = info_pass(c, c.px, pol_zy);
+            InfoNorms P = info_pass(c, pxfn, pol_zy);
             bool okp = (P.pri < I.pri && P.dua < I.dua) || (P.pri < I.pri && I.dua < 1e-10) || (P.dua < I.dua && I.pri < 1e-10);
             if (okp) {
                 obj = (0.5 * P.xPx + P.qx) / c.c;
                 status_polish = 1;
-                for (int k = lane; k < d.n; k += 32) c.x[k] = c.px[k];
-                rows_pass(c, c.px, [&](int g, double a) {
-                    double z, y; pol_zy(g, c.E[g] * a, z, y);
-                    c.z[g] = z; c.y[g] = y;
-                });
+                use_px = true;     // x <- px; the polished dual is rc = E*y_pol left by info_pass
             } else status_polish = -1;
         } else status_polish = -1;
         __syncwarp();
     }
+    PROF(6);
     // ---------------- store_solution + LOptimizer unpack ----------------
     const double cinv = 1.0 / c.c;
-    const long long ib = inst;
-    for (int kg = lane; kg < d.n; kg += 32) {
-        double xv = has_solution ? c.D[kg] * c.x[kg] : NAN;
-        c.x[kg] = xv;   // unscaled from here on
-        if (o.sol_x) o.sol_x[ib * d.n + ref_var(d, kg)] = xv;
+    for (int i = 0; i <= d.ph; ++i) {
+        const double* S = SRP(i); const double* Dg = DRP(i);
+        int vo = c.voff(i), ro = d.roff(i);
+        for (int k = lane; k < d.bcount(i); k += 32) {
+            double xs = use_px ? px[vo + k] : Dg[k];
+            double xv = has_solution ? S[d.oD + k] * xs : NAN;
+            tg[vo + k] = xv;     // unscaled solution, flat stage-major
+            if (o.sol_x) o.sol_x[ib * d.n + ref_var(d, i, k)] = xv;
+        }
+        if (o.sol_y) for (int r = lane; r < d.rcount(i); r += 32) {
+            double yv = use_px ? rc[ro + r] : S[d.oE + r] * Dg[d.oY + r];
+            o.sol_y[ib * d.m + ref_row(d, i, r)] = has_solution ? cinv * yv : NAN;
+        }
     }
-    if (o.sol_y) for (int g = lane; g < d.m; g += 32) o.sol_y[ib * d.m + ref_row(d, g)] = has_solution ? cinv * c.E[g] * c.y[g] : NAN;
+    if (o.sol_y) for (int r = lane; r < d.ne; r += 32) {
+        double yv = use_px ? rc[r] : e0E[r] * e0y[r];
+        o.sol_y[ib * d.m + r] = has_solution ? cinv * yv : NAN;
+    }
     __syncwarp();
+    const double* xu = tg;
     for (int k = lane; k < d.nu; k += 32) {
         int st = d.ph >= 1 ? 1 : 0;    // sequence.input.row(0) = x_u(1)  (LOptimizer.hpp:316-327,341)
-        double v = c.x[int_var_e(d, st, d.nx + k)];
+        double v = xu[c.voff(st) + d.nx + k];
         o.cmd[ib * d.nu + k] = v; o.prev_cmd[ib * d.nu + k] = v;
     }
     if (o.seq_state) for (int e = lane; e < (d.ph + 1) * d.nx; e += 32) {
         int i = e / d.nx, k = e - i * d.nx;
-        o.seq_state[ib * (d.ph + 1) * d.nx + e] = c.x[int_var_e(d, i, k)];
+        o.seq_state[ib * (d.ph + 1) * d.nx + e] = xu[c.voff(i) + k];
     }
     if (o.seq_input) for (int e = lane; e < (d.ph + 1) * d.nu; e += 32) {
         int i = e / d.nu, k = e - i * d.nu;
         int st = (i + 1 < d.ph + 1) ? i + 1 : i;
-        o.seq_input[ib * (d.ph + 1) * d.nu + e] = c.x[int_var_e(d, st, d.nx + k)];
+        o.seq_input[ib * (d.ph + 1) * d.nu + e] = xu[c.voff(st) + d.nx + k];
     }
     if (o.seq_output) for (int e = lane; e < (d.ph + 1) * d.ny; e += 32) {
         int i = e / d.ny, r = e - i * d.ny;
         int j = i > 0 ? i - 1 : 0;
         double acc = 0;
-        for (int k = 0; k < d.nx; ++k) acc += c.Cm[r * d.ldC + k] * c.x[int_var_e(d, i, k)];
+        for (int k = 0; k < d.nx; ++k) acc += Cm[r * d.ldC + k] * xu[c.voff(i) + k];
         for (int q = 0; q < d.ndu; ++q) acc += ldp(c.pr.Dd, inst, r * d.ndu + q) * ldp(c.pr.uMeas, inst, j * d.ndu + q);
         o.seq_output[ib * (d.ph + 1) * d.ny + e] = acc;
     }
@@ -967,36 +1240,39 @@ __device__ void solve_instance(Ctx& c, const Out& o) {
         o.feasible[inst] = (status == OSQP_SOLVED || status == OSQP_SOLVED_INACCURATE || status == OSQP_MAX_ITER_REACHED) ? 1 : 0;
         o.iters[inst] = iters; o.rho_updates[inst] = rho_updates; o.polish[inst] = status_polish;
     }
+    ring_reset(c);
+    PROF(7);
+    if (o.prof && lane == 0) { for (int k = 0; k < 8; ++k) { o.prof[ib * 16 + k] = pt[k]; o.prof[ib * 16 + 8 + k] = c.sp[k]; } }
+#undef PROF
 }
 
 // ---- persistent kernel: warps pull instances from a global counter ------------------------------------------------
-__global__ void __launch_bounds__(256) lmpc_solve_kernel(const __grid_constant__ Dm d, const __grid_constant__ Params p,
+template <class DM>
+__global__ void __launch_bounds__(128) lmpc_solve_kernel(const __grid_constant__ DM d, const __grid_constant__ Params p,
                                                         const __grid_constant__ Prob pr, const __grid_constant__ Out o,
                                                         int batch, double* workspace, size_t ws_stride, int* counter) {
-    extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int slot = blockIdx.x * wpb + warp;
-    Ctx c(d, p, pr);
+    Ctx<DM> c(d, p, pr);
     c.lane = lane;
-    double* sm = smem + (size_t)warp * d.smem_doubles();
-    c.G = sm; sm += d.ne * d.ldG;
-    c.Cm = sm; sm += d.ny * d.ldC;
-    c.s = sm; sm += d.ne;
-    c.uxc = sm; sm += d.b; c.uxn = sm; sm += d.b; c.vtmp = sm; sm += d.b; c.tA = sm; sm += d.b; c.tB = sm; sm += d.b;
-    c.xn = sm; sm += d.ne; c.veqp = sm; sm += d.ne;
-    c.vrowA = sm; sm += d.RS;
-    c.yv = sm; sm += d.ny;
-    sm = (double*)(((uintptr_t)sm + 15) & ~(uintptr_t)15);
-    // union: factor scratch | factor ring
-    c.fb0 = sm; c.fb1 = sm + d.FS;
-    c.S = sm; c.Li = c.S + d.b * d.ldb; c.Hc = c.Li + d.b * d.ldb; c.Lc = c.Hc + d.ne * d.ldb; c.Pblk = c.Lc + d.ne * d.ldb;
-    double* ws = workspace + (size_t)slot * ws_stride;
-    c.D = ws; ws += d.n; c.qs = ws; ws += d.n; c.x = ws; ws += d.n; c.t = ws; ws += d.n; c.va = ws; ws += d.n; c.px = ws; ws += d.n;
-    c.E = ws; ws += d.m; c.lo = ws; ws += d.m; c.up = ws; ws += d.m; c.z = ws; ws += d.m; c.y = ws; ws += d.m;
-    c.ra = ws; ws += d.m; c.rb = ws; ws += d.m; c.rc = ws; ws += d.m;
-    c.fac = ws; ws += (size_t)(d.ph + 1) * d.FS;
-    c.rtype = reinterpret_cast<int8_t*>(ws);
+    c.sb = warp * d.smem_doubles();
+    c.ws = workspace + (size_t)slot * ws_stride;
+    // Ruiz working arrays: in shared memory (the ring area past Pblk) when they fit, else in the workspace
+    {
+        size_t need = d.ruiz_doubles();
+        if ((size_t)(d.nx * d.nx) + need <= (size_t)d.ring_doubles()) c.wD = smem + c.sb + d.nx * d.nx;
+        else c.wD = c.ws + d.wRUIZ();
+        c.wq = c.wD + d.n; c.wE = c.wq + d.n;
+    }
+    if (lane == 0) {
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + c.sb + d.sBARS());
+        for (int k = 0; k < kRing; ++k) mbar_init(&bars[k], 1);
+        fence_mbar_init();
+    }
+    c.rres = 0; c.rflags = 0;
+    fence_proxy_async();
+    __syncwarp();
     for (;;) {
         int inst = 0;
         if (lane == 0) inst = atomicAdd(counter, 1);

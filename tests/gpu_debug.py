@@ -34,6 +34,13 @@ for ph, B in ((10, 1024), (20, 4096)):
     c.setOptimizerParameters(L.LParameters(maximum_iteration=250))
     rng = np.random.default_rng(1)
     x0 = rng.uniform(-1, 1, (B, 12)) * np.array([0.2, 0.2, 0.5, 0.5, 0.5, 0.5] + [0.3] * 6)
+    c.profile()
     for rep in range(3):
         t = time.time(); res = c.optimize(x0, np.zeros((B, 4))); dt = time.time() - t
         print(f"ph={ph} B={B}: {dt*1e3:.1f} ms -> {B/dt:.0f} solves/s; iters mean {res.iterations.mean():.1f} max {res.iterations.max()} status {np.unique(res.solver_status, return_counts=True)} info {c.info()}")
+    pr = c.profile(fetch=True).astype(float)
+    names = ['setup', 'factor', 'sweeps', 'info', 'polprep', 'polfac', 'polsolve', 'unpack']
+    tot = pr[:, :8].sum(1).mean()
+    sn = ['f_acq', 'f_rows_cols', 'f_linv', 'f_carry', 'b_acq', 'b_solve', 'b_rows', '-']
+    print('  sweep split (cycles/instance):', {n: int(v) for n, v in zip(sn, pr[:, 8:].mean(0))})
+    print('  phase cycles/instance:', {n: int(v) for n, v in zip(names, pr[:, :8].mean(0))}, 'total', int(tot), ' per-iter sweep', int(pr[:,2].mean()/res.iterations.mean()))
