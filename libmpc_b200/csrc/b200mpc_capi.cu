@@ -321,14 +321,21 @@ static int configure_t(b200mpc_lmpc* h) {
     size_t smem_warp = (size_t)dm.smem_doubles() * sizeof(double);
     int dev_max_smem = 0;
     CK(cudaDeviceGetAttribute(&dev_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    int wpc = h->req_wpc > 0 ? h->req_wpc : 4;
-    while (wpc > 1 && smem_warp * wpc > (size_t)dev_max_smem) --wpc;
-    if (smem_warp * wpc > (size_t)dev_max_smem) return fail(B200MPC_EINVAL, "problem dimensions exceed shared memory of one warp");
+    // warps per CTA: the request, else the value in 1..4 that maximises resident warps per SM
+    int best_wpc = 0, best_occ = 0;
+    for (int wpc = (h->req_wpc > 0 ? h->req_wpc : 4); wpc >= 1; --wpc) {
+        size_t smem_cta = smem_warp * wpc;
+        if (smem_cta > (size_t)dev_max_smem) { if (h->req_wpc > 0 && wpc == h->req_wpc) continue; else continue; }
+        CK(cudaFuncSetAttribute(lmpc_solve_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lmpc_solve_kernel<DM>, wpc * 32, smem_cta));
+        if (occ * wpc > best_occ * best_wpc) { best_occ = occ; best_wpc = wpc; }
+        if (h->req_wpc > 0) break;
+    }
+    if (best_wpc == 0 || best_occ < 1) return fail(B200MPC_EINVAL, "problem dimensions exceed the shared memory of an SM");
+    int wpc = best_wpc, occ = best_occ;
     size_t smem_cta = smem_warp * wpc;
     CK(cudaFuncSetAttribute(lmpc_solve_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lmpc_solve_kernel<DM>, wpc * 32, smem_cta));
-    if (occ < 1) return fail(B200MPC_ECUDA, "kernel does not fit on an SM");
     int cps = h->req_cps > 0 ? (h->req_cps < occ ? h->req_cps : occ) : occ;
     int grid = h->num_sms * cps;
     int need = (h->batch + wpc - 1) / wpc;

@@ -31,7 +31,8 @@ namespace b200mpc {
 
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3, kRhoTol = 1e-4;
 constexpr double kOsqpInfty = 1e30, kMinScaling = 1e-4, kMaxScaling = 1e4;
-constexpr int kRing = 3;
+constexpr int kRingF = 2;   // factor-block ring slots
+constexpr int kRingV = 3;   // vector-record ring slots
 
 // OSQP status_val (constants.h of v0.6.3)
 enum { OSQP_DUAL_INFEASIBLE_INACCURATE = 4, OSQP_PRIMAL_INFEASIBLE_INACCURATE = 3, OSQP_SOLVED_INACCURATE = 2,
@@ -46,7 +47,7 @@ enum { RS_SUCCESS = 0, RS_MAX_ITERATION = 1, RS_INFEASIBLE = 2, RS_ERROR = 3, RS
 // and the slot's workspace pointer): pointers derived that way stay in registers and shared accesses compile to LDS.
 #define B200_LAYOUT_HOST_DEVICE                                                                                    \
     __host__ __device__ int sBARS() const { return ring_doubles(); }                                                \
-    __host__ __device__ int sG() const { return sBARS() + kRing + 1; }                                              \
+    __host__ __device__ int sG() const { return sBARS() + kRingF + kRingV + 1; }                                              \
     __host__ __device__ int sC() const { return sG() + ne * ldG; }                                                  \
     __host__ __device__ int sS() const { return sC() + ny * ldC; }                                                  \
     __host__ __device__ int sUXC() const { return sS() + ne; }                                                      \
@@ -59,8 +60,14 @@ enum { RS_SUCCESS = 0, RS_MAX_ITERATION = 1, RS_INFEASIBLE = 2, RS_ERROR = 3, RS
     __host__ __device__ int sCARRY() const { return sVEQP() + ne; }                                                 \
     __host__ __device__ int sVROW() const { return sCARRY() + ne; }                                                 \
     __host__ __device__ int sYV() const { return sVROW() + RS; }                                                    \
-    __host__ __device__ int smem_doubles() const { return (sYV() + ny + 3) & ~1; }                                  \
-    __host__ __device__ size_t wDREC() const { return (size_t)(ph + 1) * SRS; }                                      \
+    __host__ __device__ int sW() const { return sYV() + ny; }                                                       \
+    __host__ __device__ int sVROW2() const { return sW() + b; }                                                     \
+    __host__ __device__ int sUX2() const { return sVROW2() + RS; }                                                  \
+    __host__ __device__ int sAROW() const { return sUX2() + b; }                                                    \
+    __host__ __device__ int sWST() const { return sAROW() + RS; }                                                   \
+    __host__ __device__ int smem_doubles() const { return (sWST() + ny + 2 * nu + 3) & ~1; }                                \
+    __host__ __device__ size_t wVREC() const { return (size_t)(ph + 1) * FS; }                                       \
+    __host__ __device__ size_t wDREC() const { return wVREC() + (size_t)(ph + 1) * VSS; }                            \
     __host__ __device__ size_t wE0() const { return wDREC() + (size_t)(ph + 1) * DRS; }                              \
     __host__ __device__ size_t wT0() const { return wE0() + 5 * (size_t)ne; }                                        \
     __host__ __device__ size_t wT() const { return wT0() + (ne + 7) / 8 + 1; }                                       \
@@ -78,7 +85,8 @@ enum { RS_SUCCESS = 0, RS_MAX_ITERATION = 1, RS_INFEASIBLE = 2, RS_ERROR = 3, RS
     __host__ __device__ int bcount(int i) const { return i < ph ? b : ne; }                                        \
     __host__ __device__ size_t ruiz_doubles() const { return 2 * (size_t)n + (size_t)m + 8; }                        \
     __host__ __device__ int fac_doubles() const { return nx * nx + 2 * b * ldb + 2 * ne * ldb; }                    \
-    __host__ __device__ int ring_doubles() const { int r = kRing * SLOT, f = fac_doubles(); return ((r > f ? r : f) + 1) & ~1; } \
+    __host__ __device__ int ringF_doubles() const { return kRingF * FS; }                                           \
+    __host__ __device__ int ring_doubles() const { int r = kRingF * FS + kRingV * VSLOT, f = fac_doubles(); return ((r > f ? r : f) + 1) & ~1; } \
     B200_LAYOUT_HOST_DEVICE
 
 // Runtime dimensions (any shape).
@@ -88,8 +96,8 @@ struct Dm {
     int RS, RSL, oBOX, oOUT, oSC, oEQ, oDU;      // rows owned by a stage and the offsets of its groups
     int ldG, ldC, ldb;                           // odd leading dimensions (conflict-free column walks)
     int oLc, FS;                                 // factor block: packed Linv (b(b+1)/2) + Lc (ne x ldb)
-    int oD, oQ, oE, oT, RT, oLO, oUP, SRS;       // static record
-    int oZ, oY, DRS, SLOT;                       // dynamic record ([x | z | y]) and ring slot size
+    int oD, oQ, oE, oT, RT, oLO, oUP, oWO, oWU, oWDU, VSS;   // static vector record [D | q | E | types | lo | up | wO | wU | wDU]
+    int oZ, oY, DRS, VSLOT;                      // dynamic record ([x | z | y]); V-ring slot = VSS + DRS
     int M0, M1, M2, M3;                          // reference row offsets (ProblemBuilder.hpp:70-76)
     __host__ __device__ void derive() {
         ne = nx + nu; b = ne + nu;
@@ -100,9 +108,10 @@ struct Dm {
         ldG = b | 1; ldC = nx | 1; ldb = b | 1;
         oLc = (b * (b + 1) / 2 + 1) & ~1;
         FS = (oLc + ne * ldb + 1) & ~1;
-        oD = FS; oQ = oD + b; oE = oQ + b; oT = oE + RS; RT = (RS + 7) / 8; oLO = oT + RT; oUP = oLO + RS;
-        SRS = (oUP + RS + 1) & ~1;
-        oZ = b; oY = b + RS; DRS = (b + 2 * RS + 1) & ~1; SLOT = SRS + DRS;
+        oD = 0; oQ = oD + b; oE = oQ + b; oT = oE + RS; RT = (RS + 7) / 8; oLO = oT + RT; oUP = oLO + RS;
+        oWO = oUP + RS; oWU = oWO + ny; oWDU = oWU + nu;
+        VSS = (oWDU + nu + 1) & ~1;
+        oZ = b; oY = b + RS; DRS = (b + 2 * RS + 1) & ~1; VSLOT = VSS + DRS;
         M0 = (ph + 1) * ne; M1 = 2 * (ph + 1) * ne; M2 = M1 + (ph + 1) * ny; M3 = M2 + ph * nu;
     }
     __host__ __device__ void from(const Dm& d) { *this = d; }
@@ -120,9 +129,10 @@ struct SDm {
     static constexpr int ldG = b | 1, ldC = nx | 1, ldb = b | 1;
     static constexpr int oLc = (b * (b + 1) / 2 + 1) & ~1;
     static constexpr int FS = (oLc + ne * ldb + 1) & ~1;
-    static constexpr int oD = FS, oQ = oD + b, oE = oQ + b, oT = oE + RS, RT = (RS + 7) / 8, oLO = oT + RT, oUP = oLO + RS;
-    static constexpr int SRS = (oUP + RS + 1) & ~1;
-    static constexpr int oZ = b, oY = b + RS, DRS = (b + 2 * RS + 1) & ~1, SLOT = SRS + DRS;
+    static constexpr int oD = 0, oQ = oD + b, oE = oQ + b, oT = oE + RS, RT = (RS + 7) / 8, oLO = oT + RT, oUP = oLO + RS;
+    static constexpr int oWO = oUP + RS, oWU = oWO + ny, oWDU = oWU + nu;
+    static constexpr int VSS = (oWDU + nu + 1) & ~1;
+    static constexpr int oZ = b, oY = b + RS, DRS = (b + 2 * RS + 1) & ~1, VSLOT = VSS + DRS;
     int ph, ch, n, m, M0, M1, M2, M3;
     __host__ __device__ void from(const Dm& d) { ph = d.ph; ch = d.ch; n = d.n; m = d.m; M0 = d.M0; M1 = d.M1; M2 = d.M2; M3 = d.M3; }
     B200_DERIVED_HOST_DEVICE
@@ -209,7 +219,8 @@ struct Ctx {
     int sb;                          // this warp's offset (doubles) into the dynamic shared memory
     double* ws;                      // this slot's workspace
     double *wD, *wq, *wE;            // Ruiz working arrays (shared memory when they fit, workspace otherwise)
-    uint32_t rres, rflags;           // ring state: 3 x 10-bit resident stage+1 | pending bits [0..2], parity bits [4..6]
+    unsigned long long fres, vres;   // resident stage+1 per ring slot, 16 bits each (F ring: 3 slots, V ring: 4 slots)
+    uint32_t rflags;                 // pending bits: F [0..2], V [3..6]; parity bits: F [8..10], V [11..14]
     double c;                        // cost scaling
     double rsel[3], rinv[3];         // rho by row type
     long long sp[8];                 // sweep-phase cycle counters (profiling aid)
@@ -244,8 +255,14 @@ struct Ctx {
     double* const carry = sm_ + d.sCARRY();                                                                        \
     double* const vrow = sm_ + d.sVROW();                                                                          \
     double* const yv = sm_ + d.sYV();                                                                              \
+    double* const wbuf = sm_ + d.sW();                                                                             \
+    double* const vrow2 = sm_ + d.sVROW2();                                                                        \
+    double* const ux2 = sm_ + d.sUX2();                                                                            \
+    double* const arow = sm_ + d.sAROW();                                                                          \
+    double* const wst = sm_ + d.sWST();                                                                            \
     double* const ws_ = (c).ws;                                                                                    \
-    double* const srec = ws_;                                                                                      \
+    double* const frec = ws_;                                                                                      \
+    double* const srec = ws_ + d.wVREC();                                                                          \
     double* const drec = ws_ + d.wDREC();                                                                          \
     double* const e0E = ws_ + d.wE0();                                                                             \
     double* const e0lo = e0E + d.ne;                                                                               \
@@ -264,53 +281,83 @@ struct Ctx {
     const double csc = (c).c;                                                                                      \
     (void)ring; (void)Pblk; (void)Sf; (void)Li; (void)Hc; (void)Lcs; (void)bars; (void)G; (void)Cm; (void)sv; (void)uxc; \
     (void)uxn; (void)vtmp; (void)tcur; (void)xcur; (void)xn; (void)veqp; (void)carry; (void)vrow; (void)yv; (void)srec;  \
-    (void)drec; (void)e0E; (void)e0lo; (void)e0up; (void)e0z; (void)e0y; (void)e0t; (void)tg; (void)va; (void)px;       \
+    (void)drec; (void)frec; (void)wbuf; (void)vrow2; (void)ux2; (void)arow; (void)wst; (void)e0E; (void)e0lo; (void)e0up; (void)e0z; (void)e0y; (void)e0t; (void)tg; (void)va; (void)px;       \
     (void)ra; (void)rb; (void)rc; (void)rs0; (void)rs1; (void)rs2; (void)ri0; (void)ri1; (void)ri2; (void)csc; (void)lane
-#define SRP(i) (srec + (size_t)(i) * d.SRS)
+#define SRP(i) (srec + (size_t)(i) * d.VSS)
+#define FRP(i) (frec + (size_t)(i) * d.FS)
 #define DRP(i) (drec + (size_t)(i) * d.DRS)
 #define RHO_OF(ty) ((ty) == 0 ? rs0 : ((ty) == 1 ? rs1 : rs2))
 #define RINV_OF(ty) ((ty) == 0 ? ri0 : ((ty) == 1 ? ri1 : ri2))
 
-// ---- ring management (state packed in two registers of the context) -----------------------------------------------
-__device__ __forceinline__ int ring_res(uint32_t rres, int slot) { return (int)((rres >> (10 * slot)) & 1023u) - 1; }
+// ---- TMA rings (state packed in registers of the context) ------------------------------------------------------------
+// F ring: kRingF slots of FS doubles (factor block of a stage).  V ring: kRingV slots of VSLOT doubles (static vector
+// record + dynamic record of a stage).  Slot = stage mod ring size; a slot is re-armed only by the sweep that knows the
+// stage it held is finished.
+__device__ __forceinline__ int ring_res(unsigned long long w, int slot) { return (int)((w >> (16 * slot)) & 0xffffull) - 1; }
 template <class DM>
 __device__ __forceinline__ void ring_reset(Ctx<DM>& c) {
     // called after generic-proxy stores changed records: make them visible to the async proxy, drop residency
     fence_proxy_async();
     __syncwarp();
-    c.rres = 0; c.rflags &= 0x70u;   // keep the parities, clear pending
+    c.fres = 0; c.vres = 0; c.rflags &= 0x7f00u;   // keep the parities, clear pending
 }
 template <class DM>
-__device__ __forceinline__ void ring_issue(Ctx<DM>& c, int i) {
+__device__ __forceinline__ void ringF_issue(Ctx<DM>& c, int i) {
     const DM& d = c.d;
     if (i < 0 || i > d.ph) return;
-    int slot = i % kRing;
-    if (ring_res(c.rres, slot) == i) return;
-    c.rres = (c.rres & ~(1023u << (10 * slot))) | ((uint32_t)(i + 1) << (10 * slot));
+    int slot = i % kRingF;
+    if (ring_res(c.fres, slot) == i) return;
+    c.fres = (c.fres & ~(0xffffull << (16 * slot))) | ((unsigned long long)(i + 1) << (16 * slot));
     c.rflags |= (1u << slot);
     if (c.lane == 0) {
         double* const sm_ = smem + c.sb;
         uint64_t* const bars = reinterpret_cast<uint64_t*>(sm_ + d.sBARS());
-        double* dst = sm_ + slot * d.SLOT;
-        const double* srec = c.ws;
-        const double* drec = c.ws + d.wDREC();
-        mbar_expect_tx(&bars[slot], (uint32_t)(d.SLOT * sizeof(double)));
-        tma_load_1d(dst, srec + (size_t)i * d.SRS, (uint32_t)(d.SRS * sizeof(double)), &bars[slot]);
-        tma_load_1d(dst + d.SRS, drec + (size_t)i * d.DRS, (uint32_t)(d.DRS * sizeof(double)), &bars[slot]);
+        mbar_expect_tx(&bars[slot], (uint32_t)(d.FS * sizeof(double)));
+        tma_load_1d(sm_ + slot * d.FS, c.ws + (size_t)i * d.FS, (uint32_t)(d.FS * sizeof(double)), &bars[slot]);
     }
 }
 template <class DM>
-__device__ __forceinline__ double* ring_acquire(Ctx<DM>& c, int i) {
+__device__ __forceinline__ double* ringF_acquire(Ctx<DM>& c, int i) {
     const DM& d = c.d;
-    int slot = i % kRing;
-    if (ring_res(c.rres, slot) != i) ring_issue(c, i);
+    int slot = i % kRingF;
+    if (ring_res(c.fres, slot) != i) ringF_issue(c, i);
     double* const sm_ = smem + c.sb;
     if (c.rflags & (1u << slot)) {
         uint64_t* const bars = reinterpret_cast<uint64_t*>(sm_ + d.sBARS());
-        mbar_wait(&bars[slot], (c.rflags >> (4 + slot)) & 1u);
-        c.rflags = (c.rflags ^ (1u << (4 + slot))) & ~(1u << slot);
+        mbar_wait(&bars[slot], (c.rflags >> (8 + slot)) & 1u);
+        c.rflags = (c.rflags ^ (1u << (8 + slot))) & ~(1u << slot);
     }
-    return sm_ + slot * d.SLOT;
+    return sm_ + slot * d.FS;
+}
+template <class DM>
+__device__ __forceinline__ void ringV_issue(Ctx<DM>& c, int i) {
+    const DM& d = c.d;
+    if (i < 0 || i > d.ph) return;
+    int slot = i % kRingV;
+    if (ring_res(c.vres, slot) == i) return;
+    c.vres = (c.vres & ~(0xffffull << (16 * slot))) | ((unsigned long long)(i + 1) << (16 * slot));
+    c.rflags |= (1u << (3 + slot));
+    if (c.lane == 0) {
+        double* const sm_ = smem + c.sb;
+        uint64_t* const bars = reinterpret_cast<uint64_t*>(sm_ + d.sBARS()) + kRingF;
+        double* dst = sm_ + d.ringF_doubles() + slot * d.VSLOT;
+        mbar_expect_tx(&bars[slot], (uint32_t)(d.VSLOT * sizeof(double)));
+        tma_load_1d(dst, c.ws + d.wVREC() + (size_t)i * d.VSS, (uint32_t)(d.VSS * sizeof(double)), &bars[slot]);
+        tma_load_1d(dst + d.VSS, c.ws + d.wDREC() + (size_t)i * d.DRS, (uint32_t)(d.DRS * sizeof(double)), &bars[slot]);
+    }
+}
+template <class DM>
+__device__ __forceinline__ double* ringV_acquire(Ctx<DM>& c, int i) {
+    const DM& d = c.d;
+    int slot = i % kRingV;
+    if (ring_res(c.vres, slot) != i) ringV_issue(c, i);
+    double* const sm_ = smem + c.sb;
+    if (c.rflags & (1u << (3 + slot))) {
+        uint64_t* const bars = reinterpret_cast<uint64_t*>(sm_ + d.sBARS()) + kRingF;
+        mbar_wait(&bars[slot], (c.rflags >> (11 + slot)) & 1u);
+        c.rflags = (c.rflags ^ (1u << (11 + slot))) & ~(1u << (3 + slot));
+    }
+    return sm_ + d.ringF_doubles() + slot * d.VSLOT;
 }
 
 // ---- model to shared memory ---------------------------------------------------------------------------------
@@ -395,18 +442,33 @@ __device__ __forceinline__ void stage_bounds(Ctx<DM>& c, int i, int r, double& l
     }
 }
 
+// stage weights [wO | wU | wDU] of stage i -> shared memory (one batched global load; caller syncs)
+template <class DM>
+__device__ __forceinline__ void load_wst(Ctx<DM>& c, int i) {
+    B200_LOCALS(c);
+    for (int r = lane; r < d.ny + 2 * d.nu; r += 32) {
+        double v;
+        if (r < d.ny) v = c.wO(i, r);
+        else if (r < d.ny + d.nu) v = c.wU(i, r - d.ny);
+        else v = i < d.ph ? c.wDU(i, r - d.ny - d.nu) : 0.0;
+        wst[r] = v;
+    }
+}
+
 // ---- Pblk = C' diag(wO_i) C (nx x nx), cached across stages with identical weights -----------------------------
 template <class DM>
 __device__ void stage_Pblk(Ctx<DM>& c, int i, bool& valid) {
     B200_LOCALS(c);
-    bool same = valid && i > 0;
+    // wst holds this stage's weights (load_wst + sync done by the caller); yv holds the weights Pblk was built with
+    bool same = valid;
     if (same) {
         bool diff = false;
-        for (int r = lane; r < d.ny; r += 32) diff |= (c.wO(i, r) != c.wO(i - 1, r));
+        for (int r = lane; r < d.ny; r += 32) diff |= (wst[r] != yv[r]);
         same = !wany(diff);
     }
     if (same) return;
-    for (int r = lane; r < d.ny; r += 32) yv[r] = c.wO(i, r);
+    __syncwarp();
+    for (int r = lane; r < d.ny; r += 32) yv[r] = wst[r];
     __syncwarp();
     for (int e = lane; e < d.nx * d.nx; e += 32) {
         int a = e / d.nx, k = e - a * d.nx;
@@ -425,8 +487,8 @@ __device__ __forceinline__ double Pcol_norm(Ctx<DM>& c, int i, int k, const doub
         double mx = 0;
         for (int j = 0; j < d.nx; ++j) mx = fmax(mx, dcur[j] * fabs(Pblk[j * d.nx + k]));
         return mx * dcur[k];
-    } else if (k < d.ne) return dcur[k] * dcur[k] * fabs(c.wU(i, k - d.nx));
-    return dcur[k] * dcur[k] * fabs(c.wDU(i, k - d.ne));
+    } else if (k < d.ne) return dcur[k] * dcur[k] * fabs(wst[d.ny + k - d.nx]);
+    return dcur[k] * dcur[k] * fabs(wst[d.ny + d.nu + k - d.ne]);
 }
 
 // ---- setup: q, Ruiz equilibration (scaling.c scale_data), scaled bounds, row types ------------------------------
@@ -448,10 +510,11 @@ __device__ bool setup_and_scale(Ctx<DM>& c) {
     double pending_c = 1.0;
     double* Dt = va; double* Et = ra;
     double* dcur = uxc; double* dnxt = uxn; double* erow = vrow; double* eprev = veqp;
+    bool pv = false;
     for (int it = 0; it < c.p.scaling; ++it) {
-        bool pv = false;
         for (int i = 0; i <= d.ph; ++i) {
             int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
+            load_wst(c, i);
             for (int k = lane; k < bi; k += 32) dcur[k] = wD[vo + k];
             if (i < d.ph) for (int k = lane; k < d.ne; k += 32) dnxt[k] = wD[vo + d.b + k];
             for (int r = lane; r < rs; r += 32) erow[r] = wE[ro + r];
@@ -485,10 +548,10 @@ __device__ bool setup_and_scale(Ctx<DM>& c) {
             __syncwarp();
         }
         double psum = 0, qmax = 0;
-        pv = false;
         for (int g = lane; g < d.m; g += 32) wE[g] *= Et[g];
         for (int i = 0; i <= d.ph; ++i) {
             int bi = d.bcount(i), vo = c.voff(i);
+            load_wst(c, i);
             for (int k = lane; k < bi; k += 32) {
                 double dn = wD[vo + k] * Dt[vo + k];
                 wD[vo + k] = dn; dcur[k] = dn;
@@ -514,6 +577,13 @@ __device__ bool setup_and_scale(Ctx<DM>& c) {
         double* S = SRP(i);
         int8_t* rt = reinterpret_cast<int8_t*>(S + d.oT);
         for (int k = lane; k < bi; k += 32) { S[d.oD + k] = wD[vo + k]; S[d.oQ + k] = wq[vo + k] * pending_c; }
+        for (int r = lane; r < d.ny + 2 * d.nu; r += 32) {
+            double v;
+            if (r < d.ny) v = c.wO(i, r);
+            else if (r < d.ny + d.nu) v = c.wU(i, r - d.ny);
+            else v = i < d.ph ? c.wDU(i, r - d.ny - d.nu) : 0.0;
+            S[d.oWO + r] = v;
+        }
         for (int r = lane; r < rs; r += 32) {
             double l, u; stage_bounds(c, i, r, l, u);
             bad |= (l > u);
@@ -562,13 +632,15 @@ __device__ bool factorize(Ctx<DM>& c, double sigma) {
         int bi = d.bcount(i), rs = d.rcount(i);
         const int bprev = d.b;
         double* Sg = SRP(i);
+        double* Fg = FRP(i);
         const int8_t* rt = reinterpret_cast<const int8_t*>(Sg + d.oT);
         for (int r = lane; r < rs; r += 32) { double e = Sg[d.oE + r]; rw[r] = RHO_OF(rt[r]) * e * e; }
         if (i == 0) for (int r = lane; r < d.ne; r += 32) { double e = e0E[r]; rwp[r] = RHO_OF(e0t[r]) * e * e; }
         for (int k = lane; k < bi; k += 32) dw[k] = Sg[d.oD + k];
+        for (int r = lane; r < d.ny + 2 * d.nu; r += 32) wst[r] = Sg[d.oWO + r];
         if (i < d.ph) { const double* Sn = SRP(i + 1); for (int k = lane; k < d.ne; k += 32) dn[k] = Sn[d.oD + k]; }
         __syncwarp();
-        for (int r = lane; r < d.ny; r += 32) yv[r] = c.c * c.wO(i, r) + rw[d.oOUT + r];
+        for (int r = lane; r < d.ny; r += 32) yv[r] = csc * wst[r] + rw[d.oOUT + r];
         __syncwarp();
         int npairs = bi * (bi + 1) / 2;
         for (int pidx = lane; pidx < npairs; pidx += 32) {
@@ -580,9 +652,9 @@ __device__ bool factorize(Ctx<DM>& c, double sigma) {
                 if (r < d.nx) for (int j = 0; j < d.ny; ++j) v += Cm[j * d.ldC + r] * yv[j] * Cm[j * d.ldC + k];
                 if (r == k) {
                     v += rwp[k] + rw[d.oBOX + k];
-                    if (k >= d.nx) v += c.c * c.wU(i, k - d.nx);
+                    if (k >= d.nx) v += csc * wst[d.ny + k - d.nx];
                 }
-            } else if (r == k) v += c.c * c.wDU(i, k - d.ne) + rw[d.oDU + k - d.ne];
+            } else if (r == k) v += csc * wst[d.ny + d.nu + k - d.ne] + rw[d.oDU + k - d.ne];
             v = dw[r] * v * dw[k];
             if (r == k) v += sigma;
             if (i > 0 && r < d.ne) {   // Schur complement of the previous stage: Lc_{i-1} Lc_{i-1}'
@@ -622,7 +694,7 @@ __device__ bool factorize(Ctx<DM>& c, double sigma) {
         __syncwarp();
         for (int pidx = lane; pidx < npairs; pidx += 32) {
             int r, k; unrank_pair(pidx, r, k);
-            Sg[pidx] = Li[r * ldb + k];
+            Fg[pidx] = Li[r * ldb + k];
         }
         if (i < d.ph) {
             // Hc = -(D_e(i+1) rho'_eq(i+1)) G Dw ;  Lc = Hc Li'
@@ -636,7 +708,7 @@ __device__ bool factorize(Ctx<DM>& c, double sigma) {
                 double acc = 0;
                 for (int q = 0; q <= k; ++q) acc += Hc[r * ldb + q] * Li[k * ldb + q];
                 Lcs[r * ldb + k] = acc;
-                Sg[d.oLc + r * ldb + k] = acc;
+                Fg[d.oLc + r * ldb + k] = acc;
             }
             __syncwarp();
             for (int r = lane; r < d.ne; r += 32) rwp[r] = rw[d.oEQ + r];
@@ -656,89 +728,184 @@ __device__ __forceinline__ double sdot(const double* a, int sa, const double* x,
     return a0 + a1;
 }
 
+// predicated dot product, 4 independent accumulators; `maxn` is a compile-time bound for static dimensions
+__device__ __forceinline__ double dotp(const double* a, int sa, const double* x, int cnt, int maxn) {
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+    for (int q = 0; q < maxn; q += 4) {
+        if (q < cnt) a0 = fma(a[q * sa], x[q], a0);
+        if (q + 1 < cnt) a1 = fma(a[(q + 1) * sa], x[q + 1], a1);
+        if (q + 2 < cnt) a2 = fma(a[(q + 2) * sa], x[q + 2], a2);
+        if (q + 3 < cnt) a3 = fma(a[(q + 3) * sa], x[q + 3], a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
 // ---- one reduced-KKT solve fused with the ADMM updates (MODE 0) or with the polish bookkeeping (MODE 1) -----------
 //  MODE 0: rhs = sigma x - q + A'(rho z - y);  x~ = H^-1 rhs;  then x,z,y updates of osqp.c (update_x/z/y)
 //  MODE 1: rhs = r1 + A'(w r2) (w = act/delta); dx = H^-1 rhs; px += dx; pnu += w (A dx - r2)      [r1=va, r2=rc, pnu=rb]
-// Every stage's data comes from the TMA ring; t (forward result) goes through global memory lane-to-same-lane.
+//
+// Both sweeps are software pipelined so that only the block recurrence (two dependent mat-vecs per stage) is on the
+// critical path: the forward sweep assembles the right-hand side of stage i+1 while stage i is substituted, the
+// backward sweep applies A x~ / projection / dual update of stage i+1 while stage i is back-substituted.  Stage data
+// arrives through the TMA rings (factor blocks: F ring; D,q,E,types,bounds,x,z,y: V ring).
 template <class DM, int MODE>
 __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
     B200_LOCALS(c);
     const int ldb = d.ldb;
     const double sigma = c.p.sigma, alpha = c.p.alpha;
-    long long q0 = clock64(), q1;
+    long long q0 = 0, q1 = 0;
+#ifdef B200_SWEEP_PROFILE
+    q0 = clock64();
+#endif
+#ifdef B200_SWEEP_PROFILE
 #define SPROF(slot) do { q1 = clock64(); c.sp[slot] += q1 - q0; q0 = q1; } while (0)
-    // ---------------- forward ----------------
-    ring_issue(c, 0); ring_issue(c, 1); ring_issue(c, 2);
-    for (int r = lane; r < d.ne; r += 32) {
-        int ty = e0t[r];
-        veqp[r] = MODE == 0 ? e0E[r] * (RHO_OF(ty) * e0z[r] - e0y[r]) : e0E[r] * (RHO_OF(ty) * rc[r]);
-    }
-    for (int i = 0; i <= d.ph; ++i) {
-        const int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
-        const double* S = ring_acquire(c, i);
-        SPROF(0);
-        const double* Dy = S + d.SRS;
-        const int8_t* rt = reinterpret_cast<const int8_t*>(S + d.oT);
-        for (int r = lane; r < rs; r += 32) {
+#else
+#define SPROF(slot) do { (void)q0; (void)q1; } while (0)
+#endif
+    // =========================================== forward ===========================================
+    for (int k = 0; k < kRingF; ++k) ringF_issue(c, k);
+    for (int k = 0; k < kRingV; ++k) ringV_issue(c, k);
+    double* vc = vrow; double* vn = vrow2;     // row weights v = E (rho z - y) of the current / next stage
+    // row weights of a stage (elementwise)
+    auto rows_v = [&](int j, const double* V, double* dst) {
+        const double* Dy = V + d.VSS;
+        const int8_t* rt = reinterpret_cast<const int8_t*>(V + d.oT);
+        const int rsj = d.rcount(j), roj = d.roff(j);
+        for (int r = lane; r < rsj; r += 32) {
             int ty = rt[r];
-            vrow[r] = MODE == 0 ? S[d.oE + r] * (RHO_OF(ty) * Dy[d.oZ + r] - Dy[d.oY + r]) : S[d.oE + r] * (RHO_OF(ty) * rc[ro + r]);
+            dst[r] = MODE == 0 ? V[d.oE + r] * (RHO_OF(ty) * Dy[d.oZ + r] - Dy[d.oY + r]) : V[d.oE + r] * (RHO_OF(ty) * rc[roj + r]);
+        }
+    };
+    // unscaled A' v for variable k of stage j: own rows in vj, the eq(j) rows (owned by stage j-1) in vprev
+    auto col_au = [&](int j, int k, const double* vj, const double* vprev) {
+        double au;
+        if (k < d.ne) {
+            au = vj[d.oBOX + k] - vprev[k] + sv[k] * vj[d.oSC];
+            au += dotp(Cm + k, d.ldC, vj + d.oOUT, k < d.nx ? d.ny : 0, d.ny);
+        } else au = vj[d.oDU + k - d.ne];
+        if (j < d.ph) au += dotp(G + k, d.ldG, vj + d.oEQ, d.ne, d.ne);
+        return au;
+    };
+    {   // prologue: right-hand side of stage 0 -> wbuf
+        const double* V = ringV_acquire(c, 0);
+        for (int r = lane; r < d.ne; r += 32) {
+            int ty = e0t[r];
+            veqp[r] = MODE == 0 ? e0E[r] * (RHO_OF(ty) * e0z[r] - e0y[r]) : e0E[r] * (RHO_OF(ty) * rc[r]);
+        }
+        rows_v(0, V, vc);
+        __syncwarp();
+        const double* Dy = V + d.VSS;
+        for (int k = lane; k < d.bcount(0); k += 32) {
+            double au = col_au(0, k, vc, veqp);
+            wbuf[k] = MODE == 0 ? (sigma * Dy[k] - V[d.oQ + k] + V[d.oD + k] * au) : (va[k] + V[d.oD + k] * au);
         }
         __syncwarp();
-        for (int k = lane; k < bi; k += 32) {
-            double au;
-            if (k < d.ne) {
-                au = vrow[d.oBOX + k] - veqp[k] + sv[k] * vrow[d.oSC];
-                if (k < d.nx) au += sdot(Cm + k, d.ldC, vrow + d.oOUT, d.ny);
-            } else au = vrow[d.oDU + k - d.ne];
-            if (i < d.ph) au += sdot(G + k, d.ldG, vrow + d.oEQ, d.ne);
-            double rhs;
-            if (MODE == 0) rhs = sigma * Dy[k] - S[d.oQ + k] + S[d.oD + k] * au;
-            else rhs = va[vo + k] + S[d.oD + k] * au;
-            if (i > 0 && k < d.ne) rhs -= carry[k];
-            vtmp[k] = rhs;
-        }
-        __syncwarp();
+    }
+    SPROF(0);
+    for (int i = 0; i <= d.ph; ++i) {
+        const int bi = d.bcount(i), vo = c.voff(i);
+        const double* F = ringF_acquire(c, i);
+        const double* Vn = (i < d.ph) ? ringV_acquire(c, i + 1) : nullptr;
         SPROF(1);
+        // [B || Q1]  t_i = Linv_i w   ||   row weights of stage i+1
         for (int k = lane; k < bi; k += 32) {
-            double acc = sdot(S + k * (k + 1) / 2, 1, vtmp, k + 1);
+            double acc = dotp(F + k * (k + 1) / 2, 1, wbuf, k + 1, d.b);
             tcur[k] = acc; tg[vo + k] = acc;
         }
+        if (i < d.ph) rows_v(i + 1, Vn, vn);
         __syncwarp();
         SPROF(2);
+        // [C || Q2]  carry = Lc_i t_i   ||   assemble rhs of stage i+1;  w_{i+1} = rhs - carry
         if (i < d.ph) {
-            for (int k = lane; k < d.ne; k += 32) {
-                carry[k] = sdot(S + d.oLc + k * ldb, 1, tcur, d.b);
-                veqp[k] = vrow[d.oEQ + k];
+            const double* Dyn = Vn + d.VSS;
+            const int bn = d.bcount(i + 1), von = c.voff(i + 1);
+            for (int k = lane; k < bn; k += 32) {
+                double au = col_au(i + 1, k, vn, vc + d.oEQ);
+                double rhs = MODE == 0 ? (sigma * Dyn[k] - Vn[d.oQ + k] + Vn[d.oD + k] * au) : (va[von + k] + Vn[d.oD + k] * au);
+                if (k < d.ne) rhs -= dotp(F + d.oLc + k * ldb, 1, tcur, d.b, d.b);
+                wbuf[k] = rhs;
             }
         }
         __syncwarp();
-        ring_issue(c, i + kRing);
         SPROF(3);
+        double* tt = vc; vc = vn; vn = tt;
+        ringF_issue(c, i + kRingF);
+        ringV_issue(c, i + kRingV);
     }
-    // ---------------- backward ----------------
+    // =========================================== backward ==========================================
+    double* u0 = uxc; double* u1 = uxn; double* u2 = ux2;      // D*x~ of stages i, i+1, i+2
+    double* xa = xcur; double* xb = xn;                         // scaled x~ of stage i (being written) / i+1
     double tnext = 0;
     if (lane < d.bcount(d.ph)) tnext = tg[c.voff(d.ph) + lane];
+    // deferred row work of stage j (uj = D x~_j, ujn = D x~_{j+1})
+    auto rows_dot = [&](int j, const double* uj, const double* ujn) {       // R1: a_r . ux -> arow
+        const int T = d.ny + 1 + (j < d.ph ? d.ne : 0);                      // dot rows: out, sc, eq
+        for (int t = lane; t < T; t += 32) {
+            const double* cp; int cnt, row; double extra = 0;
+            if (t < d.ny) { cp = Cm + t * d.ldC; cnt = d.nx; row = d.oOUT + t; }
+            else if (t == d.ny) { cp = sv; cnt = d.ne; row = d.oSC; }
+            else { int r = t - d.ny - 1; cp = G + r * d.ldG; cnt = d.b; row = d.oEQ + r; extra = ujn[r]; }
+            arow[row] = dotp(cp, 1, uj, cnt, d.b) - extra;
+        }
+        for (int r = lane; r < d.ne; r += 32) arow[d.oBOX + r] = uj[r];
+        if (j < d.ph) for (int r = lane; r < d.nu; r += 32) arow[d.oDU + r] = uj[d.ne + r];
+    };
+    auto rows_upd = [&](int j, double* V) {                                  // R2: relax / project / dual update
+        double* Dy = V + d.VSS;
+        double* Dg = DRP(j);
+        const int8_t* rt = reinterpret_cast<const int8_t*>(V + d.oT);
+        const int rsj = d.rcount(j), roj = d.roff(j);
+        for (int r = lane; r < rsj; r += 32) {
+            int ty = rt[r];
+            double a = arow[r];
+            if (MODE == 0) {
+                double zt = V[d.oE + r] * a;
+                double zo = Dy[d.oZ + r];
+                double zr = alpha * zt + (1.0 - alpha) * zo;
+                double yo = Dy[d.oY + r];
+                double zn = fmin(fmax(zr + RINV_OF(ty) * yo, V[d.oLO + r]), V[d.oUP + r]);
+                double dy = RHO_OF(ty) * (zr - zn);
+                double yn = yo + dy;
+                Dy[d.oY + r] = yn; Dy[d.oZ + r] = zn; Dg[d.oY + r] = yn; Dg[d.oZ + r] = zn;
+                if (store_delta) ra[roj + r] = dy;
+            } else {
+                double dnu = RHO_OF(ty) * (V[d.oE + r] * a - rc[roj + r]);
+                rb[roj + r] = first ? dnu : rb[roj + r] + dnu;
+            }
+        }
+    };
+    SPROF(4);
     for (int i = d.ph; i >= 0; --i) {
-        const int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
-        double* S = ring_acquire(c, i);
-        SPROF(4);
-        double* Dy = S + d.SRS;
+        const int bi = d.bcount(i), vo = c.voff(i);
+        const double* F = ringF_acquire(c, i);
+        double* V = ringV_acquire(c, i);
+        double* Vp = (i < d.ph) ? ringV_acquire(c, i + 1) : nullptr;
+        double* Dy = V + d.VSS;
         double* Dg = DRP(i);
-        const int8_t* rt = reinterpret_cast<const int8_t*>(S + d.oT);
+        SPROF(5);
         double tk = tnext;
-        if (i > 0 && lane < d.b) tnext = tg[c.voff(i - 1) + lane];     // prefetch for the next step
+        if (i > 0 && lane < d.b) tnext = tg[c.voff(i - 1) + lane];          // prefetch for the next step
+        // [A || R1(i+1)]   u = t_i - Lc_i' x~_{i+1}   ||   row dots of stage i+1
         for (int k = lane; k < bi; k += 32) {
             double w = (k == lane) ? tk : tg[vo + k];
-            if (i < d.ph) w -= sdot(S + d.oLc + k, ldb, xn, d.ne);
+            if (i < d.ph) w -= dotp(F + d.oLc + k, ldb, xb, d.ne, d.ne);
             vtmp[k] = w;
         }
+        if (i < d.ph) rows_dot(i + 1, u1, u2);
         __syncwarp();
+        SPROF(6);
+        // [B || R2(i+1)]   x~_i = Linv_i' u ; x update   ||   z,y update of stage i+1
         for (int k = lane; k < bi; k += 32) {
-            double a0 = 0, a1 = 0;
-            int r = k;
-            for (; r + 1 < bi; r += 2) { a0 = fma(S[r * (r + 1) / 2 + k], vtmp[r], a0); a1 = fma(S[(r + 1) * (r + 2) / 2 + k], vtmp[r + 1], a1); }
-            if (r < bi) a0 = fma(S[r * (r + 1) / 2 + k], vtmp[r], a0);
-            double xt = a0 + a1;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+            for (int r = 0; r < d.b; r += 4) {
+                if (r >= k && r < bi) a0 = fma(F[r * (r + 1) / 2 + k], vtmp[r], a0);
+                if (r + 1 >= k && r + 1 < bi) a1 = fma(F[(r + 1) * (r + 2) / 2 + k], vtmp[r + 1], a1);
+                if (r + 2 >= k && r + 2 < bi) a2 = fma(F[(r + 2) * (r + 3) / 2 + k], vtmp[r + 2], a2);
+                if (r + 3 >= k && r + 3 < bi) a3 = fma(F[(r + 3) * (r + 4) / 2 + k], vtmp[r + 3], a3);
+            }
+            double xt = (a0 + a1) + (a2 + a3);
             if (MODE == 0) {
                 double xo = Dy[k];
                 double xnew = alpha * xt + (1.0 - alpha) * xo;
@@ -747,58 +914,39 @@ __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
             } else {
                 px[vo + k] = first ? xt : (px[vo + k] + xt);
             }
-            uxc[k] = S[d.oD + k] * xt;
-            xcur[k] = xt;
+            u0[k] = V[d.oD + k] * xt;
+            xa[k] = xt;
         }
+        if (i < d.ph) rows_upd(i + 1, Vp);
         __syncwarp();
-        SPROF(5);
-        // rows owned by stage i
-        for (int r = lane; r < rs; r += 32) {
-            double a;
-            if (r < d.oOUT) a = uxc[r];
-            else if (r < d.oSC) a = sdot(Cm + (r - d.oOUT) * d.ldC, 1, uxc, d.nx);
-            else if (r < d.oEQ) a = sdot(sv, 1, uxc, d.ne);
-            else if (r < d.oDU) a = sdot(G + (r - d.oEQ) * d.ldG, 1, uxc, d.b) - uxn[r - d.oEQ];
-            else a = uxc[d.ne + r - d.oDU];
-            int ty = rt[r];
+        SPROF(7);
+        { double* tt = u2; u2 = u1; u1 = u0; u0 = tt; }
+        { double* tt = xa; xa = xb; xb = tt; }
+        ringF_issue(c, i - kRingF);
+        ringV_issue(c, i + 1 - kRingV);
+    }
+    // epilogue: rows of stage 0 and the eq(0) rows (u1 = D x~_0, u2 = D x~_1)
+    {
+        double* V = ringV_acquire(c, 0);
+        rows_dot(0, u1, u2);
+        __syncwarp();
+        rows_upd(0, V);
+        for (int r = lane; r < d.ne; r += 32) {
+            int ty = e0t[r];
+            double a = -u1[r];
             if (MODE == 0) {
-                double zt = S[d.oE + r] * a;
-                double zo = Dy[d.oZ + r];
+                double zt = e0E[r] * a, zo = e0z[r];
                 double zr = alpha * zt + (1.0 - alpha) * zo;
-                double yo = Dy[d.oY + r];
-                double zn = fmin(fmax(zr + RINV_OF(ty) * yo, S[d.oLO + r]), S[d.oUP + r]);
+                double yo = e0y[r];
+                double zn = fmin(fmax(zr + RINV_OF(ty) * yo, e0lo[r]), e0up[r]);
                 double dy = RHO_OF(ty) * (zr - zn);
-                double yn = yo + dy;
-                Dy[d.oY + r] = yn; Dy[d.oZ + r] = zn; Dg[d.oY + r] = yn; Dg[d.oZ + r] = zn;
-                if (store_delta) ra[ro + r] = dy;
+                e0y[r] = yo + dy; e0z[r] = zn;
+                if (store_delta) ra[r] = dy;
             } else {
-                double dnu = RHO_OF(ty) * (S[d.oE + r] * a - rc[ro + r]);
-                rb[ro + r] = first ? dnu : rb[ro + r] + dnu;
+                double dnu = RHO_OF(ty) * (e0E[r] * a - rc[r]);
+                rb[r] = first ? dnu : rb[r] + dnu;
             }
         }
-        if (i == 0) {
-            for (int r = lane; r < d.ne; r += 32) {
-                int ty = e0t[r];
-                double a = -uxc[r];
-                if (MODE == 0) {
-                    double zt = e0E[r] * a, zo = e0z[r];
-                    double zr = alpha * zt + (1.0 - alpha) * zo;
-                    double yo = e0y[r];
-                    double zn = fmin(fmax(zr + RINV_OF(ty) * yo, e0lo[r]), e0up[r]);
-                    double dy = RHO_OF(ty) * (zr - zn);
-                    e0y[r] = yo + dy; e0z[r] = zn;
-                    if (store_delta) ra[r] = dy;
-                } else {
-                    double dnu = RHO_OF(ty) * (e0E[r] * a - rc[r]);
-                    rb[r] = first ? dnu : rb[r] + dnu;
-                }
-            }
-        }
-        __syncwarp();
-        for (int r = lane; r < d.ne; r += 32) { uxn[r] = uxc[r]; xn[r] = xcur[r]; }
-        __syncwarp();
-        if (i >= kRing) ring_issue(c, i - kRing);
-        SPROF(6);
     }
 #undef SPROF
     // global x,z,y were rewritten by generic stores: order them before the TMA reads of the next sweep
@@ -806,25 +954,25 @@ __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
     __syncwarp();
 }
 
-// ---- generic structured products (record data through the ring) --------------------------------------------------
+// ---- generic structured products (vector records through the V ring) ---------------------------------------------
 // rows_pass: for every row:  rowfn(i, r, g, S, Dy, a_g . ux)  with ux = D*xfn(i,k,Dy) (unscaled variable values);
 // i = -1 marks the eq(0) rows (S, Dy null).
 template <class DM, class XFn, class RowFn>
 __device__ void rows_pass(Ctx<DM>& c, XFn xfn, RowFn rowfn) {
     B200_LOCALS(c);
-    ring_issue(c, 0); ring_issue(c, 1); ring_issue(c, 2);
+    for (int k = 0; k < kRingV; ++k) ringV_issue(c, k);
     {
-        const double* S0 = ring_acquire(c, 0);
-        for (int k = lane; k < d.bcount(0); k += 32) uxc[k] = S0[d.oD + k] * xfn(0, k, S0 + d.SRS);
+        const double* S0 = ringV_acquire(c, 0);
+        for (int k = lane; k < d.bcount(0); k += 32) uxc[k] = S0[d.oD + k] * xfn(0, k, S0 + d.VSS);
     }
     __syncwarp();
     for (int i = 0; i <= d.ph; ++i) {
         const int rs = d.rcount(i), ro = d.roff(i);
-        double* S = ring_acquire(c, i);
-        double* Dy = S + d.SRS;
+        double* S = ringV_acquire(c, i);
+        double* Dy = S + d.VSS;
         if (i < d.ph) {
-            const double* Sn = ring_acquire(c, i + 1);
-            for (int k = lane; k < d.bcount(i + 1); k += 32) uxn[k] = Sn[d.oD + k] * xfn(i + 1, k, Sn + d.SRS);
+            const double* Sn = ringV_acquire(c, i + 1);
+            for (int k = lane; k < d.bcount(i + 1); k += 32) uxn[k] = Sn[d.oD + k] * xfn(i + 1, k, Sn + d.VSS);
         }
         __syncwarp();
         for (int r = lane; r < rs; r += 32) {
@@ -838,7 +986,7 @@ __device__ void rows_pass(Ctx<DM>& c, XFn xfn, RowFn rowfn) {
         }
         if (i == 0) for (int r = lane; r < d.ne; r += 32) rowfn(-1, r, r, (double*)nullptr, (double*)nullptr, -uxc[r]);
         __syncwarp();
-        ring_issue(c, i + kRing);
+        ringV_issue(c, i + kRingV);
         double* tt = uxc; uxc = uxn; uxn = tt;
     }
 }
@@ -847,17 +995,17 @@ __device__ void rows_pass(Ctx<DM>& c, XFn xfn, RowFn rowfn) {
 template <class DM, bool WITHP, class XFn, class RowVal, class ColFn>
 __device__ void cols_pass(Ctx<DM>& c, XFn xfn, RowVal rowval, ColFn colfn) {
     B200_LOCALS(c);
-    ring_issue(c, 0); ring_issue(c, 1); ring_issue(c, 2);
+    for (int k = 0; k < kRingV; ++k) ringV_issue(c, k);
     for (int r = lane; r < d.ne; r += 32) veqp[r] = rowval(-1, r, r, (double*)nullptr, (double*)nullptr);
     for (int i = 0; i <= d.ph; ++i) {
         const int bi = d.bcount(i), rs = d.rcount(i), ro = d.roff(i), vo = c.voff(i);
-        double* S = ring_acquire(c, i);
-        double* Dy = S + d.SRS;
+        double* S = ringV_acquire(c, i);
+        double* Dy = S + d.VSS;
         for (int r = lane; r < rs; r += 32) vrow[r] = rowval(i, r, ro + r, S, Dy);
         if (WITHP) for (int k = lane; k < bi; k += 32) uxc[k] = S[d.oD + k] * xfn(i, k, Dy);
         __syncwarp();
         if (WITHP) {
-            for (int r = lane; r < d.ny; r += 32) yv[r] = c.wO(i, r) * sdot(Cm + r * d.ldC, 1, uxc, d.nx);
+            for (int r = lane; r < d.ny; r += 32) yv[r] = S[d.oWO + r] * sdot(Cm + r * d.ldC, 1, uxc, d.nx);
             __syncwarp();
         }
         for (int k = lane; k < bi; k += 32) {
@@ -869,16 +1017,16 @@ __device__ void cols_pass(Ctx<DM>& c, XFn xfn, RowVal rowval, ColFn colfn) {
             if (i < d.ph) au += sdot(G + k, d.ldG, vrow + d.oEQ, d.ne);
             if (WITHP) {
                 if (k < d.nx) pu = sdot(Cm + k, d.ldC, yv, d.ny);
-                else if (k < d.ne) pu = c.wU(i, k - d.nx) * uxc[k];
-                else pu = c.wDU(i, k - d.ne) * uxc[k];
-                pu *= c.c * S[d.oD + k];
+                else if (k < d.ne) pu = S[d.oWU + k - d.nx] * uxc[k];
+                else pu = S[d.oWDU + k - d.ne] * uxc[k];
+                pu *= csc * S[d.oD + k];
             }
             colfn(i, k, vo + k, S, Dy, S[d.oD + k] * au, pu);
         }
         __syncwarp();
         if (i < d.ph) for (int r = lane; r < d.ne; r += 32) veqp[r] = vrow[d.oEQ + r];
         __syncwarp();
-        ring_issue(c, i + kRing);
+        ringV_issue(c, i + kRingV);
     }
 }
 
@@ -1267,10 +1415,10 @@ __global__ void __launch_bounds__(128) lmpc_solve_kernel(const __grid_constant__
     }
     if (lane == 0) {
         uint64_t* bars = reinterpret_cast<uint64_t*>(smem + c.sb + d.sBARS());
-        for (int k = 0; k < kRing; ++k) mbar_init(&bars[k], 1);
+        for (int k = 0; k < kRingF + kRingV; ++k) mbar_init(&bars[k], 1);
         fence_mbar_init();
     }
-    c.rres = 0; c.rflags = 0;
+    c.fres = 0; c.vres = 0; c.rflags = 0;
     fence_proxy_async();
     __syncwarp();
     for (;;) {

@@ -41,6 +41,6 @@ for ph, B in ((10, 1024), (20, 4096)):
     pr = c.profile(fetch=True).astype(float)
     names = ['setup', 'factor', 'sweeps', 'info', 'polprep', 'polfac', 'polsolve', 'unpack']
     tot = pr[:, :8].sum(1).mean()
-    sn = ['f_acq', 'f_rows_cols', 'f_linv', 'f_carry', 'b_acq', 'b_solve', 'b_rows', '-']
+    sn = ['f_prologue', 'f_acq', 'f_B||Q1', 'f_C||Q2', 'b_setup', 'b_acq', 'b_A||R1', 'b_B||R2']
     print('  sweep split (cycles/instance):', {n: int(v) for n, v in zip(sn, pr[:, 8:].mean(0))})
     print('  phase cycles/instance:', {n: int(v) for n, v in zip(names, pr[:, :8].mean(0))}, 'total', int(tot), ' per-iter sweep', int(pr[:,2].mean()/res.iterations.mean()))
