@@ -119,8 +119,9 @@ def cpu_baseline(ph, max_iter, n_solves, cores):
     x0, r = synth_inputs(0, n_solves)
     try:
         from oracle import c_oracle   # C port (oracle/Makefile), preferred when built
+        c_oracle.lib()
         return c_oracle.time_batch(ph, x0, r, max_iter, cores)
-    except Exception:
+    except RuntimeError:
         pass
     jobs = [(ph, x0[k], r[k], max_iter) for k in range(n_solves)]
     t = time.perf_counter()
@@ -164,7 +165,7 @@ def main():
         if rank != 0:
             return
         cores = os.cpu_count() or 1
-        per_step = a.cpu_sample or max(cores, 8)
+        per_step = a.cpu_sample or 64 * cores
         vals = []
         for s in range(a.warmup + a.steps):
             cb = cpu_baseline(ph, a.max_iter, per_step, cores)
@@ -301,7 +302,7 @@ def main():
         }
         if world == 1 and not a.no_cpu_baseline:
             cores = 1
-            n = a.cpu_sample or 12
+            n = a.cpu_sample or 2048
             line["cpu_baseline"] = cpu_baseline(ph, a.max_iter, n, cores)
         print(json.dumps(line))
     if world > 1:
