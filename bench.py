@@ -274,6 +274,12 @@ def main():
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
         flops = sum(algorithmic_flops(ph, int(i), int(u), int(p == 1)) for i, u, p in zip(res.iterations, res.rho_updates, res.status_polish))
         tfl = flops / (kernel_ms * 1e-3) / 1e12
+        fp64_peak, fp64_src = 37.0, "nominal B200 FP64 vector"
+        try:
+            fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["fp64_tflops"]
+            fp64_src = "measured DFMA throughput on this pool (tools/ubench.cu -> profiles/fp64_peak.json)"
+        except Exception:
+            pass
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -291,8 +297,8 @@ def main():
                          "traffic": traffic, "peak_source": peak_src,
                          "note": "algorithmic bytes/solve (SURVEY 8d) x batch / kernel time; the solve is FP64-latency/L2 bound, "
                                  "see roofline_fp64 and DESIGN.md"},
-            "roofline_fp64": {"bound": "fp64-pipe", "achieved": tfl, "peak": 37.0, "unit": "TFLOP/s", "frac": tfl / 37.0,
-                              "peak_source": "nominal B200 FP64 vector (no measured figure in MEASURED_PEAKS.json)",
+            "roofline_fp64": {"bound": "fp64-pipe", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak,
+                              "peak_source": fp64_src,
                               "flops_per_solve_mean": flops / B},
             "solver": {"iterations_mean": float(res.iterations.mean()), "iterations_max": int(res.iterations.max()),
                        "rho_updates_mean": float(res.rho_updates.mean()), "solved": int((res.solver_status == 1).sum()),
