@@ -39,10 +39,12 @@ def synth_inputs(first, count, seed=20):
     return x0, r
 
 
-def algorithmic_bytes(ph):
-    """per-instance model + weights + bounds + (x0,u0) + references over the horizon + outputs."""
+def algorithmic_bytes(ph, shared_model):
+    """per-instance model + weights + bounds + (x0,u0) + references over the horizon + outputs; the
+    shared-model variant drops the model/weights/bounds term (3 296 B for the quadrotor)."""
     nx, nu, ny = NX, NU, NY
-    return 8 * (nx * nx + nx * nu + ny * nx + (ny + 2 * nu) + 2 * (nx + nu + ny) + (nx + nu) + ph * (ny + 2 * nu)) + (8 * nu + 16)
+    model = 8 * (nx * nx + nx * nu + ny * nx + (ny + 2 * nu) + 2 * (nx + nu + ny))
+    return (0 if shared_model else model) + 8 * ((nx + nu) + ph * (ny + 2 * nu)) + (8 * nu + 16)
 
 
 def algorithmic_flops(ph, iters, rho_updates, polished):
@@ -86,14 +88,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def build_controller(L, ph, batch, max_iter):
+def build_controller(L, ph, batch, max_iter, per_instance_model=False):
     from oracle.lmpc_formulation import quadrotor_formulation, quadrotor_model
     f = quadrotor_formulation(ph)
     c = L.LMPC(NX, NU, NDU, NY, ph, ph, batch=batch, device=int(os.environ.get("LOCAL_RANK", 0)))
     Ad, Bd = quadrotor_model()
-    # per-instance copies of the model (the algorithmic-bytes figure counts A,B,C per instance)
-    c.setStateSpaceModel(np.broadcast_to(Ad, (batch, NX, NX)), np.broadcast_to(Bd, (batch, NX, NU)),
-                         np.broadcast_to(np.eye(NX), (batch, NY, NX)))
+    if per_instance_model:   # batch copies of A,B,C (the per-instance-model variant of SURVEY 8d)
+        c.setStateSpaceModel(np.broadcast_to(Ad, (batch, NX, NX)), np.broadcast_to(Bd, (batch, NX, NU)),
+                             np.broadcast_to(np.eye(NX), (batch, NY, NX)))
+    else:                    # the quadrotor_ex model/weights/bounds, per-instance x0 / yRef
+        c.setStateSpaceModel(Ad, Bd, np.eye(NX))
     c.setObjectiveWeights(f.wOutput[:, 1], f.wU[:, 1], f.wDeltaU[:, 0], (0, ph))
     c.setStateBounds(f.minX[:, 1], f.maxX[:, 1], (0, ph))
     c.setInputBounds(f.minU[:, 0], f.maxU[:, 0], (0, ph))
@@ -148,6 +152,7 @@ def main():
     ap.add_argument("--max-iter", type=int, default=250)
     ap.add_argument("--cpu-sample", type=int, default=0, help="solves in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-instance-model", action="store_true", help="give every instance its own copy of A,B,C")
     ap.add_argument("--warps-per-cta", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     a = ap.parse_args()
@@ -156,7 +161,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     ph, B = a.ph, a.batch
     config = {"workload": f"quadrotor LMPC nx=12 nu=4 ny=12 ph=ch={ph}, batch={B} per GPU, maximum_iteration={a.max_iter}, "
-                          f"per-instance model, x0/yRef synthetic seed 20 (BASELINE.json configs[1])",
+                          f"{'per-instance' if a.per_instance_model else 'shared'} model, per-instance x0/yRef synthetic seed 20 (BASELINE.json configs[1])",
               "batch_per_gpu": B, "global_batch": B * world, "ph": ph, "parallelism": f"dp{world}",
               "l2": "L2 flushed (512 MiB write) between timed steps; each step timed by its own CUDA-event pair"}
 
@@ -188,7 +193,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    f, c = build_controller(L, ph, B, a.max_iter)
+    f, c = build_controller(L, ph, B, a.max_iter, a.per_instance_model)
     if a.warps_per_cta or a.ctas_per_sm:
         c.set_launch(a.warps_per_cta, a.ctas_per_sm)
     stream = torch.cuda.current_stream()
@@ -270,7 +275,7 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         kernel_ms = ms  # one kernel per step; at N>1 the all-gather is inside the step time too
-        abytes = algorithmic_bytes(ph) * B
+        abytes = algorithmic_bytes(ph, not a.per_instance_model) * B
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
         flops = sum(algorithmic_flops(ph, int(i), int(u), int(p == 1)) for i, u, p in zip(res.iterations, res.rho_updates, res.status_polish))
         tfl = flops / (kernel_ms * 1e-3) / 1e12

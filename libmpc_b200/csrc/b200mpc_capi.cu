@@ -51,6 +51,7 @@ struct b200mpc_lmpc {
     int req_wpc = 0, req_cps = 0;
     size_t smem_cta = 0;
     bool force_generic = false;
+    int model_shared = 0;
     long long launches = 0;
     std::vector<double> stage;   // host staging
 };
@@ -92,6 +93,7 @@ static int upload(b200mpc_lmpc* h, DevBuf& b, const double* src, int per_instanc
         CK(cudaStreamSynchronize(h->stream));
         cudaFree(b.p);
         b.p = np; b.per_instance = pi;
+        if (h->workspace) { cudaFree(h->workspace); h->workspace = nullptr; }   // launch geometry depends on what is shared
     }
     if (total) CK(cudaMemcpyAsync(b.p, src, total * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     return B200MPC_OK;
@@ -318,13 +320,17 @@ typedef SDm<12, 4, 4, 12> DmQuad;    // quadrotor_ex / BASELINE configs[1],[4]
 template <class DM>
 static int configure_t(b200mpc_lmpc* h) {
     DM dm; dm.from(h->d);
-    size_t smem_warp = (size_t)dm.smem_doubles() * sizeof(double);
+    const bool mshared = !h->A.per_instance && !h->B.per_instance && !h->C.per_instance && !h->SX.per_instance && !h->SU.per_instance;
+    h->model_shared = mshared ? 1 : 0;
+    size_t smem_model = (size_t)dm.model_doubles() * sizeof(double);
+    size_t smem_warp = (size_t)dm.smem_doubles() * sizeof(double) + (mshared ? 0 : smem_model);
+    size_t smem_fixed = mshared ? smem_model : 0;
     int dev_max_smem = 0;
     CK(cudaDeviceGetAttribute(&dev_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     // warps per CTA: the request, else the value in 1..4 that maximises resident warps per SM
     int best_wpc = 0, best_occ = 0;
-    for (int wpc = (h->req_wpc > 0 ? h->req_wpc : 4); wpc >= 1; --wpc) {
-        size_t smem_cta = smem_warp * wpc;
+    for (int wpc = (h->req_wpc > 0 ? h->req_wpc : B200_MAX_THREADS / 32); wpc >= 1; --wpc) {
+        size_t smem_cta = smem_warp * wpc + smem_fixed;
         if (smem_cta > (size_t)dev_max_smem) { if (h->req_wpc > 0 && wpc == h->req_wpc) continue; else continue; }
         CK(cudaFuncSetAttribute(lmpc_solve_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
         int occ = 0;
@@ -334,7 +340,7 @@ static int configure_t(b200mpc_lmpc* h) {
     }
     if (best_wpc == 0 || best_occ < 1) return fail(B200MPC_EINVAL, "problem dimensions exceed the shared memory of an SM");
     int wpc = best_wpc, occ = best_occ;
-    size_t smem_cta = smem_warp * wpc;
+    size_t smem_cta = smem_warp * wpc + smem_fixed;
     CK(cudaFuncSetAttribute(lmpc_solve_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     int cps = h->req_cps > 0 ? (h->req_cps < occ ? h->req_cps : occ) : occ;
     int grid = h->num_sms * cps;
@@ -352,7 +358,7 @@ template <class DM>
 static int launch_t(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
     DM dm; dm.from(h->d);
     lmpc_solve_kernel<DM><<<h->grid, h->warps_per_cta * 32, h->smem_cta, h->stream>>>(dm, h->p, pr, o, h->batch, h->workspace,
-                                                                                      h->ws_stride, h->counter);
+                                                                                      h->ws_stride, h->counter, h->model_shared);
     CK(cudaGetLastError());
     return B200MPC_OK;
 }
@@ -370,7 +376,7 @@ static int launch(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
 
 extern "C" int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm) {
     HCHECK();
-    if (warps_per_cta < -4 || warps_per_cta > 4 || ctas_per_sm < 0) return fail(B200MPC_EINVAL, "bad launch geometry");
+    if (warps_per_cta < -(B200_MAX_THREADS / 32) || warps_per_cta > B200_MAX_THREADS / 32 || ctas_per_sm < 0) return fail(B200MPC_EINVAL, "bad launch geometry");
     h->force_generic = warps_per_cta < 0;   // negative: use the runtime-dimension kernel (parity testing of both instantiations)
     if (warps_per_cta < 0) warps_per_cta = -warps_per_cta;
     CK(cudaStreamSynchronize(h->stream));

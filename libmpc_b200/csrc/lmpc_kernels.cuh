@@ -31,6 +31,9 @@ namespace b200mpc {
 
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3, kRhoTol = 1e-4;
 constexpr double kOsqpInfty = 1e30, kMinScaling = 1e-4, kMaxScaling = 1e4;
+#ifndef B200_MAX_THREADS
+#define B200_MAX_THREADS 384   // up to 12 warps per CTA -> at most 170 registers per thread
+#endif
 constexpr int kRingF = 2;   // factor-block ring slots
 constexpr int kRingV = 3;   // vector-record ring slots
 
@@ -47,10 +50,8 @@ enum { RS_SUCCESS = 0, RS_MAX_ITERATION = 1, RS_INFEASIBLE = 2, RS_ERROR = 3, RS
 // and the slot's workspace pointer): pointers derived that way stay in registers and shared accesses compile to LDS.
 #define B200_LAYOUT_HOST_DEVICE                                                                                    \
     __host__ __device__ int sBARS() const { return ring_doubles(); }                                                \
-    __host__ __device__ int sG() const { return sBARS() + kRingF + kRingV + 1; }                                              \
-    __host__ __device__ int sC() const { return sG() + ne * ldG; }                                                  \
-    __host__ __device__ int sS() const { return sC() + ny * ldC; }                                                  \
-    __host__ __device__ int sUXC() const { return sS() + ne; }                                                      \
+    __host__ __device__ int model_doubles() const { return (ne * ldG + ny * ldC + ne + 1) & ~1; }                   \
+    __host__ __device__ int sUXC() const { return sBARS() + kRingF + kRingV + 1; }                                                      \
     __host__ __device__ int sUXN() const { return sUXC() + b; }                                                     \
     __host__ __device__ int sVTMP() const { return sUXN() + b; }                                                    \
     __host__ __device__ int sTCUR() const { return sVTMP() + b; }                                                   \
@@ -60,11 +61,12 @@ enum { RS_SUCCESS = 0, RS_MAX_ITERATION = 1, RS_INFEASIBLE = 2, RS_ERROR = 3, RS
     __host__ __device__ int sCARRY() const { return sVEQP() + ne; }                                                 \
     __host__ __device__ int sVROW() const { return sCARRY() + ne; }                                                 \
     __host__ __device__ int sYV() const { return sVROW() + RS; }                                                    \
-    __host__ __device__ int sW() const { return sYV() + ny; }                                                       \
-    __host__ __device__ int sVROW2() const { return sW() + b; }                                                     \
-    __host__ __device__ int sUX2() const { return sVROW2() + RS; }                                                  \
-    __host__ __device__ int sAROW() const { return sUX2() + b; }                                                    \
-    __host__ __device__ int sWST() const { return sAROW() + RS; }                                                   \
+    /* forward-only buffers alias backward-only ones: wbuf~vtmp, ux2~tcur, arow~vrow2 */                            \
+    __host__ __device__ int sW() const { return sVTMP(); }                                                          \
+    __host__ __device__ int sVROW2() const { return sYV() + ny; }                                                   \
+    __host__ __device__ int sUX2() const { return sTCUR(); }                                                        \
+    __host__ __device__ int sAROW() const { return sVROW2(); }                                                      \
+    __host__ __device__ int sWST() const { return sVROW2() + RS; }                                                  \
     __host__ __device__ int smem_doubles() const { return (sWST() + ny + 2 * nu + 3) & ~1; }                                \
     __host__ __device__ size_t wVREC() const { return (size_t)(ph + 1) * FS; }                                       \
     __host__ __device__ size_t wDREC() const { return wVREC() + (size_t)(ph + 1) * VSS; }                            \
@@ -76,7 +78,8 @@ enum { RS_SUCCESS = 0, RS_MAX_ITERATION = 1, RS_INFEASIBLE = 2, RS_ERROR = 3, RS
     __host__ __device__ size_t wRA() const { return wPX() + n; }                                                     \
     __host__ __device__ size_t wRB() const { return wRA() + m; }                                                     \
     __host__ __device__ size_t wRC() const { return wRB() + m; }                                                     \
-    __host__ __device__ size_t wRUIZ() const { return wRC() + m; }                                                   \
+    __host__ __device__ size_t wWREC() const { return wRC() + m; }                                                   \
+    __host__ __device__ size_t wRUIZ() const { return wWREC() + (size_t)(ph + 1) * (ny + 2 * nu); }                                                   \
     __host__ __device__ size_t ws_doubles() const { return wRUIZ() + ruiz_doubles() + 32; }
 
 #define B200_DERIVED_HOST_DEVICE                                                                                   \
@@ -96,7 +99,7 @@ struct Dm {
     int RS, RSL, oBOX, oOUT, oSC, oEQ, oDU;      // rows owned by a stage and the offsets of its groups
     int ldG, ldC, ldb;                           // odd leading dimensions (conflict-free column walks)
     int oLc, FS;                                 // factor block: packed Linv (b(b+1)/2) + Lc (ne x ldb)
-    int oD, oQ, oE, oT, RT, oLO, oUP, oWO, oWU, oWDU, VSS;   // static vector record [D | q | E | types | lo | up | wO | wU | wDU]
+    int oD, oQ, oE, oT, RT, oLO, oUP, VSS;       // static vector record [D | q | E | types | lo | up]
     int oZ, oY, DRS, VSLOT;                      // dynamic record ([x | z | y]); V-ring slot = VSS + DRS
     int M0, M1, M2, M3;                          // reference row offsets (ProblemBuilder.hpp:70-76)
     __host__ __device__ void derive() {
@@ -109,8 +112,7 @@ struct Dm {
         oLc = (b * (b + 1) / 2 + 1) & ~1;
         FS = (oLc + ne * ldb + 1) & ~1;
         oD = 0; oQ = oD + b; oE = oQ + b; oT = oE + RS; RT = (RS + 7) / 8; oLO = oT + RT; oUP = oLO + RS;
-        oWO = oUP + RS; oWU = oWO + ny; oWDU = oWU + nu;
-        VSS = (oWDU + nu + 1) & ~1;
+        VSS = (oUP + RS + 1) & ~1;
         oZ = b; oY = b + RS; DRS = (b + 2 * RS + 1) & ~1; VSLOT = VSS + DRS;
         M0 = (ph + 1) * ne; M1 = 2 * (ph + 1) * ne; M2 = M1 + (ph + 1) * ny; M3 = M2 + ph * nu;
     }
@@ -130,8 +132,7 @@ struct SDm {
     static constexpr int oLc = (b * (b + 1) / 2 + 1) & ~1;
     static constexpr int FS = (oLc + ne * ldb + 1) & ~1;
     static constexpr int oD = 0, oQ = oD + b, oE = oQ + b, oT = oE + RS, RT = (RS + 7) / 8, oLO = oT + RT, oUP = oLO + RS;
-    static constexpr int oWO = oUP + RS, oWU = oWO + ny, oWDU = oWU + nu;
-    static constexpr int VSS = (oWDU + nu + 1) & ~1;
+    static constexpr int VSS = (oUP + RS + 1) & ~1;
     static constexpr int oZ = b, oY = b + RS, DRS = (b + 2 * RS + 1) & ~1, VSLOT = VSS + DRS;
     int ph, ch, n, m, M0, M1, M2, M3;
     __host__ __device__ void from(const Dm& d) { ph = d.ph; ch = d.ch; n = d.n; m = d.m; M0 = d.M0; M1 = d.M1; M2 = d.M2; M3 = d.M3; }
@@ -217,6 +218,8 @@ struct Ctx {
     const DM& d; const Params& p; const Prob& pr; int inst; int lane;
     __device__ Ctx(const DM& d_, const Params& p_, const Prob& pr_) : d(d_), p(p_), pr(pr_) {}
     int sb;                          // this warp's offset (doubles) into the dynamic shared memory
+    int model_shared;
+    int mb;                          // offset of the model block [G | C | s] (per warp, or one per CTA when the batch shares the model)
     double* ws;                      // this slot's workspace
     double *wD, *wq, *wE;            // Ruiz working arrays (shared memory when they fit, workspace otherwise)
     unsigned long long fres, vres;   // resident stage+1 per ring slot, 16 bits each (F ring: 3 slots, V ring: 4 slots)
@@ -242,9 +245,9 @@ struct Ctx {
     double* const Hc = Li + d.b * d.ldb;                                                                           \
     double* const Lcs = Hc + d.ne * d.ldb;                                                                         \
     uint64_t* const bars = reinterpret_cast<uint64_t*>(sm_ + d.sBARS());                                           \
-    double* const G = sm_ + d.sG();                                                                                \
-    double* const Cm = sm_ + d.sC();                                                                               \
-    double* const sv = sm_ + d.sS();                                                                               \
+    double* const G = smem + (c).mb;                                                                               \
+    double* const Cm = G + d.ne * d.ldG;                                                                           \
+    double* const sv = Cm + d.ny * d.ldC;                                                                          \
     double* uxc = sm_ + d.sUXC();                                                                                  \
     double* uxn = sm_ + d.sUXN();                                                                                  \
     double* const vtmp = sm_ + d.sVTMP();                                                                          \
@@ -262,6 +265,7 @@ struct Ctx {
     double* const wst = sm_ + d.sWST();                                                                            \
     double* const ws_ = (c).ws;                                                                                    \
     double* const frec = ws_;                                                                                      \
+    double* const wrec = ws_ + d.wWREC();                                                                          \
     double* const srec = ws_ + d.wVREC();                                                                          \
     double* const drec = ws_ + d.wDREC();                                                                          \
     double* const e0E = ws_ + d.wE0();                                                                             \
@@ -281,7 +285,7 @@ struct Ctx {
     const double csc = (c).c;                                                                                      \
     (void)ring; (void)Pblk; (void)Sf; (void)Li; (void)Hc; (void)Lcs; (void)bars; (void)G; (void)Cm; (void)sv; (void)uxc; \
     (void)uxn; (void)vtmp; (void)tcur; (void)xcur; (void)xn; (void)veqp; (void)carry; (void)vrow; (void)yv; (void)srec;  \
-    (void)drec; (void)frec; (void)wbuf; (void)vrow2; (void)ux2; (void)arow; (void)wst; (void)e0E; (void)e0lo; (void)e0up; (void)e0z; (void)e0y; (void)e0t; (void)tg; (void)va; (void)px;       \
+    (void)drec; (void)frec; (void)wrec; (void)wbuf; (void)vrow2; (void)ux2; (void)arow; (void)wst; (void)e0E; (void)e0lo; (void)e0up; (void)e0z; (void)e0y; (void)e0t; (void)tg; (void)va; (void)px;       \
     (void)ra; (void)rb; (void)rc; (void)rs0; (void)rs1; (void)rs2; (void)ri0; (void)ri1; (void)ri2; (void)csc; (void)lane
 #define SRP(i) (srec + (size_t)(i) * d.VSS)
 #define FRP(i) (frec + (size_t)(i) * d.FS)
@@ -582,7 +586,7 @@ __device__ bool setup_and_scale(Ctx<DM>& c) {
             if (r < d.ny) v = c.wO(i, r);
             else if (r < d.ny + d.nu) v = c.wU(i, r - d.ny);
             else v = i < d.ph ? c.wDU(i, r - d.ny - d.nu) : 0.0;
-            S[d.oWO + r] = v;
+            wrec[(size_t)i * (d.ny + 2 * d.nu) + r] = v;
         }
         for (int r = lane; r < rs; r += 32) {
             double l, u; stage_bounds(c, i, r, l, u);
@@ -637,7 +641,7 @@ __device__ bool factorize(Ctx<DM>& c, double sigma) {
         for (int r = lane; r < rs; r += 32) { double e = Sg[d.oE + r]; rw[r] = RHO_OF(rt[r]) * e * e; }
         if (i == 0) for (int r = lane; r < d.ne; r += 32) { double e = e0E[r]; rwp[r] = RHO_OF(e0t[r]) * e * e; }
         for (int k = lane; k < bi; k += 32) dw[k] = Sg[d.oD + k];
-        for (int r = lane; r < d.ny + 2 * d.nu; r += 32) wst[r] = Sg[d.oWO + r];
+        for (int r = lane; r < d.ny + 2 * d.nu; r += 32) wst[r] = wrec[(size_t)i * (d.ny + 2 * d.nu) + r];
         if (i < d.ph) { const double* Sn = SRP(i + 1); for (int k = lane; k < d.ne; k += 32) dn[k] = Sn[d.oD + k]; }
         __syncwarp();
         for (int r = lane; r < d.ny; r += 32) yv[r] = csc * wst[r] + rw[d.oOUT + r];
@@ -1005,7 +1009,10 @@ __device__ void cols_pass(Ctx<DM>& c, XFn xfn, RowVal rowval, ColFn colfn) {
         if (WITHP) for (int k = lane; k < bi; k += 32) uxc[k] = S[d.oD + k] * xfn(i, k, Dy);
         __syncwarp();
         if (WITHP) {
-            for (int r = lane; r < d.ny; r += 32) yv[r] = S[d.oWO + r] * sdot(Cm + r * d.ldC, 1, uxc, d.nx);
+            const double* wr = wrec + (size_t)i * (d.ny + 2 * d.nu);
+            for (int r = lane; r < d.ny + 2 * d.nu; r += 32) wst[r] = wr[r];
+            __syncwarp();
+            for (int r = lane; r < d.ny; r += 32) yv[r] = wst[r] * sdot(Cm + r * d.ldC, 1, uxc, d.nx);
             __syncwarp();
         }
         for (int k = lane; k < bi; k += 32) {
@@ -1017,8 +1024,8 @@ __device__ void cols_pass(Ctx<DM>& c, XFn xfn, RowVal rowval, ColFn colfn) {
             if (i < d.ph) au += sdot(G + k, d.ldG, vrow + d.oEQ, d.ne);
             if (WITHP) {
                 if (k < d.nx) pu = sdot(Cm + k, d.ldC, yv, d.ny);
-                else if (k < d.ne) pu = S[d.oWU + k - d.nx] * uxc[k];
-                else pu = S[d.oWDU + k - d.ne] * uxc[k];
+                else if (k < d.ne) pu = wst[d.ny + k - d.nx] * uxc[k];
+                else pu = wst[d.ny + d.nu + k - d.ne] * uxc[k];
                 pu *= csc * S[d.oD + k];
             }
             colfn(i, k, vo + k, S, Dy, S[d.oD + k] * au, pu);
@@ -1196,7 +1203,7 @@ __device__ void solve_instance(Ctx<DM>& c, const Out& o) {
     for (int k = 0; k < 8; ++k) c.sp[k] = 0;
     long long t0 = clock64(), t1;
 #define PROF(slot) do { t1 = clock64(); pt[slot] += t1 - t0; t0 = t1; } while (0)
-    load_model(c);
+    if (!c.model_shared) load_model(c);
     bool valid = setup_and_scale(c);
     PROF(0);
     int status = OSQP_UNSOLVED; double obj = 0; int iters = 0, rho_updates = 0, status_polish = 0;
@@ -1396,15 +1403,17 @@ __device__ void solve_instance(Ctx<DM>& c, const Out& o) {
 
 // ---- persistent kernel: warps pull instances from a global counter ------------------------------------------------
 template <class DM>
-__global__ void __launch_bounds__(128) lmpc_solve_kernel(const __grid_constant__ DM d, const __grid_constant__ Params p,
+__global__ void __launch_bounds__(B200_MAX_THREADS, 1) lmpc_solve_kernel(const __grid_constant__ DM d, const __grid_constant__ Params p,
                                                         const __grid_constant__ Prob pr, const __grid_constant__ Out o,
-                                                        int batch, double* workspace, size_t ws_stride, int* counter) {
+                                                        int batch, double* workspace, size_t ws_stride, int* counter, int model_shared) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int slot = blockIdx.x * wpb + warp;
     Ctx<DM> c(d, p, pr);
     c.lane = lane;
     c.sb = warp * d.smem_doubles();
+    c.model_shared = model_shared;
+    c.mb = wpb * d.smem_doubles() + (model_shared ? 0 : warp * d.model_doubles());
     c.ws = workspace + (size_t)slot * ws_stride;
     // Ruiz working arrays: in shared memory (the ring area past Pblk) when they fit, else in the workspace
     {
@@ -1421,6 +1430,11 @@ __global__ void __launch_bounds__(128) lmpc_solve_kernel(const __grid_constant__
     c.fres = 0; c.vres = 0; c.rflags = 0;
     fence_proxy_async();
     __syncwarp();
+    if (model_shared) {            // the whole batch shares A,B,C and the scalar row: one copy per CTA
+        c.inst = 0;
+        if (warp == 0) load_model(c);
+        __syncthreads();
+    }
     for (;;) {
         int inst = 0;
         if (lane == 0) inst = atomicAdd(counter, 1);
