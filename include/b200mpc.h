@@ -140,6 +140,25 @@ int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm
 int b200mpc_lmpc_profile(b200mpc_lmpc_t h, long long* out_host);
 int b200mpc_sync(b200mpc_lmpc_t h);
 
+/* ---- NLMPC: batched evaluation of everything libmpc++ hands to its NLP solver for a decision vector z --------------
+ * (SURVEY.md kernel K5).  Replaces, for `batch` controllers at once, the four NLopt callbacks of NLOptimizer
+ * (include/mpc/NLMPC/NLOptimizer.hpp:760-997): Objective::evaluate (NLMPC/Objective.hpp:91-265),
+ * Constraints::evaluateStateModelEq (NLMPC/Constraints.hpp:325-356,490-628,844-905) and Constraints::evaluateIneq
+ * (NLMPC/Constraints.hpp:211-316,641-721), after Mapping::unwrapVector (NLMPC/Mapping.hpp:174-257).
+ * The reference's std::function callbacks (IDimensionable.hpp:94-149) cannot run on the device, so the model / cost /
+ * constraints are device functors selected by `system`; the reference's three example systems are built in.
+ *   z[batch*nz] with nz = ph*nx + ch*nu + 1 ([X_1..X_ph ; U_1..U_ch ; slack], Mapping.hpp:196-201), x0[batch*nx],
+ *   params[(batch or 1)*nparam]; outputs (any may be NULL): fval[batch], grad[batch*nz], ceq[batch*ph*nx],
+ *   Jeq[batch*ph*nx*nz], cin[batch*nineq], Jin[batch*nineq*nz]; Jacobians row-major like the reference's. */
+enum { B200MPC_SYS_VANDERPOL = 0,  /* examples/vanderpol_ex.cpp: params [Ts]                                   */
+       B200MPC_SYS_OSCNET4 = 1,    /* examples/networked_oscillators_ex.cpp with N=4: params [Ts, mu, k]         */
+       B200MPC_SYS_OSCNET6 = 2,    /* the shipped N=6                                                           */
+       B200MPC_SYS_UGV = 3 };      /* examples/ugv_ex.cpp: params [Ad(16) Bd(8) v_pref(2) obs0(x,y,r) obs1(x,y,r)] */
+int b200mpc_nlmpc_system_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq);
+int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
+                       int params_per_instance, double* fval, double* grad, double* ceq, double* Jeq, double* cin,
+                       double* Jin, int dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

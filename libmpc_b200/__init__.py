@@ -75,6 +75,8 @@ def load_library():
     lib.b200mpc_lmpc_set_launch.argtypes = [H, C.c_int, C.c_int]
     lib.b200mpc_lmpc_profile.argtypes = [H, C.c_void_p]
     lib.b200mpc_sync.argtypes = [H]
+    lib.b200mpc_nlmpc_system_dims.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
+    lib.b200mpc_nlmpc_eval.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
     _lib = lib
     return lib
 
@@ -86,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_set_input_bounds", "b200mpc_lmpc_set_output_bounds", "b200mpc_lmpc_set_scalar_constraint",
     "b200mpc_lmpc_set_references", "b200mpc_lmpc_set_exogenous_inputs", "b200mpc_lmpc_set_warm_start",
     "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
-    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_profile", "b200mpc_sync",
+    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
 ]
 
 
@@ -463,3 +465,43 @@ class LMPC:
         """Device-to-device copy of results into caller-owned device buffers (async on the handle's stream)."""
         v = lambda p: C.c_void_p(int(p)) if p else None
         _check(self.lib.b200mpc_lmpc_get_result(self._h, v(cmd_ptr), None, v(status_ptr), None, None, v(iters_ptr), None, None, 1))
+
+
+# ---- NLMPC problem evaluation (SURVEY.md K5) ------------------------------------------------------------------------
+SYS_VANDERPOL, SYS_OSCNET4, SYS_OSCNET6, SYS_UGV = 0, 1, 2, 3
+
+
+def nlmpc_system_dims(system, ph):
+    lib = load_library()
+    v = [C.c_int() for _ in range(4)]
+    _check(lib.b200mpc_nlmpc_system_dims(system, ph, *[C.byref(x) for x in v]))
+    return dict(nx=v[0].value, nu=v[1].value, nparam=v[2].value, nineq=v[3].value)
+
+
+def nlmpc_eval(system, ph, ch, z, x0, params, want=("f", "grad", "ceq", "Jeq", "cin", "Jin")):
+    """Batched Objective / Constraints evaluation with finite-difference derivatives on the GPU.
+    z [B, nz], x0 [B, nx], params [nparam] (shared) or [B, nparam].  Returns a dict of numpy arrays."""
+    lib = load_library()
+    d = nlmpc_system_dims(system, ph)
+    z = np.ascontiguousarray(np.atleast_2d(z), dtype=np.float64)
+    B, nz = z.shape
+    if nz != ph * d["nx"] + ch * d["nu"] + 1:
+        raise ValueError("z has the wrong length")
+    x0 = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(x0), (B, d["nx"])), dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    ppi = 1 if params.ndim == 2 else 0
+    if params.shape[-1] != d["nparam"]:
+        raise ValueError(f"params: expected {d['nparam']} values")
+    out = {}
+    shapes = dict(f=(B,), grad=(B, nz), ceq=(B, ph * d["nx"]), Jeq=(B, ph * d["nx"], nz), cin=(B, d["nineq"]), Jin=(B, d["nineq"], nz))
+    ptr = {}
+    for k, shp in shapes.items():
+        if k in want:
+            out[k] = np.zeros(shp)
+            ptr[k] = out[k].ctypes.data_as(C.c_void_p)
+        else:
+            ptr[k] = None
+    _check(lib.b200mpc_nlmpc_eval(system, ph, ch, B, z.ctypes.data_as(C.c_void_p), x0.ctypes.data_as(C.c_void_p),
+                                  params.ctypes.data_as(C.c_void_p), ppi, ptr["f"], ptr["grad"], ptr["ceq"], ptr["Jeq"], ptr["cin"],
+                                  ptr["Jin"], 0, None))
+    return out

@@ -5,6 +5,7 @@
 // that would compute returns B200MPC_ENOGPU.
 #include "../../include/b200mpc.h"
 #include "lmpc_kernels.cuh"
+#include "nlmpc_kernels.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -478,5 +479,96 @@ extern "C" int b200mpc_lmpc_profile(b200mpc_lmpc_t h, long long* out_host) {
 extern "C" int b200mpc_sync(b200mpc_lmpc_t h) {
     HCHECK();
     CK(cudaStreamSynchronize(h->stream));
+    return B200MPC_OK;
+}
+
+
+// ---- NLMPC problem evaluation (K5) --------------------------------------------------------------------------------
+template <class S>
+static int nl_eval_t(const NlEvalArgs& a, cudaStream_t stream) {
+    int wpb = 4;
+    size_t smem = (size_t)wpb * (a.ph + 1) * (S::nx + S::nu) * sizeof(double);
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int grid = (a.batch + wpb - 1) / wpb;
+    if (grid > sms * 8) grid = sms * 8;
+    CK(cudaFuncSetAttribute(nlmpc_eval_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nlmpc_eval_kernel<S><<<grid, wpb * 32, smem, stream>>>(a);
+    CK(cudaGetLastError());
+    return B200MPC_OK;
+}
+
+static int nl_dims(int system, int* nx, int* nu, int* nparam, int ph, int* nineq) {
+    switch (system) {
+    case B200MPC_SYS_VANDERPOL: *nx = 2; *nu = 1; *nparam = 1; *nineq = ph + 1; return 0;
+    case B200MPC_SYS_OSCNET4: *nx = 8; *nu = 4; *nparam = 3; *nineq = (ph + 1) * 4; return 0;
+    case B200MPC_SYS_OSCNET6: *nx = 12; *nu = 6; *nparam = 3; *nineq = (ph + 1) * 6; return 0;
+    case B200MPC_SYS_UGV: *nx = 4; *nu = 2; *nparam = 32; *nineq = (ph + 1) * 2; return 0;
+    default: return -1;
+    }
+}
+
+extern "C" int b200mpc_nlmpc_system_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq) {
+    int a, b, c, d;
+    if (nl_dims(system, &a, &b, &c, ph, &d)) return fail(B200MPC_EINVAL, "unknown system id");
+    if (nx) *nx = a; if (nu) *nu = b; if (nparam) *nparam = c; if (nineq) *nineq = d;
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
+                                  int params_per_instance, double* fval, double* grad, double* ceq, double* Jeq, double* cin,
+                                  double* Jin, int dev, void* stream_) {
+    if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
+    int nx, nu, np, ni;
+    if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return fail(B200MPC_EINVAL, "unknown system id");
+    if (ph < 1 || ch < 1 || ch > ph || batch < 1 || !z || !x0 || !params) return fail(B200MPC_EINVAL, "bad arguments");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int nz = ph * nx + ch * nu + 1;
+    NlEvalArgs a;
+    a.ph = ph; a.ch = ch; a.batch = batch; a.param_stride = params_per_instance ? np : 0;
+    std::vector<void*> tofree;
+    auto in = [&](const double* h, size_t n, const double** d) -> int {
+        if (dev) { *d = h; return 0; }
+        double* p = nullptr;
+        CK(cudaMalloc(&p, n * sizeof(double))); tofree.push_back(p);
+        CK(cudaMemcpyAsync(p, h, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        *d = p; return 0;
+    };
+    auto out = [&](double* h, size_t n, double** d) -> int {
+        if (!h) { *d = nullptr; return 0; }
+        if (dev) { *d = h; return 0; }
+        double* p = nullptr;
+        CK(cudaMalloc(&p, n * sizeof(double))); tofree.push_back(p);
+        *d = p; return 0;
+    };
+    int rc;
+    if ((rc = in(z, (size_t)batch * nz, &a.z))) return rc;
+    if ((rc = in(x0, (size_t)batch * nx, &a.x0))) return rc;
+    if ((rc = in(params, (size_t)(params_per_instance ? batch : 1) * np, &a.params))) return rc;
+    if ((rc = out(fval, batch, &a.fval))) return rc;
+    if ((rc = out(grad, (size_t)batch * nz, &a.grad))) return rc;
+    if ((rc = out(ceq, (size_t)batch * ph * nx, &a.ceq))) return rc;
+    if ((rc = out(Jeq, (size_t)batch * ph * nx * nz, &a.Jeq))) return rc;
+    if ((rc = out(cin, (size_t)batch * ni, &a.cin))) return rc;
+    if ((rc = out(Jin, (size_t)batch * ni * nz, &a.Jin))) return rc;
+    switch (system) {
+    case B200MPC_SYS_VANDERPOL: rc = nl_eval_t<SysVanDerPol>(a, stream); break;
+    case B200MPC_SYS_OSCNET4: rc = nl_eval_t<SysOscNet<4>>(a, stream); break;
+    case B200MPC_SYS_OSCNET6: rc = nl_eval_t<SysOscNet<6>>(a, stream); break;
+    default: rc = nl_eval_t<SysUgv>(a, stream); break;
+    }
+    if (rc) return rc;
+    if (!dev) {
+        auto back = [&](double* h, const double* d, size_t n) -> int { if (h) CK(cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, stream)); return 0; };
+        if ((rc = back(fval, a.fval, batch))) return rc;
+        if ((rc = back(grad, a.grad, (size_t)batch * nz))) return rc;
+        if ((rc = back(ceq, a.ceq, (size_t)batch * ph * nx))) return rc;
+        if ((rc = back(Jeq, a.Jeq, (size_t)batch * ph * nx * nz))) return rc;
+        if ((rc = back(cin, a.cin, (size_t)batch * ni))) return rc;
+        if ((rc = back(Jin, a.Jin, (size_t)batch * ni * nz))) return rc;
+        CK(cudaStreamSynchronize(stream));
+        for (void* p : tofree) cudaFree(p);
+    }
     return B200MPC_OK;
 }

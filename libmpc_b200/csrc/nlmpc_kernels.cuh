@@ -1,0 +1,291 @@
+// nlmpc_kernels.cuh -- batched NLMPC problem evaluation for sm_100a: everything libmpc++ hands to its NLP
+// solver for one decision vector z, for a batch of independent controllers, one warp per instance:
+//   * Mapping::unwrapVector                        include/mpc/NLMPC/Mapping.hpp:174-211  (move blocking via Iz2u :221-257)
+//   * Objective::evaluate + computeGradient        include/mpc/NLMPC/Objective.hpp:91-187,198-265  (FORWARD differences)
+//   * Constraints::getStateEqConstraints + computeStateEqJacobian + glueJacobian
+//                                                  include/mpc/NLMPC/Constraints.hpp:490-628,844-905,455-482 (CENTRAL)
+//   * Constraints::evaluateIneq + computeIneqJacobian  include/mpc/NLMPC/Constraints.hpp:211-316,641-721 (CENTRAL)
+// including the reference's finite-difference quirks (linear-index step sizes, last-row pairing of U in the objective
+// gradient but not in the inequality Jacobian; see oracle/nlmpc_formulation.py).
+//
+// The reference takes the model / cost / constraints as host std::function callbacks (IDimensionable.hpp:94-149), which
+// cannot run on the device: here they are device functors selected by a system id, with the three systems the
+// reference ships as examples built in (examples/vanderpol_ex.cpp, networked_oscillators_ex.cpp, ugv_ex.cpp).
+// Lanes parallelise over the finite-difference perturbations: every lane evaluates the whole cost / one constraint
+// component through an accessor that adds its own perturbation on the fly, so X and U are never copied.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace b200mpc {
+
+// X [(ph+1) x nx], U [(ph+1) x nu] row-major in shared memory + one (or a pair of) perturbed entries
+struct Acc {
+    const double* X; const double* U; int nx, nu;
+    int kind;      // 0 none, 1 X(row,col) += d, 2 U(row,col) += d, 3 U(row,col) and U(row+1,col) += d
+    int row, col; double d;
+    __device__ __forceinline__ double x(int i, int j) const { double v = X[i * nx + j]; return (kind == 1 && i == row && j == col) ? v + d : v; }
+    __device__ __forceinline__ double u(int i, int j) const {
+        double v = U[i * nu + j];
+        if (kind == 2 && i == row && j == col) v += d;
+        if (kind == 3 && (i == row || i == row + 1) && j == col) v += d;
+        return v;
+    }
+};
+
+// ---- built-in systems ---------------------------------------------------------------------------------------------
+// examples/vanderpol_ex.cpp:9-71 -- params: [Ts]
+struct SysVanDerPol {
+    static constexpr int nx = 2, nu = 1, ny = 2, nparam = 1;
+    static constexpr bool continuous = true;
+    __device__ static double Ts(const double* p) { return p[0]; }
+    __device__ static int nineq(int ph) { return ph + 1; }
+    __device__ static void f(double* dx, const double* x, const double* u, int, const double*) {
+        dx[0] = ((1.0 - (x[1] * x[1])) * x[0]) - x[1] + u[0];
+        dx[1] = x[0];
+    }
+    __device__ static double cost(const Acc& a, double, int ph, const double*) {
+        double sx = 0, su = 0;
+        for (int j = 0; j < nx; ++j) for (int i = 0; i <= ph; ++i) { double v = a.x(i, j); sx += v * v; }   // column-major sum order (Eigen)
+        for (int j = 0; j < nu; ++j) for (int i = 0; i <= ph; ++i) { double v = a.u(i, j); su += v * v; }
+        return sx + su;
+    }
+    __device__ static double ineq(int r, const Acc& a, double, int, const double*) { return a.u(r, 0) - 0.5; }
+};
+
+// examples/networked_oscillators_ex.cpp:5-72 -- params: [Ts, mu, k]
+template <int N>
+struct SysOscNet {
+    static constexpr int nx = 2 * N, nu = N, ny = 2 * N, nparam = 3;
+    static constexpr bool continuous = true;
+    __device__ static double Ts(const double* p) { return p[0]; }
+    __device__ static int nineq(int ph) { return (ph + 1) * nu; }
+    __device__ static void f(double* dx, const double* x, const double* u, int, const double* p) {
+        const double mu = p[1], k = p[2];
+        for (int i = 0; i < N; ++i) {
+            dx[2 * i] = x[2 * i + 1];
+            double v = mu * (1 - x[2 * i] * x[2 * i]) * x[2 * i + 1] - x[2 * i] + u[i];
+            for (int j = 0; j < N; ++j) if (i != j) v += k * (x[2 * j] - x[2 * i]);
+            dx[2 * i + 1] = v;
+        }
+    }
+    __device__ static double cost(const Acc& a, double, int ph, const double*) {
+        double sx = 0, su = 0;
+        for (int j = 0; j < nx; ++j) for (int i = 0; i <= ph; ++i) { double v = a.x(i, j); sx += v * v; }
+        for (int j = 0; j < nu; ++j) for (int i = 0; i <= ph; ++i) { double v = a.u(i, j); su += v * v; }
+        return sx + su;
+    }
+    __device__ static double ineq(int r, const Acc& a, double, int, const double*) { return a.u(r / nu, r % nu) - 0.5; }
+};
+
+// examples/ugv_ex.cpp:12-126 -- discrete double integrator, 2 circular obstacles, soft constraints.
+// params: [Ad(16) | Bd(8) | v_pref(2) | obs0(x,y,r) | obs1(x,y,r)]  (C = I, D = 0: y = x)
+struct SysUgv {
+    static constexpr int nx = 4, nu = 2, ny = 4, nparam = 16 + 8 + 2 + 6, nobs = 2;
+    static constexpr bool continuous = false;
+    __device__ static double Ts(const double*) { return 0.0; }
+    __device__ static int nineq(int ph) { return (ph + 1) * nobs; }
+    __device__ static void f(double* xn, const double* x, const double* u, int, const double* p) {
+        for (int r = 0; r < 4; ++r) {
+            double v = 0;
+            for (int c = 0; c < 4; ++c) v += p[r * 4 + c] * x[c];
+            double w = 0;
+            for (int c = 0; c < 2; ++c) w += p[16 + r * 2 + c] * u[c];
+            xn[r] = v + w;
+        }
+    }
+    __device__ static double cost(const Acc& a, double e, int ph, const double* p) {
+        double cost = 0;
+        for (int i = 0; i <= ph; ++i) {
+            double d0 = a.x(i, 2) - p[24], d1 = a.x(i, 3) - p[25];
+            cost += 1e3 * (d0 * d0 + d1 * d1);
+            double u0 = a.u(i, 0), u1 = a.u(i, 1);
+            cost += 1e-2 * (u0 * u0 + u1 * u1);
+        }
+        cost += 1e-5 * e * e;
+        return cost;
+    }
+    __device__ static double ineq(int r, const Acc& a, double, int, const double* p) {
+        int i = r / nobs, j = r % nobs;
+        double dx = a.x(i, 0) - p[26 + 3 * j], dy = a.x(i, 1) - p[26 + 3 * j + 1];
+        return p[26 + 3 * j + 2] - sqrt(dx * dx + dy * dy);
+    }
+};
+
+struct NlEvalArgs {
+    int ph, ch, batch;
+    const double* z;        // [batch, nz]
+    const double* x0;       // [batch, nx]
+    const double* params;   // [batch or 1, nparam]
+    long long param_stride;
+    double* fval;           // [batch]
+    double* grad;           // [batch, nz]
+    double* ceq;            // [batch, ph*nx]
+    double* Jeq;            // [batch, ph*nx, nz] row-major
+    double* cin;            // [batch, nineq]
+    double* Jin;            // [batch, nineq, nz] row-major
+};
+
+template <class S>
+__global__ void __launch_bounds__(128) nlmpc_eval_kernel(const NlEvalArgs a) {
+    extern __shared__ __align__(16) double nl_smem[];
+    constexpr int nx = S::nx, nu = S::nu;
+    const int ph = a.ph, ch = a.ch;
+    const int nz = ph * nx + ch * nu + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int per_warp = (ph + 1) * (nx + nu);
+    double* X = nl_smem + (size_t)warp * per_warp;
+    double* U = X + (ph + 1) * nx;
+    const double dv = 1.4901161193847656e-08;     // sqrt(DBL_EPSILON)  (Objective.hpp:283)
+    for (int inst = blockIdx.x * wpb + warp; inst < a.batch; inst += gridDim.x * wpb) {
+        const double* z = a.z + (size_t)inst * nz;
+        const double* p = a.params + (size_t)inst * a.param_stride;
+        // ---- unwrapVector: X row 0 = x0, rows 1..ph from z; U row i = block min(i, ch-1), last row repeated
+        for (int e = lane; e < (ph + 1) * nx; e += 32) {
+            int i = e / nx, j = e - i * nx;
+            X[e] = i == 0 ? a.x0[(size_t)inst * nx + j] : z[(i - 1) * nx + j];
+        }
+        for (int e = lane; e < (ph + 1) * nu; e += 32) {
+            int i = e / nu, j = e - i * nu;
+            int st = i < ph ? i : ph - 1;
+            int blk = st < ch ? st : ch - 1;
+            U[e] = z[ph * nx + blk * nu + j];
+        }
+        const double slack = z[nz - 1];
+        __syncwarp();
+        Acc base{X, U, nx, nu, 0, 0, 0, 0.0};
+        // ---- objective + forward-difference gradient
+        const double f0 = S::cost(base, slack, ph, p);
+        if (a.fval && lane == 0) a.fval[inst] = f0;
+        if (a.grad) {
+            double* g = a.grad + (size_t)inst * nz;
+            for (int e = lane; e < nz; e += 32) g[e] = 0.0;
+            __syncwarp();
+            // X entries: step uses Xa.array()(j) = linear index j of the column-major (ph+1) x nx matrix
+            for (int t = lane; t < ph * nx; t += 32) {
+                int i = t / nx, j = t - i * nx;
+                int lr = j % (ph + 1), lc = j / (ph + 1);
+                double xa = fmax(fabs(X[lr * nx + lc]), 1.0);
+                double dx = dv * xa;
+                Acc ac = base; ac.kind = 1; ac.row = i + 1; ac.col = j; ac.d = dx;
+                g[i * nx + j] = (S::cost(ac, slack, ph, p) - f0) / dx;
+            }
+            // U entries: stages 0..ph-2 alone, stage ph-1 together with the duplicated row ph; chain through Iz2u'
+            for (int t = lane; t < ph * nu; t += 32) {
+                int i = t / nu, j = t - i * nu;
+                int lr = j % (ph + 1), lc = j / (ph + 1);
+                double ua = fmax(fabs(U[lr * nu + lc]), 1.0);
+                double du = dv * ua;
+                Acc ac = base; ac.kind = (i == ph - 1) ? 3 : 2; ac.row = i; ac.col = j; ac.d = du;
+                double df = (S::cost(ac, slack, ph, p) - f0) / du;
+                int blk = i < ch ? i : ch - 1;
+                atomicAdd(&g[ph * nx + blk * nu + j], df);
+            }
+            if (lane == 0) {
+                double ea = fmax(dv, fabs(slack)), de = ea * dv;
+                g[nz - 1] = (S::cost(base, slack + de, ph, p) - S::cost(base, slack - de, ph, p)) / (2 * de);
+            }
+        }
+        // ---- dynamics equality constraints (multiple shooting) + central-difference Jacobian
+        if (a.ceq) {
+            double* c = a.ceq + (size_t)inst * ph * nx;
+            double* J = a.Jeq ? a.Jeq + (size_t)inst * ph * nx * nz : nullptr;
+            if (J) for (int e = lane; e < ph * nx * nz; e += 32) J[e] = 0.0;
+            __syncwarp();
+            const double h = S::Ts(p) / 2.0;
+            for (int i = lane; i < ph; i += 32) {
+                double xk[nx], xk1[nx], uk[nu], fk[nx], fk1[nx];
+                for (int j = 0; j < nx; ++j) { xk[j] = X[i * nx + j]; xk1[j] = X[(i + 1) * nx + j]; }
+                for (int j = 0; j < nu; ++j) uk[j] = U[i * nu + j];
+                if (S::continuous) {
+                    S::f(fk, xk, uk, i, p); S::f(fk1, xk1, uk, i, p);
+                    for (int j = 0; j < nx; ++j) c[i * nx + j] = xk[j] + (h * (fk[j] + fk1[j])) - xk1[j];
+                } else {
+                    S::f(fk, xk, uk, i, p);
+                    for (int j = 0; j < nx; ++j) c[i * nx + j] = xk1[j] - fk[j];
+                }
+            }
+            if (J) {
+                // one task = one (stage, perturbed entry): columns of A_k/B_k (and A_{k+1}/B_{k+1} when continuous)
+                const int per_stage = nx + nu;
+                for (int t = lane; t < ph * per_stage; t += 32) {
+                    int i = t / per_stage, q = t - i * per_stage;
+                    double xk[nx], xk1[nx], uk[nu], fp[nx], fm[nx];
+                    for (int j = 0; j < nx; ++j) { xk[j] = X[i * nx + j]; xk1[j] = X[(i + 1) * nx + j]; }
+                    for (int j = 0; j < nu; ++j) uk[j] = U[i * nu + j];
+                    int blk = i < ch ? i : ch - 1;
+                    if (q < nx) {
+                        // d f(xk,uk)/d xk[q]
+                        double dx = dv * fmax(fabs(xk[q]), 1.0), keep = xk[q];
+                        xk[q] = keep + dx; S::f(fp, xk, uk, i, p);
+                        xk[q] = keep - dx; S::f(fm, xk, uk, i, p);
+                        xk[q] = keep;
+                        if (S::continuous) {
+                            if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * nz + (i - 1) * nx + q] = (r == q ? 1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx));
+                            double dx1 = dv * fmax(fabs(xk1[q]), 1.0), keep1 = xk1[q];
+                            xk1[q] = keep1 + dx1; S::f(fp, xk1, uk, i, p);
+                            xk1[q] = keep1 - dx1; S::f(fm, xk1, uk, i, p);
+                            xk1[q] = keep1;
+                            for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * nz + i * nx + q] = (r == q ? -1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx1));
+                        } else {
+                            if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * nz + (i - 1) * nx + q] = -((fp[r] - fm[r]) / (2 * dx));
+                            for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * nz + i * nx + q] = (r == q ? 1.0 : 0.0);
+                        }
+                    } else {
+                        int qu = q - nx;
+                        double du = dv * fmax(fabs(uk[qu]), 1.0), keep = uk[qu];
+                        uk[qu] = keep + du; S::f(fp, xk, uk, i, p);
+                        uk[qu] = keep - du; S::f(fm, xk, uk, i, p);
+                        uk[qu] = keep;
+                        double Bk[nx];
+                        for (int r = 0; r < nx; ++r) Bk[r] = (fp[r] - fm[r]) / (2 * du);
+                        if (S::continuous) {
+                            uk[qu] = keep + du; S::f(fp, xk1, uk, i, p);
+                            uk[qu] = keep - du; S::f(fm, xk1, uk, i, p);
+                            uk[qu] = keep;
+                            for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * nz + ph * nx + blk * nu + qu], h * (Bk[r] + (fp[r] - fm[r]) / (2 * du)));
+                        } else {
+                            for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * nz + ph * nx + blk * nu + qu], -Bk[r]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- user inequality constraints + central-difference Jacobian
+        if (a.cin) {
+            const int ni = S::nineq(ph);
+            double* c = a.cin + (size_t)inst * ni;
+            for (int r = lane; r < ni; r += 32) c[r] = S::ineq(r, base, slack, ph, p);
+            if (a.Jin) {
+                double* J = a.Jin + (size_t)inst * ni * nz;
+                for (int e = lane; e < ni * nz; e += 32) J[e] = 0.0;
+                __syncwarp();
+                for (int t = lane; t < ph * nx; t += 32) {
+                    int i = t / nx, j = t - i * nx;
+                    int lr = j % (ph + 1), lc = j / (ph + 1);
+                    double dx = dv * fmax(fabs(X[lr * nx + lc]), 1.0);
+                    Acc ap = base; ap.kind = 1; ap.row = i + 1; ap.col = j; ap.d = dx;
+                    Acc am = ap; am.d = -dx;
+                    for (int r = 0; r < ni; ++r) J[(size_t)r * nz + i * nx + j] = (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * dx);
+                }
+                for (int t = lane; t < ph * nu; t += 32) {     // every one of the ph rows alone (row ph is never perturbed)
+                    int i = t / nu, j = t - i * nu;
+                    int lr = j % (ph + 1), lc = j / (ph + 1);
+                    double du = dv * fmax(fabs(U[lr * nu + lc]), 1.0);
+                    Acc ap = base; ap.kind = 2; ap.row = i; ap.col = j; ap.d = du;
+                    Acc am = ap; am.d = -du;
+                    int blk = i < ch ? i : ch - 1;
+                    for (int r = 0; r < ni; ++r)
+                        atomicAdd(&J[(size_t)r * nz + ph * nx + blk * nu + j], (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * du));
+                }
+                if (lane == 0) {
+                    double ea = fmax(dv, fabs(slack)), de = ea * dv;
+                    for (int r = 0; r < ni; ++r) J[(size_t)r * nz + nz - 1] = (S::ineq(r, base, slack + de, ph, p) - S::ineq(r, base, slack - de, ph, p)) / (2 * de);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace b200mpc

@@ -317,3 +317,51 @@ def vanderpol_formulation():
     f.obj = sum_squares_cost
     f.ineq = lambda X, Y, U, e: U[:, 0] - 0.5
     return f
+
+
+def oscnet_formulation(N, ph, ch, Ts=0.1, mu=1.0, k=0.1):
+    """examples/networked_oscillators_ex.cpp with N oscillators: nx=2N, nu=N, Tineq=(ph+1)*nu (u <= 0.5), continuous."""
+    f = NLMPCFormulation(2 * N, N, 2 * N, ph, ch, nineq=(ph + 1) * N)
+    f.continuous, f.Ts = True, Ts
+    f.f = oscillator_network_field(N, mu, k)
+    f.obj = sum_squares_cost
+    f.ineq = lambda X, Y, U, e: (U - 0.5).ravel()      # idx = i*nu + j
+    return f
+
+
+def ugv_model(Ts=0.1, m=1.0):
+    """Discretised double integrator of examples/ugv_ex.cpp:36-57 (c2d via the matrix exponential, Utils.hpp:23-47)."""
+    from oracle.lmpc_formulation import discretization
+    A = np.zeros((4, 4)); A[0:2, 2:4] = np.eye(2)
+    B = np.zeros((4, 2)); B[2:4, :] = np.eye(2) / m
+    return discretization(A, B, Ts)
+
+
+def ugv_formulation(ph=10, ch=10, v_pref=(0.0, 0.0), obstacles=((2.0, 1.0, 0.3), (1.0, 1.0, 0.3))):
+    """examples/ugv_ex.cpp:12-126: nx4 nu2 ny4, discrete, y = x, soft obstacle constraints."""
+    Ad, Bd = ugv_model()
+    obs = np.asarray(obstacles, float)
+    vp = np.asarray(v_pref, float)
+    f = NLMPCFormulation(4, 2, 4, ph, ch, nineq=(ph + 1) * len(obs))
+    f.f = lambda x, u, i=0: Ad @ x + Bd @ u
+    f.out = lambda x, u, i=0: x.copy()
+
+    def cost(X, Y, U, e):
+        c = 0.0
+        for i in range(ph + 1):
+            d = X[i, 2:4] - vp
+            c += 1e3 * (d[0] * d[0] + d[1] * d[1])
+            c += 1e-2 * (U[i, 0] * U[i, 0] + U[i, 1] * U[i, 1])
+        return c + 1e-5 * e * e
+
+    def ineq(X, Y, U, e):
+        out = np.zeros((ph + 1) * len(obs))
+        k = 0
+        for i in range(ph + 1):
+            for j in range(len(obs)):
+                out[k] = obs[j, 2] - np.hypot(X[i, 0] - obs[j, 0], X[i, 1] - obs[j, 1])
+                k += 1
+        return out
+    f.obj, f.ineq = cost, ineq
+    f.params = np.concatenate([Ad.ravel(), Bd.ravel(), vp, obs.ravel()])
+    return f
