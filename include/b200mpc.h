@@ -159,6 +159,30 @@ int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const double* z, c
                        int params_per_instance, double* fval, double* grad, double* ceq, double* Jeq, double* cin,
                        double* Jin, int dev, void* stream);
 
+/* ---- NLMPC solve -------------------------------------------------------------------------------
+ * Replaces NLOptimizer::run (include/mpc/NLMPC/NLOptimizer.hpp:412-638: nlopt::opt(LD_SLSQP) with the objective,
+ * the dynamics equalities, the user inequalities and the variable bounds) for `batch` controllers in one launch, one
+ * warp per controller, shared-memory-resident damped-BFGS SQP (libmpc_b200/csrc/nlmpc_sqp.cuh).
+ *   z0[batch*nz]: initial decision vectors (the reference's warm start: previous optimum shifted, NLOptimizer.hpp:430-470);
+ *   lb/ub[nz]: variable bounds (Constraints.hpp bounds getters; +-inf for free variables; slack lower bound 0 when hard
+ *   constraints are off, NLOptimizer.hpp:221-260); shared by the batch.
+ *   outputs: z[batch*nz], cost[batch], viol[batch] (sum |c_eq| + sum max(c_in,0) at the solution),
+ *   status[batch] (0 converged, 1 iteration limit), iters[batch] (major iterations), qp_iters[batch].
+ * The supported size is bounded by shared memory (b200mpc_nlmpc_solve_smem_bytes <= 227 KB); larger systems -> EINVAL. */
+typedef struct {
+    int32_t max_sqp;      /* major iterations (NLParameters::maximum_iteration, default 100)                 */
+    int32_t max_qp;       /* ADMM iterations per QP subproblem                                               */
+    double tol;           /* relative step tolerance (NLParameters::relative_xtol/ftol play this role)       */
+    double qp_eps;        /* QP residual tolerance                                                            */
+    double rho;           /* initial ADMM penalty                                                             */
+} b200mpc_nlmpc_params;
+void b200mpc_nlmpc_default_params(b200mpc_nlmpc_params* p);
+long long b200mpc_nlmpc_solve_smem_bytes(int system, int ph, int ch);
+int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* params, const double* z0,
+                        const double* x0, const double* sys_params, int params_per_instance, const double* lb,
+                        const double* ub, double* z, double* cost, double* viol, int32_t* status, int32_t* iters,
+                        int32_t* qp_iters, int dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,10 @@ class _Params(C.Structure):
 _lib = None
 
 
+class _NLParams(C.Structure):
+    _fields_ = [("max_sqp", C.c_int32), ("max_qp", C.c_int32), ("tol", C.c_double), ("qp_eps", C.c_double), ("rho", C.c_double)]
+
+
 def load_library():
     """dlopen the CUDA extension; raises (never falls back) when it is missing."""
     global _lib
@@ -77,6 +81,10 @@ def load_library():
     lib.b200mpc_sync.argtypes = [H]
     lib.b200mpc_nlmpc_system_dims.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
     lib.b200mpc_nlmpc_eval.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    lib.b200mpc_nlmpc_default_params.argtypes = [C.POINTER(_NLParams)]
+    lib.b200mpc_nlmpc_solve_smem_bytes.argtypes = [C.c_int] * 3
+    lib.b200mpc_nlmpc_solve_smem_bytes.restype = C.c_longlong
+    lib.b200mpc_nlmpc_solve.argtypes = [C.c_int] * 4 + [C.POINTER(_NLParams)] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p]
     _lib = lib
     return lib
 
@@ -89,6 +97,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_set_references", "b200mpc_lmpc_set_exogenous_inputs", "b200mpc_lmpc_set_warm_start",
     "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
     "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
+    "b200mpc_nlmpc_default_params", "b200mpc_nlmpc_solve_smem_bytes", "b200mpc_nlmpc_solve",
 ]
 
 
@@ -505,3 +514,187 @@ def nlmpc_eval(system, ph, ch, z, x0, params, want=("f", "grad", "ceq", "Jeq", "
                                   params.ctypes.data_as(C.c_void_p), ppi, ptr["f"], ptr["grad"], ptr["ceq"], ptr["Jeq"], ptr["cin"],
                                   ptr["Jin"], 0, None))
     return out
+
+
+# ---- NLMPC solve -----------------------------------------------------------------------------------
+FLT_INF = float(np.float32(np.inf))
+
+
+@dataclass
+class NLParameters:
+    """mpc::NLParameters (Types.hpp:121-140).  The reference's four NLopt tolerances default to "disabled" (-1), which makes
+    NLopt run to maximum_iteration; here the tightest positive one of them (else 1e-7) is the SQP's relative step tolerance."""
+    maximum_iteration: int = 100
+    time_limit: float = 0.0
+    enable_warm_start: bool = False
+    relative_ftol: float = -1.0
+    relative_xtol: float = -1.0
+    absolute_ftol: float = -1.0
+    absolute_xtol: float = -1.0
+    hard_constraints: bool = True
+    verbose: bool = False
+
+
+def nlmpc_solve(system, ph, ch, z0, x0, params, lb, ub, max_sqp=100, max_qp=1000, tol=1e-7, qp_eps=1e-9, rho=0.1):
+    """Batched NLOptimizer::run core (NLOptimizer.hpp:519): z0 [B,nz] -> dict(z, cost, viol, status, iters, qp_iters)."""
+    lib = load_library()
+    d = nlmpc_system_dims(system, ph)
+    z0 = np.ascontiguousarray(np.atleast_2d(z0), dtype=np.float64)
+    B, nz = z0.shape
+    if nz != ph * d["nx"] + ch * d["nu"] + 1:
+        raise ValueError("z0 has the wrong length")
+    x0 = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(x0), (B, d["nx"])), dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    ppi = 1 if params.ndim == 2 else 0
+    if params.shape[-1] != d["nparam"] or (ppi and params.shape[0] != B):
+        raise ValueError(f"params: expected [{d['nparam']}] or [batch, {d['nparam']}]")
+    lb = np.ascontiguousarray(lb, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
+    if lb.shape != (nz,) or ub.shape != (nz,):
+        raise ValueError("lb/ub must have nz entries")
+    q = _NLParams(int(max_sqp), int(max_qp), float(tol), float(qp_eps), float(rho))
+    out = dict(z=np.zeros((B, nz)), cost=np.zeros(B), viol=np.zeros(B), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32),
+               qp_iters=np.zeros(B, np.int32))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _check(lib.b200mpc_nlmpc_solve(system, ph, ch, B, C.byref(q), vp(z0), vp(x0), vp(params), ppi, vp(lb), vp(ub), vp(out["z"]),
+                                   vp(out["cost"]), vp(out["viol"]), vp(out["status"]), vp(out["iters"]), vp(out["qp_iters"]), 0, None))
+    return out
+
+
+class NLMPC:
+    """Batched mpc::NLMPC<Tnx,Tnu,Tny,Tph,Tch,Tineq,Teq> (include/mpc/NLMPC.hpp) for the built-in device systems.
+
+    The reference takes the model / objective / constraints as std::function callbacks (NLMPC.hpp:139-281), which cannot
+    run on the device; here `system` selects a device functor (SYS_VANDERPOL, SYS_UGV, ...) and `setSystemParameters`
+    supplies its numbers (shared or per controller).  Bounds, parameters, warm start and results follow the reference."""
+
+    def __init__(self, system, ph, ch, batch=1):
+        self.lib = load_library()
+        d = nlmpc_system_dims(system, ph)
+        self.system, self.ph, self.ch, self.batch = system, ph, ch, batch
+        self.nx, self.nu, self.nparam, self.nineq = d["nx"], d["nu"], d["nparam"], d["nineq"]
+        self.nz = ph * self.nx + ch * self.nu + 1
+        if self.lib.b200mpc_nlmpc_solve_smem_bytes(system, ph, ch) > 227 * 1024:
+            raise ValueError("problem too large for the shared-memory SQP kernel (see DESIGN.md: stage-structured kernel is next)")
+        self.lb = np.full(self.nz, -FLT_INF); self.ub = np.full(self.nz, FLT_INF)     # NLOptimizer.hpp:69-73
+        self.params = None
+        self.p = NLParameters()
+        self.ineq_tolerance = 1e-10                                                    # NLMPC.hpp:229
+        self._apply_slack_bound()
+        self.opt_vector = np.zeros((batch, self.nz))
+        self.current_slack = np.zeros(batch)
+        self.is_first_iteration = True
+        self.sequence = None
+        self.result = None
+
+    def _apply_slack_bound(self):
+        # NLOptimizer::setParameters :160-190: hard constraints pin the slack to zero, otherwise it is free in [0, inf)
+        if self.p.hard_constraints:
+            self.lb[-1] = self.ub[-1] = 0.0
+        else:
+            self.lb[-1] = 0.0; self.ub[-1] = FLT_INF
+
+    def setOptimizerParameters(self, p: NLParameters):
+        self.p = p
+        self._apply_slack_bound()
+
+    def setSystemParameters(self, params):
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.shape not in ((self.nparam,), (self.batch, self.nparam)):
+            raise ValueError(f"params: expected [{self.nparam}] or [{self.batch}, {self.nparam}]")
+        self.params = params
+        return True
+
+    def setIneqTolerance(self, tol):
+        self.ineq_tolerance = float(tol)
+
+    def _bounds(self, lo, hi, dim, horizon, offset, slice_):
+        lo = np.asarray(lo, float); hi = np.asarray(hi, float)
+        if lo.ndim == 2:                                   # mat<dim, horizon>  (NLMPC.hpp:292-330)
+            if lo.shape != (dim, horizon) or hi.shape != (dim, horizon):
+                raise ValueError("bounds matrix has the wrong shape")
+            rng = range(horizon); col = lambda a, i: a[:, i]
+        else:                                              # vector + HorizonSlice (NLMPC.hpp:362-400)
+            if lo.shape != (dim,) or hi.shape != (dim,):
+                raise ValueError("bounds vector has the wrong shape")
+            s = _slice(slice_)
+            if s.start == -1 and s.end == -1:
+                rng = range(horizon)
+            else:
+                a = 0 if s.start == -1 else s.start
+                b = horizon if s.end == -1 else s.end
+                if not (0 <= a < b <= horizon):
+                    return False
+                rng = range(a, b)
+            col = lambda a, i: a
+        for i in rng:
+            self.lb[offset + i * dim: offset + (i + 1) * dim] = col(lo, i)
+            self.ub[offset + i * dim: offset + (i + 1) * dim] = col(hi, i)
+        return True
+
+    def setStateBounds(self, XMin, XMax, slice=None):
+        return self._bounds(XMin, XMax, self.nx, self.ph, 0, slice)
+
+    def setInputBounds(self, UMin, UMax, slice=None):
+        return self._bounds(UMin, UMax, self.nu, self.ch, self.ph * self.nx, slice)
+
+    def setOutputBounds(self, YMin, YMax, slice=None):
+        return False                                       # the reference ignores them too (NLMPC.hpp:342-349,410-417)
+
+    def _initial_guess(self, x0, u0):
+        """NLOptimizer::run :431-510 -- cold tile or previous optimum, fixOptimalSolution (:705-716), one-stage shift."""
+        B, ph, ch, nx, nu = self.batch, self.ph, self.ch, self.nx, self.nu
+        z = self.opt_vector
+        if self.is_first_iteration or not self.p.enable_warm_start:
+            z[:, :ph * nx] = np.tile(x0, (1, ph))
+            z[:, ph * nx:ph * nx + ch * nu] = np.tile(u0, (1, ch))
+        bad = (z < self.lb) | (z > self.ub)
+        with np.errstate(invalid="ignore"):
+            z = np.where(bad, (self.ub - self.lb) / 2.0, z)
+        out = z.copy()
+        X = z[:, :ph * nx].reshape(B, ph, nx)
+        out[:, :ph * nx] = np.concatenate([X[:, 1:], X[:, -1:]], axis=1).reshape(B, -1)
+        Uz = z[:, ph * nx:ph * nx + ch * nu].reshape(B, ch, nu)
+        blk = np.minimum(np.arange(ph), ch - 1)            # Iz2u: stage -> control block (Mapping.hpp:100-140)
+        Umv = Uz[:, blk]                                   # [B, ph, nu]
+        Umv = np.concatenate([Umv[:, 1:], Umv[:, -1:]], axis=1)
+        res = Umv[:, :ch]                                  # Iu2z picks the first stage of every block (Mapping.hpp:245-256)
+        out[:, ph * nx:ph * nx + ch * nu] = res.reshape(B, -1)
+        out[:, -1] = self.current_slack
+        return out
+
+    def optimize(self, x0, lastU):
+        if self.params is None:
+            raise RuntimeError("setSystemParameters has not been called")
+        B = self.batch
+        x0 = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(x0, float)), (B, self.nx)))
+        u0 = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(lastU, float)), (B, self.nu)))
+        z0 = self._initial_guess(x0, u0)
+        tols = [t for t in (self.p.relative_xtol, self.p.relative_ftol, self.p.absolute_xtol, self.p.absolute_ftol) if t > 0]
+        r = nlmpc_solve(self.system, self.ph, self.ch, z0, x0, self.params, self.lb, self.ub, max_sqp=self.p.maximum_iteration,
+                        tol=min(tols) if tols else 1e-7)
+        z = r["z"]
+        self.opt_vector = z.copy()
+        self.is_first_iteration = False
+        self.current_slack = z[:, -1].copy()
+        ph, ch, nx, nu = self.ph, self.ch, self.nx, self.nu
+        X = np.concatenate([x0[:, None, :], z[:, :ph * nx].reshape(B, ph, nx)], axis=1)
+        blk = np.minimum(np.minimum(np.arange(ph + 1), ph - 1), ch - 1)
+        U = z[:, ph * nx:ph * nx + ch * nu].reshape(B, ch, nu)[:, blk]
+        feas = np.ones(B, bool)
+        if self.nineq:
+            cin = nlmpc_eval(self.system, ph, ch, z, x0, self.params, want=("cin",))["cin"]
+            feas = ~(cin > self.ineq_tolerance).any(axis=1)       # Constraints::isFeasible (Constraints.hpp:157-201)
+        status = np.where(r["status"] == 0, 0, 1).astype(np.int32)            # SUCCESS / MAX_ITERATION (Types.hpp:87-94)
+        solver_status = np.where(r["status"] == 0, 4, 5).astype(np.int32)     # nlopt::XTOL_REACHED / MAXEVAL_REACHED
+        self.result = Result(U[:, 0].copy(), r["cost"], status, solver_status, feas, r["iters"], r["qp_iters"], np.zeros(B, np.int32))
+        self.result.viol = r["viol"]
+        self.sequence = OptSequence(X, U, X.copy())               # built-in systems use the identity output map
+        return self.result
+
+    step = optimize
+
+    def getLastResult(self):
+        return self.result
+
+    def getOptimalSequence(self):
+        return self.sequence

@@ -6,6 +6,7 @@
 #include "../../include/b200mpc.h"
 #include "lmpc_kernels.cuh"
 #include "nlmpc_kernels.cuh"
+#include "nlmpc_sqp.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -570,5 +571,103 @@ extern "C" int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const d
         CK(cudaStreamSynchronize(stream));
         for (void* p : tofree) cudaFree(p);
     }
+    return B200MPC_OK;
+}
+
+
+// ---- NLMPC solve (K6/K7) ---------------------------------------------------------------------------------------------
+extern "C" void b200mpc_nlmpc_default_params(b200mpc_nlmpc_params* p) {
+    if (!p) return;
+    p->max_sqp = 100; p->max_qp = 1000; p->tol = 1e-7; p->qp_eps = 1e-9; p->rho = 0.1;
+}
+
+static size_t nl_solve_smem(int system, int ph, int ch) {
+    int nx, nu, np, ni;
+    if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return 0;
+    return NlWs::doubles(ph * nx + ch * nu + 1, ph * nx, ni, ph, nx, nu) * sizeof(double);
+}
+extern "C" long long b200mpc_nlmpc_solve_smem_bytes(int system, int ph, int ch) { return (long long)nl_solve_smem(system, ph, ch); }
+
+template <class S>
+static int nl_solve_t(const NlSolveArgs& a, size_t per_warp, cudaStream_t stream) {
+    int dev = 0, sms = 0, maxsm = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (per_warp > (size_t)maxsm) return fail(B200MPC_EINVAL, "NLMPC problem too large for the shared-memory SQP kernel");
+    int wpb = (2 * per_warp <= (size_t)maxsm / 2) ? 2 : 1;      // keep >= 2 CTAs per SM when the problem is small
+    size_t smem = per_warp * wpb;
+    CK(cudaFuncSetAttribute(nlmpc_solve_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nlmpc_solve_kernel<S>, wpb * 32, smem));
+    if (occ < 1) occ = 1;
+    int grid = (a.batch + wpb - 1) / wpb;
+    if (grid > sms * occ) grid = sms * occ;
+    nlmpc_solve_kernel<S><<<grid, wpb * 32, smem, stream>>>(a);
+    CK(cudaGetLastError());
+    return B200MPC_OK;
+}
+
+extern "C" int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* prm, const double* z0,
+                                   const double* x0, const double* sys_params, int params_per_instance, const double* lb,
+                                   const double* ub, double* z, double* cost, double* viol, int32_t* status, int32_t* iters,
+                                   int32_t* qp_iters, int dev, void* stream_) {
+    if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
+    int nx, nu, np, ni;
+    if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return fail(B200MPC_EINVAL, "unknown system id");
+    if (ph < 1 || ch < 1 || ch > ph || batch < 1 || !z0 || !x0 || !sys_params || !lb || !ub || !z) return fail(B200MPC_EINVAL, "bad arguments");
+    b200mpc_nlmpc_params q;
+    if (prm) q = *prm; else b200mpc_nlmpc_default_params(&q);
+    if (q.max_sqp < 1 || q.max_qp < 25 || !(q.tol > 0) || !(q.qp_eps > 0) || !(q.rho > 0)) return fail(B200MPC_EINVAL, "bad NLMPC parameters");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int nz = ph * nx + ch * nu + 1;
+    const size_t per_warp = nl_solve_smem(system, ph, ch);
+    NlSolveArgs a;
+    a.ph = ph; a.ch = ch; a.batch = batch; a.param_stride = params_per_instance ? np : 0;
+    a.max_sqp = q.max_sqp; a.max_qp = q.max_qp; a.tol = q.tol; a.qp_eps = q.qp_eps; a.rho0 = q.rho;
+    std::vector<void*> tofree;
+    struct Free { std::vector<void*>& v; ~Free() { for (void* p : v) cudaFree(p); } } freer{tofree};
+    auto in = [&](const double* h, size_t n, const double** d) -> int {
+        if (dev) { *d = h; return 0; }
+        double* p = nullptr;
+        CK(cudaMalloc(&p, n * sizeof(double))); tofree.push_back(p);
+        CK(cudaMemcpyAsync(p, h, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        *d = p; return 0;
+    };
+    auto out = [&](void* h, size_t bytes, void** d) -> int {
+        if (dev && h) { *d = h; return 0; }
+        void* p = nullptr;
+        CK(cudaMalloc(&p, bytes)); tofree.push_back(p);
+        *d = p; return 0;
+    };
+    int rc;
+    if ((rc = in(z0, (size_t)batch * nz, &a.z0))) return rc;
+    if ((rc = in(x0, (size_t)batch * nx, &a.x0))) return rc;
+    if ((rc = in(sys_params, (size_t)(params_per_instance ? batch : 1) * np, &a.params))) return rc;
+    if ((rc = in(lb, nz, &a.lb))) return rc;
+    if ((rc = in(ub, nz, &a.ub))) return rc;
+    if ((rc = out(z, (size_t)batch * nz * 8, (void**)&a.z_out))) return rc;
+    if ((rc = out(cost, (size_t)batch * 8, (void**)&a.cost))) return rc;
+    if ((rc = out(viol, (size_t)batch * 8, (void**)&a.viol))) return rc;
+    if ((rc = out(status, (size_t)batch * 4, (void**)&a.status))) return rc;
+    if ((rc = out(iters, (size_t)batch * 4, (void**)&a.iters))) return rc;
+    if ((rc = out(qp_iters, (size_t)batch * 4, (void**)&a.qp_iters))) return rc;
+    switch (system) {
+    case B200MPC_SYS_VANDERPOL: rc = nl_solve_t<SysVanDerPol>(a, per_warp, stream); break;
+    case B200MPC_SYS_OSCNET4: rc = nl_solve_t<SysOscNet<4>>(a, per_warp, stream); break;
+    case B200MPC_SYS_OSCNET6: rc = nl_solve_t<SysOscNet<6>>(a, per_warp, stream); break;
+    default: rc = nl_solve_t<SysUgv>(a, per_warp, stream); break;
+    }
+    if (rc) return rc;
+    if (!dev) {
+        auto back = [&](void* h, const void* d, size_t bytes) -> int { if (h) CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream)); return 0; };
+        if ((rc = back(z, a.z_out, (size_t)batch * nz * 8))) return rc;
+        if ((rc = back(cost, a.cost, (size_t)batch * 8))) return rc;
+        if ((rc = back(viol, a.viol, (size_t)batch * 8))) return rc;
+        if ((rc = back(status, a.status, (size_t)batch * 4))) return rc;
+        if ((rc = back(iters, a.iters, (size_t)batch * 4))) return rc;
+        if ((rc = back(qp_iters, a.qp_iters, (size_t)batch * 4))) return rc;
+    }
+    CK(cudaStreamSynchronize(stream));     // temporaries are freed on return
     return B200MPC_OK;
 }

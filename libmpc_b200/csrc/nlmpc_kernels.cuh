@@ -126,6 +126,156 @@ struct NlEvalArgs {
     double* Jin;            // [batch, nineq, nz] row-major
 };
 
+// ---- evaluation of one instance by one warp (shared by the evaluation kernel and by the SQP kernel) ------------------
+// X,U: shared-memory scratch [(ph+1)*nx], [(ph+1)*nu].  Output pointers may be global or shared; Jacobians are row-major
+// with row stride ldj.  Any output pointer may be null.  All 32 lanes must call; ends with __syncwarp().
+template <class S>
+__device__ void nl_eval_instance(int lane, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
+                                 double* fval, double* grad, double* ceq, double* Jeq, double* cin, double* Jin, int ldj) {
+    constexpr int nx = S::nx, nu = S::nu;
+    const int nz = ph * nx + ch * nu + 1;
+    const double dv = 1.4901161193847656e-08;     // sqrt(DBL_EPSILON)  (Objective.hpp:283)
+    // unwrapVector: X row 0 = x0, rows 1..ph from z; U row i = block min(i, ch-1), last row repeated
+    for (int e = lane; e < (ph + 1) * nx; e += 32) {
+        int i = e / nx, j = e - i * nx;
+        X[e] = i == 0 ? x0[j] : z[(i - 1) * nx + j];
+    }
+    for (int e = lane; e < (ph + 1) * nu; e += 32) {
+        int i = e / nu, j = e - i * nu;
+        int st = i < ph ? i : ph - 1;
+        int blk = st < ch ? st : ch - 1;
+        U[e] = z[ph * nx + blk * nu + j];
+    }
+    const double slack = z[nz - 1];
+    __syncwarp();
+    Acc base{X, U, nx, nu, 0, 0, 0, 0.0};
+    double f0 = 0;
+    if (fval || grad) {
+        f0 = S::cost(base, slack, ph, p);
+        if (fval && lane == 0) *fval = f0;
+    }
+    if (grad) {
+        double* g = grad;
+        for (int e = lane; e < nz; e += 32) g[e] = 0.0;
+        __syncwarp();
+        for (int t = lane; t < ph * nx; t += 32) {          // step uses Xa.array()(j): linear index j (column-major)
+            int i = t / nx, j = t - i * nx;
+            int lr = j % (ph + 1), lc = j / (ph + 1);
+            double dx = dv * fmax(fabs(X[lr * nx + lc]), 1.0);
+            Acc ac = base; ac.kind = 1; ac.row = i + 1; ac.col = j; ac.d = dx;
+            g[i * nx + j] = (S::cost(ac, slack, ph, p) - f0) / dx;
+        }
+        for (int t = lane; t < ph * nu; t += 32) {          // stage ph-1 moves together with the duplicated row ph
+            int i = t / nu, j = t - i * nu;
+            int lr = j % (ph + 1), lc = j / (ph + 1);
+            double du = dv * fmax(fabs(U[lr * nu + lc]), 1.0);
+            Acc ac = base; ac.kind = (i == ph - 1) ? 3 : 2; ac.row = i; ac.col = j; ac.d = du;
+            double df = (S::cost(ac, slack, ph, p) - f0) / du;
+            int blk = i < ch ? i : ch - 1;
+            atomicAdd(&g[ph * nx + blk * nu + j], df);
+        }
+        if (lane == 0) {
+            double ea = fmax(dv, fabs(slack)), de = ea * dv;
+            g[nz - 1] = (S::cost(base, slack + de, ph, p) - S::cost(base, slack - de, ph, p)) / (2 * de);
+        }
+    }
+    if (ceq) {
+        double* c = ceq;
+        double* J = Jeq;
+        if (J) for (int e = lane; e < ph * nx * ldj; e += 32) J[e] = 0.0;
+        __syncwarp();
+        const double h = S::Ts(p) / 2.0;
+        for (int i = lane; i < ph; i += 32) {
+            double xk[nx], xk1[nx], uk[nu], fk[nx], fk1[nx];
+            for (int j = 0; j < nx; ++j) { xk[j] = X[i * nx + j]; xk1[j] = X[(i + 1) * nx + j]; }
+            for (int j = 0; j < nu; ++j) uk[j] = U[i * nu + j];
+            if (S::continuous) {
+                S::f(fk, xk, uk, i, p); S::f(fk1, xk1, uk, i, p);
+                for (int j = 0; j < nx; ++j) c[i * nx + j] = xk[j] + (h * (fk[j] + fk1[j])) - xk1[j];
+            } else {
+                S::f(fk, xk, uk, i, p);
+                for (int j = 0; j < nx; ++j) c[i * nx + j] = xk1[j] - fk[j];
+            }
+        }
+        if (J) {
+            const int per_stage = nx + nu;
+            for (int t = lane; t < ph * per_stage; t += 32) {
+                int i = t / per_stage, q = t - i * per_stage;
+                double xk[nx], xk1[nx], uk[nu], fp[nx], fm[nx];
+                for (int j = 0; j < nx; ++j) { xk[j] = X[i * nx + j]; xk1[j] = X[(i + 1) * nx + j]; }
+                for (int j = 0; j < nu; ++j) uk[j] = U[i * nu + j];
+                int blk = i < ch ? i : ch - 1;
+                if (q < nx) {
+                    double dx = dv * fmax(fabs(xk[q]), 1.0), keep = xk[q];
+                    xk[q] = keep + dx; S::f(fp, xk, uk, i, p);
+                    xk[q] = keep - dx; S::f(fm, xk, uk, i, p);
+                    xk[q] = keep;
+                    if (S::continuous) {
+                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = (r == q ? 1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx));
+                        double dx1 = dv * fmax(fabs(xk1[q]), 1.0), keep1 = xk1[q];
+                        xk1[q] = keep1 + dx1; S::f(fp, xk1, uk, i, p);
+                        xk1[q] = keep1 - dx1; S::f(fm, xk1, uk, i, p);
+                        xk1[q] = keep1;
+                        for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? -1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx1));
+                    } else {
+                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = -((fp[r] - fm[r]) / (2 * dx));
+                        for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? 1.0 : 0.0);
+                    }
+                } else {
+                    int qu = q - nx;
+                    double du = dv * fmax(fabs(uk[qu]), 1.0), keep = uk[qu];
+                    uk[qu] = keep + du; S::f(fp, xk, uk, i, p);
+                    uk[qu] = keep - du; S::f(fm, xk, uk, i, p);
+                    uk[qu] = keep;
+                    double Bk[nx];
+                    for (int r = 0; r < nx; ++r) Bk[r] = (fp[r] - fm[r]) / (2 * du);
+                    if (S::continuous) {
+                        uk[qu] = keep + du; S::f(fp, xk1, uk, i, p);
+                        uk[qu] = keep - du; S::f(fm, xk1, uk, i, p);
+                        uk[qu] = keep;
+                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], h * (Bk[r] + (fp[r] - fm[r]) / (2 * du)));
+                    } else {
+                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], -Bk[r]);
+                    }
+                }
+            }
+        }
+    }
+    if (cin) {
+        const int ni = S::nineq(ph);
+        double* c = cin;
+        for (int r = lane; r < ni; r += 32) c[r] = S::ineq(r, base, slack, ph, p);
+        if (Jin) {
+            double* J = Jin;
+            for (int e = lane; e < ni * ldj; e += 32) J[e] = 0.0;
+            __syncwarp();
+            for (int t = lane; t < ph * nx; t += 32) {
+                int i = t / nx, j = t - i * nx;
+                int lr = j % (ph + 1), lc = j / (ph + 1);
+                double dx = dv * fmax(fabs(X[lr * nx + lc]), 1.0);
+                Acc ap = base; ap.kind = 1; ap.row = i + 1; ap.col = j; ap.d = dx;
+                Acc am = ap; am.d = -dx;
+                for (int r = 0; r < ni; ++r) J[(size_t)r * ldj + i * nx + j] = (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * dx);
+            }
+            for (int t = lane; t < ph * nu; t += 32) {     // every one of the ph rows alone (row ph is never perturbed)
+                int i = t / nu, j = t - i * nu;
+                int lr = j % (ph + 1), lc = j / (ph + 1);
+                double du = dv * fmax(fabs(U[lr * nu + lc]), 1.0);
+                Acc ap = base; ap.kind = 2; ap.row = i; ap.col = j; ap.d = du;
+                Acc am = ap; am.d = -du;
+                int blk = i < ch ? i : ch - 1;
+                for (int r = 0; r < ni; ++r)
+                    atomicAdd(&J[(size_t)r * ldj + ph * nx + blk * nu + j], (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * du));
+            }
+            if (lane == 0) {
+                double ea = fmax(dv, fabs(slack)), de = ea * dv;
+                for (int r = 0; r < ni; ++r) J[(size_t)r * ldj + nz - 1] = (S::ineq(r, base, slack + de, ph, p) - S::ineq(r, base, slack - de, ph, p)) / (2 * de);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 template <class S>
 __global__ void __launch_bounds__(128) nlmpc_eval_kernel(const NlEvalArgs a) {
     extern __shared__ __align__(16) double nl_smem[];
@@ -133,158 +283,14 @@ __global__ void __launch_bounds__(128) nlmpc_eval_kernel(const NlEvalArgs a) {
     const int ph = a.ph, ch = a.ch;
     const int nz = ph * nx + ch * nu + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const int per_warp = (ph + 1) * (nx + nu);
-    double* X = nl_smem + (size_t)warp * per_warp;
+    double* X = nl_smem + (size_t)warp * (ph + 1) * (nx + nu);
     double* U = X + (ph + 1) * nx;
-    const double dv = 1.4901161193847656e-08;     // sqrt(DBL_EPSILON)  (Objective.hpp:283)
+    const int ni = S::nineq(ph);
     for (int inst = blockIdx.x * wpb + warp; inst < a.batch; inst += gridDim.x * wpb) {
-        const double* z = a.z + (size_t)inst * nz;
-        const double* p = a.params + (size_t)inst * a.param_stride;
-        // ---- unwrapVector: X row 0 = x0, rows 1..ph from z; U row i = block min(i, ch-1), last row repeated
-        for (int e = lane; e < (ph + 1) * nx; e += 32) {
-            int i = e / nx, j = e - i * nx;
-            X[e] = i == 0 ? a.x0[(size_t)inst * nx + j] : z[(i - 1) * nx + j];
-        }
-        for (int e = lane; e < (ph + 1) * nu; e += 32) {
-            int i = e / nu, j = e - i * nu;
-            int st = i < ph ? i : ph - 1;
-            int blk = st < ch ? st : ch - 1;
-            U[e] = z[ph * nx + blk * nu + j];
-        }
-        const double slack = z[nz - 1];
-        __syncwarp();
-        Acc base{X, U, nx, nu, 0, 0, 0, 0.0};
-        // ---- objective + forward-difference gradient
-        const double f0 = S::cost(base, slack, ph, p);
-        if (a.fval && lane == 0) a.fval[inst] = f0;
-        if (a.grad) {
-            double* g = a.grad + (size_t)inst * nz;
-            for (int e = lane; e < nz; e += 32) g[e] = 0.0;
-            __syncwarp();
-            // X entries: step uses Xa.array()(j) = linear index j of the column-major (ph+1) x nx matrix
-            for (int t = lane; t < ph * nx; t += 32) {
-                int i = t / nx, j = t - i * nx;
-                int lr = j % (ph + 1), lc = j / (ph + 1);
-                double xa = fmax(fabs(X[lr * nx + lc]), 1.0);
-                double dx = dv * xa;
-                Acc ac = base; ac.kind = 1; ac.row = i + 1; ac.col = j; ac.d = dx;
-                g[i * nx + j] = (S::cost(ac, slack, ph, p) - f0) / dx;
-            }
-            // U entries: stages 0..ph-2 alone, stage ph-1 together with the duplicated row ph; chain through Iz2u'
-            for (int t = lane; t < ph * nu; t += 32) {
-                int i = t / nu, j = t - i * nu;
-                int lr = j % (ph + 1), lc = j / (ph + 1);
-                double ua = fmax(fabs(U[lr * nu + lc]), 1.0);
-                double du = dv * ua;
-                Acc ac = base; ac.kind = (i == ph - 1) ? 3 : 2; ac.row = i; ac.col = j; ac.d = du;
-                double df = (S::cost(ac, slack, ph, p) - f0) / du;
-                int blk = i < ch ? i : ch - 1;
-                atomicAdd(&g[ph * nx + blk * nu + j], df);
-            }
-            if (lane == 0) {
-                double ea = fmax(dv, fabs(slack)), de = ea * dv;
-                g[nz - 1] = (S::cost(base, slack + de, ph, p) - S::cost(base, slack - de, ph, p)) / (2 * de);
-            }
-        }
-        // ---- dynamics equality constraints (multiple shooting) + central-difference Jacobian
-        if (a.ceq) {
-            double* c = a.ceq + (size_t)inst * ph * nx;
-            double* J = a.Jeq ? a.Jeq + (size_t)inst * ph * nx * nz : nullptr;
-            if (J) for (int e = lane; e < ph * nx * nz; e += 32) J[e] = 0.0;
-            __syncwarp();
-            const double h = S::Ts(p) / 2.0;
-            for (int i = lane; i < ph; i += 32) {
-                double xk[nx], xk1[nx], uk[nu], fk[nx], fk1[nx];
-                for (int j = 0; j < nx; ++j) { xk[j] = X[i * nx + j]; xk1[j] = X[(i + 1) * nx + j]; }
-                for (int j = 0; j < nu; ++j) uk[j] = U[i * nu + j];
-                if (S::continuous) {
-                    S::f(fk, xk, uk, i, p); S::f(fk1, xk1, uk, i, p);
-                    for (int j = 0; j < nx; ++j) c[i * nx + j] = xk[j] + (h * (fk[j] + fk1[j])) - xk1[j];
-                } else {
-                    S::f(fk, xk, uk, i, p);
-                    for (int j = 0; j < nx; ++j) c[i * nx + j] = xk1[j] - fk[j];
-                }
-            }
-            if (J) {
-                // one task = one (stage, perturbed entry): columns of A_k/B_k (and A_{k+1}/B_{k+1} when continuous)
-                const int per_stage = nx + nu;
-                for (int t = lane; t < ph * per_stage; t += 32) {
-                    int i = t / per_stage, q = t - i * per_stage;
-                    double xk[nx], xk1[nx], uk[nu], fp[nx], fm[nx];
-                    for (int j = 0; j < nx; ++j) { xk[j] = X[i * nx + j]; xk1[j] = X[(i + 1) * nx + j]; }
-                    for (int j = 0; j < nu; ++j) uk[j] = U[i * nu + j];
-                    int blk = i < ch ? i : ch - 1;
-                    if (q < nx) {
-                        // d f(xk,uk)/d xk[q]
-                        double dx = dv * fmax(fabs(xk[q]), 1.0), keep = xk[q];
-                        xk[q] = keep + dx; S::f(fp, xk, uk, i, p);
-                        xk[q] = keep - dx; S::f(fm, xk, uk, i, p);
-                        xk[q] = keep;
-                        if (S::continuous) {
-                            if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * nz + (i - 1) * nx + q] = (r == q ? 1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx));
-                            double dx1 = dv * fmax(fabs(xk1[q]), 1.0), keep1 = xk1[q];
-                            xk1[q] = keep1 + dx1; S::f(fp, xk1, uk, i, p);
-                            xk1[q] = keep1 - dx1; S::f(fm, xk1, uk, i, p);
-                            xk1[q] = keep1;
-                            for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * nz + i * nx + q] = (r == q ? -1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx1));
-                        } else {
-                            if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * nz + (i - 1) * nx + q] = -((fp[r] - fm[r]) / (2 * dx));
-                            for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * nz + i * nx + q] = (r == q ? 1.0 : 0.0);
-                        }
-                    } else {
-                        int qu = q - nx;
-                        double du = dv * fmax(fabs(uk[qu]), 1.0), keep = uk[qu];
-                        uk[qu] = keep + du; S::f(fp, xk, uk, i, p);
-                        uk[qu] = keep - du; S::f(fm, xk, uk, i, p);
-                        uk[qu] = keep;
-                        double Bk[nx];
-                        for (int r = 0; r < nx; ++r) Bk[r] = (fp[r] - fm[r]) / (2 * du);
-                        if (S::continuous) {
-                            uk[qu] = keep + du; S::f(fp, xk1, uk, i, p);
-                            uk[qu] = keep - du; S::f(fm, xk1, uk, i, p);
-                            uk[qu] = keep;
-                            for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * nz + ph * nx + blk * nu + qu], h * (Bk[r] + (fp[r] - fm[r]) / (2 * du)));
-                        } else {
-                            for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * nz + ph * nx + blk * nu + qu], -Bk[r]);
-                        }
-                    }
-                }
-            }
-        }
-        // ---- user inequality constraints + central-difference Jacobian
-        if (a.cin) {
-            const int ni = S::nineq(ph);
-            double* c = a.cin + (size_t)inst * ni;
-            for (int r = lane; r < ni; r += 32) c[r] = S::ineq(r, base, slack, ph, p);
-            if (a.Jin) {
-                double* J = a.Jin + (size_t)inst * ni * nz;
-                for (int e = lane; e < ni * nz; e += 32) J[e] = 0.0;
-                __syncwarp();
-                for (int t = lane; t < ph * nx; t += 32) {
-                    int i = t / nx, j = t - i * nx;
-                    int lr = j % (ph + 1), lc = j / (ph + 1);
-                    double dx = dv * fmax(fabs(X[lr * nx + lc]), 1.0);
-                    Acc ap = base; ap.kind = 1; ap.row = i + 1; ap.col = j; ap.d = dx;
-                    Acc am = ap; am.d = -dx;
-                    for (int r = 0; r < ni; ++r) J[(size_t)r * nz + i * nx + j] = (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * dx);
-                }
-                for (int t = lane; t < ph * nu; t += 32) {     // every one of the ph rows alone (row ph is never perturbed)
-                    int i = t / nu, j = t - i * nu;
-                    int lr = j % (ph + 1), lc = j / (ph + 1);
-                    double du = dv * fmax(fabs(U[lr * nu + lc]), 1.0);
-                    Acc ap = base; ap.kind = 2; ap.row = i; ap.col = j; ap.d = du;
-                    Acc am = ap; am.d = -du;
-                    int blk = i < ch ? i : ch - 1;
-                    for (int r = 0; r < ni; ++r)
-                        atomicAdd(&J[(size_t)r * nz + ph * nx + blk * nu + j], (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * du));
-                }
-                if (lane == 0) {
-                    double ea = fmax(dv, fabs(slack)), de = ea * dv;
-                    for (int r = 0; r < ni; ++r) J[(size_t)r * nz + nz - 1] = (S::ineq(r, base, slack + de, ph, p) - S::ineq(r, base, slack - de, ph, p)) / (2 * de);
-                }
-            }
-        }
-        __syncwarp();
+        nl_eval_instance<S>(lane, ph, ch, a.z + (size_t)inst * nz, a.x0 + (size_t)inst * nx, a.params + (size_t)inst * a.param_stride, X, U,
+                            a.fval ? a.fval + inst : nullptr, a.grad ? a.grad + (size_t)inst * nz : nullptr,
+                            a.ceq ? a.ceq + (size_t)inst * ph * nx : nullptr, a.Jeq ? a.Jeq + (size_t)inst * ph * nx * nz : nullptr,
+                            a.cin ? a.cin + (size_t)inst * ni : nullptr, a.Jin ? a.Jin + (size_t)inst * ni * nz : nullptr, nz);
     }
 }
 
