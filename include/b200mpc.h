@@ -168,11 +168,13 @@ int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const double* z, c
  *   constraints are off, NLOptimizer.hpp:221-260); shared by the batch.
  *   outputs: z[batch*nz], cost[batch], viol[batch] (sum |c_eq| + sum max(c_in,0) at the solution),
  *   status[batch] (0 converged, 1 iteration limit), iters[batch] (major iterations), qp_iters[batch].
- * The supported size is bounded by shared memory (b200mpc_nlmpc_solve_smem_bytes <= 227 KB); larger systems -> EINVAL. */
+ * Problems whose matrices fit shared memory (b200mpc_nlmpc_solve_smem_bytes <= 227 KB) run entirely on chip; larger
+ * ones keep the matrices in a per-warp HBM workspace (L2-resident) and only the vectors in shared memory. */
 typedef struct {
     int32_t max_sqp;      /* major iterations (NLParameters::maximum_iteration, default 100)                 */
     int32_t max_qp;       /* ADMM iterations per QP subproblem                                               */
-    double tol;           /* relative step tolerance (NLParameters::relative_xtol/ftol play this role)       */
+    double tol;           /* relative step tolerance (NLParameters::relative_xtol plays this role)           */
+    double ftol;          /* stop when |g'd| < ftol*max(1,|f|) and feasible (NLParameters::relative_ftol)   */
     double qp_eps;        /* QP residual tolerance                                                            */
     double rho;           /* initial ADMM penalty                                                             */
 } b200mpc_nlmpc_params;

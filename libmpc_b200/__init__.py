@@ -43,7 +43,8 @@ _lib = None
 
 
 class _NLParams(C.Structure):
-    _fields_ = [("max_sqp", C.c_int32), ("max_qp", C.c_int32), ("tol", C.c_double), ("qp_eps", C.c_double), ("rho", C.c_double)]
+    _fields_ = [("max_sqp", C.c_int32), ("max_qp", C.c_int32), ("tol", C.c_double), ("ftol", C.c_double), ("qp_eps", C.c_double),
+                ("rho", C.c_double)]
 
 
 def load_library():
@@ -523,7 +524,8 @@ FLT_INF = float(np.float32(np.inf))
 @dataclass
 class NLParameters:
     """mpc::NLParameters (Types.hpp:121-140).  The reference's four NLopt tolerances default to "disabled" (-1), which makes
-    NLopt run to maximum_iteration; here the tightest positive one of them (else 1e-7) is the SQP's relative step tolerance."""
+    NLopt run to maximum_iteration; here positive xtol / ftol values become the SQP's step / |g'd| tolerances (defaults 1e-7 /
+    1e-12, i.e. convergence to the finite-difference noise floor)."""
     maximum_iteration: int = 100
     time_limit: float = 0.0
     enable_warm_start: bool = False
@@ -535,7 +537,7 @@ class NLParameters:
     verbose: bool = False
 
 
-def nlmpc_solve(system, ph, ch, z0, x0, params, lb, ub, max_sqp=100, max_qp=1000, tol=1e-7, qp_eps=1e-9, rho=0.1):
+def nlmpc_solve(system, ph, ch, z0, x0, params, lb, ub, max_sqp=100, max_qp=200, tol=1e-7, ftol=1e-12, qp_eps=1e-5, rho=0.1):
     """Batched NLOptimizer::run core (NLOptimizer.hpp:519): z0 [B,nz] -> dict(z, cost, viol, status, iters, qp_iters)."""
     lib = load_library()
     d = nlmpc_system_dims(system, ph)
@@ -551,7 +553,7 @@ def nlmpc_solve(system, ph, ch, z0, x0, params, lb, ub, max_sqp=100, max_qp=1000
     lb = np.ascontiguousarray(lb, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
     if lb.shape != (nz,) or ub.shape != (nz,):
         raise ValueError("lb/ub must have nz entries")
-    q = _NLParams(int(max_sqp), int(max_qp), float(tol), float(qp_eps), float(rho))
+    q = _NLParams(int(max_sqp), int(max_qp), float(tol), float(ftol), float(qp_eps), float(rho))
     out = dict(z=np.zeros((B, nz)), cost=np.zeros(B), viol=np.zeros(B), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32),
                qp_iters=np.zeros(B, np.int32))
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -573,8 +575,6 @@ class NLMPC:
         self.system, self.ph, self.ch, self.batch = system, ph, ch, batch
         self.nx, self.nu, self.nparam, self.nineq = d["nx"], d["nu"], d["nparam"], d["nineq"]
         self.nz = ph * self.nx + ch * self.nu + 1
-        if self.lib.b200mpc_nlmpc_solve_smem_bytes(system, ph, ch) > 227 * 1024:
-            raise ValueError("problem too large for the shared-memory SQP kernel (see DESIGN.md: stage-structured kernel is next)")
         self.lb = np.full(self.nz, -FLT_INF); self.ub = np.full(self.nz, FLT_INF)     # NLOptimizer.hpp:69-73
         self.params = None
         self.p = NLParameters()
@@ -669,9 +669,10 @@ class NLMPC:
         x0 = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(x0, float)), (B, self.nx)))
         u0 = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(lastU, float)), (B, self.nu)))
         z0 = self._initial_guess(x0, u0)
-        tols = [t for t in (self.p.relative_xtol, self.p.relative_ftol, self.p.absolute_xtol, self.p.absolute_ftol) if t > 0]
+        xt = [t for t in (self.p.relative_xtol, self.p.absolute_xtol) if t > 0]
+        ft = [t for t in (self.p.relative_ftol, self.p.absolute_ftol) if t > 0]
         r = nlmpc_solve(self.system, self.ph, self.ch, z0, x0, self.params, self.lb, self.ub, max_sqp=self.p.maximum_iteration,
-                        tol=min(tols) if tols else 1e-7)
+                        tol=min(xt) if xt else 1e-7, ftol=min(ft) if ft else 1e-12)
         z = r["z"]
         self.opt_vector = z.copy()
         self.is_first_iteration = False

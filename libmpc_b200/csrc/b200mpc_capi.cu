@@ -578,32 +578,59 @@ extern "C" int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const d
 // ---- NLMPC solve (K6/K7) ---------------------------------------------------------------------------------------------
 extern "C" void b200mpc_nlmpc_default_params(b200mpc_nlmpc_params* p) {
     if (!p) return;
-    p->max_sqp = 100; p->max_qp = 1000; p->tol = 1e-7; p->qp_eps = 1e-9; p->rho = 0.1;
+    p->max_sqp = 100; p->max_qp = 200; p->tol = 1e-7; p->ftol = 1e-12; p->qp_eps = 1e-5; p->rho = 0.1;
 }
 
+// shared memory one controller needs when the matrices are shared-memory resident (the fast path)
 static size_t nl_solve_smem(int system, int ph, int ch) {
     int nx, nu, np, ni;
     if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return 0;
-    return NlWs::doubles(ph * nx + ch * nu + 1, ph * nx, ni, ph, nx, nu) * sizeof(double);
+    int n = ph * nx + ch * nu + 1, me = ph * nx;
+    return (NlWs::vec_doubles(n, me, ni, ph, nx, nu) + NlWs::mat_doubles(n, me, ni, false)) * sizeof(double);
 }
 extern "C" long long b200mpc_nlmpc_solve_smem_bytes(int system, int ph, int ch) { return (long long)nl_solve_smem(system, ph, ch); }
 
 template <class S>
-static int nl_solve_t(const NlSolveArgs& a, size_t per_warp, cudaStream_t stream) {
+static int nl_solve_t(NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree) {
     int dev = 0, sms = 0, maxsm = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (per_warp > (size_t)maxsm) return fail(B200MPC_EINVAL, "NLMPC problem too large for the shared-memory SQP kernel");
-    int wpb = (2 * per_warp <= (size_t)maxsm / 2) ? 2 : 1;      // keep >= 2 CTAs per SM when the problem is small
-    size_t smem = per_warp * wpb;
-    CK(cudaFuncSetAttribute(nlmpc_solve_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nlmpc_solve_kernel<S>, wpb * 32, smem));
-    if (occ < 1) occ = 1;
-    int grid = (a.batch + wpb - 1) / wpb;
-    if (grid > sms * occ) grid = sms * occ;
-    nlmpc_solve_kernel<S><<<grid, wpb * 32, smem, stream>>>(a);
+    const int n = a.ph * S::nx + a.ch * S::nu + 1, me = a.ph * S::nx;
+    int ni = 0, d0, d1, d2;
+    nl_dims(S::id, &d0, &d1, &d2, a.ph, &ni);
+    const size_t vecb = NlWs::vec_doubles(n, me, ni, a.ph, S::nx, S::nu) * sizeof(double);
+    const size_t matb = NlWs::mat_doubles(n, me, ni, false) * sizeof(double);
+    a.mat_ws = nullptr;
+    if (vecb + matb <= (size_t)maxsm) {                       // matrices resident in shared memory
+        size_t per_warp = vecb + matb;
+        int wpb = (2 * per_warp <= (size_t)maxsm / 2) ? 2 : 1;
+        size_t smem = per_warp * wpb;
+        CK(cudaFuncSetAttribute(nlmpc_solve_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nlmpc_solve_kernel<S, false>, wpb * 32, smem));
+        if (occ < 1) occ = 1;
+        int grid = (a.batch + wpb - 1) / wpb;
+        if (grid > sms * occ) grid = sms * occ;
+        nlmpc_solve_kernel<S, false><<<grid, wpb * 32, smem, stream>>>(a);
+    } else {                                                  // matrices in a per-warp-slot HBM workspace (L2-resident)
+        if (vecb > (size_t)maxsm) return fail(B200MPC_EINVAL, "NLMPC problem too large: its vectors do not fit shared memory");
+        int wpb = (int)((size_t)maxsm / vecb);
+        if (wpb > 4) wpb = 4;
+        size_t smem = vecb * wpb;
+        CK(cudaFuncSetAttribute(nlmpc_solve_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nlmpc_solve_kernel<S, true>, wpb * 32, smem));
+        if (occ < 1) occ = 1;
+        int grid = (a.batch + wpb - 1) / wpb;
+        if (grid > sms * occ) grid = sms * occ;
+        size_t slots = (size_t)grid * wpb, matd = NlWs::mat_doubles(n, me, ni, true);
+        void* ws = nullptr;
+        CK(cudaMalloc(&ws, slots * matd * sizeof(double)));
+        tofree.push_back(ws);
+        a.mat_ws = (double*)ws;
+        nlmpc_solve_kernel<S, true><<<grid, wpb * 32, smem, stream>>>(a);
+    }
     CK(cudaGetLastError());
     return B200MPC_OK;
 }
@@ -618,13 +645,12 @@ extern "C" int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const 
     if (ph < 1 || ch < 1 || ch > ph || batch < 1 || !z0 || !x0 || !sys_params || !lb || !ub || !z) return fail(B200MPC_EINVAL, "bad arguments");
     b200mpc_nlmpc_params q;
     if (prm) q = *prm; else b200mpc_nlmpc_default_params(&q);
-    if (q.max_sqp < 1 || q.max_qp < 25 || !(q.tol > 0) || !(q.qp_eps > 0) || !(q.rho > 0)) return fail(B200MPC_EINVAL, "bad NLMPC parameters");
+    if (q.max_sqp < 1 || q.max_qp < 25 || !(q.tol > 0) || !(q.ftol >= 0) || !(q.qp_eps > 0) || !(q.rho > 0)) return fail(B200MPC_EINVAL, "bad NLMPC parameters");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int nz = ph * nx + ch * nu + 1;
-    const size_t per_warp = nl_solve_smem(system, ph, ch);
     NlSolveArgs a;
     a.ph = ph; a.ch = ch; a.batch = batch; a.param_stride = params_per_instance ? np : 0;
-    a.max_sqp = q.max_sqp; a.max_qp = q.max_qp; a.tol = q.tol; a.qp_eps = q.qp_eps; a.rho0 = q.rho;
+    a.max_sqp = q.max_sqp; a.max_qp = q.max_qp; a.tol = q.tol; a.ftol = q.ftol; a.qp_eps = q.qp_eps; a.rho0 = q.rho;
     std::vector<void*> tofree;
     struct Free { std::vector<void*>& v; ~Free() { for (void* p : v) cudaFree(p); } } freer{tofree};
     auto in = [&](const double* h, size_t n, const double** d) -> int {
@@ -653,10 +679,10 @@ extern "C" int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const 
     if ((rc = out(iters, (size_t)batch * 4, (void**)&a.iters))) return rc;
     if ((rc = out(qp_iters, (size_t)batch * 4, (void**)&a.qp_iters))) return rc;
     switch (system) {
-    case B200MPC_SYS_VANDERPOL: rc = nl_solve_t<SysVanDerPol>(a, per_warp, stream); break;
-    case B200MPC_SYS_OSCNET4: rc = nl_solve_t<SysOscNet<4>>(a, per_warp, stream); break;
-    case B200MPC_SYS_OSCNET6: rc = nl_solve_t<SysOscNet<6>>(a, per_warp, stream); break;
-    default: rc = nl_solve_t<SysUgv>(a, per_warp, stream); break;
+    case B200MPC_SYS_VANDERPOL: rc = nl_solve_t<SysVanDerPol>(a, stream, tofree); break;
+    case B200MPC_SYS_OSCNET4: rc = nl_solve_t<SysOscNet<4>>(a, stream, tofree); break;
+    case B200MPC_SYS_OSCNET6: rc = nl_solve_t<SysOscNet<6>>(a, stream, tofree); break;
+    default: rc = nl_solve_t<SysUgv>(a, stream, tofree); break;
     }
     if (rc) return rc;
     if (!dev) {

@@ -36,6 +36,7 @@ struct Acc {
 // ---- built-in systems ---------------------------------------------------------------------------------------------
 // examples/vanderpol_ex.cpp:9-71 -- params: [Ts]
 struct SysVanDerPol {
+    static constexpr int id = 0;
     static constexpr int nx = 2, nu = 1, ny = 2, nparam = 1;
     static constexpr bool continuous = true;
     __device__ static double Ts(const double* p) { return p[0]; }
@@ -56,6 +57,7 @@ struct SysVanDerPol {
 // examples/networked_oscillators_ex.cpp:5-72 -- params: [Ts, mu, k]
 template <int N>
 struct SysOscNet {
+    static constexpr int id = N == 4 ? 1 : 2;
     static constexpr int nx = 2 * N, nu = N, ny = 2 * N, nparam = 3;
     static constexpr bool continuous = true;
     __device__ static double Ts(const double* p) { return p[0]; }
@@ -81,6 +83,7 @@ struct SysOscNet {
 // examples/ugv_ex.cpp:12-126 -- discrete double integrator, 2 circular obstacles, soft constraints.
 // params: [Ad(16) | Bd(8) | v_pref(2) | obs0(x,y,r) | obs1(x,y,r)]  (C = I, D = 0: y = x)
 struct SysUgv {
+    static constexpr int id = 3;
     static constexpr int nx = 4, nu = 2, ny = 4, nparam = 16 + 8 + 2 + 6, nobs = 2;
     static constexpr bool continuous = false;
     __device__ static double Ts(const double*) { return 0.0; }

@@ -24,13 +24,14 @@ struct NlSolveArgs {
     const double* params; long long param_stride;
     const double* lb; const double* ub;      // [nz] shared by the batch
     int max_sqp, max_qp;
-    double tol, qp_eps, rho0;
+    double tol, ftol, qp_eps, rho0;
     double* z_out;          // [batch, nz]
     double* cost;           // [batch]
     double* viol;           // [batch] sum |c_eq| + sum max(c_in,0) at the solution
     int* status;            // 0 converged, 1 iteration limit
     int* iters;             // SQP iterations
     int* qp_iters;          // total ADMM iterations
+    double* mat_ws;         // GM kernels: per-warp-slot matrix workspace [grid * warps][mat_doubles]
 };
 
 __device__ __forceinline__ double nl_wmax(double v) {
@@ -45,80 +46,109 @@ __device__ __forceinline__ double nl_wsum(double v) {
 }
 __device__ __forceinline__ double nl_lim(double v) { v = v < 1e-4 ? 1.0 : v; return v > 1e4 ? 1e4 : v; }
 
-// Per-warp shared-memory view
+// Per-warp workspace.  Vectors always live in shared memory; the four matrices (B, KKT factor, J_eq, J_in) live in shared
+// memory when the problem is small (GM = false: vanderpol, the shipped ugv) and in a per-warp-slot HBM/L2 workspace
+// otherwise (GM = true), where every matrix pass below runs with lanes along the contiguous (column) index.
 struct NlWs {
-    int n, me, mi, m, ld;
+    int n, me, mi, m, ld, nx, nu, ph, ch;
     double *B, *H, *Je, *Ji;                 // n x ld, n x ld, me x ld, mi x ld (row-major)
     double *z, *g, *g2, *d, *xs, *xt, *D, *gs, *rhs, *tmp, *glo, *sv, *zt2;     // n
-    double *E, *ls, *us, *zs, *ys, *rho, *yq, *w;                               // m
+    double *E, *ls, *us, *zs, *ys, *rho, *yq, *w, *pr, *pt;                     // m
     double *ce, *ci, *cet, *cit;                                                // me, mi, me, mi
     double *X, *U;
-    __host__ __device__ static size_t doubles(int n, int me, int mi, int ph, int nx, int nu) {
-        int ld = n | 1, m = me + mi + n;
-        return (size_t)2 * n * ld + (size_t)(me + mi) * ld + 13 * (size_t)n + 8 * (size_t)m + 2 * (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 8;
+    __host__ __device__ static int ldim(int n, bool gm) { return gm ? ((n + 3) & ~3) : (n | 1); }
+    __host__ __device__ static size_t mat_doubles(int n, int me, int mi, bool gm) { return (size_t)(2 * n + me + mi) * ldim(n, gm); }
+    __host__ __device__ static size_t vec_doubles(int n, int me, int mi, int ph, int nx, int nu) {
+        int m = me + mi + n;
+        return 13 * (size_t)n + 10 * (size_t)m + 2 * (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 8;
     }
-    __device__ void carve(double* p, int n_, int me_, int mi_, int ph, int nx, int nu) {
-        n = n_; me = me_; mi = mi_; m = me + mi + n; ld = n | 1;
-        B = p; p += (size_t)n * ld; H = p; p += (size_t)n * ld; Je = p; p += (size_t)me * ld; Ji = p; p += (size_t)mi * ld;
+    __device__ void carve(double* pm, double* p, bool gm, int n_, int me_, int mi_, int ph_, int ch_, int nx_, int nu_) {
+        n = n_; me = me_; mi = mi_; m = me + mi + n; ld = ldim(n, gm); nx = nx_; nu = nu_; ph = ph_; ch = ch_;
+        B = pm; pm += (size_t)n * ld; H = pm; pm += (size_t)n * ld; Je = pm; pm += (size_t)me * ld; Ji = pm;
         double** nv[] = {&z, &g, &g2, &d, &xs, &xt, &D, &gs, &rhs, &tmp, &glo, &sv, &zt2};
         for (auto q : nv) { *q = p; p += n; }
-        double** mv[] = {&E, &ls, &us, &zs, &ys, &rho, &yq, &w};
+        double** mv[] = {&E, &ls, &us, &zs, &ys, &rho, &yq, &w, &pr, &pt};
         for (auto q : mv) { *q = p; p += m; }
         ce = p; p += me; ci = p; p += mi; cet = p; p += me; cit = p; p += mi;
         X = p; p += (ph + 1) * nx; U = p;
     }
+    // Multiple-shooting sparsity of J_eq (Constraints.hpp:844-905): the rows of stage s touch X_{s-1}, X_s and the control
+    // block of stage s; column j is touched by the rows of at most two stages (states) or of its block's stages (inputs).
+    __device__ __forceinline__ void je_cols(int r, int& c0, int& c1, int& u0) const {
+        int s = r / nx; c0 = (s > 0 ? s - 1 : 0) * nx; c1 = (s + 1) * nx; u0 = ph * nx + (s < ch ? s : ch - 1) * nu;
+    }
+    __device__ __forceinline__ void je_rows(int j, int& r0, int& r1) const {
+        if (j < ph * nx) { int s = j / nx; r0 = s * nx; r1 = (s + 2) * nx; if (r1 > me) r1 = me; }
+        else if (j < n - 1) { int b = (j - ph * nx) / nu; r0 = b * nx; r1 = (b < ch - 1) ? (b + 1) * nx : me; }
+        else { r0 = r1 = 0; }
+    }
 };
 
-// row r of the constraint matrix A = [Je; Ji; I] (first me+mi rows only)
-__device__ __forceinline__ const double* nl_row(const NlWs& w, int r) { return r < w.me ? w.Je + (size_t)r * w.ld : w.Ji + (size_t)(r - w.me) * w.ld; }
+// out_j (+)= sum_r Je[r][j] v[r] + sum_r Ji[r][j] v[me + r], one lane per column j (coalesced / conflict-free)
+__device__ __forceinline__ double nl_col_dot(const NlWs& w, int j, const double* v) {
+    int r0, r1; w.je_rows(j, r0, r1);
+    double a = 0;
+    for (int r = r0; r < r1; ++r) a = fma(w.Je[(size_t)r * w.ld + j], v[r], a);
+    for (int r = 0; r < w.mi; ++r) a = fma(w.Ji[(size_t)r * w.ld + j], v[w.me + r], a);
+    return a;
+}
 
-// H = c D B D + sigma I + (E A D)' diag(rho) (E A D)  -> Cholesky -> inverse of the factor, all in w.H (lower triangle)
+// H = c D B D + sigma I + (E A D)' diag(rho) (E A D)  -> Cholesky -> inverse of the factor.  On return w.H holds the
+// symmetric fill S[q][i] = Linv[max(q,i)][min(q,i)], so that both triangular products of nl_kkt_apply read S down a column.
 __device__ bool nl_factor(NlWs& w, int lane, double c, double sigma) {
-    const int n = w.n, ld = w.ld, mc = w.me + w.mi;
+    const int n = w.n, ld = w.ld, me = w.me, mi = w.mi, mc = me + mi;
     for (int r = lane; r < mc; r += 32) w.w[r] = w.rho[r] * w.E[r] * w.E[r];
     __syncwarp();
-    const int npairs = n * (n + 1) / 2;
-    for (int pidx = lane; pidx < npairs; pidx += 32) {
-        int i = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= pidx) ++i;
-        while (i * (i + 1) / 2 > pidx) --i;
-        int j = pidx - i * (i + 1) / 2;
-        double acc = 0;
-        for (int r = 0; r < mc; ++r) { const double* a = nl_row(w, r); acc = fma(w.w[r] * a[i], a[j], acc); }
-        double v = w.D[i] * (c * w.B[(size_t)i * ld + j] + acc) * w.D[j];
-        if (i == j) { int rb = mc + i; v += sigma + w.rho[rb] * w.E[rb] * w.E[rb] * w.D[i] * w.D[i]; }
-        w.H[(size_t)i * ld + j] = v;
+    for (int i = 0; i < n; ++i) {                       // row i of the lower triangle, lanes along j <= i
+        int r0, r1; w.je_rows(i, r0, r1);
+        const double di = w.D[i];
+        for (int j = lane; j <= i; j += 32) {
+            double acc = 0;
+            for (int r = r0; r < r1; ++r) { const double* a = w.Je + (size_t)r * ld; acc = fma(w.w[r] * a[i], a[j], acc); }
+            for (int r = 0; r < mi; ++r) {
+                const double* a = w.Ji + (size_t)r * ld;
+                double ai = a[i];
+                if (ai != 0.0) acc = fma(w.w[me + r] * ai, a[j], acc);
+            }
+            double v = di * (c * w.B[(size_t)i * ld + j] + acc) * w.D[j];
+            if (i == j) { int rb = mc + i; v += sigma + w.rho[rb] * w.E[rb] * w.E[rb] * di * di; }
+            w.H[(size_t)i * ld + j] = v;
+        }
     }
     __syncwarp();
     bool ok = true;
-    for (int k = 0; k < n; ++k) {                       // right-looking Cholesky, lower, in place
+    for (int k = 0; k < n; ++k) {                       // right-looking Cholesky, lower, in place; column k staged in tmp
         double dkk = w.H[(size_t)k * ld + k];
         if (!(dkk > 0.0)) ok = false;
         double piv = sqrt(dkk), inv = 1.0 / piv;
         __syncwarp();
-        for (int r = k + lane; r < n; r += 32) w.H[(size_t)r * ld + k] = (r == k) ? piv : w.H[(size_t)r * ld + k] * inv;
+        for (int r = k + lane; r < n; r += 32) {
+            double v = (r == k) ? piv : w.H[(size_t)r * ld + k] * inv;
+            w.H[(size_t)r * ld + k] = v; w.tmp[r] = v;
+        }
         __syncwarp();
-        for (int r = k + 1 + lane; r < n; r += 32) {
-            double lrk = w.H[(size_t)r * ld + k];
-            for (int q = k + 1; q <= r; ++q) w.H[(size_t)r * ld + q] -= lrk * w.H[(size_t)q * ld + k];
+        for (int r = k + 1; r < n; ++r) {
+            const double lrk = w.tmp[r];
+            for (int q = k + 1 + lane; q <= r; q += 32) w.H[(size_t)r * ld + q] -= lrk * w.tmp[q];
         }
         __syncwarp();
     }
-    // in-place inverse of the lower-triangular factor (column by column from the right)
+    // inverse of the factor, built in the upper triangle as its transpose (U[q][r] = Linv[r][q]) from the last column back
     for (int j = n - 1; j >= 0; --j) {
-        double ljj = 1.0 / w.H[(size_t)j * ld + j];
+        const double ljj = 1.0 / w.H[(size_t)j * ld + j];
+        for (int q = j + 1 + lane; q < n; q += 32) w.tmp[q] = w.H[(size_t)q * ld + j];     // L[:, j]
         __syncwarp();
-        // t = Linv[j+1:, j+1:] * L[j+1:, j]
         for (int r = j + 1 + lane; r < n; r += 32) {
             double acc = 0;
-            for (int q = j + 1; q <= r; ++q) acc = fma(w.H[(size_t)r * ld + q], w.H[(size_t)q * ld + j], acc);
-            w.tmp[r] = acc;
+            for (int q = j + 1; q <= r; ++q) acc = fma(w.H[(size_t)q * ld + r], w.tmp[q], acc);
+            w.H[(size_t)j * ld + r] = -ljj * acc;
         }
-        __syncwarp();
-        for (int r = j + 1 + lane; r < n; r += 32) w.H[(size_t)r * ld + j] = -ljj * w.tmp[r];
         if (lane == 0) w.H[(size_t)j * ld + j] = ljj;
         __syncwarp();
     }
+    for (int j = 0; j < n; ++j)                         // mirror into the lower triangle
+        for (int r = j + 1 + lane; r < n; r += 32) w.H[(size_t)r * ld + j] = w.H[(size_t)j * ld + r];
+    __syncwarp();
     return !__any_sync(0xffffffffu, !ok);
 }
 
@@ -127,7 +157,7 @@ __device__ void nl_kkt_apply(NlWs& w, int lane) {
     const int n = w.n, ld = w.ld;
     for (int i = lane; i < n; i += 32) {
         double acc = 0;
-        for (int q = 0; q <= i; ++q) acc = fma(w.H[(size_t)i * ld + q], w.rhs[q], acc);
+        for (int q = 0; q <= i; ++q) acc = fma(w.H[(size_t)q * ld + i], w.rhs[q], acc);
         w.tmp[i] = acc;
     }
     __syncwarp();
@@ -138,17 +168,27 @@ __device__ void nl_kkt_apply(NlWs& w, int lane) {
     }
     __syncwarp();
 }
-// out_r = E_r * (A (D.x))_r for all m rows
+// out_r = E_r * (A (D.x))_r for all m rows: J_eq rows by their two column runs, J_in rows one warp per row
 __device__ void nl_As(NlWs& w, int lane, const double* x, double* out) {
-    const int n = w.n, mc = w.me + w.mi;
+    const int n = w.n, me = w.me, mc = w.me + w.mi, ld = w.ld;
     for (int i = lane; i < n; i += 32) w.tmp[i] = w.D[i] * x[i];
     __syncwarp();
-    for (int r = lane; r < w.m; r += 32) {
-        double a;
-        if (r < mc) { const double* row = nl_row(w, r); a = 0; for (int j = 0; j < n; ++j) a = fma(row[j], w.tmp[j], a); }
-        else a = w.tmp[r - mc];
+    for (int r = lane; r < me; r += 32) {
+        int c0, c1, u0; w.je_cols(r, c0, c1, u0);
+        const double* row = w.Je + (size_t)r * ld;
+        double a = 0;
+        for (int j = c0; j < c1; ++j) a = fma(row[j], w.tmp[j], a);
+        for (int j = u0; j < u0 + w.nu; ++j) a = fma(row[j], w.tmp[j], a);
         out[r] = w.E[r] * a;
     }
+    for (int r = 0; r < w.mi; ++r) {
+        const double* row = w.Ji + (size_t)r * ld;
+        double a = 0;
+        for (int j = lane; j < n; j += 32) a = fma(row[j], w.tmp[j], a);
+        a = nl_wsum(a);
+        if (lane == 0) out[me + r] = w.E[me + r] * a;
+    }
+    for (int j = lane; j < n; j += 32) out[mc + j] = w.E[mc + j] * w.tmp[j];
     __syncwarp();
 }
 // out_j = D_j * (A' (E.v))_j
@@ -156,12 +196,76 @@ __device__ void nl_Ats(NlWs& w, int lane, const double* v, double* out) {
     const int n = w.n, mc = w.me + w.mi;
     for (int r = lane; r < w.m; r += 32) w.w[r] = w.E[r] * v[r];
     __syncwarp();
-    for (int j = lane; j < n; j += 32) {
-        double a = w.w[mc + j];
-        for (int r = 0; r < mc; ++r) a = fma(nl_row(w, r)[j], w.w[r], a);
-        out[j] = w.D[j] * a;
+    for (int j = lane; j < n; j += 32) out[j] = w.D[j] * (w.w[mc + j] + nl_col_dot(w, j, w.w));
+    __syncwarp();
+}
+
+// out_i = (c D B D x)_i ; B symmetric, read down its columns
+__device__ void nl_Ps(NlWs& w, int lane, double c, const double* x, double* out) {
+    const int n = w.n, ld = w.ld;
+    for (int i = lane; i < n; i += 32) w.tmp[i] = w.D[i] * x[i];
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        double acc = 0;
+        for (int j = 0; j < n; ++j) acc = fma(w.B[(size_t)j * ld + i], w.tmp[j], acc);
+        out[i] = c * w.D[i] * acc;
     }
     __syncwarp();
+}
+
+// max bound violation of A x and max |P x + q + A' y| in the scaled problem (uses pt, rhs, zt2)
+__device__ void nl_qp_residuals(NlWs& w, int lane, double c, const double* x, const double* y, double& pri, double& dua) {
+    nl_As(w, lane, x, w.pt);
+    double p = 0, d = 0;
+    for (int r = lane; r < w.m; r += 32) p = fmax(p, fmax(fmax(w.ls[r] - w.pt[r], w.pt[r] - w.us[r]), 0.0));
+    nl_Ats(w, lane, y, w.rhs);
+    nl_Ps(w, lane, c, x, w.zt2);
+    for (int i = lane; i < w.n; i += 32) d = fmax(d, fabs(w.zt2[i] + w.gs[i] + w.rhs[i]));
+    pri = nl_wmax(p); dua = nl_wmax(d);
+}
+
+// OSQP polish.c on the dense QP: guess the active set from (z, y), solve the equality-constrained QP on it through the
+// same reduced system (rho = 1/delta on active rows, sigma = delta) with iterative refinement, keep the result if both
+// residuals improve.  In: xs, ys, zs.  Out: xs, ys (replaced when accepted).  Destroys H, rho, zs.
+__device__ bool nl_qp_polish(NlWs& w, int lane, double c) {
+    const int n = w.n, m = w.m;
+    const double delta = 1e-6, idelta = 1e6;
+    double pri_a, dua_a;
+    nl_qp_residuals(w, lane, c, w.xs, w.ys, pri_a, dua_a);
+    for (int r = lane; r < m; r += 32) {
+        bool lo = (w.zs[r] - w.ls[r]) < -w.ys[r], up = (w.us[r] - w.zs[r]) < w.ys[r];
+        w.rho[r] = (lo || up) ? idelta : 0.0;
+        w.zs[r] = lo ? w.ls[r] : (up ? w.us[r] : 0.0);              // b on the active rows
+        w.yq[r] = 0.0;                                              // y_p
+    }
+    for (int i = lane; i < n; i += 32) w.g2[i] = 0.0;               // x_p
+    __syncwarp();
+    if (!nl_factor(w, lane, c, delta)) return false;
+    for (int it = 0; it <= 5; ++it) {                               // first pass = the plain solve, then 5 refinements
+        nl_Ats(w, lane, w.yq, w.rhs);
+        nl_Ps(w, lane, c, w.g2, w.zt2);
+        for (int i = lane; i < n; i += 32) w.sv[i] = -w.gs[i] - w.zt2[i] - w.rhs[i];          // r1
+        nl_As(w, lane, w.g2, w.pt);
+        for (int r = lane; r < m; r += 32) w.pr[r] = w.rho[r] > 0.0 ? (w.zs[r] - w.pt[r]) * idelta : 0.0;   // r2 / delta
+        __syncwarp();
+        nl_Ats(w, lane, w.pr, w.rhs);
+        for (int i = lane; i < n; i += 32) w.rhs[i] += w.sv[i];
+        __syncwarp();
+        nl_kkt_apply(w, lane);
+        nl_As(w, lane, w.xt, w.pt);
+        for (int r = lane; r < m; r += 32) if (w.rho[r] > 0.0) w.yq[r] += w.pt[r] * idelta - w.pr[r];
+        for (int i = lane; i < n; i += 32) w.g2[i] += w.xt[i];
+        __syncwarp();
+    }
+    double pri_p, dua_p;
+    nl_qp_residuals(w, lane, c, w.g2, w.yq, pri_p, dua_p);
+    const bool ok = pri_p <= fmax(pri_a, 1e-10) && dua_p <= fmax(dua_a, 1e-10);
+    if (ok) {
+        for (int i = lane; i < n; i += 32) w.xs[i] = w.g2[i];
+        for (int r = lane; r < m; r += 32) w.ys[r] = w.yq[r];
+        __syncwarp();
+    }
+    return ok;
 }
 
 // Dense OSQP-style ADMM for the QP subproblem.  In: B, g, Je, Ji, ce, ci, z, lb, ub; warm dual yq (if have_y).
@@ -180,16 +284,28 @@ __device__ int nl_qp_solve(NlWs& w, int lane, const NlSolveArgs& a, bool have_y)
             for (int i = 0; i < n; ++i) cn = fmax(cn, w.D[i] * fabs(w.B[(size_t)i * ld + j]));
             cn *= c * w.D[j];
             double an = 0;
-            for (int r = 0; r < mc; ++r) an = fmax(an, w.E[r] * fabs(nl_row(w, r)[j]));
+            int r0, r1; w.je_rows(j, r0, r1);
+            for (int r = r0; r < r1; ++r) an = fmax(an, w.E[r] * fabs(w.Je[(size_t)r * ld + j]));
+            for (int r = 0; r < mi; ++r) an = fmax(an, w.E[me + r] * fabs(w.Ji[(size_t)r * ld + j]));
             an = fmax(an, w.E[mc + j]) * w.D[j];
             w.xt[j] = 1.0 / sqrt(nl_lim(fmax(cn, an)));
         }
-        for (int r = lane; r < m; r += 32) {        // row norms -> w
-            double rn;
-            if (r < mc) { const double* row = nl_row(w, r); rn = 0; for (int j = 0; j < n; ++j) rn = fmax(rn, fabs(row[j]) * w.D[j]); rn *= w.E[r]; }
-            else rn = w.E[r] * w.D[r - mc];
-            w.w[r] = 1.0 / sqrt(nl_lim(rn));
+        for (int r = lane; r < me; r += 32) {       // row norms -> w
+            int c0, c1, u0; w.je_cols(r, c0, c1, u0);
+            const double* row = w.Je + (size_t)r * ld;
+            double rn = 0;
+            for (int j = c0; j < c1; ++j) rn = fmax(rn, fabs(row[j]) * w.D[j]);
+            for (int j = u0; j < u0 + w.nu; ++j) rn = fmax(rn, fabs(row[j]) * w.D[j]);
+            w.w[r] = 1.0 / sqrt(nl_lim(rn * w.E[r]));
         }
+        for (int r = 0; r < mi; ++r) {
+            const double* row = w.Ji + (size_t)r * ld;
+            double rn = 0;
+            for (int j = lane; j < n; j += 32) rn = fmax(rn, fabs(row[j]) * w.D[j]);
+            rn = nl_wmax(rn);
+            if (lane == 0) w.w[me + r] = 1.0 / sqrt(nl_lim(rn * w.E[me + r]));
+        }
+        for (int j = lane; j < n; j += 32) w.w[mc + j] = 1.0 / sqrt(nl_lim(w.E[mc + j] * w.D[j]));
         __syncwarp();
         for (int j = lane; j < n; j += 32) { w.D[j] *= w.xt[j]; w.gs[j] *= w.xt[j]; }
         for (int r = lane; r < m; r += 32) w.E[r] *= w.w[r];
@@ -254,7 +370,7 @@ __device__ int nl_qp_solve(NlWs& w, int lane, const NlSolveArgs& a, bool have_y)
             double dua = 0, nq = 0, nAty = 0, nPx = 0;
             for (int i = lane; i < n; i += 32) {              // Px = c D B D x
                 double acc = 0;
-                for (int j = 0; j < n; ++j) acc = fma(w.B[(size_t)i * ld + j], w.D[j] * w.xs[j], acc);
+                for (int j = 0; j < n; ++j) acc = fma(w.B[(size_t)j * ld + i], w.D[j] * w.xs[j], acc);      // B is symmetric
                 double px = c * w.D[i] * acc;
                 dua = fmax(dua, fabs(px + w.gs[i] + w.rhs[i])); nq = fmax(nq, fabs(w.gs[i])); nAty = fmax(nAty, fabs(w.rhs[i])); nPx = fmax(nPx, fabs(px));
             }
@@ -266,21 +382,24 @@ __device__ int nl_qp_solve(NlWs& w, int lane, const NlSolveArgs& a, bool have_y)
         }
     }
     if (it > a.max_qp) it = a.max_qp;
+    nl_qp_polish(w, lane, c);
     for (int i = lane; i < n; i += 32) w.d[i] = w.D[i] * w.xs[i];
     for (int r = lane; r < m; r += 32) w.yq[r] = w.E[r] * w.ys[r] / c;
     __syncwarp();
     return it;
 }
 
-template <class S>
-__global__ void __launch_bounds__(64) nlmpc_solve_kernel(const NlSolveArgs a) {
+template <class S, bool GM>
+__global__ void __launch_bounds__(GM ? 128 : 64) nlmpc_solve_kernel(const NlSolveArgs a) {
     extern __shared__ __align__(16) double nls_smem[];
     constexpr int nx = S::nx, nu = S::nu;
     const int ph = a.ph, ch = a.ch;
     const int n = ph * nx + ch * nu + 1, me = ph * nx, mi = S::nineq(ph);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const size_t nvec = NlWs::vec_doubles(n, me, mi, ph, nx, nu), nmat = NlWs::mat_doubles(n, me, mi, GM);
     NlWs w;
-    w.carve(nls_smem + (size_t)warp * NlWs::doubles(n, me, mi, ph, nx, nu), n, me, mi, ph, nx, nu);
+    if (GM) w.carve(a.mat_ws + (size_t)(blockIdx.x * wpb + warp) * nmat, nls_smem + (size_t)warp * nvec, true, n, me, mi, ph, ch, nx, nu);
+    else { double* base = nls_smem + (size_t)warp * (nvec + nmat); w.carve(base, base + nmat, false, n, me, mi, ph, ch, nx, nu); }
     const int mc = me + mi, ld = w.ld;
     for (int inst = blockIdx.x * wpb + warp; inst < a.batch; inst += gridDim.x * wpb) {
         const double* p = a.params + (size_t)inst * a.param_stride;
@@ -294,7 +413,8 @@ __global__ void __launch_bounds__(64) nlmpc_solve_kernel(const NlSolveArgs a) {
         __syncwarp();
         double mu = 1.0;
         bool have_y = false;
-        int k = 0, qp_total = 0, status = 1;
+        int k = 0, qp_total = 0, status = 1, resets = 0;
+        bool just_reset = false;
         auto violation = [&](const double* ce, const double* ci) {
             double v = 0;
             for (int r = lane; r < me; r += 32) v += fabs(ce[r]);
@@ -312,7 +432,10 @@ __global__ void __launch_bounds__(64) nlmpc_solve_kernel(const NlSolveArgs a) {
             ymax = nl_wmax(ymax); gd = nl_wsum(gd);
             mu = fmax(mu, 1.1 * ymax);
             const double phi0 = fval + mu * v0, dphi = gd - mu * v0;
+            // Kraft's first stopping test (|g'd| and the violation below the accuracy): nothing left to gain
+            if (fabs(gd) < a.ftol * fmax(1.0, fabs(fval)) && v0 < 1e-8) { status = 0; ++k; break; }
             double t = 1.0, ft = fval;
+            bool ls_ok = false;
             for (int ls = 0; ls < 25; ++ls) {
                 for (int i = lane; i < n; i += 32) w.zt2[i] = w.z[i] + t * w.d[i];
                 __syncwarp();
@@ -320,16 +443,24 @@ __global__ void __launch_bounds__(64) nlmpc_solve_kernel(const NlSolveArgs a) {
                 ft = w.tmp[0];
                 __syncwarp();
                 double vt = violation(w.cet, w.cit);
-                if (ft + mu * vt <= phi0 + 1e-4 * t * dphi) break;
+                if (ft + mu * vt <= phi0 + 1e-4 * t * dphi) { ls_ok = true; break; }
                 t *= 0.5;
             }
+            if (!ls_ok) {
+                // no decrease of the merit along d at any step length: restart the quasi-Newton matrix once (as SLSQP
+                // does); failing again straight after the restart is the finite-difference noise floor.
+                if (just_reset || resets >= 5) { status = v0 < 1e-8 ? 0 : 1; ++k; break; }
+                for (int e = lane; e < n * ld; e += 32) { int i = e / ld, j = e - i * ld; w.B[e] = (i == j) ? 1.0 : 0.0; }
+                __syncwarp();
+                ++resets; just_reset = true;
+                continue;
+            }
+            just_reset = false;
             // s = t d ; Lagrangian gradient at the old point with the new multipliers
             for (int i = lane; i < n; i += 32) { w.sv[i] = t * w.d[i]; }
             __syncwarp();
             for (int j = lane; j < n; j += 32) {
-                double acc = w.g[j];
-                for (int r = 0; r < mc; ++r) acc = fma(nl_row(w, r)[j], w.yq[r], acc);
-                w.glo[j] = acc;
+                w.glo[j] = w.g[j] + nl_col_dot(w, j, w.yq);
             }
             for (int i = lane; i < n; i += 32) w.z[i] += w.sv[i];
             __syncwarp();
@@ -339,11 +470,9 @@ __global__ void __launch_bounds__(64) nlmpc_solve_kernel(const NlSolveArgs a) {
             // damped BFGS:  yk = gl_new - gl_old,  Bs = B s
             double sBs = 0, sy = 0;
             for (int j = lane; j < n; j += 32) {
-                double acc = w.g2[j];
-                for (int r = 0; r < mc; ++r) acc = fma(nl_row(w, r)[j], w.yq[r], acc);
-                w.rhs[j] = acc - w.glo[j];                     // yk
+                w.rhs[j] = (w.g2[j] + nl_col_dot(w, j, w.yq)) - w.glo[j];          // yk
                 double bs = 0;
-                for (int q = 0; q < n; ++q) bs = fma(w.B[(size_t)j * ld + q], w.sv[q], bs);
+                for (int q = 0; q < n; ++q) bs = fma(w.B[(size_t)q * ld + j], w.sv[q], bs);      // symmetric B, column access
                 w.xt[j] = bs;                                  // Bs
                 sBs += w.sv[j] * bs; sy += w.sv[j] * w.rhs[j];
             }

@@ -5,9 +5,10 @@ Algorithm (per instance): damped-BFGS SQP on the reference's multiple-shooting N
 with f, gradients and Jacobians evaluated exactly like the reference does (oracle/nlmpc_formulation.py: forward /
 central finite differences with the reference's step rules).  Each QP subproblem
     min 1/2 d'Bd + g'd   s.t.  J_eq d = -c_eq,  J_in d <= -c_in,  lb - z <= d <= ub - z
-is solved by a dense OSQP-style ADMM (Jacobi row/column equilibration, rho_eq = 1e3 rho, over-relaxation 1.6, fixed
-iteration budget with residual test), warm started from the previous SQP iteration; the step is globalised by an L1
-merit function with backtracking.
+is solved by a dense OSQP-style ADMM (Ruiz equilibration, rho by row class, over-relaxation 1.6, adaptive rho) run to a
+moderate accuracy and then polished (active-set guess + regularised KKT solve with iterative refinement, OSQP polish.c),
+warm started from the previous SQP iteration's multipliers; the step is globalised by an L1 merit function with
+backtracking; a failed line search restarts B = I once (as SLSQP does) and stops at the second failure in a row.
 """
 import numpy as np
 
@@ -16,8 +17,9 @@ class QPADMM:
     """Dense OSQP-style ADMM: Jacobi equilibration, rho_eq = 1e3 rho, alpha = 1.6, residual test + adaptive rho (OSQP's
     estimate, refactor when it moves by more than 5x) every `check` iterations."""
 
-    def __init__(self, rho=0.1, sigma=1e-6, alpha=1.6, max_iter=1000, eps=1e-9, check=25):
+    def __init__(self, rho=0.1, sigma=1e-6, alpha=1.6, max_iter=200, eps=1e-5, check=25, polish=True, delta=1e-6, refine=5):
         self.rho, self.sigma, self.alpha, self.max_iter, self.eps, self.check = rho, sigma, alpha, max_iter, eps, check
+        self.polish, self.delta, self.refine = polish, delta, refine
 
     def solve(self, B, g, A, l, u, x=None, y=None):
         n, m = B.shape[0], A.shape[0]
@@ -72,10 +74,41 @@ class QPADMM:
                 if est > 5 * rho0 or est < rho0 / 5:
                     rho0 = est
                     rho, L = factor(rho0)
+        if self.polish:
+            # OSQP polish.c: guess the active set from (z, y), solve the equality-constrained QP on it through the same
+            # reduced system (rho = 1/delta on active rows, sigma = delta) with iterative refinement, keep it if both
+            # residuals improve.
+            lo = (zs - ls) < -ys
+            up = (us - zs) < ys
+            act = lo | up
+            b = np.where(lo, ls, us)[act]
+            Aa = As[act]
+            dl = self.delta
+            Hp = Bs + dl * np.eye(n) + Aa.T @ Aa / dl
+            Lp = np.linalg.cholesky(Hp)
+            def kkt(r1, r2):           # [Bs+dl I, Aa'; Aa, -dl I] [x; y] = [r1; r2]
+                x = np.linalg.solve(Lp.T, np.linalg.solve(Lp, r1 + Aa.T @ r2 / dl))
+                return x, (Aa @ x - r2) / dl
+            xp, yp = kkt(-gs, b)
+            for _ in range(self.refine):
+                r1 = -gs - Bs @ xp - Aa.T @ yp
+                r2 = b - Aa @ xp
+                dx, dy = kkt(r1, r2)
+                xp, yp = xp + dx, yp + dy
+            yf = np.zeros(m); yf[act] = yp
+            Axp = As @ xp
+            pri_p = np.maximum(np.maximum(ls - Axp, Axp - us), 0).max() if m else 0.0
+            dua_p = np.abs(Bs @ xp + gs + As.T @ yf).max()
+            Ax = As @ xs
+            pri_a = np.maximum(np.maximum(ls - Ax, Ax - us), 0).max() if m else 0.0
+            dua_a = np.abs(Bs @ xs + gs + As.T @ ys).max()
+            self.polished = bool(pri_p <= max(pri_a, 1e-10) and dua_p <= max(dua_a, 1e-10))
+            if self.polished:
+                xs, ys = xp, yf
         return D * xs, E * ys / c, it
 
 
-def sqp_solve(f, x0, z0, lb, ub, max_sqp=60, tol=1e-7, qp=None, verbose=False):
+def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, verbose=False):
     qp = qp or QPADMM()
     x0 = np.asarray(x0, float)
     z = np.clip(np.array(z0, float), lb, ub)
@@ -86,28 +119,45 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=60, tol=1e-7, qp=None, verbose=False):
     ci, Ji = f.ineq_con(z, x0) if f.ineq is not None else (np.zeros(0), np.zeros((0, n)))
     me, mi = ce.size, ci.size
     mu = 1.0
-    d_prev = y_prev = None
+    y_prev = None
+    resets, just_reset = 0, False
     hist = []
     for k in range(max_sqp):
         A = np.vstack([Je, Ji, np.eye(n)])
         l = np.concatenate([-ce, np.full(mi, -np.inf), lb - z])
         u = np.concatenate([-ce, -ci, ub - z])
-        d, y, qit = qp.solve(B, g, A, l, u, d_prev, y_prev)
+        d, y, qit = qp.solve(B, g, A, l, u, None, y_prev)
+        y_prev = y
         lam_e, lam_i = y[:me], y[me:me + mi]
         viol = lambda ce_, ci_: np.abs(ce_).sum() + np.maximum(ci_, 0).sum()
         v0 = viol(ce, ci)
         mu = max(mu, 1.1 * (np.abs(y[:me + mi]).max() if me + mi else 0.0))
         phi0 = fval + mu * v0
         dphi = g @ d - mu * v0            # directional derivative bound of the L1 merit
+        # Kraft's first stopping test (SLSQP: |g'd| and the violation below the accuracy): nothing left to gain
+        if abs(g @ d) < ftol * max(1.0, abs(fval)) and v0 < 1e-8:
+            hist.append((k, fval, v0, np.abs(d).max(), 0.0, qit))
+            break
         t = 1.0
+        ls_ok = False
         for _ in range(25):
             zt = z + t * d
             ft, _ = f.objective(zt, x0, want_grad=False)
             cet, _ = f.state_eq(zt, x0, want_jac=False)
             cit = f.ineq_con(zt, x0)[0] if f.ineq is not None else np.zeros(0)
             if ft + mu * viol(cet, cit) <= phi0 + 1e-4 * t * dphi:
+                ls_ok = True
                 break
             t *= 0.5
+        if not ls_ok:
+            # no decrease of the merit along d at any step length.  Like SLSQP, restart the quasi-Newton matrix once
+            # (a poor B or an inexact QP step); failing again straight after the restart is the finite-difference noise floor.
+            hist.append((k, fval, v0, np.abs(d).max(), 0.0, qit))
+            if just_reset or resets >= 5:
+                break
+            B = np.eye(n); resets += 1; just_reset = True
+            continue
+        just_reset = False
         s = t * d
         z_new = z + s
         f_new, g_new = f.objective(z_new, x0)
@@ -129,7 +179,6 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=60, tol=1e-7, qp=None, verbose=False):
         if verbose:
             print(hist[-1])
         z, fval, g, ce, Je, ci, Ji = z_new, f_new, g_new, ce_new, Je_new, ci_new, Ji_new
-        d_prev, y_prev = None, y
         if step < tol * max(1.0, np.abs(z).max()) and viol(ce, ci) < 1e-8:
             break
     X, U, e = f.unwrap(z, x0)

@@ -14,7 +14,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from oracle import nlmpc_slsqp as S
-from oracle.nlmpc_formulation import ugv_formulation, vanderpol_formulation
+from oracle.nlmpc_formulation import oscnet_formulation, ugv_formulation, vanderpol_formulation
 from nlmpc_sqp_reference import sqp_solve
 
 
@@ -111,7 +111,44 @@ def test_bounds_are_respected_and_errors_are_loud():
     ref = S.solve(f, np.array([0.0, 1.0]), S.initial_guess(f, np.array([0.0, 1.0]), np.zeros(1), lb=lb, ub=ub), lb, ub)
     assert np.abs(r.cmd[0] - ref["cmd"]).max() < 1e-5
     with pytest.raises(ValueError):
-        L.NLMPC(L.SYS_OSCNET6, 10, 5)                      # does not fit the shared-memory SQP kernel
+        L.nlmpc_solve(L.SYS_VANDERPOL, 10, 5, np.zeros((1, 25)), np.zeros((1, 2)), np.array([0.1]), lb, ub)     # wrong nz
     with pytest.raises(RuntimeError):
-        L.nlmpc_solve(L.SYS_OSCNET6, 10, 5, np.zeros((1, 151)), np.zeros((1, 12)), np.array([0.1, 1.0, 0.1]),
-                      np.full(151, -np.inf), np.full(151, np.inf))
+        L.nlmpc_solve(17, 10, 5, np.zeros((1, 26)), np.zeros((1, 2)), np.array([0.1]), lb, ub)                  # unknown system
+
+
+def _big_case(system, f, ph, ch, x0, u0, hard):
+    import libmpc_b200 as L
+    lb, ub = S.default_bounds(f, hard)
+    if not hard:
+        lb[-1] = 0.0
+    z0 = np.stack([S.initial_guess(f, x, u0, lb=lb, ub=ub) for x in x0])
+    assert L.load_library().b200mpc_nlmpc_solve_smem_bytes(system, ph, ch) > 227 * 1024      # HBM-workspace kernel
+    out = L.nlmpc_solve(system, ph, ch, z0, x0, f.params, lb, ub, max_sqp=200)
+    assert (out["status"] == 0).all() and (out["viol"] < 1e-8).all()
+    for b in range(len(x0)):
+        ref = S.solve(f, x0[b], z0[b], lb, ub, maxiter=400)
+        assert ref["success"]
+        assert abs(out["cost"][b] - ref["cost"]) < 1e-7 * max(1.0, abs(ref["cost"]))
+        assert np.abs(_cmd(f, out["z"][b]) - ref["cmd"]).max() < 1e-5 * max(1.0, np.abs(ref["cmd"]).max())
+        assert np.abs(out["z"][b] - ref["z"]).max() < 1e-4
+    return out, z0, lb, ub
+
+
+def test_ugv_horizon_30_hbm_workspace_kernel():
+    """BASELINE.json configs[2] shape (ugv_ex, Tph = 30, obstacle inequalities, soft constraints): nz = 181."""
+    import libmpc_b200 as L
+    f = ugv_formulation(30, 30, v_pref=(0.6, 0.8))
+    x0 = np.array([[0.4, 0.5, 0.6, 0.8], [0.0, 0.0, 0.0, 0.0]])
+    out, z0, lb, ub = _big_case(L.SYS_UGV, f, 30, 30, x0, np.zeros(2), False)
+    spec = sqp_solve(f, x0[0], z0[0], lb, ub, max_sqp=200)
+    assert np.abs(out["z"][0] - spec["z"]).max() < 1e-4
+    assert abs(out["cost"][0] - spec["cost"]) < 1e-8 * abs(spec["cost"])
+
+
+def test_networked_oscillators_hbm_workspace_kernel():
+    """BASELINE.json configs[3] shape (networked_oscillators_ex, nx = 8, nu = 4, Tph = 15): nz = 153."""
+    import libmpc_b200 as L
+    f = oscnet_formulation(4, 15, 8)
+    f.params = np.array([0.1, 1.0, 0.1])
+    x0 = np.random.default_rng(1).uniform(-1, 1, (3, 8))
+    _big_case(L.SYS_OSCNET4, f, 15, 8, x0, np.zeros(4), True)
