@@ -3,10 +3,8 @@
 // object in the reference: include/mpc/LMPC/ProblemBuilder.hpp:827-857, include/mpc/LMPC/LOptimizer.hpp:518-527) and
 // launches the single persistent solve kernel.  There is no CPU fallback: without a CUDA device every entry point
 // that would compute returns B200MPC_ENOGPU.
-#include "../../include/b200mpc.h"
+#include "capi_common.h"
 #include "lmpc_kernels.cuh"
-#include "nlmpc_kernels.cuh"
-#include "nlmpc_sqp.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -18,12 +16,7 @@
 using namespace b200mpc;
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail(B200MPC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
+int b200mpc::fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct DevBuf {
     double* p = nullptr;
@@ -480,220 +473,5 @@ extern "C" int b200mpc_lmpc_profile(b200mpc_lmpc_t h, long long* out_host) {
 extern "C" int b200mpc_sync(b200mpc_lmpc_t h) {
     HCHECK();
     CK(cudaStreamSynchronize(h->stream));
-    return B200MPC_OK;
-}
-
-
-// ---- NLMPC problem evaluation (K5) --------------------------------------------------------------------------------
-template <class S>
-static int nl_eval_t(const NlEvalArgs& a, cudaStream_t stream) {
-    int wpb = 4;
-    size_t smem = (size_t)wpb * (a.ph + 1) * (S::nx + S::nu) * sizeof(double);
-    int dev = 0, sms = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int grid = (a.batch + wpb - 1) / wpb;
-    if (grid > sms * 8) grid = sms * 8;
-    CK(cudaFuncSetAttribute(nlmpc_eval_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nlmpc_eval_kernel<S><<<grid, wpb * 32, smem, stream>>>(a);
-    CK(cudaGetLastError());
-    return B200MPC_OK;
-}
-
-static int nl_dims(int system, int* nx, int* nu, int* nparam, int ph, int* nineq) {
-    switch (system) {
-    case B200MPC_SYS_VANDERPOL: *nx = 2; *nu = 1; *nparam = 1; *nineq = ph + 1; return 0;
-    case B200MPC_SYS_OSCNET4: *nx = 8; *nu = 4; *nparam = 3; *nineq = (ph + 1) * 4; return 0;
-    case B200MPC_SYS_OSCNET6: *nx = 12; *nu = 6; *nparam = 3; *nineq = (ph + 1) * 6; return 0;
-    case B200MPC_SYS_UGV: *nx = 4; *nu = 2; *nparam = 32; *nineq = (ph + 1) * 2; return 0;
-    default: return -1;
-    }
-}
-
-extern "C" int b200mpc_nlmpc_system_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq) {
-    int a, b, c, d;
-    if (nl_dims(system, &a, &b, &c, ph, &d)) return fail(B200MPC_EINVAL, "unknown system id");
-    if (nx) *nx = a; if (nu) *nu = b; if (nparam) *nparam = c; if (nineq) *nineq = d;
-    return B200MPC_OK;
-}
-
-extern "C" int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
-                                  int params_per_instance, double* fval, double* grad, double* ceq, double* Jeq, double* cin,
-                                  double* Jin, int dev, void* stream_) {
-    if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
-    int nx, nu, np, ni;
-    if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return fail(B200MPC_EINVAL, "unknown system id");
-    if (ph < 1 || ch < 1 || ch > ph || batch < 1 || !z || !x0 || !params) return fail(B200MPC_EINVAL, "bad arguments");
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int nz = ph * nx + ch * nu + 1;
-    NlEvalArgs a;
-    a.ph = ph; a.ch = ch; a.batch = batch; a.param_stride = params_per_instance ? np : 0;
-    std::vector<void*> tofree;
-    auto in = [&](const double* h, size_t n, const double** d) -> int {
-        if (dev) { *d = h; return 0; }
-        double* p = nullptr;
-        CK(cudaMalloc(&p, n * sizeof(double))); tofree.push_back(p);
-        CK(cudaMemcpyAsync(p, h, n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        *d = p; return 0;
-    };
-    auto out = [&](double* h, size_t n, double** d) -> int {
-        if (!h) { *d = nullptr; return 0; }
-        if (dev) { *d = h; return 0; }
-        double* p = nullptr;
-        CK(cudaMalloc(&p, n * sizeof(double))); tofree.push_back(p);
-        *d = p; return 0;
-    };
-    int rc;
-    if ((rc = in(z, (size_t)batch * nz, &a.z))) return rc;
-    if ((rc = in(x0, (size_t)batch * nx, &a.x0))) return rc;
-    if ((rc = in(params, (size_t)(params_per_instance ? batch : 1) * np, &a.params))) return rc;
-    if ((rc = out(fval, batch, &a.fval))) return rc;
-    if ((rc = out(grad, (size_t)batch * nz, &a.grad))) return rc;
-    if ((rc = out(ceq, (size_t)batch * ph * nx, &a.ceq))) return rc;
-    if ((rc = out(Jeq, (size_t)batch * ph * nx * nz, &a.Jeq))) return rc;
-    if ((rc = out(cin, (size_t)batch * ni, &a.cin))) return rc;
-    if ((rc = out(Jin, (size_t)batch * ni * nz, &a.Jin))) return rc;
-    switch (system) {
-    case B200MPC_SYS_VANDERPOL: rc = nl_eval_t<SysVanDerPol>(a, stream); break;
-    case B200MPC_SYS_OSCNET4: rc = nl_eval_t<SysOscNet<4>>(a, stream); break;
-    case B200MPC_SYS_OSCNET6: rc = nl_eval_t<SysOscNet<6>>(a, stream); break;
-    default: rc = nl_eval_t<SysUgv>(a, stream); break;
-    }
-    if (rc) return rc;
-    if (!dev) {
-        auto back = [&](double* h, const double* d, size_t n) -> int { if (h) CK(cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, stream)); return 0; };
-        if ((rc = back(fval, a.fval, batch))) return rc;
-        if ((rc = back(grad, a.grad, (size_t)batch * nz))) return rc;
-        if ((rc = back(ceq, a.ceq, (size_t)batch * ph * nx))) return rc;
-        if ((rc = back(Jeq, a.Jeq, (size_t)batch * ph * nx * nz))) return rc;
-        if ((rc = back(cin, a.cin, (size_t)batch * ni))) return rc;
-        if ((rc = back(Jin, a.Jin, (size_t)batch * ni * nz))) return rc;
-        CK(cudaStreamSynchronize(stream));
-        for (void* p : tofree) cudaFree(p);
-    }
-    return B200MPC_OK;
-}
-
-
-// ---- NLMPC solve (K6/K7) ---------------------------------------------------------------------------------------------
-extern "C" void b200mpc_nlmpc_default_params(b200mpc_nlmpc_params* p) {
-    if (!p) return;
-    p->max_sqp = 100; p->max_qp = 200; p->tol = 1e-7; p->ftol = 1e-12; p->qp_eps = 1e-5; p->rho = 0.1;
-}
-
-// shared memory one controller needs when the matrices are shared-memory resident (the fast path)
-static size_t nl_solve_smem(int system, int ph, int ch) {
-    int nx, nu, np, ni;
-    if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return 0;
-    int n = ph * nx + ch * nu + 1, me = ph * nx;
-    return (NlWs::vec_doubles(n, me, ni, ph, nx, nu) + NlWs::mat_doubles(n, me, ni, false)) * sizeof(double);
-}
-extern "C" long long b200mpc_nlmpc_solve_smem_bytes(int system, int ph, int ch) { return (long long)nl_solve_smem(system, ph, ch); }
-
-template <class S>
-static int nl_solve_t(NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree) {
-    int dev = 0, sms = 0, maxsm = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int n = a.ph * S::nx + a.ch * S::nu + 1, me = a.ph * S::nx;
-    int ni = 0, d0, d1, d2;
-    nl_dims(S::id, &d0, &d1, &d2, a.ph, &ni);
-    const size_t vecb = NlWs::vec_doubles(n, me, ni, a.ph, S::nx, S::nu) * sizeof(double);
-    const size_t matb = NlWs::mat_doubles(n, me, ni, false) * sizeof(double);
-    a.mat_ws = nullptr;
-    if (vecb + matb <= (size_t)maxsm) {                       // matrices resident in shared memory
-        size_t per_warp = vecb + matb;
-        int wpb = (2 * per_warp <= (size_t)maxsm / 2) ? 2 : 1;
-        size_t smem = per_warp * wpb;
-        CK(cudaFuncSetAttribute(nlmpc_solve_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nlmpc_solve_kernel<S, false>, wpb * 32, smem));
-        if (occ < 1) occ = 1;
-        int grid = (a.batch + wpb - 1) / wpb;
-        if (grid > sms * occ) grid = sms * occ;
-        nlmpc_solve_kernel<S, false><<<grid, wpb * 32, smem, stream>>>(a);
-    } else {                                                  // matrices in a per-warp-slot HBM workspace (L2-resident)
-        if (vecb > (size_t)maxsm) return fail(B200MPC_EINVAL, "NLMPC problem too large: its vectors do not fit shared memory");
-        int wpb = (int)((size_t)maxsm / vecb);
-        if (wpb > 4) wpb = 4;
-        size_t smem = vecb * wpb;
-        CK(cudaFuncSetAttribute(nlmpc_solve_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nlmpc_solve_kernel<S, true>, wpb * 32, smem));
-        if (occ < 1) occ = 1;
-        int grid = (a.batch + wpb - 1) / wpb;
-        if (grid > sms * occ) grid = sms * occ;
-        size_t slots = (size_t)grid * wpb, matd = NlWs::mat_doubles(n, me, ni, true);
-        void* ws = nullptr;
-        CK(cudaMalloc(&ws, slots * matd * sizeof(double)));
-        tofree.push_back(ws);
-        a.mat_ws = (double*)ws;
-        nlmpc_solve_kernel<S, true><<<grid, wpb * 32, smem, stream>>>(a);
-    }
-    CK(cudaGetLastError());
-    return B200MPC_OK;
-}
-
-extern "C" int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* prm, const double* z0,
-                                   const double* x0, const double* sys_params, int params_per_instance, const double* lb,
-                                   const double* ub, double* z, double* cost, double* viol, int32_t* status, int32_t* iters,
-                                   int32_t* qp_iters, int dev, void* stream_) {
-    if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
-    int nx, nu, np, ni;
-    if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return fail(B200MPC_EINVAL, "unknown system id");
-    if (ph < 1 || ch < 1 || ch > ph || batch < 1 || !z0 || !x0 || !sys_params || !lb || !ub || !z) return fail(B200MPC_EINVAL, "bad arguments");
-    b200mpc_nlmpc_params q;
-    if (prm) q = *prm; else b200mpc_nlmpc_default_params(&q);
-    if (q.max_sqp < 1 || q.max_qp < 25 || !(q.tol > 0) || !(q.ftol >= 0) || !(q.qp_eps > 0) || !(q.rho > 0)) return fail(B200MPC_EINVAL, "bad NLMPC parameters");
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int nz = ph * nx + ch * nu + 1;
-    NlSolveArgs a;
-    a.ph = ph; a.ch = ch; a.batch = batch; a.param_stride = params_per_instance ? np : 0;
-    a.max_sqp = q.max_sqp; a.max_qp = q.max_qp; a.tol = q.tol; a.ftol = q.ftol; a.qp_eps = q.qp_eps; a.rho0 = q.rho;
-    std::vector<void*> tofree;
-    struct Free { std::vector<void*>& v; ~Free() { for (void* p : v) cudaFree(p); } } freer{tofree};
-    auto in = [&](const double* h, size_t n, const double** d) -> int {
-        if (dev) { *d = h; return 0; }
-        double* p = nullptr;
-        CK(cudaMalloc(&p, n * sizeof(double))); tofree.push_back(p);
-        CK(cudaMemcpyAsync(p, h, n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        *d = p; return 0;
-    };
-    auto out = [&](void* h, size_t bytes, void** d) -> int {
-        if (dev && h) { *d = h; return 0; }
-        void* p = nullptr;
-        CK(cudaMalloc(&p, bytes)); tofree.push_back(p);
-        *d = p; return 0;
-    };
-    int rc;
-    if ((rc = in(z0, (size_t)batch * nz, &a.z0))) return rc;
-    if ((rc = in(x0, (size_t)batch * nx, &a.x0))) return rc;
-    if ((rc = in(sys_params, (size_t)(params_per_instance ? batch : 1) * np, &a.params))) return rc;
-    if ((rc = in(lb, nz, &a.lb))) return rc;
-    if ((rc = in(ub, nz, &a.ub))) return rc;
-    if ((rc = out(z, (size_t)batch * nz * 8, (void**)&a.z_out))) return rc;
-    if ((rc = out(cost, (size_t)batch * 8, (void**)&a.cost))) return rc;
-    if ((rc = out(viol, (size_t)batch * 8, (void**)&a.viol))) return rc;
-    if ((rc = out(status, (size_t)batch * 4, (void**)&a.status))) return rc;
-    if ((rc = out(iters, (size_t)batch * 4, (void**)&a.iters))) return rc;
-    if ((rc = out(qp_iters, (size_t)batch * 4, (void**)&a.qp_iters))) return rc;
-    switch (system) {
-    case B200MPC_SYS_VANDERPOL: rc = nl_solve_t<SysVanDerPol>(a, stream, tofree); break;
-    case B200MPC_SYS_OSCNET4: rc = nl_solve_t<SysOscNet<4>>(a, stream, tofree); break;
-    case B200MPC_SYS_OSCNET6: rc = nl_solve_t<SysOscNet<6>>(a, stream, tofree); break;
-    default: rc = nl_solve_t<SysUgv>(a, stream, tofree); break;
-    }
-    if (rc) return rc;
-    if (!dev) {
-        auto back = [&](void* h, const void* d, size_t bytes) -> int { if (h) CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream)); return 0; };
-        if ((rc = back(z, a.z_out, (size_t)batch * nz * 8))) return rc;
-        if ((rc = back(cost, a.cost, (size_t)batch * 8))) return rc;
-        if ((rc = back(viol, a.viol, (size_t)batch * 8))) return rc;
-        if ((rc = back(status, a.status, (size_t)batch * 4))) return rc;
-        if ((rc = back(iters, a.iters, (size_t)batch * 4))) return rc;
-        if ((rc = back(qp_iters, a.qp_iters, (size_t)batch * 4))) return rc;
-    }
-    CK(cudaStreamSynchronize(stream));     // temporaries are freed on return
     return B200MPC_OK;
 }

@@ -40,7 +40,7 @@ struct SysVanDerPol {
     static constexpr int nx = 2, nu = 1, ny = 2, nparam = 1;
     static constexpr bool continuous = true;
     __device__ static double Ts(const double* p) { return p[0]; }
-    __device__ static int nineq(int ph) { return ph + 1; }
+    __host__ __device__ static int nineq(int ph) { return ph + 1; }
     __device__ static void f(double* dx, const double* x, const double* u, int, const double*) {
         dx[0] = ((1.0 - (x[1] * x[1])) * x[0]) - x[1] + u[0];
         dx[1] = x[0];
@@ -61,7 +61,7 @@ struct SysOscNet {
     static constexpr int nx = 2 * N, nu = N, ny = 2 * N, nparam = 3;
     static constexpr bool continuous = true;
     __device__ static double Ts(const double* p) { return p[0]; }
-    __device__ static int nineq(int ph) { return (ph + 1) * nu; }
+    __host__ __device__ static int nineq(int ph) { return (ph + 1) * nu; }
     __device__ static void f(double* dx, const double* x, const double* u, int, const double* p) {
         const double mu = p[1], k = p[2];
         for (int i = 0; i < N; ++i) {
@@ -87,7 +87,7 @@ struct SysUgv {
     static constexpr int nx = 4, nu = 2, ny = 4, nparam = 16 + 8 + 2 + 6, nobs = 2;
     static constexpr bool continuous = false;
     __device__ static double Ts(const double*) { return 0.0; }
-    __device__ static int nineq(int ph) { return (ph + 1) * nobs; }
+    __host__ __device__ static int nineq(int ph) { return (ph + 1) * nobs; }
     __device__ static void f(double* xn, const double* x, const double* u, int, const double* p) {
         for (int r = 0; r < 4; ++r) {
             double v = 0;
@@ -115,6 +115,41 @@ struct SysUgv {
     }
 };
 
+// ---- the threads that cooperate on one controller -------------------------------------------------------------------
+// NT = 32: one warp (several controllers per CTA); NT > 32: the whole CTA works on one controller.
+template <int NT>
+struct NlGrp {
+    static constexpr int nt = NT, nw = NT / 32;
+    int tid, lane, wid;
+    double* red;                                   // nw doubles of shared scratch (unused when NT == 32)
+    __device__ __forceinline__ void sync() const { if (NT == 32) __syncwarp(); else __syncthreads(); }
+    __device__ __forceinline__ double sum(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (NT == 32) return v;
+        __syncthreads();
+        if (lane == 0) red[wid] = v;
+        __syncthreads();
+        double t = 0;
+#pragma unroll
+        for (int k = 0; k < nw; ++k) t += red[k];
+        return t;
+    }
+    __device__ __forceinline__ double max(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (NT == 32) return v;
+        __syncthreads();
+        if (lane == 0) red[wid] = v;
+        __syncthreads();
+        double t = red[0];
+#pragma unroll
+        for (int k = 1; k < nw; ++k) t = fmax(t, red[k]);
+        return t;
+    }
+    __device__ __forceinline__ bool any(bool b) const { return NT == 32 ? __any_sync(0xffffffffu, b) : (bool)__syncthreads_or(b); }
+};
+
 struct NlEvalArgs {
     int ph, ch, batch;
     const double* z;        // [batch, nz]
@@ -129,46 +164,46 @@ struct NlEvalArgs {
     double* Jin;            // [batch, nineq, nz] row-major
 };
 
-// ---- evaluation of one instance by one warp (shared by the evaluation kernel and by the SQP kernel) ------------------
+// ---- evaluation of one instance by one thread group (shared by the evaluation kernel and by the SQP kernel) ----------
 // X,U: shared-memory scratch [(ph+1)*nx], [(ph+1)*nu].  Output pointers may be global or shared; Jacobians are row-major
-// with row stride ldj.  Any output pointer may be null.  All 32 lanes must call; ends with __syncwarp().
-template <class S>
-__device__ void nl_eval_instance(int lane, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
+// with row stride ldj.  Any output pointer may be null.  The whole group must call; ends with a group barrier.
+template <class S, class G>
+__device__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
                                  double* fval, double* grad, double* ceq, double* Jeq, double* cin, double* Jin, int ldj) {
     constexpr int nx = S::nx, nu = S::nu;
     const int nz = ph * nx + ch * nu + 1;
     const double dv = 1.4901161193847656e-08;     // sqrt(DBL_EPSILON)  (Objective.hpp:283)
     // unwrapVector: X row 0 = x0, rows 1..ph from z; U row i = block min(i, ch-1), last row repeated
-    for (int e = lane; e < (ph + 1) * nx; e += 32) {
+    for (int e = g_.tid; e < (ph + 1) * nx; e += G::nt) {
         int i = e / nx, j = e - i * nx;
         X[e] = i == 0 ? x0[j] : z[(i - 1) * nx + j];
     }
-    for (int e = lane; e < (ph + 1) * nu; e += 32) {
+    for (int e = g_.tid; e < (ph + 1) * nu; e += G::nt) {
         int i = e / nu, j = e - i * nu;
         int st = i < ph ? i : ph - 1;
         int blk = st < ch ? st : ch - 1;
         U[e] = z[ph * nx + blk * nu + j];
     }
     const double slack = z[nz - 1];
-    __syncwarp();
+    g_.sync();
     Acc base{X, U, nx, nu, 0, 0, 0, 0.0};
     double f0 = 0;
     if (fval || grad) {
         f0 = S::cost(base, slack, ph, p);
-        if (fval && lane == 0) *fval = f0;
+        if (fval && g_.tid == 0) *fval = f0;
     }
     if (grad) {
         double* g = grad;
-        for (int e = lane; e < nz; e += 32) g[e] = 0.0;
-        __syncwarp();
-        for (int t = lane; t < ph * nx; t += 32) {          // step uses Xa.array()(j): linear index j (column-major)
+        for (int e = g_.tid; e < nz; e += G::nt) g[e] = 0.0;
+        g_.sync();
+        for (int t = g_.tid; t < ph * nx; t += G::nt) {          // step uses Xa.array()(j): linear index j (column-major)
             int i = t / nx, j = t - i * nx;
             int lr = j % (ph + 1), lc = j / (ph + 1);
             double dx = dv * fmax(fabs(X[lr * nx + lc]), 1.0);
             Acc ac = base; ac.kind = 1; ac.row = i + 1; ac.col = j; ac.d = dx;
             g[i * nx + j] = (S::cost(ac, slack, ph, p) - f0) / dx;
         }
-        for (int t = lane; t < ph * nu; t += 32) {          // stage ph-1 moves together with the duplicated row ph
+        for (int t = g_.tid; t < ph * nu; t += G::nt) {          // stage ph-1 moves together with the duplicated row ph
             int i = t / nu, j = t - i * nu;
             int lr = j % (ph + 1), lc = j / (ph + 1);
             double du = dv * fmax(fabs(U[lr * nu + lc]), 1.0);
@@ -177,7 +212,7 @@ __device__ void nl_eval_instance(int lane, int ph, int ch, const double* z, cons
             int blk = i < ch ? i : ch - 1;
             atomicAdd(&g[ph * nx + blk * nu + j], df);
         }
-        if (lane == 0) {
+        if (g_.tid == 0) {
             double ea = fmax(dv, fabs(slack)), de = ea * dv;
             g[nz - 1] = (S::cost(base, slack + de, ph, p) - S::cost(base, slack - de, ph, p)) / (2 * de);
         }
@@ -185,10 +220,10 @@ __device__ void nl_eval_instance(int lane, int ph, int ch, const double* z, cons
     if (ceq) {
         double* c = ceq;
         double* J = Jeq;
-        if (J) for (int e = lane; e < ph * nx * ldj; e += 32) J[e] = 0.0;
-        __syncwarp();
+        if (J) for (int e = g_.tid; e < ph * nx * ldj; e += G::nt) J[e] = 0.0;
+        g_.sync();
         const double h = S::Ts(p) / 2.0;
-        for (int i = lane; i < ph; i += 32) {
+        for (int i = g_.tid; i < ph; i += G::nt) {
             double xk[nx], xk1[nx], uk[nu], fk[nx], fk1[nx];
             for (int j = 0; j < nx; ++j) { xk[j] = X[i * nx + j]; xk1[j] = X[(i + 1) * nx + j]; }
             for (int j = 0; j < nu; ++j) uk[j] = U[i * nu + j];
@@ -202,7 +237,7 @@ __device__ void nl_eval_instance(int lane, int ph, int ch, const double* z, cons
         }
         if (J) {
             const int per_stage = nx + nu;
-            for (int t = lane; t < ph * per_stage; t += 32) {
+            for (int t = g_.tid; t < ph * per_stage; t += G::nt) {
                 int i = t / per_stage, q = t - i * per_stage;
                 double xk[nx], xk1[nx], uk[nu], fp[nx], fm[nx];
                 for (int j = 0; j < nx; ++j) { xk[j] = X[i * nx + j]; xk1[j] = X[(i + 1) * nx + j]; }
@@ -247,12 +282,12 @@ __device__ void nl_eval_instance(int lane, int ph, int ch, const double* z, cons
     if (cin) {
         const int ni = S::nineq(ph);
         double* c = cin;
-        for (int r = lane; r < ni; r += 32) c[r] = S::ineq(r, base, slack, ph, p);
+        for (int r = g_.tid; r < ni; r += G::nt) c[r] = S::ineq(r, base, slack, ph, p);
         if (Jin) {
             double* J = Jin;
-            for (int e = lane; e < ni * ldj; e += 32) J[e] = 0.0;
-            __syncwarp();
-            for (int t = lane; t < ph * nx; t += 32) {
+            for (int e = g_.tid; e < ni * ldj; e += G::nt) J[e] = 0.0;
+            g_.sync();
+            for (int t = g_.tid; t < ph * nx; t += G::nt) {
                 int i = t / nx, j = t - i * nx;
                 int lr = j % (ph + 1), lc = j / (ph + 1);
                 double dx = dv * fmax(fabs(X[lr * nx + lc]), 1.0);
@@ -260,7 +295,7 @@ __device__ void nl_eval_instance(int lane, int ph, int ch, const double* z, cons
                 Acc am = ap; am.d = -dx;
                 for (int r = 0; r < ni; ++r) J[(size_t)r * ldj + i * nx + j] = (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * dx);
             }
-            for (int t = lane; t < ph * nu; t += 32) {     // every one of the ph rows alone (row ph is never perturbed)
+            for (int t = g_.tid; t < ph * nu; t += G::nt) {     // every one of the ph rows alone (row ph is never perturbed)
                 int i = t / nu, j = t - i * nu;
                 int lr = j % (ph + 1), lc = j / (ph + 1);
                 double du = dv * fmax(fabs(U[lr * nu + lc]), 1.0);
@@ -270,13 +305,13 @@ __device__ void nl_eval_instance(int lane, int ph, int ch, const double* z, cons
                 for (int r = 0; r < ni; ++r)
                     atomicAdd(&J[(size_t)r * ldj + ph * nx + blk * nu + j], (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * du));
             }
-            if (lane == 0) {
+            if (g_.tid == 0) {
                 double ea = fmax(dv, fabs(slack)), de = ea * dv;
                 for (int r = 0; r < ni; ++r) J[(size_t)r * ldj + nz - 1] = (S::ineq(r, base, slack + de, ph, p) - S::ineq(r, base, slack - de, ph, p)) / (2 * de);
             }
         }
     }
-    __syncwarp();
+    g_.sync();
 }
 
 template <class S>
@@ -289,8 +324,9 @@ __global__ void __launch_bounds__(128) nlmpc_eval_kernel(const NlEvalArgs a) {
     double* X = nl_smem + (size_t)warp * (ph + 1) * (nx + nu);
     double* U = X + (ph + 1) * nx;
     const int ni = S::nineq(ph);
+    const NlGrp<32> grp{lane, lane, 0, nullptr};
     for (int inst = blockIdx.x * wpb + warp; inst < a.batch; inst += gridDim.x * wpb) {
-        nl_eval_instance<S>(lane, ph, ch, a.z + (size_t)inst * nz, a.x0 + (size_t)inst * nx, a.params + (size_t)inst * a.param_stride, X, U,
+        nl_eval_instance<S>(grp, ph, ch, a.z + (size_t)inst * nz, a.x0 + (size_t)inst * nx, a.params + (size_t)inst * a.param_stride, X, U,
                             a.fval ? a.fval + inst : nullptr, a.grad ? a.grad + (size_t)inst * nz : nullptr,
                             a.ceq ? a.ceq + (size_t)inst * ph * nx : nullptr, a.Jeq ? a.Jeq + (size_t)inst * ph * nx * nz : nullptr,
                             a.cin ? a.cin + (size_t)inst * ni : nullptr, a.Jin ? a.Jin + (size_t)inst * ni * nz : nullptr, nz);

@@ -1,17 +1,18 @@
-// nlmpc_sqp.cuh -- batched NLMPC solve for sm_100a: one warp per controller, the whole NLP solve in
-// shared memory.  Replaces what NLOptimizer::run hands to NLopt's SLSQP (include/mpc/NLMPC/NLOptimizer.hpp:412-638):
+// nlmpc_sqp.cuh -- batched NLMPC solve for sm_100a: one thread group (a warp for tiny problems, a CTA of
+// 4-8 warps otherwise) per controller, the whole NLP solve in one kernel.  Replaces what NLOptimizer::run hands to NLopt's SLSQP (include/mpc/NLMPC/NLOptimizer.hpp:412-638):
 //
 //     min f(z)   s.t.  c_eq(z) = 0 (multiple-shooting dynamics),  c_in(z) <= 0 (user inequalities),  lb <= z <= ub
 //
 // with f, its forward-difference gradient and the central-difference Jacobians evaluated exactly as the reference does
 // (nl_eval_instance in nlmpc_kernels.cuh).  The solver is a damped-BFGS SQP (the algorithm family of Kraft's SLSQP): every
 // major iteration solves   min 1/2 d'Bd + g'd  s.t.  J_eq d = -c_eq,  J_in d <= -c_in,  lb-z <= d <= ub-z
-// with a dense OSQP-style ADMM (Ruiz equilibration, rho_eq = 1e3 rho, over-relaxation 1.6, adaptive rho with dense
-// refactorisation), globalised by an L1 merit function with backtracking.  tests/nlmpc_sqp_reference.py is the
-// executable specification; solution-level parity is against SciPy's SLSQP on the restated formulation
-// (oracle/nlmpc_slsqp.py).  Everything (B, the KKT factor, both Jacobians, all vectors) lives in shared memory, which
-// bounds the problem size: nz up to ~64 (vanderpol nz=26, the shipped ugv nz=61); larger systems need the stage-
-// structured LTV kernel (next step).
+// with a dense OSQP-style ADMM (Ruiz equilibration, rho by row class, over-relaxation 1.6, adaptive rho with dense
+// refactorisation) run to moderate accuracy and then polished (OSQP polish.c), globalised by an L1 merit function with
+// backtracking and a quasi-Newton restart.  tests/nlmpc_sqp_reference.py is the executable specification; solution-level
+// parity is against SciPy's SLSQP on the restated formulation (oracle/nlmpc_slsqp.py).  All vectors live in shared
+// memory; the matrices (B, the KKT factor, both Jacobians) too when they fit (vanderpol nz=26, the shipped ugv nz=61),
+// otherwise in a per-CTA HBM workspace that stays L2-resident.  The dense O(nz^3) factorisation is what bounds the
+// large shapes; the stage-structured (block-tridiagonal) variant is the next step.
 #pragma once
 #include "nlmpc_kernels.cuh"
 
@@ -31,36 +32,37 @@ struct NlSolveArgs {
     int* status;            // 0 converged, 1 iteration limit
     int* iters;             // SQP iterations
     int* qp_iters;          // total ADMM iterations
-    double* mat_ws;         // GM kernels: per-warp-slot matrix workspace [grid * warps][mat_doubles]
+    double* mat_ws;         // GM kernels: per-CTA matrix workspace [grid][mat_doubles]
 };
 
-__device__ __forceinline__ double nl_wmax(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 __device__ __forceinline__ double nl_wsum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+__device__ __forceinline__ double nl_wmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 __device__ __forceinline__ double nl_lim(double v) { v = v < 1e-4 ? 1.0 : v; return v > 1e4 ? 1e4 : v; }
 
-// Per-warp workspace.  Vectors always live in shared memory; the four matrices (B, KKT factor, J_eq, J_in) live in shared
-// memory when the problem is small (GM = false: vanderpol, the shipped ugv) and in a per-warp-slot HBM/L2 workspace
-// otherwise (GM = true), where every matrix pass below runs with lanes along the contiguous (column) index.
+// Per-controller workspace.  Vectors always live in shared memory; the four matrices (B, KKT factor, J_eq, J_in) live in
+// shared memory when the problem is small (GM = false) and in a per-CTA HBM/L2 workspace otherwise (GM = true).  Every
+// matrix pass below runs with consecutive threads along the contiguous (column) index: coalesced in HBM, conflict-free
+// in shared memory.
 struct NlWs {
     int n, me, mi, m, ld, nx, nu, ph, ch;
     double *B, *H, *Je, *Ji;                 // n x ld, n x ld, me x ld, mi x ld (row-major)
     double *z, *g, *g2, *d, *xs, *xt, *D, *gs, *rhs, *tmp, *glo, *sv, *zt2;     // n
     double *E, *ls, *us, *zs, *ys, *rho, *yq, *w, *pr, *pt;                     // m
     double *ce, *ci, *cet, *cit;                                                // me, mi, me, mi
-    double *X, *U;
+    double *X, *U, *red;
     __host__ __device__ static int ldim(int n, bool gm) { return gm ? ((n + 3) & ~3) : (n | 1); }
     __host__ __device__ static size_t mat_doubles(int n, int me, int mi, bool gm) { return (size_t)(2 * n + me + mi) * ldim(n, gm); }
     __host__ __device__ static size_t vec_doubles(int n, int me, int mi, int ph, int nx, int nu) {
         int m = me + mi + n;
-        return 13 * (size_t)n + 10 * (size_t)m + 2 * (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 8;
+        return 13 * (size_t)n + 10 * (size_t)m + 2 * (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 16;
     }
     __device__ void carve(double* pm, double* p, bool gm, int n_, int me_, int mi_, int ph_, int ch_, int nx_, int nu_) {
         n = n_; me = me_; mi = mi_; m = me + mi + n; ld = ldim(n, gm); nx = nx_; nu = nu_; ph = ph_; ch = ch_;
@@ -70,7 +72,7 @@ struct NlWs {
         double** mv[] = {&E, &ls, &us, &zs, &ys, &rho, &yq, &w, &pr, &pt};
         for (auto q : mv) { *q = p; p += m; }
         ce = p; p += me; ci = p; p += mi; cet = p; p += me; cit = p; p += mi;
-        X = p; p += (ph + 1) * nx; U = p;
+        X = p; p += (ph + 1) * nx; U = p; p += (ph + 1) * nu; red = p;
     }
     // Multiple-shooting sparsity of J_eq (Constraints.hpp:844-905): the rows of stage s touch X_{s-1}, X_s and the control
     // block of stage s; column j is touched by the rows of at most two stages (states) or of its block's stages (inputs).
@@ -84,25 +86,27 @@ struct NlWs {
     }
 };
 
-// out_j (+)= sum_r Je[r][j] v[r] + sum_r Ji[r][j] v[me + r], one lane per column j (coalesced / conflict-free)
+// sum_r Je[r][j] v[r] + sum_r Ji[r][j] v[me + r]  for one column j
 __device__ __forceinline__ double nl_col_dot(const NlWs& w, int j, const double* v) {
     int r0, r1; w.je_rows(j, r0, r1);
     double a = 0;
     for (int r = r0; r < r1; ++r) a = fma(w.Je[(size_t)r * w.ld + j], v[r], a);
+#pragma unroll 4
     for (int r = 0; r < w.mi; ++r) a = fma(w.Ji[(size_t)r * w.ld + j], v[w.me + r], a);
     return a;
 }
 
 // H = c D B D + sigma I + (E A D)' diag(rho) (E A D)  -> Cholesky -> inverse of the factor.  On return w.H holds the
 // symmetric fill S[q][i] = Linv[max(q,i)][min(q,i)], so that both triangular products of nl_kkt_apply read S down a column.
-__device__ bool nl_factor(NlWs& w, int lane, double c, double sigma) {
+template <class G>
+__device__ bool nl_factor(const G& g, NlWs& w, double c, double sigma) {
     const int n = w.n, ld = w.ld, me = w.me, mi = w.mi, mc = me + mi;
-    for (int r = lane; r < mc; r += 32) w.w[r] = w.rho[r] * w.E[r] * w.E[r];
-    __syncwarp();
-    for (int i = 0; i < n; ++i) {                       // row i of the lower triangle, lanes along j <= i
+    for (int r = g.tid; r < mc; r += G::nt) w.w[r] = w.rho[r] * w.E[r] * w.E[r];
+    g.sync();
+    for (int i = g.wid; i < n; i += G::nw) {            // row i of the lower triangle: a warp per row, lanes along j <= i
         int r0, r1; w.je_rows(i, r0, r1);
         const double di = w.D[i];
-        for (int j = lane; j <= i; j += 32) {
+        for (int j = g.lane; j <= i; j += 32) {
             double acc = 0;
             for (int r = r0; r < r1; ++r) { const double* a = w.Je + (size_t)r * ld; acc = fma(w.w[r] * a[i], a[j], acc); }
             for (int r = 0; r < mi; ++r) {
@@ -115,65 +119,70 @@ __device__ bool nl_factor(NlWs& w, int lane, double c, double sigma) {
             w.H[(size_t)i * ld + j] = v;
         }
     }
-    __syncwarp();
+    g.sync();
     bool ok = true;
     for (int k = 0; k < n; ++k) {                       // right-looking Cholesky, lower, in place; column k staged in tmp
         double dkk = w.H[(size_t)k * ld + k];
         if (!(dkk > 0.0)) ok = false;
         double piv = sqrt(dkk), inv = 1.0 / piv;
-        __syncwarp();
-        for (int r = k + lane; r < n; r += 32) {
+        g.sync();
+        for (int r = k + g.tid; r < n; r += G::nt) {
             double v = (r == k) ? piv : w.H[(size_t)r * ld + k] * inv;
             w.H[(size_t)r * ld + k] = v; w.tmp[r] = v;
         }
-        __syncwarp();
-        for (int r = k + 1; r < n; ++r) {
+        g.sync();
+        for (int r = k + 1 + g.wid; r < n; r += G::nw) {
             const double lrk = w.tmp[r];
-            for (int q = k + 1 + lane; q <= r; q += 32) w.H[(size_t)r * ld + q] -= lrk * w.tmp[q];
+            for (int q = k + 1 + g.lane; q <= r; q += 32) w.H[(size_t)r * ld + q] -= lrk * w.tmp[q];
         }
-        __syncwarp();
+        g.sync();
     }
     // inverse of the factor, built in the upper triangle as its transpose (U[q][r] = Linv[r][q]) from the last column back
     for (int j = n - 1; j >= 0; --j) {
         const double ljj = 1.0 / w.H[(size_t)j * ld + j];
-        for (int q = j + 1 + lane; q < n; q += 32) w.tmp[q] = w.H[(size_t)q * ld + j];     // L[:, j]
-        __syncwarp();
-        for (int r = j + 1 + lane; r < n; r += 32) {
+        for (int q = j + 1 + g.tid; q < n; q += G::nt) w.tmp[q] = w.H[(size_t)q * ld + j];     // L[:, j]
+        g.sync();
+        for (int r = j + 1 + g.tid; r < n; r += G::nt) {
             double acc = 0;
+#pragma unroll 4
             for (int q = j + 1; q <= r; ++q) acc = fma(w.H[(size_t)q * ld + r], w.tmp[q], acc);
             w.H[(size_t)j * ld + r] = -ljj * acc;
         }
-        if (lane == 0) w.H[(size_t)j * ld + j] = ljj;
-        __syncwarp();
+        if (g.tid == 0) w.H[(size_t)j * ld + j] = ljj;
+        g.sync();
     }
-    for (int j = 0; j < n; ++j)                         // mirror into the lower triangle
-        for (int r = j + 1 + lane; r < n; r += 32) w.H[(size_t)r * ld + j] = w.H[(size_t)j * ld + r];
-    __syncwarp();
-    return !__any_sync(0xffffffffu, !ok);
+    for (int j = g.wid; j < n; j += G::nw)              // mirror into the lower triangle
+        for (int r = j + 1 + g.lane; r < n; r += 32) w.H[(size_t)r * ld + j] = w.H[(size_t)j * ld + r];
+    g.sync();
+    return !g.any(!ok);
 }
 
 // xt = (Linv' Linv) rhs
-__device__ void nl_kkt_apply(NlWs& w, int lane) {
+template <class G>
+__device__ void nl_kkt_apply(const G& g, NlWs& w) {
     const int n = w.n, ld = w.ld;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = g.tid; i < n; i += G::nt) {
         double acc = 0;
+#pragma unroll 4
         for (int q = 0; q <= i; ++q) acc = fma(w.H[(size_t)q * ld + i], w.rhs[q], acc);
         w.tmp[i] = acc;
     }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    g.sync();
+    for (int i = g.tid; i < n; i += G::nt) {
         double acc = 0;
+#pragma unroll 4
         for (int q = i; q < n; ++q) acc = fma(w.H[(size_t)q * ld + i], w.tmp[q], acc);
         w.xt[i] = acc;
     }
-    __syncwarp();
+    g.sync();
 }
 // out_r = E_r * (A (D.x))_r for all m rows: J_eq rows by their two column runs, J_in rows one warp per row
-__device__ void nl_As(NlWs& w, int lane, const double* x, double* out) {
+template <class G>
+__device__ void nl_As(const G& g, NlWs& w, const double* x, double* out) {
     const int n = w.n, me = w.me, mc = w.me + w.mi, ld = w.ld;
-    for (int i = lane; i < n; i += 32) w.tmp[i] = w.D[i] * x[i];
-    __syncwarp();
-    for (int r = lane; r < me; r += 32) {
+    for (int i = g.tid; i < n; i += G::nt) w.tmp[i] = w.D[i] * x[i];
+    g.sync();
+    for (int r = g.tid; r < me; r += G::nt) {
         int c0, c1, u0; w.je_cols(r, c0, c1, u0);
         const double* row = w.Je + (size_t)r * ld;
         double a = 0;
@@ -181,116 +190,123 @@ __device__ void nl_As(NlWs& w, int lane, const double* x, double* out) {
         for (int j = u0; j < u0 + w.nu; ++j) a = fma(row[j], w.tmp[j], a);
         out[r] = w.E[r] * a;
     }
-    for (int r = 0; r < w.mi; ++r) {
+    for (int r = g.wid; r < w.mi; r += G::nw) {
         const double* row = w.Ji + (size_t)r * ld;
         double a = 0;
-        for (int j = lane; j < n; j += 32) a = fma(row[j], w.tmp[j], a);
+        for (int j = g.lane; j < n; j += 32) a = fma(row[j], w.tmp[j], a);
         a = nl_wsum(a);
-        if (lane == 0) out[me + r] = w.E[me + r] * a;
+        if (g.lane == 0) out[me + r] = w.E[me + r] * a;
     }
-    for (int j = lane; j < n; j += 32) out[mc + j] = w.E[mc + j] * w.tmp[j];
-    __syncwarp();
+    for (int j = g.tid; j < n; j += G::nt) out[mc + j] = w.E[mc + j] * w.tmp[j];
+    g.sync();
 }
 // out_j = D_j * (A' (E.v))_j
-__device__ void nl_Ats(NlWs& w, int lane, const double* v, double* out) {
+template <class G>
+__device__ void nl_Ats(const G& g, NlWs& w, const double* v, double* out) {
     const int n = w.n, mc = w.me + w.mi;
-    for (int r = lane; r < w.m; r += 32) w.w[r] = w.E[r] * v[r];
-    __syncwarp();
-    for (int j = lane; j < n; j += 32) out[j] = w.D[j] * (w.w[mc + j] + nl_col_dot(w, j, w.w));
-    __syncwarp();
+    for (int r = g.tid; r < w.m; r += G::nt) w.w[r] = w.E[r] * v[r];
+    g.sync();
+    for (int j = g.tid; j < n; j += G::nt) out[j] = w.D[j] * (w.w[mc + j] + nl_col_dot(w, j, w.w));
+    g.sync();
 }
-
 // out_i = (c D B D x)_i ; B symmetric, read down its columns
-__device__ void nl_Ps(NlWs& w, int lane, double c, const double* x, double* out) {
+template <class G>
+__device__ void nl_Ps(const G& g, NlWs& w, double c, const double* x, double* out) {
     const int n = w.n, ld = w.ld;
-    for (int i = lane; i < n; i += 32) w.tmp[i] = w.D[i] * x[i];
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    for (int i = g.tid; i < n; i += G::nt) w.tmp[i] = w.D[i] * x[i];
+    g.sync();
+    for (int i = g.tid; i < n; i += G::nt) {
         double acc = 0;
+#pragma unroll 4
         for (int j = 0; j < n; ++j) acc = fma(w.B[(size_t)j * ld + i], w.tmp[j], acc);
         out[i] = c * w.D[i] * acc;
     }
-    __syncwarp();
+    g.sync();
 }
 
 // max bound violation of A x and max |P x + q + A' y| in the scaled problem (uses pt, rhs, zt2)
-__device__ void nl_qp_residuals(NlWs& w, int lane, double c, const double* x, const double* y, double& pri, double& dua) {
-    nl_As(w, lane, x, w.pt);
+template <class G>
+__device__ void nl_qp_residuals(const G& g, NlWs& w, double c, const double* x, const double* y, double& pri, double& dua) {
+    nl_As(g, w, x, w.pt);
     double p = 0, d = 0;
-    for (int r = lane; r < w.m; r += 32) p = fmax(p, fmax(fmax(w.ls[r] - w.pt[r], w.pt[r] - w.us[r]), 0.0));
-    nl_Ats(w, lane, y, w.rhs);
-    nl_Ps(w, lane, c, x, w.zt2);
-    for (int i = lane; i < w.n; i += 32) d = fmax(d, fabs(w.zt2[i] + w.gs[i] + w.rhs[i]));
-    pri = nl_wmax(p); dua = nl_wmax(d);
+    for (int r = g.tid; r < w.m; r += G::nt) p = fmax(p, fmax(fmax(w.ls[r] - w.pt[r], w.pt[r] - w.us[r]), 0.0));
+    nl_Ats(g, w, y, w.rhs);
+    nl_Ps(g, w, c, x, w.zt2);
+    for (int i = g.tid; i < w.n; i += G::nt) d = fmax(d, fabs(w.zt2[i] + w.gs[i] + w.rhs[i]));
+    pri = g.max(p); dua = g.max(d);
 }
 
 // OSQP polish.c on the dense QP: guess the active set from (z, y), solve the equality-constrained QP on it through the
 // same reduced system (rho = 1/delta on active rows, sigma = delta) with iterative refinement, keep the result if both
 // residuals improve.  In: xs, ys, zs.  Out: xs, ys (replaced when accepted).  Destroys H, rho, zs.
-__device__ bool nl_qp_polish(NlWs& w, int lane, double c) {
+template <class G>
+__device__ bool nl_qp_polish(const G& g, NlWs& w, double c) {
     const int n = w.n, m = w.m;
     const double delta = 1e-6, idelta = 1e6;
     double pri_a, dua_a;
-    nl_qp_residuals(w, lane, c, w.xs, w.ys, pri_a, dua_a);
-    for (int r = lane; r < m; r += 32) {
+    nl_qp_residuals(g, w, c, w.xs, w.ys, pri_a, dua_a);
+    for (int r = g.tid; r < m; r += G::nt) {
         bool lo = (w.zs[r] - w.ls[r]) < -w.ys[r], up = (w.us[r] - w.zs[r]) < w.ys[r];
         w.rho[r] = (lo || up) ? idelta : 0.0;
         w.zs[r] = lo ? w.ls[r] : (up ? w.us[r] : 0.0);              // b on the active rows
         w.yq[r] = 0.0;                                              // y_p
     }
-    for (int i = lane; i < n; i += 32) w.g2[i] = 0.0;               // x_p
-    __syncwarp();
-    if (!nl_factor(w, lane, c, delta)) return false;
+    for (int i = g.tid; i < n; i += G::nt) w.g2[i] = 0.0;           // x_p
+    g.sync();
+    if (!nl_factor(g, w, c, delta)) return false;
     for (int it = 0; it <= 5; ++it) {                               // first pass = the plain solve, then 5 refinements
-        nl_Ats(w, lane, w.yq, w.rhs);
-        nl_Ps(w, lane, c, w.g2, w.zt2);
-        for (int i = lane; i < n; i += 32) w.sv[i] = -w.gs[i] - w.zt2[i] - w.rhs[i];          // r1
-        nl_As(w, lane, w.g2, w.pt);
-        for (int r = lane; r < m; r += 32) w.pr[r] = w.rho[r] > 0.0 ? (w.zs[r] - w.pt[r]) * idelta : 0.0;   // r2 / delta
-        __syncwarp();
-        nl_Ats(w, lane, w.pr, w.rhs);
-        for (int i = lane; i < n; i += 32) w.rhs[i] += w.sv[i];
-        __syncwarp();
-        nl_kkt_apply(w, lane);
-        nl_As(w, lane, w.xt, w.pt);
-        for (int r = lane; r < m; r += 32) if (w.rho[r] > 0.0) w.yq[r] += w.pt[r] * idelta - w.pr[r];
-        for (int i = lane; i < n; i += 32) w.g2[i] += w.xt[i];
-        __syncwarp();
+        nl_Ats(g, w, w.yq, w.rhs);
+        nl_Ps(g, w, c, w.g2, w.zt2);
+        for (int i = g.tid; i < n; i += G::nt) w.sv[i] = -w.gs[i] - w.zt2[i] - w.rhs[i];          // r1
+        nl_As(g, w, w.g2, w.pt);
+        for (int r = g.tid; r < m; r += G::nt) w.pr[r] = w.rho[r] > 0.0 ? (w.zs[r] - w.pt[r]) * idelta : 0.0;   // r2 / delta
+        g.sync();
+        nl_Ats(g, w, w.pr, w.rhs);
+        for (int i = g.tid; i < n; i += G::nt) w.rhs[i] += w.sv[i];
+        g.sync();
+        nl_kkt_apply(g, w);
+        nl_As(g, w, w.xt, w.pt);
+        for (int r = g.tid; r < m; r += G::nt) if (w.rho[r] > 0.0) w.yq[r] += w.pt[r] * idelta - w.pr[r];
+        for (int i = g.tid; i < n; i += G::nt) w.g2[i] += w.xt[i];
+        g.sync();
     }
     double pri_p, dua_p;
-    nl_qp_residuals(w, lane, c, w.g2, w.yq, pri_p, dua_p);
+    nl_qp_residuals(g, w, c, w.g2, w.yq, pri_p, dua_p);
     const bool ok = pri_p <= fmax(pri_a, 1e-10) && dua_p <= fmax(dua_a, 1e-10);
     if (ok) {
-        for (int i = lane; i < n; i += 32) w.xs[i] = w.g2[i];
-        for (int r = lane; r < m; r += 32) w.ys[r] = w.yq[r];
-        __syncwarp();
+        for (int i = g.tid; i < n; i += G::nt) w.xs[i] = w.g2[i];
+        for (int r = g.tid; r < m; r += G::nt) w.ys[r] = w.yq[r];
+        g.sync();
     }
     return ok;
 }
 
 // Dense OSQP-style ADMM for the QP subproblem.  In: B, g, Je, Ji, ce, ci, z, lb, ub; warm dual yq (if have_y).
 // Out: d (step), yq (multipliers, unscaled).  Returns ADMM iterations.
-__device__ int nl_qp_solve(NlWs& w, int lane, const NlSolveArgs& a, bool have_y) {
+template <class G>
+__device__ int nl_qp_solve(const G& g, NlWs& w, const NlSolveArgs& a, bool have_y) {
     const int n = w.n, me = w.me, mi = w.mi, mc = me + mi, m = w.m, ld = w.ld;
     const double sigma = 1e-6, alpha = 1.6;
     // ---- Ruiz equilibration (10 passes) with cost normalisation
-    for (int i = lane; i < n; i += 32) { w.D[i] = 1.0; w.gs[i] = w.g[i]; }
-    for (int r = lane; r < m; r += 32) w.E[r] = 1.0;
+    for (int i = g.tid; i < n; i += G::nt) { w.D[i] = 1.0; w.gs[i] = w.g[i]; }
+    for (int r = g.tid; r < m; r += G::nt) w.E[r] = 1.0;
     double c = 1.0;
-    __syncwarp();
+    g.sync();
     for (int pass = 0; pass < 10; ++pass) {
-        for (int j = lane; j < n; j += 32) {        // column norms -> xt ; uses old D,E
+        for (int j = g.tid; j < n; j += G::nt) {    // column norms -> xt ; uses old D,E
             double cn = 0;
+#pragma unroll 4
             for (int i = 0; i < n; ++i) cn = fmax(cn, w.D[i] * fabs(w.B[(size_t)i * ld + j]));
             cn *= c * w.D[j];
             double an = 0;
             int r0, r1; w.je_rows(j, r0, r1);
             for (int r = r0; r < r1; ++r) an = fmax(an, w.E[r] * fabs(w.Je[(size_t)r * ld + j]));
+#pragma unroll 4
             for (int r = 0; r < mi; ++r) an = fmax(an, w.E[me + r] * fabs(w.Ji[(size_t)r * ld + j]));
             an = fmax(an, w.E[mc + j]) * w.D[j];
             w.xt[j] = 1.0 / sqrt(nl_lim(fmax(cn, an)));
         }
-        for (int r = lane; r < me; r += 32) {       // row norms -> w
+        for (int r = g.tid; r < me; r += G::nt) {   // row norms -> w
             int c0, c1, u0; w.je_cols(r, c0, c1, u0);
             const double* row = w.Je + (size_t)r * ld;
             double rn = 0;
@@ -298,138 +314,141 @@ __device__ int nl_qp_solve(NlWs& w, int lane, const NlSolveArgs& a, bool have_y)
             for (int j = u0; j < u0 + w.nu; ++j) rn = fmax(rn, fabs(row[j]) * w.D[j]);
             w.w[r] = 1.0 / sqrt(nl_lim(rn * w.E[r]));
         }
-        for (int r = 0; r < mi; ++r) {
+        for (int r = g.wid; r < mi; r += G::nw) {
             const double* row = w.Ji + (size_t)r * ld;
             double rn = 0;
-            for (int j = lane; j < n; j += 32) rn = fmax(rn, fabs(row[j]) * w.D[j]);
+            for (int j = g.lane; j < n; j += 32) rn = fmax(rn, fabs(row[j]) * w.D[j]);
             rn = nl_wmax(rn);
-            if (lane == 0) w.w[me + r] = 1.0 / sqrt(nl_lim(rn * w.E[me + r]));
+            if (g.lane == 0) w.w[me + r] = 1.0 / sqrt(nl_lim(rn * w.E[me + r]));
         }
-        for (int j = lane; j < n; j += 32) w.w[mc + j] = 1.0 / sqrt(nl_lim(w.E[mc + j] * w.D[j]));
-        __syncwarp();
-        for (int j = lane; j < n; j += 32) { w.D[j] *= w.xt[j]; w.gs[j] *= w.xt[j]; }
-        for (int r = lane; r < m; r += 32) w.E[r] *= w.w[r];
-        __syncwarp();
+        for (int j = g.tid; j < n; j += G::nt) w.w[mc + j] = 1.0 / sqrt(nl_lim(w.E[mc + j] * w.D[j]));
+        g.sync();
+        for (int j = g.tid; j < n; j += G::nt) { w.D[j] *= w.xt[j]; w.gs[j] *= w.xt[j]; }
+        for (int r = g.tid; r < m; r += G::nt) w.E[r] *= w.w[r];
+        g.sync();
         double psum = 0, qmax = 0;
-        for (int j = lane; j < n; j += 32) {
+        for (int j = g.tid; j < n; j += G::nt) {
             double cn = 0;
+#pragma unroll 4
             for (int i = 0; i < n; ++i) cn = fmax(cn, w.D[i] * fabs(w.B[(size_t)i * ld + j]));
             psum += c * cn * w.D[j];
             qmax = fmax(qmax, fabs(w.gs[j]));
         }
-        psum = nl_wsum(psum); qmax = nl_wmax(qmax);
+        psum = g.sum(psum); qmax = g.max(qmax);
         double ct = fmax(psum / n, nl_lim(qmax));
         ct = 1.0 / nl_lim(ct);
         c *= ct;
-        for (int j = lane; j < n; j += 32) w.gs[j] *= ct;
-        __syncwarp();
+        for (int j = g.tid; j < n; j += G::nt) w.gs[j] *= ct;
+        g.sync();
     }
     // ---- scaled bounds, rho per row
     double rho0 = a.rho0;
-    for (int r = lane; r < m; r += 32) {
+    for (int r = g.tid; r < m; r += G::nt) {
         double l, u;
         if (r < me) { l = u = -w.ce[r]; }
         else if (r < mc) { l = -INFINITY; u = -w.ci[r - me]; }
         else { int j = r - mc; l = a.lb[j] - w.z[j]; u = a.ub[j] - w.z[j]; }
         w.ls[r] = w.E[r] * l; w.us[r] = w.E[r] * u;
     }
-    __syncwarp();
+    g.sync();
     auto set_rho = [&](double r0) {
-        for (int r = lane; r < m; r += 32)         // OSQP's row classes: no bounds -> RHO_MIN, equality -> 1e3 rho
+        for (int r = g.tid; r < m; r += G::nt)     // OSQP's row classes: no bounds -> RHO_MIN, equality -> 1e3 rho
             w.rho[r] = (w.ls[r] < -1e20 && w.us[r] > 1e20) ? 1e-6 : ((w.us[r] - w.ls[r]) < 1e-9) ? 1e3 * r0 : r0;
-        __syncwarp();
+        g.sync();
     };
     set_rho(rho0);
-    nl_factor(w, lane, c, sigma);
+    nl_factor(g, w, c, sigma);
     // ---- start: x = 0, y = warm (scaled), z = clip(A x)
-    for (int i = lane; i < n; i += 32) w.xs[i] = 0.0;
-    for (int r = lane; r < m; r += 32) { w.ys[r] = have_y ? c * w.yq[r] / w.E[r] : 0.0; w.zs[r] = fmin(fmax(0.0, w.ls[r]), w.us[r]); }
-    __syncwarp();
+    for (int i = g.tid; i < n; i += G::nt) w.xs[i] = 0.0;
+    for (int r = g.tid; r < m; r += G::nt) { w.ys[r] = have_y ? c * w.yq[r] / w.E[r] : 0.0; w.zs[r] = fmin(fmax(0.0, w.ls[r]), w.us[r]); }
+    g.sync();
     int it = 0;
     for (it = 1; it <= a.max_qp; ++it) {
-        for (int r = lane; r < m; r += 32) w.yq[r] = w.rho[r] * w.zs[r] - w.ys[r];     // yq as temp
-        __syncwarp();
-        nl_Ats(w, lane, w.yq, w.rhs);
-        for (int i = lane; i < n; i += 32) w.rhs[i] += sigma * w.xs[i] - w.gs[i];
-        __syncwarp();
-        nl_kkt_apply(w, lane);
-        nl_As(w, lane, w.xt, w.yq);                                                    // z~ in yq
-        for (int i = lane; i < n; i += 32) w.xs[i] = alpha * w.xt[i] + (1 - alpha) * w.xs[i];
-        for (int r = lane; r < m; r += 32) {
+        for (int r = g.tid; r < m; r += G::nt) w.yq[r] = w.rho[r] * w.zs[r] - w.ys[r];     // yq as temp
+        g.sync();
+        nl_Ats(g, w, w.yq, w.rhs);
+        for (int i = g.tid; i < n; i += G::nt) w.rhs[i] += sigma * w.xs[i] - w.gs[i];
+        g.sync();
+        nl_kkt_apply(g, w);
+        nl_As(g, w, w.xt, w.yq);                                                       // z~ in yq
+        for (int i = g.tid; i < n; i += G::nt) w.xs[i] = alpha * w.xt[i] + (1 - alpha) * w.xs[i];
+        for (int r = g.tid; r < m; r += G::nt) {
             double zr = alpha * w.yq[r] + (1 - alpha) * w.zs[r];
             double zn = fmin(fmax(zr + w.ys[r] / w.rho[r], w.ls[r]), w.us[r]);
             w.ys[r] += w.rho[r] * (zr - zn);
             w.zs[r] = zn;
         }
-        __syncwarp();
+        g.sync();
         if (it % 25 == 0) {
-            nl_As(w, lane, w.xs, w.yq);                       // Ax
+            nl_As(g, w, w.xs, w.yq);                          // Ax
             double pri = 0, nz = 0, nAx = 0;
-            for (int r = lane; r < m; r += 32) { pri = fmax(pri, fabs(w.yq[r] - w.zs[r])); nz = fmax(nz, fabs(w.zs[r])); nAx = fmax(nAx, fabs(w.yq[r])); }
-            nl_Ats(w, lane, w.ys, w.rhs);                     // A'y
+            for (int r = g.tid; r < m; r += G::nt) { pri = fmax(pri, fabs(w.yq[r] - w.zs[r])); nz = fmax(nz, fabs(w.zs[r])); nAx = fmax(nAx, fabs(w.yq[r])); }
+            nl_Ats(g, w, w.ys, w.rhs);                        // A'y
+            nl_Ps(g, w, c, w.xs, w.zt2);                      // Px
             double dua = 0, nq = 0, nAty = 0, nPx = 0;
-            for (int i = lane; i < n; i += 32) {              // Px = c D B D x
-                double acc = 0;
-                for (int j = 0; j < n; ++j) acc = fma(w.B[(size_t)j * ld + i], w.D[j] * w.xs[j], acc);      // B is symmetric
-                double px = c * w.D[i] * acc;
+            for (int i = g.tid; i < n; i += G::nt) {
+                double px = w.zt2[i];
                 dua = fmax(dua, fabs(px + w.gs[i] + w.rhs[i])); nq = fmax(nq, fabs(w.gs[i])); nAty = fmax(nAty, fabs(w.rhs[i])); nPx = fmax(nPx, fabs(px));
             }
-            pri = nl_wmax(pri); nz = nl_wmax(nz); nAx = nl_wmax(nAx); dua = nl_wmax(dua); nq = nl_wmax(nq); nAty = nl_wmax(nAty); nPx = nl_wmax(nPx);
+            pri = g.max(pri); nz = g.max(nz); nAx = g.max(nAx); dua = g.max(dua); nq = g.max(nq); nAty = g.max(nAty); nPx = g.max(nPx);
             if (pri < a.qp_eps && dua < a.qp_eps) break;
             double pn = pri / (fmax(nz, nAx) + 1e-10), dn = dua / (fmax(fmax(nq, nAty), nPx) + 1e-10);
             double est = fmin(fmax(rho0 * sqrt(pn / (dn + 1e-10)), 1e-6), 1e6);
-            if (est > 5 * rho0 || est < rho0 / 5) { rho0 = est; set_rho(rho0); nl_factor(w, lane, c, sigma); }
+            if (est > 5 * rho0 || est < rho0 / 5) { rho0 = est; set_rho(rho0); nl_factor(g, w, c, sigma); }
         }
     }
     if (it > a.max_qp) it = a.max_qp;
-    nl_qp_polish(w, lane, c);
-    for (int i = lane; i < n; i += 32) w.d[i] = w.D[i] * w.xs[i];
-    for (int r = lane; r < m; r += 32) w.yq[r] = w.E[r] * w.ys[r] / c;
-    __syncwarp();
+    nl_qp_polish(g, w, c);
+    for (int i = g.tid; i < n; i += G::nt) w.d[i] = w.D[i] * w.xs[i];
+    for (int r = g.tid; r < m; r += G::nt) w.yq[r] = w.E[r] * w.ys[r] / c;
+    g.sync();
     return it;
 }
 
-template <class S, bool GM>
-__global__ void __launch_bounds__(GM ? 128 : 64) nlmpc_solve_kernel(const NlSolveArgs a) {
+// One controller per thread group of NT threads: NT = 32 -> one warp, several controllers per CTA; NT > 32 -> the CTA.
+template <class S, bool GM, int NT>
+__global__ void __launch_bounds__(NT == 32 ? 64 : NT) nlmpc_solve_kernel(const NlSolveArgs a) {
     extern __shared__ __align__(16) double nls_smem[];
     constexpr int nx = S::nx, nu = S::nu;
+    using G = NlGrp<NT>;
     const int ph = a.ph, ch = a.ch;
     const int n = ph * nx + ch * nu + 1, me = ph * nx, mi = S::nineq(ph);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int gpb = blockDim.x / NT, gi = threadIdx.x / NT;            // groups per CTA, this thread's group
     const size_t nvec = NlWs::vec_doubles(n, me, mi, ph, nx, nu), nmat = NlWs::mat_doubles(n, me, mi, GM);
     NlWs w;
-    if (GM) w.carve(a.mat_ws + (size_t)(blockIdx.x * wpb + warp) * nmat, nls_smem + (size_t)warp * nvec, true, n, me, mi, ph, ch, nx, nu);
-    else { double* base = nls_smem + (size_t)warp * (nvec + nmat); w.carve(base, base + nmat, false, n, me, mi, ph, ch, nx, nu); }
+    if (GM) w.carve(a.mat_ws + (size_t)(blockIdx.x * gpb + gi) * nmat, nls_smem + (size_t)gi * nvec, true, n, me, mi, ph, ch, nx, nu);
+    else { double* base = nls_smem + (size_t)gi * (nvec + nmat); w.carve(base, base + nmat, false, n, me, mi, ph, ch, nx, nu); }
+    const G g{(int)(threadIdx.x % NT), (int)(threadIdx.x & 31), (int)((threadIdx.x % NT) >> 5), w.red};
     const int mc = me + mi, ld = w.ld;
-    for (int inst = blockIdx.x * wpb + warp; inst < a.batch; inst += gridDim.x * wpb) {
+    for (int inst = blockIdx.x * gpb + gi; inst < a.batch; inst += gridDim.x * gpb) {
         const double* p = a.params + (size_t)inst * a.param_stride;
         const double* x0 = a.x0 + (size_t)inst * nx;
-        for (int i = lane; i < n; i += 32) w.z[i] = fmin(fmax(a.z0[(size_t)inst * n + i], a.lb[i]), a.ub[i]);
-        for (int e = lane; e < n * ld; e += 32) { int i = e / ld, j = e - i * ld; w.B[e] = (i == j) ? 1.0 : 0.0; }
-        __syncwarp();
+        for (int i = g.tid; i < n; i += NT) w.z[i] = fmin(fmax(a.z0[(size_t)inst * n + i], a.lb[i]), a.ub[i]);
+        for (int e = g.tid; e < n * ld; e += NT) { int i = e / ld, j = e - i * ld; w.B[e] = (i == j) ? 1.0 : 0.0; }
+        g.sync();
         double fval = 0;
-        nl_eval_instance<S>(lane, ph, ch, w.z, x0, p, w.X, w.U, w.tmp, w.g, w.ce, w.Je, w.ci, w.Ji, ld);
+        nl_eval_instance<S>(g, ph, ch, w.z, x0, p, w.X, w.U, w.tmp, w.g, w.ce, w.Je, w.ci, w.Ji, ld);
         fval = w.tmp[0];
-        __syncwarp();
+        g.sync();
         double mu = 1.0;
         bool have_y = false;
         int k = 0, qp_total = 0, status = 1, resets = 0;
         bool just_reset = false;
         auto violation = [&](const double* ce, const double* ci) {
             double v = 0;
-            for (int r = lane; r < me; r += 32) v += fabs(ce[r]);
-            for (int r = lane; r < mi; r += 32) v += fmax(ci[r], 0.0);
-            return nl_wsum(v);
+            for (int r = g.tid; r < me; r += NT) v += fabs(ce[r]);
+            for (int r = g.tid; r < mi; r += NT) v += fmax(ci[r], 0.0);
+            return g.sum(v);
         };
         for (k = 0; k < a.max_sqp; ++k) {
-            qp_total += nl_qp_solve(w, lane, a, have_y);
+            qp_total += nl_qp_solve(g, w, a, have_y);
             have_y = true;
             // L1 merit line search
             double v0 = violation(w.ce, w.ci);
             double ymax = 0, gd = 0;
-            for (int r = lane; r < mc; r += 32) ymax = fmax(ymax, fabs(w.yq[r]));
-            for (int i = lane; i < n; i += 32) gd += w.g[i] * w.d[i];
-            ymax = nl_wmax(ymax); gd = nl_wsum(gd);
+            for (int r = g.tid; r < mc; r += NT) ymax = fmax(ymax, fabs(w.yq[r]));
+            for (int i = g.tid; i < n; i += NT) gd += w.g[i] * w.d[i];
+            ymax = g.max(ymax); gd = g.sum(gd);
             mu = fmax(mu, 1.1 * ymax);
             const double phi0 = fval + mu * v0, dphi = gd - mu * v0;
             // Kraft's first stopping test (|g'd| and the violation below the accuracy): nothing left to gain
@@ -437,11 +456,11 @@ __global__ void __launch_bounds__(GM ? 128 : 64) nlmpc_solve_kernel(const NlSolv
             double t = 1.0, ft = fval;
             bool ls_ok = false;
             for (int ls = 0; ls < 25; ++ls) {
-                for (int i = lane; i < n; i += 32) w.zt2[i] = w.z[i] + t * w.d[i];
-                __syncwarp();
-                nl_eval_instance<S>(lane, ph, ch, w.zt2, x0, p, w.X, w.U, w.tmp, nullptr, w.cet, nullptr, w.cit, nullptr, ld);
+                for (int i = g.tid; i < n; i += NT) w.zt2[i] = w.z[i] + t * w.d[i];
+                g.sync();
+                nl_eval_instance<S>(g, ph, ch, w.zt2, x0, p, w.X, w.U, w.tmp, nullptr, w.cet, nullptr, w.cit, nullptr, ld);
                 ft = w.tmp[0];
-                __syncwarp();
+                g.sync();
                 double vt = violation(w.cet, w.cit);
                 if (ft + mu * vt <= phi0 + 1e-4 * t * dphi) { ls_ok = true; break; }
                 t *= 0.5;
@@ -450,60 +469,59 @@ __global__ void __launch_bounds__(GM ? 128 : 64) nlmpc_solve_kernel(const NlSolv
                 // no decrease of the merit along d at any step length: restart the quasi-Newton matrix once (as SLSQP
                 // does); failing again straight after the restart is the finite-difference noise floor.
                 if (just_reset || resets >= 5) { status = v0 < 1e-8 ? 0 : 1; ++k; break; }
-                for (int e = lane; e < n * ld; e += 32) { int i = e / ld, j = e - i * ld; w.B[e] = (i == j) ? 1.0 : 0.0; }
-                __syncwarp();
+                for (int e = g.tid; e < n * ld; e += NT) { int i = e / ld, j = e - i * ld; w.B[e] = (i == j) ? 1.0 : 0.0; }
+                g.sync();
                 ++resets; just_reset = true;
                 continue;
             }
             just_reset = false;
             // s = t d ; Lagrangian gradient at the old point with the new multipliers
-            for (int i = lane; i < n; i += 32) { w.sv[i] = t * w.d[i]; }
-            __syncwarp();
-            for (int j = lane; j < n; j += 32) {
-                w.glo[j] = w.g[j] + nl_col_dot(w, j, w.yq);
-            }
-            for (int i = lane; i < n; i += 32) w.z[i] += w.sv[i];
-            __syncwarp();
-            nl_eval_instance<S>(lane, ph, ch, w.z, x0, p, w.X, w.U, w.tmp, w.g2, w.ce, w.Je, w.ci, w.Ji, ld);
+            for (int i = g.tid; i < n; i += NT) w.sv[i] = t * w.d[i];
+            for (int j = g.tid; j < n; j += NT) w.glo[j] = w.g[j] + nl_col_dot(w, j, w.yq);
+            g.sync();
+            for (int i = g.tid; i < n; i += NT) w.z[i] += w.sv[i];
+            g.sync();
+            nl_eval_instance<S>(g, ph, ch, w.z, x0, p, w.X, w.U, w.tmp, w.g2, w.ce, w.Je, w.ci, w.Ji, ld);
             fval = w.tmp[0];
-            __syncwarp();
+            g.sync();
             // damped BFGS:  yk = gl_new - gl_old,  Bs = B s
             double sBs = 0, sy = 0;
-            for (int j = lane; j < n; j += 32) {
+            for (int j = g.tid; j < n; j += NT) {
                 w.rhs[j] = (w.g2[j] + nl_col_dot(w, j, w.yq)) - w.glo[j];          // yk
                 double bs = 0;
+#pragma unroll 4
                 for (int q = 0; q < n; ++q) bs = fma(w.B[(size_t)q * ld + j], w.sv[q], bs);      // symmetric B, column access
                 w.xt[j] = bs;                                  // Bs
                 sBs += w.sv[j] * bs; sy += w.sv[j] * w.rhs[j];
             }
-            sBs = nl_wsum(sBs); sy = nl_wsum(sy);
-            __syncwarp();
+            sBs = g.sum(sBs); sy = g.sum(sy);
+            g.sync();
             if (sBs > 1e-300) {
                 double theta = (sy >= 0.2 * sBs) ? 1.0 : 0.8 * sBs / (sBs - sy);
                 double sr = 0;
-                for (int j = lane; j < n; j += 32) { double r = theta * w.rhs[j] + (1 - theta) * w.xt[j]; w.rhs[j] = r; sr += w.sv[j] * r; }
-                sr = nl_wsum(sr);
-                __syncwarp();
-                for (int e = lane; e < n * n; e += 32) {
+                for (int j = g.tid; j < n; j += NT) { double r = theta * w.rhs[j] + (1 - theta) * w.xt[j]; w.rhs[j] = r; sr += w.sv[j] * r; }
+                sr = g.sum(sr);
+                g.sync();
+                for (int e = g.tid; e < n * n; e += NT) {
                     int i = e / n, j = e - i * n;
                     w.B[(size_t)i * ld + j] += -w.xt[i] * w.xt[j] / sBs + w.rhs[i] * w.rhs[j] / sr;
                 }
             }
-            for (int i = lane; i < n; i += 32) w.g[i] = w.g2[i];
-            __syncwarp();
+            for (int i = g.tid; i < n; i += NT) w.g[i] = w.g2[i];
+            g.sync();
             double step = 0, zmax = 0;
             // the full QP step d is small only at a KKT point (t*d can be small far from one)
-            for (int i = lane; i < n; i += 32) { step = fmax(step, fabs(w.d[i])); zmax = fmax(zmax, fabs(w.z[i])); }
-            step = nl_wmax(step); zmax = nl_wmax(zmax);
+            for (int i = g.tid; i < n; i += NT) { step = fmax(step, fabs(w.d[i])); zmax = fmax(zmax, fabs(w.z[i])); }
+            step = g.max(step); zmax = g.max(zmax);
             double v1 = violation(w.ce, w.ci);
             if (step < a.tol * fmax(1.0, zmax) && v1 < 1e-8) { status = 0; ++k; break; }
         }
         double vf = violation(w.ce, w.ci);
-        for (int i = lane; i < n; i += 32) a.z_out[(size_t)inst * n + i] = w.z[i];
-        if (lane == 0) {
+        for (int i = g.tid; i < n; i += NT) a.z_out[(size_t)inst * n + i] = w.z[i];
+        if (g.tid == 0) {
             a.cost[inst] = fval; a.viol[inst] = vf; a.status[inst] = status; a.iters[inst] = k; a.qp_iters[inst] = qp_total;
         }
-        __syncwarp();
+        g.sync();
     }
 }
 
