@@ -105,7 +105,7 @@ static size_t nl_solve_smem(int system, int ph, int ch) {
     int nx, nu, np, ni;
     if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return 0;
     int n = ph * nx + ch * nu + 1, me = ph * nx;
-    return (NlWs::vec_doubles(n, me, ni, ph, nx, nu) + NlWs::mat_doubles(n, me, ni, false)) * sizeof(double);
+    return NlWs::smem_doubles(0, n, me, ni, ph, nx, nu) * sizeof(double);
 }
 extern "C" long long b200mpc_nlmpc_solve_smem_bytes(int system, int ph, int ch) { return (long long)nl_solve_smem(system, ph, ch); }
 

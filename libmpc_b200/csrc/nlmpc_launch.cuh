@@ -21,10 +21,10 @@ int nl_eval_t(const NlEvalArgs& a, cudaStream_t stream) {
     return B200MPC_OK;
 }
 
-template <class S, bool GM, int NT>
-int nl_launch_t(NlSolveArgs& a, size_t smem_per_group, int groups_per_cta, size_t mat_doubles, int sms, cudaStream_t stream,
-                       std::vector<void*>& tofree) {
-    auto kern = nlmpc_solve_kernel<S, GM, NT>;
+template <class S, int MODE, int NT>
+int nl_launch_t(NlSolveArgs& a, size_t smem_per_group, int groups_per_cta, size_t gmem_doubles, int sms, cudaStream_t stream,
+                std::vector<void*>& tofree) {
+    auto kern = nlmpc_solve_kernel<S, MODE, NT>;
     const size_t smem = smem_per_group * groups_per_cta;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
@@ -33,9 +33,9 @@ int nl_launch_t(NlSolveArgs& a, size_t smem_per_group, int groups_per_cta, size_
     int grid = (a.batch + groups_per_cta - 1) / groups_per_cta;
     if (grid > sms * occ) grid = sms * occ;
     a.mat_ws = nullptr;
-    if (GM) {
+    if (MODE) {
         void* ws = nullptr;
-        CK(cudaMalloc(&ws, (size_t)grid * groups_per_cta * mat_doubles * sizeof(double)));
+        CK(cudaMalloc(&ws, (size_t)grid * groups_per_cta * gmem_doubles * sizeof(double)));
         tofree.push_back(ws);
         a.mat_ws = (double*)ws;
     }
@@ -44,8 +44,9 @@ int nl_launch_t(NlSolveArgs& a, size_t smem_per_group, int groups_per_cta, size_
     return B200MPC_OK;
 }
 
-// Launch policy: matrices in shared memory when they fit (a warp per controller for tiny problems, a 4-warp CTA otherwise),
-// else an 8-warp CTA per controller with the matrices in a per-CTA HBM workspace.
+// Launch policy (NlWs residency modes): everything in shared memory when it fits (a warp per controller for tiny problems,
+// a 4-warp CTA otherwise); else the packed KKT factor in shared memory and B / J in a per-CTA HBM workspace (8 warps);
+// else everything in the workspace.
 template <class S>
 int nl_solve_t(NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree) {
     int dev = 0, sms = 0, maxsm = 0;
@@ -54,16 +55,15 @@ int nl_solve_t(NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree) 
     CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int n = a.ph * S::nx + a.ch * S::nu + 1, me = a.ph * S::nx;
     const int ni = S::nineq(a.ph);
-    const size_t vecb = NlWs::vec_doubles(n, me, ni, a.ph, S::nx, S::nu) * sizeof(double);
-    const size_t matb = NlWs::mat_doubles(n, me, ni, false) * sizeof(double);
-    if (vecb + matb <= (size_t)maxsm) {
-        if (n <= 32) return nl_launch_t<S, false, 32>(a, vecb + matb, 2 * (vecb + matb) <= (size_t)maxsm / 2 ? 2 : 1, 0, sms, stream, tofree);
-        return nl_launch_t<S, false, 128>(a, vecb + matb, 1, 0, sms, stream, tofree);
+    auto sm = [&](int mode) { return NlWs::smem_doubles(mode, n, me, ni, a.ph, S::nx, S::nu) * sizeof(double); };
+    if (sm(0) <= (size_t)maxsm) {
+        if (n <= 32) return nl_launch_t<S, 0, 32>(a, sm(0), 2 * sm(0) <= (size_t)maxsm / 2 ? 2 : 1, 0, sms, stream, tofree);
+        return nl_launch_t<S, 0, 128>(a, sm(0), 1, 0, sms, stream, tofree);
     }
-    if (vecb > (size_t)maxsm) return fail(B200MPC_EINVAL, "NLMPC problem too large: its vectors do not fit shared memory");
-    return nl_launch_t<S, true, 256>(a, vecb, 1, NlWs::mat_doubles(n, me, ni, true), sms, stream, tofree);
+    if (sm(1) <= (size_t)maxsm) return nl_launch_t<S, 1, 256>(a, sm(1), 1, NlWs::gmem_doubles(1, n, me, ni), sms, stream, tofree);
+    if (sm(2) > (size_t)maxsm) return fail(B200MPC_EINVAL, "NLMPC problem too large: its vectors do not fit shared memory");
+    return nl_launch_t<S, 2, 256>(a, sm(2), 1, NlWs::gmem_doubles(2, n, me, ni), sms, stream, tofree);
 }
-
 
 #define B200MPC_INSTANTIATE_NL_SYSTEM(S)                                                         \
     template int nl_eval_t<S>(const NlEvalArgs&, cudaStream_t);                                   \

@@ -32,7 +32,7 @@ struct NlSolveArgs {
     int* status;            // 0 converged, 1 iteration limit
     int* iters;             // SQP iterations
     int* qp_iters;          // total ADMM iterations
-    double* mat_ws;         // GM kernels: per-CTA matrix workspace [grid][mat_doubles]
+    double* mat_ws;         // MODE 1/2 kernels: per-CTA matrix workspace [grid][NlWs::gmem_doubles]
 };
 
 __device__ __forceinline__ double nl_wsum(double v) {
@@ -47,26 +47,41 @@ __device__ __forceinline__ double nl_wmax(double v) {
 }
 __device__ __forceinline__ double nl_lim(double v) { v = v < 1e-4 ? 1.0 : v; return v > 1e4 ? 1e4 : v; }
 
-// Per-controller workspace.  Vectors always live in shared memory; the four matrices (B, KKT factor, J_eq, J_in) live in
-// shared memory when the problem is small (GM = false) and in a per-CTA HBM/L2 workspace otherwise (GM = true).  Every
-// matrix pass below runs with consecutive threads along the contiguous (column) index: coalesced in HBM, conflict-free
-// in shared memory.
+// Per-controller workspace.  Vectors always live in shared memory.  The KKT factor H is held PACKED (lower triangle,
+// row-major: element (i,j), j <= i, at i(i+1)/2 + j -- row walks by consecutive threads are bank-conflict free because
+// triangular numbers are a permutation mod 32, column walks are contiguous).  Residency (template parameter MODE):
+//   0: B, J_eq, J_in and H in shared memory                       (vanderpol, the shipped ugv)
+//   1: H in shared memory, B / J_eq / J_in in a per-CTA HBM workspace (L2-resident)   (ugv Tph=30, oscillator network N=4)
+//   2: everything in the HBM workspace                            (nz > ~190)
+// Matrix passes over B / J run with consecutive threads along the contiguous (column) index.
 struct NlWs {
     int n, me, mi, m, ld, nx, nu, ph, ch;
-    double *B, *H, *Je, *Ji;                 // n x ld, n x ld, me x ld, mi x ld (row-major)
+    double *B, *H, *Je, *Ji;                 // n x ld, packed n(n+1)/2, me x ld, mi x ld (row-major)
     double *z, *g, *g2, *d, *xs, *xt, *D, *gs, *rhs, *tmp, *glo, *sv, *zt2;     // n
     double *E, *ls, *us, *zs, *ys, *rho, *yq, *w, *pr, *pt;                     // m
     double *ce, *ci, *cet, *cit;                                                // me, mi, me, mi
     double *X, *U, *red;
-    __host__ __device__ static int ldim(int n, bool gm) { return gm ? ((n + 3) & ~3) : (n | 1); }
-    __host__ __device__ static size_t mat_doubles(int n, int me, int mi, bool gm) { return (size_t)(2 * n + me + mi) * ldim(n, gm); }
+    __host__ __device__ static int ldim(int n, bool global) { return global ? ((n + 3) & ~3) : (n | 1); }
+    __host__ __device__ static size_t h_doubles(int n) { return ((size_t)n * (n + 1) / 2 + 1) & ~(size_t)1; }
+    __host__ __device__ static size_t mat_doubles(int n, int me, int mi, bool global) { return (size_t)(n + me + mi) * ldim(n, global); }
     __host__ __device__ static size_t vec_doubles(int n, int me, int mi, int ph, int nx, int nu) {
         int m = me + mi + n;
         return 13 * (size_t)n + 10 * (size_t)m + 2 * (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 16;
     }
-    __device__ void carve(double* pm, double* p, bool gm, int n_, int me_, int mi_, int ph_, int ch_, int nx_, int nu_) {
-        n = n_; me = me_; mi = mi_; m = me + mi + n; ld = ldim(n, gm); nx = nx_; nu = nu_; ph = ph_; ch = ch_;
-        B = pm; pm += (size_t)n * ld; H = pm; pm += (size_t)n * ld; Je = pm; pm += (size_t)me * ld; Ji = pm;
+    // shared / global doubles one controller needs in each residency mode
+    __host__ __device__ static size_t smem_doubles(int mode, int n, int me, int mi, int ph, int nx, int nu) {
+        return vec_doubles(n, me, mi, ph, nx, nu) + (mode <= 1 ? h_doubles(n) : 0) + (mode == 0 ? mat_doubles(n, me, mi, false) : 0);
+    }
+    __host__ __device__ static size_t gmem_doubles(int mode, int n, int me, int mi) {
+        return (mode >= 1 ? mat_doubles(n, me, mi, true) : 0) + (mode == 2 ? h_doubles(n) : 0);
+    }
+    __device__ void carve(int mode, double* sm, double* gm, int n_, int me_, int mi_, int ph_, int ch_, int nx_, int nu_) {
+        n = n_; me = me_; mi = mi_; m = me + mi + n; ld = ldim(n, mode >= 1); nx = nx_; nu = nu_; ph = ph_; ch = ch_;
+        double*& pm = mode >= 1 ? gm : sm;
+        B = pm; pm += (size_t)n * ld; Je = pm; pm += (size_t)me * ld; Ji = pm; pm += (size_t)mi * ld;
+        double*& phh = mode == 2 ? gm : sm;
+        H = phh; phh += h_doubles(n);
+        double* p = sm;
         double** nv[] = {&z, &g, &g2, &d, &xs, &xt, &D, &gs, &rhs, &tmp, &glo, &sv, &zt2};
         for (auto q : nv) { *q = p; p += n; }
         double** mv[] = {&E, &ls, &us, &zs, &ys, &rho, &yq, &w, &pr, &pt};
@@ -74,6 +89,7 @@ struct NlWs {
         ce = p; p += me; ci = p; p += mi; cet = p; p += me; cit = p; p += mi;
         X = p; p += (ph + 1) * nx; U = p; p += (ph + 1) * nu; red = p;
     }
+    __device__ __forceinline__ static size_t tri(int i) { return (size_t)i * (i + 1) / 2; }
     // Multiple-shooting sparsity of J_eq (Constraints.hpp:844-905): the rows of stage s touch X_{s-1}, X_s and the control
     // block of stage s; column j is touched by the rows of at most two stages (states) or of its block's stages (inputs).
     __device__ __forceinline__ void je_cols(int r, int& c0, int& c1, int& u0) const {
@@ -96,8 +112,7 @@ __device__ __forceinline__ double nl_col_dot(const NlWs& w, int j, const double*
     return a;
 }
 
-// H = c D B D + sigma I + (E A D)' diag(rho) (E A D)  -> Cholesky -> inverse of the factor.  On return w.H holds the
-// symmetric fill S[q][i] = Linv[max(q,i)][min(q,i)], so that both triangular products of nl_kkt_apply read S down a column.
+// H = c D B D + sigma I + (E A D)' diag(rho) (E A D)  -> Cholesky -> in-place inverse of the factor (packed lower).
 template <class G>
 __device__ bool nl_factor(const G& g, NlWs& w, double c, double sigma) {
     const int n = w.n, ld = w.ld, me = w.me, mi = w.mi, mc = me + mi;
@@ -106,6 +121,7 @@ __device__ bool nl_factor(const G& g, NlWs& w, double c, double sigma) {
     for (int i = g.wid; i < n; i += G::nw) {            // row i of the lower triangle: a warp per row, lanes along j <= i
         int r0, r1; w.je_rows(i, r0, r1);
         const double di = w.D[i];
+        double* hrow = w.H + NlWs::tri(i);
         for (int j = g.lane; j <= i; j += 32) {
             double acc = 0;
             for (int r = r0; r < r1; ++r) { const double* a = w.Je + (size_t)r * ld; acc = fma(w.w[r] * a[i], a[j], acc); }
@@ -116,89 +132,102 @@ __device__ bool nl_factor(const G& g, NlWs& w, double c, double sigma) {
             }
             double v = di * (c * w.B[(size_t)i * ld + j] + acc) * w.D[j];
             if (i == j) { int rb = mc + i; v += sigma + w.rho[rb] * w.E[rb] * w.E[rb] * di * di; }
-            w.H[(size_t)i * ld + j] = v;
+            hrow[j] = v;
         }
     }
     g.sync();
     bool ok = true;
-    for (int k = 0; k < n; ++k) {                       // right-looking Cholesky, lower, in place; column k staged in tmp
-        double dkk = w.H[(size_t)k * ld + k];
+    for (int k = 0; k < n; ++k) {                       // right-looking Cholesky, in place; column k staged in tmp
+        double dkk = w.H[NlWs::tri(k) + k];
         if (!(dkk > 0.0)) ok = false;
         double piv = sqrt(dkk), inv = 1.0 / piv;
         g.sync();
         for (int r = k + g.tid; r < n; r += G::nt) {
-            double v = (r == k) ? piv : w.H[(size_t)r * ld + k] * inv;
-            w.H[(size_t)r * ld + k] = v; w.tmp[r] = v;
+            double* e = w.H + NlWs::tri(r) + k;
+            double v = (r == k) ? piv : *e * inv;
+            *e = v; w.tmp[r] = v;
         }
         g.sync();
         for (int r = k + 1 + g.wid; r < n; r += G::nw) {
             const double lrk = w.tmp[r];
-            for (int q = k + 1 + g.lane; q <= r; q += 32) w.H[(size_t)r * ld + q] -= lrk * w.tmp[q];
+            double* hrow = w.H + NlWs::tri(r);
+            for (int q = k + 1 + g.lane; q <= r; q += 32) hrow[q] -= lrk * w.tmp[q];
         }
         g.sync();
     }
-    // inverse of the factor, built in the upper triangle as its transpose (U[q][r] = Linv[r][q]) from the last column back
+    // in-place inverse of the lower-triangular factor, column by column from the right:
+    // Linv[r][j] = -(1/L[j][j]) * sum_{q=j+1..r} Linv[r][q] L[q][j]
     for (int j = n - 1; j >= 0; --j) {
-        const double ljj = 1.0 / w.H[(size_t)j * ld + j];
-        for (int q = j + 1 + g.tid; q < n; q += G::nt) w.tmp[q] = w.H[(size_t)q * ld + j];     // L[:, j]
+        const double ljj = 1.0 / w.H[NlWs::tri(j) + j];
+        for (int q = j + 1 + g.tid; q < n; q += G::nt) w.tmp[q] = w.H[NlWs::tri(q) + j];     // L[:, j]
         g.sync();
         for (int r = j + 1 + g.tid; r < n; r += G::nt) {
-            double acc = 0;
-#pragma unroll 4
-            for (int q = j + 1; q <= r; ++q) acc = fma(w.H[(size_t)q * ld + r], w.tmp[q], acc);
-            w.H[(size_t)j * ld + r] = -ljj * acc;
+            double* hrow = w.H + NlWs::tri(r);
+            double a0 = 0, a1 = 0;
+            int q = j + 1;
+            for (; q + 1 <= r; q += 2) { a0 = fma(hrow[q], w.tmp[q], a0); a1 = fma(hrow[q + 1], w.tmp[q + 1], a1); }
+            if (q <= r) a0 = fma(hrow[q], w.tmp[q], a0);
+            hrow[j] = -ljj * (a0 + a1);
         }
-        if (g.tid == 0) w.H[(size_t)j * ld + j] = ljj;
+        if (g.tid == 0) w.H[NlWs::tri(j) + j] = ljj;
         g.sync();
     }
-    for (int j = g.wid; j < n; j += G::nw)              // mirror into the lower triangle
-        for (int r = j + 1 + g.lane; r < n; r += 32) w.H[(size_t)r * ld + j] = w.H[(size_t)j * ld + r];
-    g.sync();
     return !g.any(!ok);
 }
 
-// xt = (Linv' Linv) rhs
+// xt = (Linv' Linv) rhs ; optionally dxt = D .* xt (the input nl_As_core wants)
 template <class G>
-__device__ void nl_kkt_apply(const G& g, NlWs& w) {
-    const int n = w.n, ld = w.ld;
-    for (int i = g.tid; i < n; i += G::nt) {
-        double acc = 0;
-#pragma unroll 4
-        for (int q = 0; q <= i; ++q) acc = fma(w.H[(size_t)q * ld + i], w.rhs[q], acc);
-        w.tmp[i] = acc;
+__device__ void nl_kkt_apply(const G& g, NlWs& w, double* dxt = nullptr) {
+    const int n = w.n;
+    for (int i = g.tid; i < n; i += G::nt) {            // row walk: conflict-free across consecutive rows (packed storage)
+        const double* hrow = w.H + NlWs::tri(i);
+        double a0 = 0, a1 = 0;
+        int q = 0;
+        for (; q + 1 <= i; q += 2) { a0 = fma(hrow[q], w.rhs[q], a0); a1 = fma(hrow[q + 1], w.rhs[q + 1], a1); }
+        if (q <= i) a0 = fma(hrow[q], w.rhs[q], a0);
+        w.tmp[i] = a0 + a1;
     }
     g.sync();
-    for (int i = g.tid; i < n; i += G::nt) {
-        double acc = 0;
-#pragma unroll 4
-        for (int q = i; q < n; ++q) acc = fma(w.H[(size_t)q * ld + i], w.tmp[q], acc);
-        w.xt[i] = acc;
+    for (int i = g.tid; i < n; i += G::nt) {            // column walk: contiguous across threads
+        double a0 = 0, a1 = 0;
+        size_t t = NlWs::tri(i) + i;
+        int q = i;
+        for (; q + 1 < n; q += 2) { a0 = fma(w.H[t], w.tmp[q], a0); t += q + 1; a1 = fma(w.H[t], w.tmp[q + 1], a1); t += q + 2; }
+        if (q < n) a0 = fma(w.H[t], w.tmp[q], a0);
+        double v = a0 + a1;
+        w.xt[i] = v;
+        if (dxt) dxt[i] = w.D[i] * v;
     }
     g.sync();
 }
-// out_r = E_r * (A (D.x))_r for all m rows: J_eq rows by their two column runs, J_in rows one warp per row
+// out_r = E_r * (A dx)_r for all m rows, dx = D.*x already formed: J_eq rows by their two column runs, J_in rows one
+// warp per row.  Ends with a barrier.
 template <class G>
-__device__ void nl_As(const G& g, NlWs& w, const double* x, double* out) {
+__device__ void nl_As_core(const G& g, NlWs& w, const double* dx, double* out) {
     const int n = w.n, me = w.me, mc = w.me + w.mi, ld = w.ld;
-    for (int i = g.tid; i < n; i += G::nt) w.tmp[i] = w.D[i] * x[i];
-    g.sync();
     for (int r = g.tid; r < me; r += G::nt) {
         int c0, c1, u0; w.je_cols(r, c0, c1, u0);
         const double* row = w.Je + (size_t)r * ld;
         double a = 0;
-        for (int j = c0; j < c1; ++j) a = fma(row[j], w.tmp[j], a);
-        for (int j = u0; j < u0 + w.nu; ++j) a = fma(row[j], w.tmp[j], a);
+        for (int j = c0; j < c1; ++j) a = fma(row[j], dx[j], a);
+        for (int j = u0; j < u0 + w.nu; ++j) a = fma(row[j], dx[j], a);
         out[r] = w.E[r] * a;
     }
     for (int r = g.wid; r < w.mi; r += G::nw) {
         const double* row = w.Ji + (size_t)r * ld;
         double a = 0;
-        for (int j = g.lane; j < n; j += 32) a = fma(row[j], w.tmp[j], a);
+        for (int j = g.lane; j < n; j += 32) a = fma(row[j], dx[j], a);
         a = nl_wsum(a);
         if (g.lane == 0) out[me + r] = w.E[me + r] * a;
     }
-    for (int j = g.tid; j < n; j += G::nt) out[mc + j] = w.E[mc + j] * w.tmp[j];
+    for (int j = g.tid; j < n; j += G::nt) out[mc + j] = w.E[mc + j] * dx[j];
     g.sync();
+}
+template <class G>
+__device__ void nl_As(const G& g, NlWs& w, const double* x, double* out) {
+    for (int i = g.tid; i < w.n; i += G::nt) w.tmp[i] = w.D[i] * x[i];
+    g.sync();
+    nl_As_core(g, w, w.tmp, out);
 }
 // out_j = D_j * (A' (E.v))_j
 template <class G>
@@ -364,13 +393,14 @@ __device__ int nl_qp_solve(const G& g, NlWs& w, const NlSolveArgs& a, bool have_
     g.sync();
     int it = 0;
     for (it = 1; it <= a.max_qp; ++it) {
-        for (int r = g.tid; r < m; r += G::nt) w.yq[r] = w.rho[r] * w.zs[r] - w.ys[r];     // yq as temp
+        // rhs = sigma x - q + A'(rho z - y)  (scaled), 2 barriers
+        for (int r = g.tid; r < m; r += G::nt) w.w[r] = w.E[r] * (w.rho[r] * w.zs[r] - w.ys[r]);
         g.sync();
-        nl_Ats(g, w, w.yq, w.rhs);
-        for (int i = g.tid; i < n; i += G::nt) w.rhs[i] += sigma * w.xs[i] - w.gs[i];
+        for (int j = g.tid; j < n; j += G::nt)
+            w.rhs[j] = w.D[j] * (w.w[mc + j] + nl_col_dot(w, j, w.w)) + sigma * w.xs[j] - w.gs[j];
         g.sync();
-        nl_kkt_apply(g, w);
-        nl_As(g, w, w.xt, w.yq);                                                       // z~ in yq
+        nl_kkt_apply(g, w, w.zt2);                                                      // x~ in xt, D.*x~ in zt2
+        nl_As_core(g, w, w.zt2, w.yq);                                                  // z~ in yq
         for (int i = g.tid; i < n; i += G::nt) w.xs[i] = alpha * w.xt[i] + (1 - alpha) * w.xs[i];
         for (int r = g.tid; r < m; r += G::nt) {
             double zr = alpha * w.yq[r] + (1 - alpha) * w.zs[r];
@@ -406,7 +436,7 @@ __device__ int nl_qp_solve(const G& g, NlWs& w, const NlSolveArgs& a, bool have_
 }
 
 // One controller per thread group of NT threads: NT = 32 -> one warp, several controllers per CTA; NT > 32 -> the CTA.
-template <class S, bool GM, int NT>
+template <class S, int MODE, int NT>
 __global__ void __launch_bounds__(NT == 32 ? 64 : NT) nlmpc_solve_kernel(const NlSolveArgs a) {
     extern __shared__ __align__(16) double nls_smem[];
     constexpr int nx = S::nx, nu = S::nu;
@@ -414,10 +444,9 @@ __global__ void __launch_bounds__(NT == 32 ? 64 : NT) nlmpc_solve_kernel(const N
     const int ph = a.ph, ch = a.ch;
     const int n = ph * nx + ch * nu + 1, me = ph * nx, mi = S::nineq(ph);
     const int gpb = blockDim.x / NT, gi = threadIdx.x / NT;            // groups per CTA, this thread's group
-    const size_t nvec = NlWs::vec_doubles(n, me, mi, ph, nx, nu), nmat = NlWs::mat_doubles(n, me, mi, GM);
+    const size_t nsm = NlWs::smem_doubles(MODE, n, me, mi, ph, nx, nu), ngm = NlWs::gmem_doubles(MODE, n, me, mi);
     NlWs w;
-    if (GM) w.carve(a.mat_ws + (size_t)(blockIdx.x * gpb + gi) * nmat, nls_smem + (size_t)gi * nvec, true, n, me, mi, ph, ch, nx, nu);
-    else { double* base = nls_smem + (size_t)gi * (nvec + nmat); w.carve(base, base + nmat, false, n, me, mi, ph, ch, nx, nu); }
+    w.carve(MODE, nls_smem + (size_t)gi * nsm, MODE ? a.mat_ws + (size_t)(blockIdx.x * gpb + gi) * ngm : nullptr, n, me, mi, ph, ch, nx, nu);
     const G g{(int)(threadIdx.x % NT), (int)(threadIdx.x & 31), (int)((threadIdx.x % NT) >> 5), w.red};
     const int mc = me + mi, ld = w.ld;
     for (int inst = blockIdx.x * gpb + gi; inst < a.batch; inst += gridDim.x * gpb) {
