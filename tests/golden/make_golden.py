@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import nlmpc_slsqp as S                                                     # noqa: E402
-from oracle.lmpc_formulation import quadrotor_formulation                               # noqa: E402
+from oracle.lmpc_formulation import quadrotor_formulation, quadrotor_model                               # noqa: E402
 from oracle.nlmpc_formulation import oscnet_formulation, ugv_formulation, vanderpol_formulation  # noqa: E402
 from oracle.osqp_restated import Settings, lmpc_optimize                                # noqa: E402
 
@@ -76,6 +76,7 @@ def lmpc_fixture():
             seq_state[b] = res["state"]; seq_input[b] = res["input"]
         out.update({f"ph{ph}_x0": x0, f"ph{ph}_r": r, f"ph{ph}_cmd": cmd, f"ph{ph}_cost": cost, f"ph{ph}_meta": meta,
                     f"ph{ph}_state": seq_state, f"ph{ph}_input": seq_input})
+    out["Ad"], out["Bd"] = quadrotor_model()                      # examples/quadrotor_ex.cpp:19-45
     np.savez_compressed(os.path.join(HERE, "lmpc_quadrotor.npz"), **out)
 
 
