@@ -155,6 +155,38 @@ enum { B200MPC_SYS_VANDERPOL = 0,  /* examples/vanderpol_ex.cpp: params [Ts]    
        B200MPC_SYS_OSCNET6 = 2,    /* the shipped N=6                                                           */
        B200MPC_SYS_UGV = 3 };      /* examples/ugv_ex.cpp: params [Ad(16) Bd(8) v_pref(2) obs0(x,y,r) obs1(x,y,r)] */
 int b200mpc_nlmpc_system_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq);
+/* number of user equality constraints Teq of the system (NLMPC<...,Tineq,Teq>, NLMPC.hpp:26-30); 0 for the built-ins */
+int b200mpc_nlmpc_system_neq(int system, int ph, int* neq);
+
+/* ---- user-defined systems: NLMPC::setStateSpaceFunction / setObjectiveFunction / setIneqConFunction / setEqConFunction
+ * (NLMPC.hpp:165,139,228,261; callback typedefs IDimensionable.hpp:94-149).  The reference takes host std::function
+ * callbacks; the batched engine takes the same four pieces as CUDA source, compiled at run time (NVRTC, sm_100a) straight
+ * into its kernels.  `cuda_source` must define, at global scope, a struct named `type_name` with
+ *     static constexpr int nx, nu, ny, nparam;                 // dimensions, number of doubles in `params`
+ *     static constexpr bool continuous;                        // true: dx/dt = f (trapezoidal collocation, needs Ts)
+ *     __device__ static double Ts(const double* p);            // sampling time (setDiscretizationSamplingTime, NLMPC.hpp:80)
+ *     __host__ __device__ static int nineq(int ph);            // Tineq
+ *     __device__ static void f(double* out, const double* x, const double* u, int stage, const double* p);   // model
+ *     __device__ static double cost(const Acc& a, double slack, int ph, const double* p);                    // objective
+ *     __device__ static double ineq(int r, const Acc& a, double slack, int ph, const double* p);             // c_r <= 0
+ *   and optionally (user equality constraints)
+ *     __host__ __device__ static int neq(int ph);   __device__ static double eq(int r, const Acc& a, int ph, const double* p);
+ * where a.x(i,j) / a.u(i,j) read the unwrapped state / input sequences ((ph+1) rows, Mapping::unwrapVector) and
+ * y = x (systems with an output map apply it inside cost/ineq).  Returns a system id >= B200MPC_SYS_USER_BASE usable
+ * wherever a built-in id is.  Kernels are compiled on first use and cached per device.  Compile errors are returned as
+ * B200MPC_EINVAL with the NVRTC log in b200mpc_last_error(). */
+#define B200MPC_SYS_USER_BASE 100
+int b200mpc_nlmpc_register_system(const char* cuda_source, const char* type_name, int* system_id);
+/* Compile-only check, needs no GPU: kernel 0 = evaluation kernel, 1..4 = the four solve-kernel variants. */
+int b200mpc_nlmpc_compile_check(const char* cuda_source, const char* type_name, int kernel, size_t* cubin_bytes);
+
+/* NLMPC::setStateScale / setInputScale (NLMPC.hpp:108-130 -> Mapping::setStateScaling / setInputScaling,
+ * Mapping.hpp:108-150): host arrays [nx] / [nu] of positive factors, either may be NULL (= 1). */
+typedef struct {
+    const double* state_scale;
+    const double* input_scale;
+} b200mpc_nlmpc_scaling;
+
 int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
                        int params_per_instance, double* fval, double* grad, double* ceq, double* Jeq, double* cin,
                        double* Jin, int dev, void* stream);
@@ -178,12 +210,26 @@ typedef struct {
     double qp_eps;        /* QP residual tolerance                                                            */
     double rho;           /* initial ADMM penalty                                                             */
 } b200mpc_nlmpc_params;
+/* As b200mpc_nlmpc_eval, plus the scaling and the user equality constraints Constraints::evaluateEq
+ * (NLMPC/Constraints.hpp:365-442,731-832): cue[batch*neq], Jue[batch*neq*nz] (ignored when the system has none). */
+int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
+                          int params_per_instance, const b200mpc_nlmpc_scaling* scaling, double* fval, double* grad,
+                          double* ceq, double* Jeq, double* cin, double* Jin, double* cue, double* Jue, int dev,
+                          void* stream);
 void b200mpc_nlmpc_default_params(b200mpc_nlmpc_params* p);
 long long b200mpc_nlmpc_solve_smem_bytes(int system, int ph, int ch);
 int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* params, const double* z0,
                         const double* x0, const double* sys_params, int params_per_instance, const double* lb,
                         const double* ub, double* z, double* cost, double* viol, int32_t* status, int32_t* iters,
                         int32_t* qp_iters, int dev, void* stream);
+
+/* As b200mpc_nlmpc_solve with state / input scaling (the decision vector z is in scaled units, as in the reference;
+ * user equality constraints of the system, if any, are always enforced). */
+int b200mpc_nlmpc_solve_ex(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* params, const double* z0,
+                           const double* x0, const double* sys_params, int params_per_instance,
+                           const b200mpc_nlmpc_scaling* scaling, const double* lb, const double* ub, double* z,
+                           double* cost, double* viol, int32_t* status, int32_t* iters, int32_t* qp_iters, int dev,
+                           void* stream);
 
 #ifdef __cplusplus
 }

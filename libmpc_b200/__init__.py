@@ -82,6 +82,13 @@ def load_library():
     lib.b200mpc_sync.argtypes = [H]
     lib.b200mpc_nlmpc_system_dims.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
     lib.b200mpc_nlmpc_eval.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    lib.b200mpc_nlmpc_system_neq.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.b200mpc_nlmpc_register_system.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+    lib.b200mpc_nlmpc_compile_check.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_size_t)]
+    lib.b200mpc_nlmpc_eval_ex.argtypes = ([C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] + [C.c_void_p] * 8 +
+                                          [C.c_int, C.c_void_p])
+    lib.b200mpc_nlmpc_solve_ex.argtypes = ([C.c_int] * 4 + [C.POINTER(_NLParams)] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] +
+                                           [C.c_void_p] * 8 + [C.c_int, C.c_void_p])
     lib.b200mpc_nlmpc_default_params.argtypes = [C.POINTER(_NLParams)]
     lib.b200mpc_nlmpc_solve_smem_bytes.argtypes = [C.c_int] * 3
     lib.b200mpc_nlmpc_solve_smem_bytes.restype = C.c_longlong
@@ -99,6 +106,8 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
     "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
     "b200mpc_nlmpc_default_params", "b200mpc_nlmpc_solve_smem_bytes", "b200mpc_nlmpc_solve",
+    "b200mpc_nlmpc_system_neq", "b200mpc_nlmpc_register_system", "b200mpc_nlmpc_compile_check", "b200mpc_nlmpc_eval_ex",
+    "b200mpc_nlmpc_solve_ex",
 ]
 
 
@@ -483,14 +492,57 @@ SYS_VANDERPOL, SYS_OSCNET4, SYS_OSCNET6, SYS_UGV = 0, 1, 2, 3
 
 def nlmpc_system_dims(system, ph):
     lib = load_library()
-    v = [C.c_int() for _ in range(4)]
-    _check(lib.b200mpc_nlmpc_system_dims(system, ph, *[C.byref(x) for x in v]))
-    return dict(nx=v[0].value, nu=v[1].value, nparam=v[2].value, nineq=v[3].value)
+    v = [C.c_int() for _ in range(5)]
+    _check(lib.b200mpc_nlmpc_system_dims(system, ph, *[C.byref(x) for x in v[:4]]))
+    _check(lib.b200mpc_nlmpc_system_neq(system, ph, C.byref(v[4])))
+    return dict(nx=v[0].value, nu=v[1].value, nparam=v[2].value, nineq=v[3].value, neq=v[4].value)
 
 
-def nlmpc_eval(system, ph, ch, z, x0, params, want=("f", "grad", "ceq", "Jeq", "cin", "Jin")):
+def register_system(cuda_source, type_name):
+    """NLMPC::setStateSpaceFunction / setObjectiveFunction / setIneqConFunction / setEqConFunction for the batched engine:
+    the model, cost and constraints as CUDA source (contract in include/b200mpc.h), compiled with NVRTC into the solver
+    kernels.  Returns a system id usable wherever SYS_VANDERPOL etc. are."""
+    lib = load_library()
+    sid = C.c_int()
+    _check(lib.b200mpc_nlmpc_register_system(cuda_source.encode(), type_name.encode(), C.byref(sid)))
+    return sid.value
+
+
+def compile_check(cuda_source, type_name, kernel=0):
+    """NVRTC-compile a user system into one engine kernel (0 = evaluation, 1..4 = solve variants) without a GPU.
+    Returns the cubin size; raises with the compiler log on error."""
+    lib = load_library()
+    n = C.c_size_t()
+    _check(lib.b200mpc_nlmpc_compile_check(cuda_source.encode(), type_name.encode(), int(kernel), C.byref(n)))
+    return n.value
+
+
+class _NLScaling(C.Structure):
+    _fields_ = [("state_scale", C.c_void_p), ("input_scale", C.c_void_p)]
+
+
+def _scaling_arg(d, state_scale, input_scale):
+    """-> (ctypes pointer or None, keep-alive tuple)."""
+    if state_scale is None and input_scale is None:
+        return None, ()
+    keep = []
+    def one(a, n):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape != (n,):
+            raise ValueError("scaling vector has the wrong length")
+        keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
+    sc = _NLScaling(one(state_scale, d["nx"]), one(input_scale, d["nu"]))
+    keep.append(sc)
+    return C.byref(sc), tuple(keep)
+
+
+def nlmpc_eval(system, ph, ch, z, x0, params, want=("f", "grad", "ceq", "Jeq", "cin", "Jin"), state_scale=None, input_scale=None):
     """Batched Objective / Constraints evaluation with finite-difference derivatives on the GPU.
-    z [B, nz], x0 [B, nx], params [nparam] (shared) or [B, nparam].  Returns a dict of numpy arrays."""
+    z [B, nz], x0 [B, nx], params [nparam] (shared) or [B, nparam].  Returns a dict of numpy arrays ("cue"/"Jue": the
+    user equality constraints of systems that define them)."""
     lib = load_library()
     d = nlmpc_system_dims(system, ph)
     z = np.ascontiguousarray(np.atleast_2d(z), dtype=np.float64)
@@ -503,7 +555,8 @@ def nlmpc_eval(system, ph, ch, z, x0, params, want=("f", "grad", "ceq", "Jeq", "
     if params.shape[-1] != d["nparam"]:
         raise ValueError(f"params: expected {d['nparam']} values")
     out = {}
-    shapes = dict(f=(B,), grad=(B, nz), ceq=(B, ph * d["nx"]), Jeq=(B, ph * d["nx"], nz), cin=(B, d["nineq"]), Jin=(B, d["nineq"], nz))
+    shapes = dict(f=(B,), grad=(B, nz), ceq=(B, ph * d["nx"]), Jeq=(B, ph * d["nx"], nz), cin=(B, d["nineq"]), Jin=(B, d["nineq"], nz),
+                  cue=(B, d["neq"]), Jue=(B, d["neq"], nz))
     ptr = {}
     for k, shp in shapes.items():
         if k in want:
@@ -511,9 +564,11 @@ def nlmpc_eval(system, ph, ch, z, x0, params, want=("f", "grad", "ceq", "Jeq", "
             ptr[k] = out[k].ctypes.data_as(C.c_void_p)
         else:
             ptr[k] = None
-    _check(lib.b200mpc_nlmpc_eval(system, ph, ch, B, z.ctypes.data_as(C.c_void_p), x0.ctypes.data_as(C.c_void_p),
-                                  params.ctypes.data_as(C.c_void_p), ppi, ptr["f"], ptr["grad"], ptr["ceq"], ptr["Jeq"], ptr["cin"],
-                                  ptr["Jin"], 0, None))
+    sc, keep = _scaling_arg(d, state_scale, input_scale)
+    _check(lib.b200mpc_nlmpc_eval_ex(system, ph, ch, B, z.ctypes.data_as(C.c_void_p), x0.ctypes.data_as(C.c_void_p),
+                                     params.ctypes.data_as(C.c_void_p), ppi, sc, ptr["f"], ptr["grad"], ptr["ceq"], ptr["Jeq"],
+                                     ptr["cin"], ptr["Jin"], ptr["cue"], ptr["Jue"], 0, None))
+    del keep
     return out
 
 
@@ -537,7 +592,8 @@ class NLParameters:
     verbose: bool = False
 
 
-def nlmpc_solve(system, ph, ch, z0, x0, params, lb, ub, max_sqp=100, max_qp=200, tol=1e-7, ftol=1e-12, qp_eps=1e-5, rho=0.1):
+def nlmpc_solve(system, ph, ch, z0, x0, params, lb, ub, max_sqp=100, max_qp=200, tol=1e-7, ftol=1e-12, qp_eps=1e-5, rho=0.1,
+                state_scale=None, input_scale=None):
     """Batched NLOptimizer::run core (NLOptimizer.hpp:519): z0 [B,nz] -> dict(z, cost, viol, status, iters, qp_iters)."""
     lib = load_library()
     d = nlmpc_system_dims(system, ph)
@@ -557,8 +613,10 @@ def nlmpc_solve(system, ph, ch, z0, x0, params, lb, ub, max_sqp=100, max_qp=200,
     out = dict(z=np.zeros((B, nz)), cost=np.zeros(B), viol=np.zeros(B), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32),
                qp_iters=np.zeros(B, np.int32))
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    _check(lib.b200mpc_nlmpc_solve(system, ph, ch, B, C.byref(q), vp(z0), vp(x0), vp(params), ppi, vp(lb), vp(ub), vp(out["z"]),
-                                   vp(out["cost"]), vp(out["viol"]), vp(out["status"]), vp(out["iters"]), vp(out["qp_iters"]), 0, None))
+    sc, keep = _scaling_arg(d, state_scale, input_scale)
+    _check(lib.b200mpc_nlmpc_solve_ex(system, ph, ch, B, C.byref(q), vp(z0), vp(x0), vp(params), ppi, sc, vp(lb), vp(ub), vp(out["z"]),
+                                      vp(out["cost"]), vp(out["viol"]), vp(out["status"]), vp(out["iters"]), vp(out["qp_iters"]), 0, None))
+    del keep
     return out
 
 

@@ -16,32 +16,74 @@ extern template int nl_solve_t<SysVanDerPol>(NlSolveArgs&, cudaStream_t, std::ve
 extern template int nl_solve_t<SysOscNet<4>>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);
 extern template int nl_solve_t<SysOscNet<6>>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);
 extern template int nl_solve_t<SysUgv>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);
+// user-defined systems (b200mpc_nlmpc_rtc.cu)
+bool rtc_is_user(int system);
+int rtc_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq, int* neq);
+int rtc_eval(int system, const NlEvalArgs& a, cudaStream_t stream);
+int rtc_solve(int system, NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree);
 }
 
 // ---- NLMPC problem evaluation (K5) --------------------------------------------------------------------------------
-static int nl_dims(int system, int* nx, int* nu, int* nparam, int ph, int* nineq) {
+static int nl_dims(int system, int* nx, int* nu, int* nparam, int ph, int* nineq, int* neq) {
+    *neq = 0;
     switch (system) {
     case B200MPC_SYS_VANDERPOL: *nx = 2; *nu = 1; *nparam = 1; *nineq = ph + 1; return 0;
     case B200MPC_SYS_OSCNET4: *nx = 8; *nu = 4; *nparam = 3; *nineq = (ph + 1) * 4; return 0;
     case B200MPC_SYS_OSCNET6: *nx = 12; *nu = 6; *nparam = 3; *nineq = (ph + 1) * 6; return 0;
     case B200MPC_SYS_UGV: *nx = 4; *nu = 2; *nparam = 32; *nineq = (ph + 1) * 2; return 0;
-    default: return -1;
+    default:
+        if (rtc_is_user(system)) return rtc_dims(system, ph, nx, nu, nparam, nineq, neq);
+        return fail(B200MPC_EINVAL, "unknown system id");
     }
 }
 
 extern "C" int b200mpc_nlmpc_system_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq) {
-    int a, b, c, d;
-    if (nl_dims(system, &a, &b, &c, ph, &d)) return fail(B200MPC_EINVAL, "unknown system id");
+    int a, b, c, d, e;
+    int rc = nl_dims(system, &a, &b, &c, ph, &d, &e);
+    if (rc) return rc;
     if (nx) *nx = a; if (nu) *nu = b; if (nparam) *nparam = c; if (nineq) *nineq = d;
     return B200MPC_OK;
+}
+extern "C" int b200mpc_nlmpc_system_neq(int system, int ph, int* neq) {
+    int a, b, c, d, e;
+    int rc = nl_dims(system, &a, &b, &c, ph, &d, &e);
+    if (rc) return rc;
+    if (neq) *neq = e;
+    return B200MPC_OK;
+}
+
+// state / input scaling vectors are tiny host arrays: stage them with stream-ordered allocations
+static int stage_scaling(const b200mpc_nlmpc_scaling* sc, int nx, int nu, const double** dsx, const double** dsu, cudaStream_t stream,
+                         std::vector<void*>& async_free) {
+    *dsx = *dsu = nullptr;
+    if (!sc) return 0;
+    auto up = [&](const double* h, int n, const double** d) -> int {
+        if (!h) return 0;
+        for (int i = 0; i < n; ++i) if (!(h[i] > 0.0)) return fail(B200MPC_EINVAL, "scaling factors must be positive");
+        double* p = nullptr;
+        CK(cudaMallocAsync(&p, n * sizeof(double), stream)); async_free.push_back(p);
+        CK(cudaMemcpyAsync(p, h, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        *d = p; return 0;
+    };
+    int rc;
+    if ((rc = up(sc->state_scale, nx, dsx))) return rc;
+    return up(sc->input_scale, nu, dsu);
 }
 
 extern "C" int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
                                   int params_per_instance, double* fval, double* grad, double* ceq, double* Jeq, double* cin,
                                   double* Jin, int dev, void* stream_) {
+    return b200mpc_nlmpc_eval_ex(system, ph, ch, batch, z, x0, params, params_per_instance, nullptr, fval, grad, ceq, Jeq, cin, Jin,
+                                 nullptr, nullptr, dev, stream_);
+}
+
+extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
+                                     int params_per_instance, const b200mpc_nlmpc_scaling* scaling, double* fval, double* grad,
+                                     double* ceq, double* Jeq, double* cin, double* Jin, double* cue, double* Jue, int dev,
+                                     void* stream_) {
     if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
-    int nx, nu, np, ni;
-    if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return fail(B200MPC_EINVAL, "unknown system id");
+    int nx, nu, np, ni, nue, rc0;
+    if ((rc0 = nl_dims(system, &nx, &nu, &np, ph, &ni, &nue))) return rc0;
     if (ph < 1 || ch < 1 || ch > ph || batch < 1 || !z || !x0 || !params) return fail(B200MPC_EINVAL, "bad arguments");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int nz = ph * nx + ch * nu + 1;
@@ -72,12 +114,18 @@ extern "C" int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const d
     if ((rc = out(Jeq, (size_t)batch * ph * nx * nz, &a.Jeq))) return rc;
     if ((rc = out(cin, (size_t)batch * ni, &a.cin))) return rc;
     if ((rc = out(Jin, (size_t)batch * ni * nz, &a.Jin))) return rc;
+    if ((rc = out(nue ? cue : nullptr, (size_t)batch * nue, &a.cue))) return rc;
+    if ((rc = out(nue ? Jue : nullptr, (size_t)batch * nue * nz, &a.Jue))) return rc;
+    std::vector<void*> async_free;
+    if ((rc = stage_scaling(scaling, nx, nu, &a.sx, &a.su, stream, async_free))) return rc;
     switch (system) {
     case B200MPC_SYS_VANDERPOL: rc = nl_eval_t<SysVanDerPol>(a, stream); break;
     case B200MPC_SYS_OSCNET4: rc = nl_eval_t<SysOscNet<4>>(a, stream); break;
     case B200MPC_SYS_OSCNET6: rc = nl_eval_t<SysOscNet<6>>(a, stream); break;
-    default: rc = nl_eval_t<SysUgv>(a, stream); break;
+    case B200MPC_SYS_UGV: rc = nl_eval_t<SysUgv>(a, stream); break;
+    default: rc = rtc_eval(system, a, stream); break;
     }
+    for (void* p : async_free) cudaFreeAsync(p, stream);
     if (rc) return rc;
     if (!dev) {
         auto back = [&](double* h, const double* d, size_t n) -> int { if (h) CK(cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, stream)); return 0; };
@@ -87,6 +135,8 @@ extern "C" int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const d
         if ((rc = back(Jeq, a.Jeq, (size_t)batch * ph * nx * nz))) return rc;
         if ((rc = back(cin, a.cin, (size_t)batch * ni))) return rc;
         if ((rc = back(Jin, a.Jin, (size_t)batch * ni * nz))) return rc;
+        if (nue && (rc = back(cue, a.cue, (size_t)batch * nue))) return rc;
+        if (nue && (rc = back(Jue, a.Jue, (size_t)batch * nue * nz))) return rc;
         CK(cudaStreamSynchronize(stream));
         for (void* p : tofree) cudaFree(p);
     }
@@ -102,10 +152,10 @@ extern "C" void b200mpc_nlmpc_default_params(b200mpc_nlmpc_params* p) {
 
 // shared memory one controller needs when the matrices are shared-memory resident (the fast path)
 static size_t nl_solve_smem(int system, int ph, int ch) {
-    int nx, nu, np, ni;
-    if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return 0;
+    int nx, nu, np, ni, nue;
+    if (nl_dims(system, &nx, &nu, &np, ph, &ni, &nue)) return 0;
     int n = ph * nx + ch * nu + 1, me = ph * nx;
-    return NlWs::smem_doubles(0, n, me, ni, ph, nx, nu) * sizeof(double);
+    return NlWs::smem_doubles(0, n, me, ni + nue, ph, nx, nu) * sizeof(double);
 }
 extern "C" long long b200mpc_nlmpc_solve_smem_bytes(int system, int ph, int ch) { return (long long)nl_solve_smem(system, ph, ch); }
 
@@ -113,9 +163,18 @@ extern "C" int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const 
                                    const double* x0, const double* sys_params, int params_per_instance, const double* lb,
                                    const double* ub, double* z, double* cost, double* viol, int32_t* status, int32_t* iters,
                                    int32_t* qp_iters, int dev, void* stream_) {
+    return b200mpc_nlmpc_solve_ex(system, ph, ch, batch, prm, z0, x0, sys_params, params_per_instance, nullptr, lb, ub, z, cost, viol,
+                                  status, iters, qp_iters, dev, stream_);
+}
+
+extern "C" int b200mpc_nlmpc_solve_ex(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* prm, const double* z0,
+                                      const double* x0, const double* sys_params, int params_per_instance,
+                                      const b200mpc_nlmpc_scaling* scaling, const double* lb, const double* ub, double* z,
+                                      double* cost, double* viol, int32_t* status, int32_t* iters, int32_t* qp_iters, int dev,
+                                      void* stream_) {
     if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
-    int nx, nu, np, ni;
-    if (nl_dims(system, &nx, &nu, &np, ph, &ni)) return fail(B200MPC_EINVAL, "unknown system id");
+    int nx, nu, np, ni, nue, rc0;
+    if ((rc0 = nl_dims(system, &nx, &nu, &np, ph, &ni, &nue))) return rc0;
     if (ph < 1 || ch < 1 || ch > ph || batch < 1 || !z0 || !x0 || !sys_params || !lb || !ub || !z) return fail(B200MPC_EINVAL, "bad arguments");
     b200mpc_nlmpc_params q;
     if (prm) q = *prm; else b200mpc_nlmpc_default_params(&q);
@@ -152,11 +211,13 @@ extern "C" int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const 
     if ((rc = out(status, (size_t)batch * 4, (void**)&a.status))) return rc;
     if ((rc = out(iters, (size_t)batch * 4, (void**)&a.iters))) return rc;
     if ((rc = out(qp_iters, (size_t)batch * 4, (void**)&a.qp_iters))) return rc;
+    if ((rc = stage_scaling(scaling, nx, nu, &a.sx, &a.su, stream, tofree))) return rc;      // freed after the final synchronise
     switch (system) {
     case B200MPC_SYS_VANDERPOL: rc = nl_solve_t<SysVanDerPol>(a, stream, tofree); break;
     case B200MPC_SYS_OSCNET4: rc = nl_solve_t<SysOscNet<4>>(a, stream, tofree); break;
     case B200MPC_SYS_OSCNET6: rc = nl_solve_t<SysOscNet<6>>(a, stream, tofree); break;
-    default: rc = nl_solve_t<SysUgv>(a, stream, tofree); break;
+    case B200MPC_SYS_UGV: rc = nl_solve_t<SysUgv>(a, stream, tofree); break;
+    default: rc = rtc_solve(system, a, stream, tofree); break;
     }
     if (rc) return rc;
     if (!dev) {

@@ -14,10 +14,20 @@
 // Lanes parallelise over the finite-difference perturbations: every lane evaluates the whole cost / one constraint
 // component through an accessor that adds its own perturbation on the fly, so X and U are never copied.
 #pragma once
+#ifndef __CUDACC_RTC__          // NVRTC (user-defined systems, b200mpc_nlmpc_register_system) has these built in
 #include <cuda_runtime.h>
 #include <math.h>
+#endif
 
 namespace b200mpc {
+
+#define B200_INF (__longlong_as_double(0x7ff0000000000000LL))
+
+// Optional user equality constraints (NLMPC::setEqConFunction, NLMPC.hpp:261-281): a system may define
+//   __host__ __device__ static int neq(int ph);   __device__ static double eq(int r, const Acc&, int ph, const double* p);
+template <class S, class = void> struct NlHasEq { static constexpr bool value = false; };
+template <class S> struct NlHasEq<S, decltype((void)S::neq(1))> { static constexpr bool value = true; };
+template <class S> __host__ __device__ inline int nl_neq(int ph) { if constexpr (NlHasEq<S>::value) return S::neq(ph); else return 0; }
 
 // X [(ph+1) x nx], U [(ph+1) x nu] row-major in shared memory + one (or a pair of) perturbed entries
 struct Acc {
@@ -162,27 +172,41 @@ struct NlEvalArgs {
     double* Jeq;            // [batch, ph*nx, nz] row-major
     double* cin;            // [batch, nineq]
     double* Jin;            // [batch, nineq, nz] row-major
+    double* cue;            // [batch, neq]       user equality constraints (Constraints::evaluateEq)
+    double* Jue;            // [batch, neq, nz]
+    const double* sx;       // [nx] state scaling  (NLMPC::setStateScale, Mapping.hpp:108-130); null = 1
+    const double* su;       // [nu] input scaling  (NLMPC::setInputScale); null = 1
 };
 
 // ---- evaluation of one instance by one thread group (shared by the evaluation kernel and by the SQP kernel) ----------
 // X,U: shared-memory scratch [(ph+1)*nx], [(ph+1)*nu].  Output pointers may be global or shared; Jacobians are row-major
 // with row stride ldj.  Any output pointer may be null.  The whole group must call; ends with a group barrier.
+// sx / su: state / input scaling (null = none).  The reference divides X (row 0 = x0 included) by the state scaling and
+// multiplies U by the input scaling in unwrapVector (Mapping.hpp:174-211,221-257), divides the dynamics residual by the
+// state scaling (Constraints.hpp:528,588), forms the dynamics blocks as I + h Sx A Tx (Constraints.hpp:553-575), scales the
+// state columns of the user-constraint Jacobians but NOT of the objective gradient, and maps every input derivative
+// through Iz2u (x input scaling).  cue/Jue: user equality constraints, rows [0, neq).
 template <class S, class G>
-__device__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
-                                 double* fval, double* grad, double* ceq, double* Jeq, double* cin, double* Jin, int ldj) {
+__device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
+                                 double* fval, double* grad, double* ceq, double* Jeq, double* cin, double* Jin, int ldj,
+                                 const double* sx, const double* su, double* cue, double* Jue) {
     constexpr int nx = S::nx, nu = S::nu;
     const int nz = ph * nx + ch * nu + 1;
+    auto SX = [&](int j) { return sx ? sx[j] : 1.0; };
+    auto SU = [&](int j) { return su ? su[j] : 1.0; };
     const double dv = 1.4901161193847656e-08;     // sqrt(DBL_EPSILON)  (Objective.hpp:283)
     // unwrapVector: X row 0 = x0, rows 1..ph from z; U row i = block min(i, ch-1), last row repeated
     for (int e = g_.tid; e < (ph + 1) * nx; e += G::nt) {
         int i = e / nx, j = e - i * nx;
-        X[e] = i == 0 ? x0[j] : z[(i - 1) * nx + j];
+        double v = i == 0 ? x0[j] : z[(i - 1) * nx + j];
+        X[e] = sx ? v / sx[j] : v;
     }
     for (int e = g_.tid; e < (ph + 1) * nu; e += G::nt) {
         int i = e / nu, j = e - i * nu;
         int st = i < ph ? i : ph - 1;
         int blk = st < ch ? st : ch - 1;
-        U[e] = z[ph * nx + blk * nu + j];
+        double v = z[ph * nx + blk * nu + j];
+        U[e] = su ? su[j] * v : v;
     }
     const double slack = z[nz - 1];
     g_.sync();
@@ -210,7 +234,7 @@ __device__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, c
             Acc ac = base; ac.kind = (i == ph - 1) ? 3 : 2; ac.row = i; ac.col = j; ac.d = du;
             double df = (S::cost(ac, slack, ph, p) - f0) / du;
             int blk = i < ch ? i : ch - 1;
-            atomicAdd(&g[ph * nx + blk * nu + j], df);
+            atomicAdd(&g[ph * nx + blk * nu + j], SU(j) * df);
         }
         if (g_.tid == 0) {
             double ea = fmax(dv, fabs(slack)), de = ea * dv;
@@ -229,10 +253,10 @@ __device__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, c
             for (int j = 0; j < nu; ++j) uk[j] = U[i * nu + j];
             if (S::continuous) {
                 S::f(fk, xk, uk, i, p); S::f(fk1, xk1, uk, i, p);
-                for (int j = 0; j < nx; ++j) c[i * nx + j] = xk[j] + (h * (fk[j] + fk1[j])) - xk1[j];
+                for (int j = 0; j < nx; ++j) c[i * nx + j] = (xk[j] + (h * (fk[j] + fk1[j])) - xk1[j]) / SX(j);
             } else {
                 S::f(fk, xk, uk, i, p);
-                for (int j = 0; j < nx; ++j) c[i * nx + j] = xk1[j] - fk[j];
+                for (int j = 0; j < nx; ++j) c[i * nx + j] = (xk1[j] - fk[j]) / SX(j);
             }
         }
         if (J) {
@@ -249,14 +273,14 @@ __device__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, c
                     xk[q] = keep - dx; S::f(fm, xk, uk, i, p);
                     xk[q] = keep;
                     if (S::continuous) {
-                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = (r == q ? 1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx));
+                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = (r == q ? 1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx)) * (SX(q) / SX(r));
                         double dx1 = dv * fmax(fabs(xk1[q]), 1.0), keep1 = xk1[q];
                         xk1[q] = keep1 + dx1; S::f(fp, xk1, uk, i, p);
                         xk1[q] = keep1 - dx1; S::f(fm, xk1, uk, i, p);
                         xk1[q] = keep1;
-                        for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? -1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx1));
+                        for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? -1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx1)) * (SX(q) / SX(r));
                     } else {
-                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = -((fp[r] - fm[r]) / (2 * dx));
+                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = -((fp[r] - fm[r]) / (2 * dx)) * (SX(q) / SX(r));
                         for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? 1.0 : 0.0);
                     }
                 } else {
@@ -271,9 +295,9 @@ __device__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, c
                         uk[qu] = keep + du; S::f(fp, xk1, uk, i, p);
                         uk[qu] = keep - du; S::f(fm, xk1, uk, i, p);
                         uk[qu] = keep;
-                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], h * (Bk[r] + (fp[r] - fm[r]) / (2 * du)));
+                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], h * (Bk[r] + (fp[r] - fm[r]) / (2 * du)) * (SU(qu) / SX(r)));
                     } else {
-                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], -Bk[r]);
+                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], -Bk[r] * (SU(qu) / SX(r)));
                     }
                 }
             }
@@ -293,7 +317,7 @@ __device__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, c
                 double dx = dv * fmax(fabs(X[lr * nx + lc]), 1.0);
                 Acc ap = base; ap.kind = 1; ap.row = i + 1; ap.col = j; ap.d = dx;
                 Acc am = ap; am.d = -dx;
-                for (int r = 0; r < ni; ++r) J[(size_t)r * ldj + i * nx + j] = (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * dx);
+                for (int r = 0; r < ni; ++r) J[(size_t)r * ldj + i * nx + j] = (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * dx) * SX(j);
             }
             for (int t = g_.tid; t < ph * nu; t += G::nt) {     // every one of the ph rows alone (row ph is never perturbed)
                 int i = t / nu, j = t - i * nu;
@@ -303,7 +327,7 @@ __device__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, c
                 Acc am = ap; am.d = -du;
                 int blk = i < ch ? i : ch - 1;
                 for (int r = 0; r < ni; ++r)
-                    atomicAdd(&J[(size_t)r * ldj + ph * nx + blk * nu + j], (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * du));
+                    atomicAdd(&J[(size_t)r * ldj + ph * nx + blk * nu + j], (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * du) * SU(j));
             }
             if (g_.tid == 0) {
                 double ea = fmax(dv, fabs(slack)), de = ea * dv;
@@ -311,7 +335,53 @@ __device__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, c
             }
         }
     }
+    if constexpr (NlHasEq<S>::value) {
+        // Constraints::evaluateEq + computeEqJacobian (Constraints.hpp:365-442,731-832): c_eq(X,U) = 0, central differences;
+        // steps use Xa(i+1,j) for states and Ua(ph-1,j) for EVERY input column (the reference's indexing); the last stage
+        // moves together with the duplicated row ph; no slack column.
+        if (cue) {
+            const int ne = S::neq(ph);
+            for (int r = g_.tid; r < ne; r += G::nt) cue[r] = S::eq(r, base, ph, p);
+            if (Jue) {
+                double* J = Jue;
+                for (int e = g_.tid; e < ne * ldj; e += G::nt) J[e] = 0.0;
+                g_.sync();
+                for (int t = g_.tid; t < ph * nx; t += G::nt) {
+                    int i = t / nx, j = t - i * nx;
+                    double dx = dv * fmax(fabs(X[(i + 1) * nx + j]), 1.0);
+                    Acc ap = base; ap.kind = 1; ap.row = i + 1; ap.col = j; ap.d = dx;
+                    Acc am = ap; am.d = -dx;
+                    for (int r = 0; r < ne; ++r) J[(size_t)r * ldj + i * nx + j] = (S::eq(r, ap, ph, p) - S::eq(r, am, ph, p)) / (2 * dx) * SX(j);
+                }
+                for (int t = g_.tid; t < ph * nu; t += G::nt) {
+                    int i = t / nu, j = t - i * nu;
+                    double du = dv * fmax(fabs(U[(ph - 1) * nu + j]), 1.0);
+                    Acc ap = base; ap.kind = (i == ph - 1) ? 3 : 2; ap.row = i; ap.col = j; ap.d = du;
+                    Acc am = ap; am.d = -du;
+                    int blk = i < ch ? i : ch - 1;
+                    for (int r = 0; r < ne; ++r)
+                        atomicAdd(&J[(size_t)r * ldj + ph * nx + blk * nu + j], (S::eq(r, ap, ph, p) - S::eq(r, am, ph, p)) / (2 * du) * SU(j));
+                }
+            }
+        }
+    }
     g_.sync();
+}
+
+template <class S, class G>
+__device__ __noinline__ void nl_eval_instance_call(const G& g_, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
+                                 double* fval, double* grad, double* ceq, double* Jeq, double* cin, double* Jin, int ldj,
+                                 const double* sx, const double* su, double* cue, double* Jue) {
+    nl_eval_instance_impl<S>(g_, ph, ch, z, x0, p, X, U, fval, grad, ceq, Jeq, cin, Jin, ldj, sx, su, cue, Jue);
+}
+// A warp per controller (tiny problems: the evaluation is a large share of the solve) inlines the evaluation at every call
+// site; CTA-sized groups call one shared copy (4x less code to compile, and measurably faster for the shared-memory CTA kernel).
+template <class S, class G>
+__device__ __forceinline__ void nl_eval_instance(const G& g_, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
+                                 double* fval, double* grad, double* ceq, double* Jeq, double* cin, double* Jin, int ldj,
+                                 const double* sx = nullptr, const double* su = nullptr, double* cue = nullptr, double* Jue = nullptr) {
+    if constexpr (G::nt == 32) nl_eval_instance_impl<S>(g_, ph, ch, z, x0, p, X, U, fval, grad, ceq, Jeq, cin, Jin, ldj, sx, su, cue, Jue);
+    else nl_eval_instance_call<S>(g_, ph, ch, z, x0, p, X, U, fval, grad, ceq, Jeq, cin, Jin, ldj, sx, su, cue, Jue);
 }
 
 template <class S>
@@ -323,13 +393,14 @@ __global__ void __launch_bounds__(128) nlmpc_eval_kernel(const NlEvalArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     double* X = nl_smem + (size_t)warp * (ph + 1) * (nx + nu);
     double* U = X + (ph + 1) * nx;
-    const int ni = S::nineq(ph);
+    const int ni = S::nineq(ph), nue = nl_neq<S>(ph);
     const NlGrp<32> grp{lane, lane, 0, nullptr};
     for (int inst = blockIdx.x * wpb + warp; inst < a.batch; inst += gridDim.x * wpb) {
         nl_eval_instance<S>(grp, ph, ch, a.z + (size_t)inst * nz, a.x0 + (size_t)inst * nx, a.params + (size_t)inst * a.param_stride, X, U,
                             a.fval ? a.fval + inst : nullptr, a.grad ? a.grad + (size_t)inst * nz : nullptr,
                             a.ceq ? a.ceq + (size_t)inst * ph * nx : nullptr, a.Jeq ? a.Jeq + (size_t)inst * ph * nx * nz : nullptr,
-                            a.cin ? a.cin + (size_t)inst * ni : nullptr, a.Jin ? a.Jin + (size_t)inst * ni * nz : nullptr, nz);
+                            a.cin ? a.cin + (size_t)inst * ni : nullptr, a.Jin ? a.Jin + (size_t)inst * ni * nz : nullptr, nz, a.sx, a.su,
+                            a.cue ? a.cue + (size_t)inst * nue : nullptr, a.Jue ? a.Jue + (size_t)inst * nue * nz : nullptr);
     }
 }
 

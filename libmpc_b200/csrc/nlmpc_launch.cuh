@@ -54,7 +54,7 @@ int nl_solve_t(NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree) 
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int n = a.ph * S::nx + a.ch * S::nu + 1, me = a.ph * S::nx;
-    const int ni = S::nineq(a.ph);
+    const int ni = S::nineq(a.ph) + nl_neq<S>(a.ph);
     auto sm = [&](int mode) { return NlWs::smem_doubles(mode, n, me, ni, a.ph, S::nx, S::nu) * sizeof(double); };
     if (sm(0) <= (size_t)maxsm) {
         if (n <= 32) return nl_launch_t<S, 0, 32>(a, sm(0), 2 * sm(0) <= (size_t)maxsm / 2 ? 2 : 1, 0, sms, stream, tofree);

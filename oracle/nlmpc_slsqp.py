@@ -47,6 +47,8 @@ def solve(f, x0, z0, lb, ub, maxiter=200, ftol=1e-12):
     cons = [{"type": "eq", "fun": lambda z: f.state_eq(z, x0, want_jac=False)[0], "jac": lambda z: f.state_eq(z, x0)[1]}]
     if f.ineq is not None:     # NLopt convention c(z) <= 0; SciPy wants >= 0
         cons.append({"type": "ineq", "fun": lambda z: -f.ineq_con(z, x0)[0], "jac": lambda z: -f.ineq_con(z, x0)[1]})
+    if getattr(f, "eq", None) is not None:     # user equality constraints (NLOptimizer::bindUserEq, NLOptimizer.hpp:314)
+        cons.append({"type": "eq", "fun": lambda z: f.eq_con(z, x0)[0], "jac": lambda z: f.eq_con(z, x0)[1]})
     bounds = [(None if not np.isfinite(l) else l, None if not np.isfinite(u) else u) for l, u in zip(lb, ub)]
     res = minimize(lambda z: f.objective(z, x0, want_grad=False)[0], z0, jac=lambda z: f.objective(z, x0)[1],
                    method="SLSQP", bounds=bounds, constraints=cons, options=dict(maxiter=maxiter, ftol=ftol))

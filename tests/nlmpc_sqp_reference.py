@@ -116,7 +116,15 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
     B = np.eye(n)
     fval, g = f.objective(z, x0)
     ce, Je = f.state_eq(z, x0)
-    ci, Ji = f.ineq_con(z, x0) if f.ineq is not None else (np.zeros(0), np.zeros((0, n)))
+    # dense block = [user inequalities ; user equalities] (the kernel's J_in block, first mii rows are inequalities)
+    def dense(zz, jac=True):
+        ci_, Ji_ = f.ineq_con(zz, x0) if f.ineq is not None else (np.zeros(0), np.zeros((0, n)))
+        if getattr(f, "eq", None) is not None:
+            cu_, Ju_ = f.eq_con(zz, x0)
+            ci_, Ji_ = np.concatenate([ci_, cu_]), np.vstack([Ji_, Ju_])
+        return ci_, Ji_
+    mii = f.nineq if f.ineq is not None else 0
+    ci, Ji = dense(z)
     me, mi = ce.size, ci.size
     mu = 1.0
     y_prev = None
@@ -124,12 +132,12 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
     hist = []
     for k in range(max_sqp):
         A = np.vstack([Je, Ji, np.eye(n)])
-        l = np.concatenate([-ce, np.full(mi, -np.inf), lb - z])
+        l = np.concatenate([-ce, np.full(mii, -np.inf), -ci[mii:], lb - z])
         u = np.concatenate([-ce, -ci, ub - z])
         d, y, qit = qp.solve(B, g, A, l, u, None, y_prev)
         y_prev = y
         lam_e, lam_i = y[:me], y[me:me + mi]
-        viol = lambda ce_, ci_: np.abs(ce_).sum() + np.maximum(ci_, 0).sum()
+        viol = lambda ce_, ci_: np.abs(ce_).sum() + np.maximum(ci_[:mii], 0).sum() + np.abs(ci_[mii:]).sum()
         v0 = viol(ce, ci)
         mu = max(mu, 1.1 * (np.abs(y[:me + mi]).max() if me + mi else 0.0))
         phi0 = fval + mu * v0
@@ -144,7 +152,7 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
             zt = z + t * d
             ft, _ = f.objective(zt, x0, want_grad=False)
             cet, _ = f.state_eq(zt, x0, want_jac=False)
-            cit = f.ineq_con(zt, x0)[0] if f.ineq is not None else np.zeros(0)
+            cit = dense(zt)[0]
             if ft + mu * viol(cet, cit) <= phi0 + 1e-4 * t * dphi:
                 ls_ok = True
                 break
@@ -162,7 +170,7 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
         z_new = z + s
         f_new, g_new = f.objective(z_new, x0)
         ce_new, Je_new = f.state_eq(z_new, x0)
-        ci_new, Ji_new = f.ineq_con(z_new, x0) if f.ineq is not None else (np.zeros(0), np.zeros((0, n)))
+        ci_new, Ji_new = dense(z_new)
         # damped BFGS on the Lagrangian gradient
         gl_new = g_new + Je_new.T @ lam_e + Ji_new.T @ lam_i
         gl_old = g + Je.T @ lam_e + Ji.T @ lam_i
@@ -182,4 +190,5 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
         if step < tol * max(1.0, np.abs(z).max()) and viol(ce, ci) < 1e-8:
             break
     X, U, e = f.unwrap(z, x0)
-    return dict(z=z, cmd=U[0].copy(), cost=fval, nit=k + 1, viol=float(np.abs(ce).sum() + np.maximum(ci, 0).sum()), hist=hist)
+    return dict(z=z, cmd=U[0].copy(), cost=fval, nit=k + 1,
+                viol=float(np.abs(ce).sum() + np.maximum(ci[:mii], 0).sum() + np.abs(ci[mii:]).sum()), hist=hist)

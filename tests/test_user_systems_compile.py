@@ -1,0 +1,23 @@
+"""CPU: user-defined NLMPC systems (the CUDA-source counterpart of NLMPC::setStateSpaceFunction / setObjectiveFunction /
+setIneqConFunction / setEqConFunction) compile with NVRTC for sm_100a into the engine's kernels; no GPU is needed for
+the compile step.  The run-time behaviour is covered by tests/test_gpu_user_systems.py."""
+import pytest
+
+from user_systems import BROKEN_SRC, PENDULUM_SRC, VANDERPOL_SRC
+
+
+def test_user_system_compiles_eval_kernel():
+    import libmpc_b200 as L
+    assert L.compile_check(VANDERPOL_SRC, "UserVanDerPol", 0) > 10_000
+
+
+def test_user_system_with_equality_constraints_compiles_solve_kernel():
+    import libmpc_b200 as L
+    assert L.compile_check(PENDULUM_SRC, "UserPendulum", 0) > 10_000
+    assert L.compile_check(PENDULUM_SRC, "UserPendulum", 1) > 50_000       # warp-per-controller solve variant
+
+
+def test_compile_error_is_reported_with_the_nvrtc_log():
+    import libmpc_b200 as L
+    with pytest.raises(RuntimeError, match="NVRTC could not compile"):
+        L.compile_check(BROKEN_SRC, "Broken", 0)

@@ -1,0 +1,86 @@
+"""CUDA sources of user-defined NLMPC systems for the tests (the device-side counterpart of the std::function callbacks
+the reference's NLMPC setters take; contract in include/b200mpc.h), each with the matching oracle formulation."""
+import numpy as np
+
+from oracle.nlmpc_formulation import NLMPCFormulation, sum_squares_cost, vanderpol_field
+
+# examples/vanderpol_ex.cpp written as a user system: must reproduce the built-in SYS_VANDERPOL bit for bit.
+VANDERPOL_SRC = r"""
+struct UserVanDerPol {
+    static constexpr int nx = 2, nu = 1, ny = 2, nparam = 1;
+    static constexpr bool continuous = true;
+    __device__ static double Ts(const double* p) { return p[0]; }
+    __host__ __device__ static int nineq(int ph) { return ph + 1; }
+    __device__ static void f(double* dx, const double* x, const double* u, int, const double*) {
+        dx[0] = ((1.0 - (x[1] * x[1])) * x[0]) - x[1] + u[0];
+        dx[1] = x[0];
+    }
+    __device__ static double cost(const Acc& a, double, int ph, const double*) {
+        double sx = 0, su = 0;
+        for (int j = 0; j < nx; ++j) for (int i = 0; i <= ph; ++i) { double v = a.x(i, j); sx += v * v; }
+        for (int j = 0; j < nu; ++j) for (int i = 0; i <= ph; ++i) { double v = a.u(i, j); su += v * v; }
+        return sx + su;
+    }
+    __device__ static double ineq(int r, const Acc& a, double, int, const double*) { return a.u(r, 0) - 0.5; }
+};
+"""
+
+# A system the reference does not ship: damped pendulum on a cart-less pivot, discrete (explicit Euler), quadratic
+# tracking cost, input limit as inequality, and a USER EQUALITY constraint tying the terminal state to the upright
+# position through params (exercises NLMPC::setEqConFunction, NLMPC.hpp:261-281).  params = [Ts, damping, target angle].
+PENDULUM_SRC = r"""
+struct UserPendulum {
+    static constexpr int nx = 2, nu = 1, ny = 2, nparam = 3;
+    static constexpr bool continuous = false;
+    __device__ static double Ts(const double*) { return 0.0; }
+    __host__ __device__ static int nineq(int ph) { return 2 * (ph + 1); }
+    __host__ __device__ static int neq(int) { return 2; }
+    __device__ static void f(double* xn, const double* x, const double* u, int, const double* p) {
+        xn[0] = x[0] + p[0] * x[1];
+        xn[1] = x[1] + p[0] * (-9.81 * sin(x[0]) - p[1] * x[1] + u[0]);
+    }
+    __device__ static double cost(const Acc& a, double e, int ph, const double* p) {
+        double c = 0;
+        for (int i = 0; i <= ph; ++i) {
+            double d0 = a.x(i, 0) - p[2], d1 = a.x(i, 1), u0 = a.u(i, 0);
+            c += 10.0 * d0 * d0 + d1 * d1 + 0.1 * u0 * u0;
+        }
+        return c + 1e-3 * e * e;
+    }
+    __device__ static double ineq(int r, const Acc& a, double, int ph, const double*) {
+        int i = r / 2;
+        return (r & 1) ? (-a.u(i, 0) - 8.0) : (a.u(i, 0) - 8.0);
+    }
+    __device__ static double eq(int r, const Acc& a, int ph, const double* p) {
+        return r == 0 ? (a.x(ph, 0) - p[2]) + 0.5 * a.x(ph, 1) : a.x(ph / 2, 0) * a.x(ph / 2, 0) + a.x(ph / 2, 1) - 0.1;
+    }
+};
+"""
+
+BROKEN_SRC = "struct Broken { static constexpr int nx = 2; int oops( };"
+
+
+def vanderpol_user_formulation():
+    f = NLMPCFormulation(2, 1, 2, 10, 5, nineq=11)
+    f.continuous, f.Ts, f.f, f.obj = True, 0.1, vanderpol_field, sum_squares_cost
+    f.ineq = lambda X, Y, U, e: U[:, 0] - 0.5
+    f.params = np.array([0.1])
+    return f
+
+
+def pendulum_formulation(ph=10, ch=5, Ts=0.1, damping=0.3, target=0.4):
+    f = NLMPCFormulation(2, 1, 2, ph, ch, nineq=2 * (ph + 1), neq=2)
+    f.continuous = False
+    f.f = lambda x, u, i=0: np.array([x[0] + Ts * x[1], x[1] + Ts * (-9.81 * np.sin(x[0]) - damping * x[1] + u[0])])
+
+    def cost(X, Y, U, e):
+        c = 0.0
+        for i in range(ph + 1):
+            d0 = X[i, 0] - target
+            c += 10.0 * d0 * d0 + X[i, 1] * X[i, 1] + 0.1 * U[i, 0] * U[i, 0]
+        return c + 1e-3 * e * e
+    f.obj = cost
+    f.ineq = lambda X, Y, U, e: np.stack([U[:, 0] - 8.0, -U[:, 0] - 8.0], axis=1).ravel()
+    f.eq = lambda X, U: np.array([(X[ph, 0] - target) + 0.5 * X[ph, 1], X[ph // 2, 0] * X[ph // 2, 0] + X[ph // 2, 1] - 0.1])
+    f.params = np.array([Ts, damping, target])
+    return f
