@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="solves in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-instance-model", action="store_true", help="give every instance its own copy of A,B,C")
+    ap.add_argument("--schedule", default="gang", choices=["gang", "free"], help="persistent-warp scheduling (include/b200mpc.h)")
     ap.add_argument("--warps-per-cta", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     a = ap.parse_args()
@@ -196,6 +197,7 @@ def main():
     f, c = build_controller(L, ph, B, a.max_iter, a.per_instance_model)
     if a.warps_per_cta or a.ctas_per_sm:
         c.set_launch(a.warps_per_cta, a.ctas_per_sm)
+    c.set_schedule(a.schedule == "gang")
     stream = torch.cuda.current_stream()
     c.set_stream(stream.cuda_stream)
     x0_h, r = synth_inputs(rank * B, B)

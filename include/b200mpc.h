@@ -135,6 +135,13 @@ int b200mpc_lmpc_cmd_device_ptr(b200mpc_lmpc_t h, double** cmd_dev);
 int b200mpc_lmpc_info(b200mpc_lmpc_t h, int* warp_slots, size_t* workspace_bytes_per_slot, long long* launches);
 /* Override launch geometry (0 = auto): warps per CTA and CTAs per SM of the persistent solve kernel. */
 int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm);
+/* How the persistent warps draw instances.  GANG (default): the warps of a CTA draw and start their instances together
+ * and wait for the slowest before drawing again -- they run the same phase of the program at the same time and share its
+ * instruction-cache footprint (measured: 95k vs 48k solves/s at batch 32768, profiles/r01_icache.md).  FREE: every warp
+ * draws on its own as soon as it is done (no waiting, but the phases interleave and the kernel becomes instruction-fetch
+ * bound).  Results are identical. */
+enum { B200MPC_SCHEDULE_FREE = 0, B200MPC_SCHEDULE_GANG = 1 };
+int b200mpc_lmpc_set_schedule(b200mpc_lmpc_t h, int schedule);
 /* Profiling aid: first call (out_host ignored) enables per-instance phase cycle counters; later calls copy
  * batch*8 counters [setup, factorize, admm sweeps, info, polish prep, polish factor, polish solve, unpack] to the host. */
 int b200mpc_lmpc_profile(b200mpc_lmpc_t h, long long* out_host);

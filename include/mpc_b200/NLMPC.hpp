@@ -6,10 +6,12 @@
 // shift of the decision vector (NLOptimizer::run, NLOptimizer.hpp:412-510,705-716), Result / OptSequence / ResultStatus.
 //
 // What cannot carry over: the reference receives the model, the objective and the constraints as host std::function
-// callbacks (setStateSpaceFunction / setObjectiveFunction / setIneqConFunction, NLMPC.hpp:139-281); a device kernel
-// cannot call them.  They are replaced by ONE call, setSystem(system_id, params), that selects a device functor compiled
-// into the engine (the reference's three example systems: B200MPC_SYS_VANDERPOL, _OSCNET4/6, _UGV) and supplies its
-// numbers.  The three callback setters are kept so that existing call sites fail with a clear message, not silently.
+// callbacks (setStateSpaceFunction / setObjectiveFunction / setIneqConFunction / setEqConFunction, NLMPC.hpp:139-281); a
+// device kernel cannot call them.  They are replaced by ONE call: setSystem(system_id, params) selects a device functor
+// compiled into the engine (the reference's three example systems: B200MPC_SYS_VANDERPOL, _OSCNET4/6, _UGV), or
+// setSystemSource(cuda_source, type_name, params) takes the user's own model / cost / constraints as CUDA source, which
+// the engine compiles with NVRTC into its kernels (contract in include/b200mpc.h).  The callback setters are kept so that
+// existing call sites fail with a clear message, not silently.
 //
 // Batch extension: NLMPC(batch) holds `batch` independent controllers; optimizeBatch solves them in one launch.
 #pragma once
@@ -40,9 +42,20 @@ public:
         detail::check(b200mpc_nlmpc_system_dims(system_id, ph_, &nx, &nu, &np, &ni));
         if (nx != nx_ || nu != nu_) throw std::runtime_error("setSystem: system dimensions do not match the template sizes");
         if (ineq_ >= 0 && ni != ineq_) throw std::runtime_error("setSystem: Tineq does not match the system's inequality count");
+        int ne = 0;
+        detail::check(b200mpc_nlmpc_system_neq(system_id, ph_, &ne));
+        if (eq_ >= 0 && ne != eq_) throw std::runtime_error("setSystem: Teq does not match the system's equality count");
+        neq_ = ne;
         if (params.size() != (size_t)np * (per_instance ? batch_ : 1)) throw std::runtime_error("setSystem: wrong parameter count");
         system_ = system_id; params_ = params; per_instance_ = per_instance; nparam_ = np;
         return true;
+    }
+    // the user's own system as CUDA source: struct `type_name` with static f / cost / ineq [/ eq] device functions
+    bool setSystemSource(const std::string& cuda_source, const std::string& type_name, const std::vector<double>& params,
+                         bool per_instance = false) {
+        int id = -1;
+        detail::check(b200mpc_nlmpc_register_system(cuda_source.c_str(), type_name.c_str(), &id));
+        return setSystem(id, params, per_instance);
     }
     template <class F> bool setStateSpaceFunction(F&&, float = 1e-10f) { return noCallback("setStateSpaceFunction"); }
     template <class F> bool setObjectiveFunction(F&&) { return noCallback("setObjectiveFunction"); }
@@ -50,6 +63,7 @@ public:
     template <class F> bool setIneqConFunction(F&&, float tol = 1e-10f) { (void)tol; return noCallback("setIneqConFunction"); }
     template <class F> bool setEqConFunction(F&&, float = 1e-10f) { return noCallback("setEqConFunction"); }
     void setIneqTolerance(double tol) { ineq_tol_ = tol; }                       // the `tol` of setIneqConFunction (NLMPC.hpp:229)
+    void setEqTolerance(double tol) { eq_tol_ = tol; }                           // the `tol` of setEqConFunction (NLMPC.hpp:262)
 
     // NLMPC.hpp:80-95: continuous-time systems take their sampling time through the parameter vector (slot 0)
     bool setDiscretizationSamplingTime(const double ts) {
@@ -58,8 +72,9 @@ public:
         for (int b = 0; b < (per_instance_ ? batch_ : 1); ++b) params_[(size_t)b * nparam_] = ts;
         return true;
     }
-    void setInputScale(const cvec<Tnu>) { throw std::runtime_error("b200mpc NLMPC: input scaling is not implemented"); }
-    void setStateScale(const cvec<Tnx>) { throw std::runtime_error("b200mpc NLMPC: state scaling is not implemented"); }
+    // NLMPC.hpp:108-130 -> Mapping::setInputScaling / setStateScaling (Mapping.hpp:108-150)
+    void setInputScale(const cvec<Tnu> scaling) { su_.assign(scaling.data(), scaling.data() + nu_); }
+    void setStateScale(const cvec<Tnx> scaling) { sx_.assign(scaling.data(), scaling.data() + nx_); }
 
     void setOptimizerParameters(const Parameters& param) {                       // NLMPC.hpp:97-100, NLOptimizer.hpp:150-190
         const auto* np = dynamic_cast<const NLParameters*>(&param);
@@ -112,16 +127,19 @@ public:
         if (ft > 0) q.ftol = ft;
         std::vector<double> cost(batch_), viol(batch_);
         std::vector<int32_t> st(batch_), it(batch_), qit(batch_);
-        detail::check(b200mpc_nlmpc_solve(system_, ph_, ch_, batch_, &q, z0.data(), x0, params_.data(), per_instance_ ? 1 : 0, lb_.data(),
-                                          ub_.data(), opt_.data(), cost.data(), viol.data(), st.data(), it.data(), qit.data(), 0, nullptr));
+        const b200mpc_nlmpc_scaling sc{sx_.empty() ? nullptr : sx_.data(), su_.empty() ? nullptr : su_.data()};
+        detail::check(b200mpc_nlmpc_solve_ex(system_, ph_, ch_, batch_, &q, z0.data(), x0, params_.data(), per_instance_ ? 1 : 0, &sc,
+                                             lb_.data(), ub_.data(), opt_.data(), cost.data(), viol.data(), st.data(), it.data(),
+                                             qit.data(), 0, nullptr));
         first_ = false;
         // feasibility as Constraints::isFeasible (Constraints.hpp:157-201): user inequalities against their tolerance
         int ni = 0;
         detail::check(b200mpc_nlmpc_system_dims(system_, ph_, nullptr, nullptr, nullptr, &ni));
-        std::vector<double> cin((size_t)batch_ * std::max(ni, 1));
-        if (ni > 0)
-            detail::check(b200mpc_nlmpc_eval(system_, ph_, ch_, batch_, opt_.data(), x0, params_.data(), per_instance_ ? 1 : 0, nullptr, nullptr,
-                                             nullptr, nullptr, cin.data(), nullptr, 0, nullptr));
+        std::vector<double> cin((size_t)batch_ * std::max(ni, 1)), cue((size_t)batch_ * std::max(neq_, 1));
+        if (ni > 0 || neq_ > 0)
+            detail::check(b200mpc_nlmpc_eval_ex(system_, ph_, ch_, batch_, opt_.data(), x0, params_.data(), per_instance_ ? 1 : 0, &sc,
+                                                nullptr, nullptr, nullptr, nullptr, ni > 0 ? cin.data() : nullptr, nullptr,
+                                                neq_ > 0 ? cue.data() : nullptr, nullptr, 0, nullptr));
         last_.assign(batch_, Result<Tnu>());
         x0_.assign(x0, x0 + (size_t)batch_ * nx_);
         for (int b = 0; b < batch_; ++b) {
@@ -129,12 +147,13 @@ public:
             const double* z = opt_.data() + (size_t)b * nz;
             slack_[b] = z[nz - 1];
             r.cmd.resize(nu_, 1);
-            for (int k = 0; k < nu_; ++k) r.cmd(k) = z[ph_ * nx_ + k];
+            for (int k = 0; k < nu_; ++k) r.cmd(k) = (su_.empty() ? 1.0 : su_[k]) * z[ph_ * nx_ + k];
             r.cost = cost[b];
             r.status = st[b] == 0 ? ResultStatus::SUCCESS : ResultStatus::MAX_ITERATION;
             r.solver_status = st[b] == 0 ? 4 : 5;                                // nlopt::XTOL_REACHED / MAXEVAL_REACHED
             r.is_feasible = true;
             for (int k = 0; k < ni; ++k) if (cin[(size_t)b * ni + k] > ineq_tol_) r.is_feasible = false;
+            for (int k = 0; k < neq_; ++k) if (std::fabs(cue[(size_t)b * neq_ + k]) > eq_tol_) r.is_feasible = false;
         }
         return last_;
     }
@@ -147,9 +166,10 @@ public:
         if (x0_.empty()) return q;
         const double* z = opt_.data() + (size_t)instance * nz_;
         for (int t = 0; t <= ph_; ++t) {
-            for (int k = 0; k < nx_; ++k) q.state(t, k) = t == 0 ? x0_[(size_t)instance * nx_ + k] : z[(t - 1) * nx_ + k];
+            for (int k = 0; k < nx_; ++k)                                                     // X / state scaling, row 0 = x0 included
+                q.state(t, k) = (t == 0 ? x0_[(size_t)instance * nx_ + k] : z[(t - 1) * nx_ + k]) / (sx_.empty() ? 1.0 : sx_[k]);
             int blk = std::min(std::min(t, ph_ - 1), ch_ - 1);
-            for (int k = 0; k < nu_; ++k) q.input(t, k) = z[ph_ * nx_ + blk * nu_ + k];
+            for (int k = 0; k < nu_; ++k) q.input(t, k) = (su_.empty() ? 1.0 : su_[k]) * z[ph_ * nx_ + blk * nu_ + k];
             for (int k = 0; k < ny_ && k < nx_; ++k) q.output(t, k) = q.state(t, k);      // built-in systems: y = x
         }
         return q;
@@ -157,8 +177,7 @@ public:
 
 private:
     void init(int nx, int nu, int ny, int ph, int ch, int ineq, int eq, int batch) {
-        if (eq > 0) throw std::runtime_error("b200mpc NLMPC: user equality constraints are not implemented");
-        nx_ = nx; nu_ = nu; ny_ = ny; ph_ = ph; ch_ = ch; ineq_ = ineq; batch_ = batch;
+        nx_ = nx; nu_ = nu; ny_ = ny; ph_ = ph; ch_ = ch; ineq_ = ineq; eq_ = eq; batch_ = batch;
         nz_ = ph * nx + ch * nu + 1;
         const double finf = std::numeric_limits<float>::infinity();                  // NLOptimizer.hpp:69-73
         lb_.assign(nz_, -finf); ub_.assign(nz_, finf);
@@ -197,10 +216,11 @@ private:
         out[nz_ - 1] = slack_[b];
     }
 
-    int nx_ = 0, nu_ = 0, ny_ = 0, ph_ = 0, ch_ = 0, ineq_ = -1, batch_ = 1, nz_ = 0;
+    int nx_ = 0, nu_ = 0, ny_ = 0, ph_ = 0, ch_ = 0, ineq_ = -1, eq_ = -1, neq_ = 0, batch_ = 1, nz_ = 0;
     int system_ = -1, nparam_ = 0;
     bool per_instance_ = false, first_ = true;
-    double ineq_tol_ = 1e-10;
+    double ineq_tol_ = 1e-10, eq_tol_ = 1e-10;
+    std::vector<double> sx_, su_;
     NLParameters p_;
     std::vector<double> params_, lb_, ub_, opt_, slack_, x0_;
     std::vector<Result<Tnu>> last_;

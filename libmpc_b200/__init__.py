@@ -19,7 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200mpc.so")
+LIB_PATH = os.environ.get("B200MPC_LIB") or os.path.join(_HERE, "libb200mpc.so")      # env override: kernel build experiments
 
 inf = float("inf")
 
@@ -78,6 +78,7 @@ def load_library():
     lib.b200mpc_lmpc_cmd_device_ptr.argtypes = [H, C.POINTER(C.c_void_p)]
     lib.b200mpc_lmpc_info.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_longlong)]
     lib.b200mpc_lmpc_set_launch.argtypes = [H, C.c_int, C.c_int]
+    lib.b200mpc_lmpc_set_schedule.argtypes = [H, C.c_int]
     lib.b200mpc_lmpc_profile.argtypes = [H, C.c_void_p]
     lib.b200mpc_sync.argtypes = [H]
     lib.b200mpc_nlmpc_system_dims.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
@@ -104,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_set_input_bounds", "b200mpc_lmpc_set_output_bounds", "b200mpc_lmpc_set_scalar_constraint",
     "b200mpc_lmpc_set_references", "b200mpc_lmpc_set_exogenous_inputs", "b200mpc_lmpc_set_warm_start",
     "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
-    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
+    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_set_schedule", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
     "b200mpc_nlmpc_default_params", "b200mpc_nlmpc_solve_smem_bytes", "b200mpc_nlmpc_solve",
     "b200mpc_nlmpc_system_neq", "b200mpc_nlmpc_register_system", "b200mpc_nlmpc_compile_check", "b200mpc_nlmpc_eval_ex",
     "b200mpc_nlmpc_solve_ex",
@@ -427,6 +428,10 @@ class LMPC:
     def set_launch(self, warps_per_cta=0, ctas_per_sm=0):
         _check(self.lib.b200mpc_lmpc_set_launch(self._h, warps_per_cta, ctas_per_sm))
 
+    def set_schedule(self, gang=True):
+        """Gang (default) or free scheduling of the persistent warps (include/b200mpc.h); results are identical."""
+        _check(self.lib.b200mpc_lmpc_set_schedule(self._h, 1 if gang else 0))
+
     def info(self):
         a, b, c = C.c_int(), C.c_size_t(), C.c_longlong()
         _check(self.lib.b200mpc_lmpc_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
@@ -624,14 +629,17 @@ class NLMPC:
     """Batched mpc::NLMPC<Tnx,Tnu,Tny,Tph,Tch,Tineq,Teq> (include/mpc/NLMPC.hpp) for the built-in device systems.
 
     The reference takes the model / objective / constraints as std::function callbacks (NLMPC.hpp:139-281), which cannot
-    run on the device; here `system` selects a device functor (SYS_VANDERPOL, SYS_UGV, ...) and `setSystemParameters`
-    supplies its numbers (shared or per controller).  Bounds, parameters, warm start and results follow the reference."""
+    run on the device; here `system` selects a device functor (SYS_VANDERPOL, SYS_UGV, ..., or the id `register_system`
+    returns for the user's own CUDA source) and `setSystemParameters` supplies its numbers (shared or per controller).
+    Bounds, scaling, parameters, warm start and results follow the reference."""
 
     def __init__(self, system, ph, ch, batch=1):
         self.lib = load_library()
         d = nlmpc_system_dims(system, ph)
         self.system, self.ph, self.ch, self.batch = system, ph, ch, batch
-        self.nx, self.nu, self.nparam, self.nineq = d["nx"], d["nu"], d["nparam"], d["nineq"]
+        self.nx, self.nu, self.nparam, self.nineq, self.neq = d["nx"], d["nu"], d["nparam"], d["nineq"], d["neq"]
+        self.state_scale = self.input_scale = None
+        self.eq_tolerance = 1e-10                                                      # NLMPC.hpp:262
         self.nz = ph * self.nx + ch * self.nu + 1
         self.lb = np.full(self.nz, -FLT_INF); self.ub = np.full(self.nz, FLT_INF)     # NLOptimizer.hpp:69-73
         self.params = None
@@ -664,6 +672,17 @@ class NLMPC:
 
     def setIneqTolerance(self, tol):
         self.ineq_tolerance = float(tol)
+
+    def setEqTolerance(self, tol):
+        self.eq_tolerance = float(tol)
+
+    def setStateScale(self, scaling):
+        """NLMPC::setStateScale (NLMPC.hpp:122-130)."""
+        self.state_scale = np.ascontiguousarray(scaling, dtype=np.float64).reshape(self.nx)
+
+    def setInputScale(self, scaling):
+        """NLMPC::setInputScale (NLMPC.hpp:108-116)."""
+        self.input_scale = np.ascontiguousarray(scaling, dtype=np.float64).reshape(self.nu)
 
     def _bounds(self, lo, hi, dim, horizon, offset, slice_):
         lo = np.asarray(lo, float); hi = np.asarray(hi, float)
@@ -730,7 +749,8 @@ class NLMPC:
         xt = [t for t in (self.p.relative_xtol, self.p.absolute_xtol) if t > 0]
         ft = [t for t in (self.p.relative_ftol, self.p.absolute_ftol) if t > 0]
         r = nlmpc_solve(self.system, self.ph, self.ch, z0, x0, self.params, self.lb, self.ub, max_sqp=self.p.maximum_iteration,
-                        tol=min(xt) if xt else 1e-7, ftol=min(ft) if ft else 1e-12)
+                        tol=min(xt) if xt else 1e-7, ftol=min(ft) if ft else 1e-12, state_scale=self.state_scale,
+                        input_scale=self.input_scale)
         z = r["z"]
         self.opt_vector = z.copy()
         self.is_first_iteration = False
@@ -739,10 +759,18 @@ class NLMPC:
         X = np.concatenate([x0[:, None, :], z[:, :ph * nx].reshape(B, ph, nx)], axis=1)
         blk = np.minimum(np.minimum(np.arange(ph + 1), ph - 1), ch - 1)
         U = z[:, ph * nx:ph * nx + ch * nu].reshape(B, ch, nu)[:, blk]
+        if self.state_scale is not None:
+            X = X / self.state_scale                              # Mapping::unwrapVector (row 0 = x0 included)
+        if self.input_scale is not None:
+            U = U * self.input_scale
         feas = np.ones(B, bool)
-        if self.nineq:
-            cin = nlmpc_eval(self.system, ph, ch, z, x0, self.params, want=("cin",))["cin"]
-            feas = ~(cin > self.ineq_tolerance).any(axis=1)       # Constraints::isFeasible (Constraints.hpp:157-201)
+        if self.nineq or self.neq:
+            ev = nlmpc_eval(self.system, ph, ch, z, x0, self.params, want=("cin", "cue"), state_scale=self.state_scale,
+                            input_scale=self.input_scale)
+            if self.nineq:
+                feas &= ~(ev["cin"] > self.ineq_tolerance).any(axis=1)       # Constraints::isFeasible (Constraints.hpp:157-201)
+            if self.neq:
+                feas &= ~(np.abs(ev["cue"]) > self.eq_tolerance).any(axis=1)
         status = np.where(r["status"] == 0, 0, 1).astype(np.int32)            # SUCCESS / MAX_ITERATION (Types.hpp:87-94)
         solver_status = np.where(r["status"] == 0, 4, 5).astype(np.int32)     # nlopt::XTOL_REACHED / MAXEVAL_REACHED
         self.result = Result(U[:, 0].copy(), r["cost"], status, solver_status, feas, r["iters"], r["qp_iters"], np.zeros(B, np.int32))

@@ -46,6 +46,7 @@ struct b200mpc_lmpc {
     int req_wpc = 0, req_cps = 0;
     size_t smem_cta = 0;
     bool force_generic = false;
+    int gang = getenv("B200MPC_GANG") ? atoi(getenv("B200MPC_GANG")) : 1;     // B200MPC_SCHEDULE_GANG unless overridden
     int model_shared = 0;
     long long launches = 0;
     std::vector<double> stage;   // host staging
@@ -353,7 +354,7 @@ template <class DM>
 static int launch_t(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
     DM dm; dm.from(h->d);
     lmpc_solve_kernel<DM><<<h->grid, h->warps_per_cta * 32, h->smem_cta, h->stream>>>(dm, h->p, pr, o, h->batch, h->workspace,
-                                                                                      h->ws_stride, h->counter, h->model_shared);
+                                                                                      h->ws_stride, h->counter, h->model_shared, h->gang);
     CK(cudaGetLastError());
     return B200MPC_OK;
 }
@@ -369,6 +370,11 @@ static int launch(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
     return launch_t<Dm>(h, pr, o);
 }
 
+extern "C" int b200mpc_lmpc_set_schedule(b200mpc_lmpc_t h, int schedule) {
+    if (!h || (schedule != B200MPC_SCHEDULE_FREE && schedule != B200MPC_SCHEDULE_GANG)) return fail(B200MPC_EINVAL, "bad schedule");
+    h->gang = schedule;
+    return B200MPC_OK;
+}
 extern "C" int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm) {
     HCHECK();
     if (warps_per_cta < -(B200_MAX_THREADS / 32) || warps_per_cta > B200_MAX_THREADS / 32 || ctas_per_sm < 0) return fail(B200MPC_EINVAL, "bad launch geometry");

@@ -1407,7 +1407,9 @@ __device__ void solve_instance(Ctx<DM>& c, const Out& o) {
 template <class DM>
 __global__ void __launch_bounds__(B200_MAX_THREADS, 1) lmpc_solve_kernel(const __grid_constant__ DM d, const __grid_constant__ Params p,
                                                         const __grid_constant__ Prob pr, const __grid_constant__ Out o,
-                                                        int batch, double* workspace, size_t ws_stride, int* counter, int model_shared) {
+                                                        int batch, double* workspace, size_t ws_stride, int* counter, int model_shared,
+                                                        int gang) {
+    __shared__ int gang_base, gang_take;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int slot = blockIdx.x * wpb + warp;
@@ -1437,13 +1439,39 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, 1) lmpc_solve_kernel(const _
         if (warp == 0) load_model(c);
         __syncthreads();
     }
+    // Gang scheduling: the warps of a CTA draw their instances together and start them together, so that at any time
+    // most of them execute the same phase of the (large) program and share its instruction-cache footprint; a CTA waits
+    // for its slowest member before drawing again.  Free scheduling: every warp draws on its own.
+    int gang_round = 0;
     for (;;) {
         int inst = 0;
-        if (lane == 0) inst = atomicAdd(counter, 1);
-        inst = __shfl_sync(0xffffffffu, inst, 0);
-        if (inst >= batch) break;
-        c.inst = inst;
-        solve_instance(c, o);
+        if (gang) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                // full gangs for the rounds every CTA can fill; the remainder is split evenly over the CTAs instead of
+                // leaving most of them idle in the last round
+                const int per_round = (int)gridDim.x * wpb;
+                int take = wpb;
+                if (gang_round >= batch / per_round) {
+                    take = (batch % per_round + (int)gridDim.x - 1) / (int)gridDim.x;
+                    take = take < 1 ? 1 : (take > wpb ? wpb : take);
+                }
+                gang_take = take;
+                gang_base = atomicAdd(counter, take);
+            }
+            ++gang_round;
+            __syncthreads();
+            if (gang_base >= batch) break;
+            inst = warp < gang_take ? gang_base + warp : batch;
+        } else {
+            if (lane == 0) inst = atomicAdd(counter, 1);
+            inst = __shfl_sync(0xffffffffu, inst, 0);
+            if (inst >= batch) break;
+        }
+        if (inst < batch) {
+            c.inst = inst;
+            solve_instance(c, o);
+        }
         __syncwarp();
     }
 }

@@ -7,7 +7,7 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PROGRAMS = ["quadrotor_kat", "vanderpol_kat"]
+PROGRAMS = ["quadrotor_kat", "vanderpol_kat", "user_system_kat"]
 
 
 def _build(name):
