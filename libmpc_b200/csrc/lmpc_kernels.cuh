@@ -38,8 +38,13 @@ constexpr int kDotUnroll = B200_DOT_UNROLL;
 #ifndef B200_MAX_THREADS
 #define B200_MAX_THREADS 384   // up to 12 warps per CTA -> at most 170 registers per thread
 #endif
-constexpr int kRingF = 2;   // factor-block ring slots
-constexpr int kRingV = 3;   // vector-record ring slots
+#ifndef B200_RING_V
+#define B200_RING_V 3          // 3 slots: 18.1 KB of shared memory per warp (12 warps/SM).  Measured alternatives (gang
+                               // scheduling, batch 4096 / 32768): 2 slots + 12 warps 73k / 85k, 2 slots + 13 warps 67k / 77k,
+                               // 2 slots + 14 warps (448 threads, 144 regs) 76k / 82k, against 77k / 94k for this setting
+#endif
+constexpr int kRingF = 2;            // factor-block ring slots
+constexpr int kRingV = B200_RING_V;  // vector-record ring slots
 
 // OSQP status_val (constants.h of v0.6.3)
 enum { OSQP_DUAL_INFEASIBLE_INACCURATE = 4, OSQP_PRIMAL_INFEASIBLE_INACCURATE = 3, OSQP_SOLVED_INACCURATE = 2,
@@ -885,9 +890,7 @@ __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
     for (int i = d.ph; i >= 0; --i) {
         const int bi = d.bcount(i), vo = c.voff(i);
         const double* F = ringF_acquire(c, i);
-        double* V = ringV_acquire(c, i);
         double* Vp = (i < d.ph) ? ringV_acquire(c, i + 1) : nullptr;
-        double* Dy = V + d.VSS;
         double* Dg = DRP(i);
         SPROF(5);
         double tk = tnext;
@@ -900,6 +903,8 @@ __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
         }
         if (i < d.ph) rows_dot(i + 1, u1, u2);
         __syncwarp();
+        double* V = ringV_acquire(c, i);          // with a 2-slot ring this record was requested one phase ago
+        double* Dy = V + d.VSS;
         SPROF(6);
         // [B || R2(i+1)]   x~_i = Linv_i' u ; x update   ||   z,y update of stage i+1
         for (int k = lane; k < bi; k += 32) {
