@@ -102,6 +102,7 @@ enum { RS_SUCCESS = 0, RS_MAX_ITERATION = 1, RS_INFEASIBLE = 2, RS_ERROR = 3, RS
 
 // Runtime dimensions (any shape).
 struct Dm {
+    static constexpr bool is_static = false;
     int nx, nu, ndu, ny, ph, ch;
     int ne, b, n, m;
     int RS, RSL, oBOX, oOUT, oSC, oEQ, oDU;      // rows owned by a stage and the offsets of its groups
@@ -132,6 +133,7 @@ struct Dm {
 // known (full unrolling, constant-folded index arithmetic).  ph/ch stay runtime.
 template <int NX_, int NU_, int NDU_, int NY_>
 struct SDm {
+    static constexpr bool is_static = true;
     static constexpr int nx = NX_, nu = NU_, ndu = NDU_, ny = NY_;
     static constexpr int ne = NX_ + NU_, b = NX_ + 2 * NU_;
     static constexpr int oBOX = 0, oOUT = ne, oSC = ne + ny, oEQ = ne + ny + 1, oDU = oEQ + ne;
@@ -740,7 +742,7 @@ __device__ __forceinline__ double sdot(const double* a, int sa, const double* x,
 }
 
 // predicated dot product, 4 independent accumulators; `maxn` is a compile-time bound for static dimensions
-__device__ __forceinline__ double dotp(const double* a, int sa, const double* x, int cnt, int maxn) {
+__device__ __forceinline__ double dotp_inl(const double* a, int sa, const double* x, int cnt, int maxn) {
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll (kDotUnroll)
     for (int q = 0; q < maxn; q += 4) {
@@ -750,6 +752,23 @@ __device__ __forceinline__ double dotp(const double* a, int sa, const double* x,
         if (q + 3 < cnt) a3 = fma(a[(q + 3) * sa], x[q + 3], a3);
     }
     return (a0 + a1) + (a2 + a3);
+}
+#ifndef B200_DOT_CALL
+#define B200_DOT_CALL 0   // 1: the unrolled dot products become shared subroutines (one copy per length class) instead of being
+#endif                    //    inlined.  Measured (gang scheduling, batch 32768): 82k solves/s against 94k inlined -- the call overhead
+                          //    costs more than the 0.5k instructions of footprint it saves; kept as a knob
+template <int MAXN>
+__device__ __noinline__ double dotp_call(const double* a, int sa, const double* x, int cnt) { return dotp_inl(a, sa, x, cnt, MAXN); }
+template <class DM>
+__device__ __forceinline__ double dotp(const double* a, int sa, const double* x, int cnt, int maxn) {
+#if B200_DOT_CALL
+    if constexpr (DM::is_static) {          // maxn is a constant after inlining: the chain folds to one call
+        if (maxn <= 12) return dotp_call<12>(a, sa, x, cnt);
+        if (maxn <= 16) return dotp_call<16>(a, sa, x, cnt);
+        if (maxn <= 20) return dotp_call<20>(a, sa, x, cnt);
+    }
+#endif
+    return dotp_inl(a, sa, x, cnt, maxn);
 }
 
 // ---- one reduced-KKT solve fused with the ADMM updates (MODE 0) or with the polish bookkeeping (MODE 1) -----------
@@ -793,9 +812,9 @@ __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
         double au;
         if (k < d.ne) {
             au = vj[d.oBOX + k] - vprev[k] + sv[k] * vj[d.oSC];
-            au += dotp(Cm + k, d.ldC, vj + d.oOUT, k < d.nx ? d.ny : 0, d.ny);
+            au += dotp<DM>(Cm + k, d.ldC, vj + d.oOUT, k < d.nx ? d.ny : 0, d.ny);
         } else au = vj[d.oDU + k - d.ne];
-        if (j < d.ph) au += dotp(G + k, d.ldG, vj + d.oEQ, d.ne, d.ne);
+        if (j < d.ph) au += dotp<DM>(G + k, d.ldG, vj + d.oEQ, d.ne, d.ne);
         return au;
     };
     {   // prologue: right-hand side of stage 0 -> wbuf
@@ -821,7 +840,7 @@ __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
         SPROF(1);
         // [B || Q1]  t_i = Linv_i w   ||   row weights of stage i+1
         for (int k = lane; k < bi; k += 32) {
-            double acc = dotp(F + k * (k + 1) / 2, 1, wbuf, k + 1, d.b);
+            double acc = dotp<DM>(F + k * (k + 1) / 2, 1, wbuf, k + 1, d.b);
             tcur[k] = acc; tg[vo + k] = acc;
         }
         if (i < d.ph) rows_v(i + 1, Vn, vn);
@@ -834,7 +853,7 @@ __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
             for (int k = lane; k < bn; k += 32) {
                 double au = col_au(i + 1, k, vn, vc + d.oEQ);
                 double rhs = MODE == 0 ? (sigma * Dyn[k] - Vn[d.oQ + k] + Vn[d.oD + k] * au) : (va[von + k] + Vn[d.oD + k] * au);
-                if (k < d.ne) rhs -= dotp(F + d.oLc + k * ldb, 1, tcur, d.b, d.b);
+                if (k < d.ne) rhs -= dotp<DM>(F + d.oLc + k * ldb, 1, tcur, d.b, d.b);
                 wbuf[k] = rhs;
             }
         }
@@ -857,7 +876,7 @@ __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
             if (t < d.ny) { cp = Cm + t * d.ldC; cnt = d.nx; row = d.oOUT + t; }
             else if (t == d.ny) { cp = sv; cnt = d.ne; row = d.oSC; }
             else { int r = t - d.ny - 1; cp = G + r * d.ldG; cnt = d.b; row = d.oEQ + r; extra = ujn[r]; }
-            arow[row] = dotp(cp, 1, uj, cnt, d.b) - extra;
+            arow[row] = dotp<DM>(cp, 1, uj, cnt, d.b) - extra;
         }
         for (int r = lane; r < d.ne; r += 32) arow[d.oBOX + r] = uj[r];
         if (j < d.ph) for (int r = lane; r < d.nu; r += 32) arow[d.oDU + r] = uj[d.ne + r];
@@ -898,7 +917,7 @@ __device__ void kkt_sweeps(Ctx<DM>& c, bool store_delta, bool first) {
         // [A || R1(i+1)]   u = t_i - Lc_i' x~_{i+1}   ||   row dots of stage i+1
         for (int k = lane; k < bi; k += 32) {
             double w = (k == lane) ? tk : tg[vo + k];
-            if (i < d.ph) w -= dotp(F + d.oLc + k, ldb, xb, d.ne, d.ne);
+            if (i < d.ph) w -= dotp<DM>(F + d.oLc + k, ldb, xb, d.ne, d.ne);
             vtmp[k] = w;
         }
         if (i < d.ph) rows_dot(i + 1, u1, u2);
