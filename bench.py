@@ -164,6 +164,7 @@ def main():
     config = {"workload": f"quadrotor LMPC nx=12 nu=4 ny=12 ph=ch={ph}, batch={B} per GPU, maximum_iteration={a.max_iter}, "
                           f"{'per-instance' if a.per_instance_model else 'shared'} model, per-instance x0/yRef synthetic seed 20 (BASELINE.json configs[1])",
               "batch_per_gpu": B, "global_batch": B * world, "ph": ph, "parallelism": f"dp{world}",
+              "schedule": a.schedule,
               "l2": "L2 flushed (512 MiB write) between timed steps; each step timed by its own CUDA-event pair"}
 
     if a.impl == "reference":

@@ -371,7 +371,7 @@ static int launch(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
 }
 
 extern "C" int b200mpc_lmpc_set_schedule(b200mpc_lmpc_t h, int schedule) {
-    if (!h || (schedule != B200MPC_SCHEDULE_FREE && schedule != B200MPC_SCHEDULE_GANG)) return fail(B200MPC_EINVAL, "bad schedule");
+    if (!h || schedule < 0 || schedule > 8) return fail(B200MPC_EINVAL, "bad schedule");
     h->gang = schedule;
     return B200MPC_OK;
 }

@@ -1467,26 +1467,31 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, 1) lmpc_solve_kernel(const _
     // most of them execute the same phase of the (large) program and share its instruction-cache footprint; a CTA waits
     // for its slowest member before drawing again.  Free scheduling: every warp draws on its own.
     int gang_round = 0;
+    int sub = 0;                      // gang > 1: every member runs `gang` instances back to back between two CTA barriers
     for (;;) {
         int inst = 0;
         if (gang) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                // full gangs for the rounds every CTA can fill; the remainder is split evenly over the CTAs instead of
-                // leaving most of them idle in the last round
-                const int per_round = (int)gridDim.x * wpb;
-                int take = wpb;
-                if (gang_round >= batch / per_round) {
-                    take = (batch % per_round + (int)gridDim.x - 1) / (int)gridDim.x;
-                    take = take < 1 ? 1 : (take > wpb ? wpb : take);
+            if (sub == 0) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    // full gangs for the rounds every CTA can fill; the remainder is split evenly over the CTAs instead of
+                    // leaving most of them idle in the last round
+                    const int per_round = (int)gridDim.x * wpb * gang;
+                    int take = wpb * gang;
+                    if (gang_round >= batch / per_round) {
+                        take = (batch % per_round + (int)gridDim.x - 1) / (int)gridDim.x;
+                        take = take < 1 ? 1 : (take > wpb * gang ? wpb * gang : take);
+                    }
+                    gang_take = take;
+                    gang_base = atomicAdd(counter, take);
                 }
-                gang_take = take;
-                gang_base = atomicAdd(counter, take);
+                ++gang_round;
+                __syncthreads();
+                if (gang_base >= batch) break;
             }
-            ++gang_round;
-            __syncthreads();
-            if (gang_base >= batch) break;
-            inst = warp < gang_take ? gang_base + warp : batch;
+            const int k = sub * wpb + warp;
+            inst = k < gang_take ? gang_base + k : batch;
+            if (++sub == gang) sub = 0;
         } else {
             if (lane == 0) inst = atomicAdd(counter, 1);
             inst = __shfl_sync(0xffffffffu, inst, 0);

@@ -116,7 +116,7 @@ __device__ __forceinline__ double nl_col_dot(const NlWs& w, int j, const double*
 
 // H = c D B D + sigma I + (E A D)' diag(rho) (E A D)  -> Cholesky -> in-place inverse of the factor (packed lower).
 template <class G>
-__device__ __noinline__ bool nl_factor(const G& g, NlWs& w, double c, double sigma) {
+__device__ __forceinline__ bool nl_factor_impl(const G& g, NlWs& w, double c, double sigma) {
     const int n = w.n, ld = w.ld, me = w.me, mi = w.mi, mc = me + mi;
     for (int r = g.tid; r < mc; r += G::nt) w.w[r] = w.rho[r] * w.E[r] * w.E[r];
     g.sync();
@@ -175,6 +175,14 @@ __device__ __noinline__ bool nl_factor(const G& g, NlWs& w, double c, double sig
         g.sync();
     }
     return !g.any(!ok);
+}
+
+template <class G>
+__device__ __noinline__ bool nl_factor_call(const G& g, NlWs& w, double c, double sigma) { return nl_factor_impl(g, w, c, sigma); }
+// a warp per controller inlines (tiny problems, measured 82k vs 60k solves/s on vanderpol_ex); CTA groups share one copy
+template <class G>
+__device__ __forceinline__ bool nl_factor(const G& g, NlWs& w, double c, double sigma) {
+    if constexpr (G::nt == 32) return nl_factor_impl(g, w, c, sigma); else return nl_factor_call(g, w, c, sigma);
 }
 
 // xt = (Linv' Linv) rhs ; optionally dxt = D .* xt (the input nl_As_core wants)
@@ -257,7 +265,7 @@ __device__ void nl_Ps(const G& g, NlWs& w, double c, const double* x, double* ou
 
 // max bound violation of A x and max |P x + q + A' y| in the scaled problem (uses pt, rhs, zt2)
 template <class G>
-__device__ __noinline__ void nl_qp_residuals(const G& g, NlWs& w, double c, const double* x, const double* y, double& pri, double& dua) {
+__device__ void nl_qp_residuals(const G& g, NlWs& w, double c, const double* x, const double* y, double& pri, double& dua) {
     nl_As(g, w, x, w.pt);
     double p = 0, d = 0;
     for (int r = g.tid; r < w.m; r += G::nt) p = fmax(p, fmax(fmax(w.ls[r] - w.pt[r], w.pt[r] - w.us[r]), 0.0));
@@ -271,7 +279,7 @@ __device__ __noinline__ void nl_qp_residuals(const G& g, NlWs& w, double c, cons
 // same reduced system (rho = 1/delta on active rows, sigma = delta) with iterative refinement, keep the result if both
 // residuals improve.  In: xs, ys, zs.  Out: xs, ys (replaced when accepted).  Destroys H, rho, zs.
 template <class G>
-__device__ __noinline__ bool nl_qp_polish(const G& g, NlWs& w, double c) {
+__device__ __forceinline__ bool nl_qp_polish_impl(const G& g, NlWs& w, double c) {
     const int n = w.n, m = w.m;
     const double delta = 1e-6, idelta = 1e6;
     double pri_a, dua_a;
@@ -310,6 +318,13 @@ __device__ __noinline__ bool nl_qp_polish(const G& g, NlWs& w, double c) {
         g.sync();
     }
     return ok;
+}
+
+template <class G>
+__device__ __noinline__ bool nl_qp_polish_call(const G& g, NlWs& w, double c) { return nl_qp_polish_impl(g, w, c); }
+template <class G>
+__device__ __forceinline__ bool nl_qp_polish(const G& g, NlWs& w, double c) {
+    if constexpr (G::nt == 32) return nl_qp_polish_impl(g, w, c); else return nl_qp_polish_call(g, w, c);
 }
 
 // Dense OSQP-style ADMM for the QP subproblem.  In: B, g, Je, Ji, ce, ci, z, lb, ub; warm dual yq (if have_y).
