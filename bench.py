@@ -292,9 +292,24 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                if tj.get("batch") == B and tj.get("ph", 20) == ph:      # the capture is of the default launch only
+                    traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # per-solve latency of ONE controller (batch = 1: what a single mpc::LMPC<> object sees), host buffers, p50 of 15
+        lat1 = None
+        if world == 1:
+            f1, c1 = build_controller(L, ph, 1, a.max_iter, False)
+            yr1 = np.zeros((1, NY, ph)); yr1[:, 2, :] = r[0]
+            c1.setReferences(yr1, np.zeros((NU, ph)), np.zeros((NU, ph)))
+            ts1 = []
+            for s in range(18):
+                t0 = time.perf_counter()
+                c1.optimize(x0_h[:1], np.zeros((1, NU)))
+                ts1.append(time.perf_counter() - t0)
+            lat1 = float(np.median(ts1[3:])) * 1e3
+            del c1
         line = {
             "metric": "LMPC solves/sec (batched)", "value": value, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -303,8 +318,8 @@ def main():
             "gpu_launches": a.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "note": "algorithmic bytes/solve (SURVEY 8d) x batch / kernel time; the solve is FP64-latency/L2 bound, "
-                                 "see roofline_fp64 and DESIGN.md"},
+                         "note": "algorithmic bytes/solve (SURVEY 8d) x batch / kernel time; the solve is bound by instruction issue / "
+                                 "dependent latency of the stage recurrence, not by HBM: see roofline_fp64, DESIGN.md 5, profiles/r01_icache.md"},
             "roofline_fp64": {"bound": "fp64-pipe", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak,
                               "peak_source": fp64_src,
                               "flops_per_solve_mean": flops / B},
@@ -312,12 +327,15 @@ def main():
                        "rho_updates_mean": float(res.rho_updates.mean()), "solved": int((res.solver_status == 1).sum()),
                        "polished": int((res.status_polish == 1).sum()), **c.info()},
             "p50_latency_us_per_solve": 1e3 * ms / B,
+            "latency": {"amortised_us_per_solve": 1e3 * ms / B, "single_controller_p50_ms": lat1,
+                        "note": "single_controller = batch 1 through the public API with host buffers (one mpc::LMPC<> object)"},
             "clocks": sampler.summary(),
         }
         if world == 1 and not a.no_cpu_baseline:
             cores = 1
             n = a.cpu_sample or 2048
             line["cpu_baseline"] = cpu_baseline(ph, a.max_iter, n, cores)
+            line["latency"]["cpu_port_ms_per_solve"] = 1e3 / line["cpu_baseline"]["value"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -117,6 +117,17 @@ int b200mpc_lmpc_get_warm_start(b200mpc_lmpc_t h, double* primal, double* dual, 
  * Results stay on the device until fetched. */
 int b200mpc_lmpc_solve(b200mpc_lmpc_t h, const double* x0, const double* u0, int dev);
 
+/* Closed loop on the device: the control loop every example wraps around optimize()
+ * (examples/quadrotor_ex.cpp, ugv_ex.cpp:143-166: optimize -> apply cmd -> step the plant -> repeat) for `steps` control
+ * steps without leaving the GPU: step k solves from (x_k, u_{k-1}), applies u_k = cmd and advances the plant
+ * x_{k+1} = Ap x_k + Bp u_k.  Ap[nx*nx] / Bp[nx*nu] row-major (plant_per_instance: batch copies); NULL = the controller's
+ * own model.  With enable_warm_start every solve starts from the previous optimum exactly as LOptimizer::run does
+ * (LOptimizer.hpp:268-281).  Outputs: traj_x[(steps+1)*batch*nx] (x_0..x_steps), traj_u[steps*batch*nu],
+ * traj_status / traj_iters[steps*batch] (may be NULL).  2 kernel launches per step, no host round trip; synchronises at the end. */
+int b200mpc_lmpc_closed_loop(b200mpc_lmpc_t h, const double* x0, const double* u0, int steps, const double* Ap,
+                             const double* Bp, int plant_per_instance, double* traj_x, double* traj_u,
+                             int32_t* traj_status, int32_t* traj_iters, int dev);
+
 /* mpc::Result<nu> fields (Types.hpp:168-182), one entry per instance.  Any pointer may be NULL.
  *   cmd[batch*nu], cost[batch], status[batch] (ResultStatus), solver_status[batch] (OSQP status_val),
  *   is_feasible[batch] (0/1), iterations[batch], rho_updates[batch], status_polish[batch]

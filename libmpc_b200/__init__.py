@@ -73,6 +73,7 @@ def load_library():
     lib.b200mpc_lmpc_set_warm_start.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int]
     lib.b200mpc_lmpc_get_warm_start.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int]
     lib.b200mpc_lmpc_solve.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int]
+    lib.b200mpc_lmpc_closed_loop.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
     lib.b200mpc_lmpc_get_result.argtypes = [H] + [C.c_void_p] * 8 + [C.c_int]
     lib.b200mpc_lmpc_get_sequence.argtypes = [H] + [C.c_void_p] * 3 + [C.c_int]
     lib.b200mpc_lmpc_cmd_device_ptr.argtypes = [H, C.POINTER(C.c_void_p)]
@@ -104,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_set_disturbances", "b200mpc_lmpc_set_weights", "b200mpc_lmpc_set_state_bounds",
     "b200mpc_lmpc_set_input_bounds", "b200mpc_lmpc_set_output_bounds", "b200mpc_lmpc_set_scalar_constraint",
     "b200mpc_lmpc_set_references", "b200mpc_lmpc_set_exogenous_inputs", "b200mpc_lmpc_set_warm_start",
-    "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
+    "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_closed_loop", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
     "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_set_schedule", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
     "b200mpc_nlmpc_default_params", "b200mpc_nlmpc_solve_smem_bytes", "b200mpc_nlmpc_solve",
     "b200mpc_nlmpc_system_neq", "b200mpc_nlmpc_register_system", "b200mpc_nlmpc_compile_check", "b200mpc_nlmpc_eval_ex",
@@ -470,6 +471,27 @@ class LMPC:
         return self._last
 
     step = optimize   # pre-0.5.0 name of the same call (CHANGELOG.md:64-65)
+
+    def closed_loop(self, x0, u0, steps, plant=None):
+        """`steps` control steps on the device: optimize -> apply cmd -> x+ = Ap x + Bp u (the loop of the reference's
+        examples).  plant = (Ap, Bp), shared [nx,nx],[nx,nu] or per instance [B,...]; None = the controller's model.
+        Returns dict(x [steps+1,B,nx], u [steps,B,nu], status [steps,B], iterations [steps,B])."""
+        B = self.batch
+        x0 = np.ascontiguousarray(np.broadcast_to(np.asarray(x0, float), (B, self.nx)))
+        u0 = np.ascontiguousarray(np.broadcast_to(np.asarray(u0, float), (B, self.nu)))
+        Ap = Bp = None
+        ppi = 0
+        if plant is not None:
+            Ap = np.ascontiguousarray(plant[0], dtype=np.float64); Bp = np.ascontiguousarray(plant[1], dtype=np.float64)
+            ppi = 1 if Ap.ndim == 3 else 0
+            if Ap.shape[-2:] != (self.nx, self.nx) or Bp.shape[-2:] != (self.nx, self.nu):
+                raise ValueError("plant matrices have the wrong shape")
+        out = dict(x=np.empty((steps + 1, B, self.nx)), u=np.empty((steps, B, self.nu)), status=np.empty((steps, B), np.int32),
+                   iterations=np.empty((steps, B), np.int32))
+        _check(self.lib.b200mpc_lmpc_closed_loop(self._h, self._p(x0), self._p(u0), int(steps), None if Ap is None else self._p(Ap),
+                                                 None if Bp is None else self._p(Bp), ppi, self._p(out["x"]), self._p(out["u"]),
+                                                 self._p(out["status"]), self._p(out["iterations"]), 0))
+        return out
 
     def getLastResult(self):
         return self._last

@@ -415,6 +415,81 @@ extern "C" int b200mpc_lmpc_solve(b200mpc_lmpc_t h, const double* x0, const doub
     return B200MPC_OK;
 }
 
+// ---- closed loop on the device ---------------------------------------------------------------------
+// x_next = Ap x + Bp cmd for one (instance, row) per thread; records the step's command / status / iteration count.
+__global__ void plant_step_kernel(int batch, int nx, int nu, const double* Ap, long long sA, const double* Bp, long long sB,
+                                  const double* x, const double* cmd, double* x_next, double* u_out, const int* status, const int* iters,
+                                  int* status_out, int* iters_out) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)batch * nx) return;
+    int b = (int)(t / nx), r = (int)(t - (long long)b * nx);
+    const double* A = Ap + (long long)b * sA + (long long)r * nx;
+    const double* Bm = Bp + (long long)b * sB + (long long)r * nu;
+    double acc = 0;
+    for (int k = 0; k < nx; ++k) acc = fma(A[k], x[(long long)b * nx + k], acc);
+    for (int k = 0; k < nu; ++k) acc = fma(Bm[k], cmd[(long long)b * nu + k], acc);
+    x_next[(long long)b * nx + r] = acc;
+    if (r < nu) u_out[(long long)b * nu + r] = cmd[(long long)b * nu + r];
+    for (int k = nx + r; k < nu; k += nx) u_out[(long long)b * nu + k] = cmd[(long long)b * nu + k];     // nu > nx
+    if (r == 0) { if (status_out) status_out[b] = status[b]; if (iters_out) iters_out[b] = iters[b]; }
+}
+
+extern "C" int b200mpc_lmpc_closed_loop(b200mpc_lmpc_t h, const double* x0, const double* u0, int steps, const double* Ap, const double* Bp,
+                                        int plant_per_instance, double* traj_x, double* traj_u, int32_t* traj_status, int32_t* traj_iters,
+                                        int dev) {
+    HCHECK();
+    if (!x0 || !u0 || steps < 1 || !traj_x || !traj_u || ((Ap == nullptr) != (Bp == nullptr))) return fail(B200MPC_EINVAL, "bad arguments");
+    const Dm& d = h->d;
+    const size_t Bn = (size_t)h->batch, nX = Bn * d.nx, nU = Bn * d.nu;
+    std::vector<void*> tmp;
+    struct Free { std::vector<void*>& v; ~Free() { for (void* p : v) cudaFree(p); } } freer{tmp};
+    auto dbuf = [&](void** p, size_t bytes) -> int { CK(cudaMalloc(p, bytes ? bytes : 8)); tmp.push_back(*p); return 0; };
+    double *dX = traj_x, *dU = traj_u; int *dS = traj_status, *dI = traj_iters;
+    double* dU0 = nullptr;
+    const double *dA = h->A.p, *dB = h->B.p;
+    long long sA = h->A.per_instance ? (long long)d.nx * d.nx : 0, sB = h->B.per_instance ? (long long)d.nx * d.nu : 0;
+    int rc;
+    if (!dev) {
+        if ((rc = dbuf((void**)&dX, (steps + 1) * nX * 8)) || (rc = dbuf((void**)&dU, steps * nU * 8))) return rc;
+        if (traj_status && (rc = dbuf((void**)&dS, steps * Bn * 4))) return rc;
+        if (traj_iters && (rc = dbuf((void**)&dI, steps * Bn * 4))) return rc;
+    }
+    if ((rc = dbuf((void**)&dU0, nU * 8))) return rc;
+    cudaMemcpyKind kin = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CK(cudaMemcpyAsync(dX, x0, nX * 8, kin, h->stream));
+    CK(cudaMemcpyAsync(dU0, u0, nU * 8, kin, h->stream));
+    if (Ap) {
+        size_t na = (size_t)d.nx * d.nx * (plant_per_instance ? Bn : 1), nb = (size_t)d.nx * d.nu * (plant_per_instance ? Bn : 1);
+        if (dev) { dA = Ap; dB = Bp; }
+        else {
+            double *pa, *pb;
+            if ((rc = dbuf((void**)&pa, na * 8)) || (rc = dbuf((void**)&pb, nb * 8))) return rc;
+            CK(cudaMemcpyAsync(pa, Ap, na * 8, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(pb, Bp, nb * 8, cudaMemcpyHostToDevice, h->stream));
+            dA = pa; dB = pb;
+        }
+        sA = plant_per_instance ? (long long)d.nx * d.nx : 0; sB = plant_per_instance ? (long long)d.nx * d.nu : 0;
+    }
+    const unsigned blocks = (unsigned)((nX + 255) / 256);
+    for (int k = 0; k < steps; ++k) {
+        const double* xk = dX + (size_t)k * nX;
+        const double* uk = k == 0 ? dU0 : dU + (size_t)(k - 1) * nU;
+        if ((rc = b200mpc_lmpc_solve(h, xk, uk, 1))) return rc;       // IOptimizer::run on the current state, previous command
+        plant_step_kernel<<<blocks, 256, 0, h->stream>>>(h->batch, d.nx, d.nu, dA, sA, dB, sB, xk, h->cmd, dX + (size_t)(k + 1) * nX,
+                                                          dU + (size_t)k * nU, h->status, h->iters, dS ? dS + (size_t)k * Bn : nullptr,
+                                                          dI ? dI + (size_t)k * Bn : nullptr);
+        CK(cudaGetLastError());
+    }
+    if (!dev) {
+        CK(cudaMemcpyAsync(traj_x, dX, (steps + 1) * nX * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(traj_u, dU, steps * nU * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (traj_status) CK(cudaMemcpyAsync(traj_status, dS, steps * Bn * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (traj_iters) CK(cudaMemcpyAsync(traj_iters, dI, steps * Bn * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));      // temporaries are freed on return
+    return B200MPC_OK;
+}
+
 template <class T>
 static int fetch(b200mpc_lmpc* h, T* dst, const T* src, size_t n, int dev) {
     if (!dst || !n) return B200MPC_OK;
