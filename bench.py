@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-instance-model", action="store_true", help="give every instance its own copy of A,B,C")
     ap.add_argument("--schedule", default="gang", choices=["gang", "free"], help="persistent-warp scheduling (include/b200mpc.h)")
+    ap.add_argument("--no-history-order", action="store_true",
+                    help="do not draw instances in the order of their previous solve's iteration counts (include/b200mpc.h)")
     ap.add_argument("--warps-per-cta", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     a = ap.parse_args()
@@ -164,7 +166,9 @@ def main():
     config = {"workload": f"quadrotor LMPC nx=12 nu=4 ny=12 ph=ch={ph}, batch={B} per GPU, maximum_iteration={a.max_iter}, "
                           f"{'per-instance' if a.per_instance_model else 'shared'} model, per-instance x0/yRef synthetic seed 20 (BASELINE.json configs[1])",
               "batch_per_gpu": B, "global_batch": B * world, "ph": ph, "parallelism": f"dp{world}",
-              "schedule": a.schedule,
+              "schedule": a.schedule + ("" if a.no_history_order else ", instances drawn longest-first by the iteration counts of the handle's "
+                                         "previous solve (every timed step repeats the same batch, so that history is exact here; "
+                                         "value_cold_order is the same measurement without it)"),
               "l2": "L2 flushed (512 MiB write) between timed steps; each step timed by its own CUDA-event pair"}
 
     if a.impl == "reference":
@@ -199,6 +203,7 @@ def main():
     if a.warps_per_cta or a.ctas_per_sm:
         c.set_launch(a.warps_per_cta, a.ctas_per_sm)
     c.set_schedule(a.schedule == "gang")
+    c.set_history_order(not a.no_history_order)
     stream = torch.cuda.current_stream()
     c.set_stream(stream.cuda_stream)
     x0_h, r = synth_inputs(rank * B, B)
@@ -243,6 +248,22 @@ def main():
         ms = float(t.item())
     res = c.fetch_result()
     value = world * B / (ms * 1e-3)
+    # the same measurement with history ordering off (what the FIRST solve of a handle, or a batch of unrelated problems, gets)
+    cold_ms = None
+    if not a.no_history_order:
+        c.set_history_order(False)
+        step(); torch.cuda.synchronize()
+        cevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(a.steps, 5))]
+        for e0, e1 in cevs:
+            flush.zero_()
+            e0.record(stream); step(); e1.record(stream)
+        torch.cuda.synchronize()
+        cold_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in cevs]))
+        if world > 1:
+            t = torch.tensor([cold_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cold_ms = float(t.item())
+        c.set_history_order(True)
 
     # end-to-end through the public API with host buffers (pinned), H2D + D2H inside the timed region
     x0_pin = torch.from_numpy(x0_h).pin_memory()
@@ -314,6 +335,7 @@ def main():
             "metric": "LMPC solves/sec (batched)", "value": value, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
+            "value_cold_order": (world * B / (cold_ms * 1e-3)) if cold_ms else None,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": a.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

@@ -80,6 +80,7 @@ def load_library():
     lib.b200mpc_lmpc_info.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_longlong)]
     lib.b200mpc_lmpc_set_launch.argtypes = [H, C.c_int, C.c_int]
     lib.b200mpc_lmpc_set_schedule.argtypes = [H, C.c_int]
+    lib.b200mpc_lmpc_set_history_order.argtypes = [H, C.c_int]
     lib.b200mpc_lmpc_profile.argtypes = [H, C.c_void_p]
     lib.b200mpc_sync.argtypes = [H]
     lib.b200mpc_nlmpc_system_dims.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
@@ -106,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_set_input_bounds", "b200mpc_lmpc_set_output_bounds", "b200mpc_lmpc_set_scalar_constraint",
     "b200mpc_lmpc_set_references", "b200mpc_lmpc_set_exogenous_inputs", "b200mpc_lmpc_set_warm_start",
     "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_closed_loop", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
-    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_set_schedule", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
+    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_set_schedule", "b200mpc_lmpc_set_history_order", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
     "b200mpc_nlmpc_default_params", "b200mpc_nlmpc_solve_smem_bytes", "b200mpc_nlmpc_solve",
     "b200mpc_nlmpc_system_neq", "b200mpc_nlmpc_register_system", "b200mpc_nlmpc_compile_check", "b200mpc_nlmpc_eval_ex",
     "b200mpc_nlmpc_solve_ex",
@@ -432,6 +433,10 @@ class LMPC:
     def set_schedule(self, gang=True):
         """Gang (default) or free scheduling of the persistent warps (include/b200mpc.h); results are identical."""
         _check(self.lib.b200mpc_lmpc_set_schedule(self._h, 1 if gang else 0))
+
+    def set_history_order(self, enable=True):
+        """Draw instances in the order of their previous solve's iteration counts, longest first (scheduling only)."""
+        _check(self.lib.b200mpc_lmpc_set_history_order(self._h, 1 if enable else 0))
 
     def info(self):
         a, b, c = C.c_int(), C.c_size_t(), C.c_longlong()

@@ -30,7 +30,7 @@ struct b200mpc_lmpc {
     cudaStream_t stream = 0;
     Params p;
     int enable_warm_start = 0;
-    bool has_prev = false, model_set = false;
+    bool has_prev = false, model_set = false, has_iters = false;
     DevBuf A, B, C, Bd, Dd, OW, UW, DUW, XMin, XMax, YMin, YMax, UMin, UMax, SMin, SMax, SX, SU, yRef, uRef, duRef, uMeas;
     double *x0 = nullptr, *u0 = nullptr;
     // results
@@ -42,6 +42,8 @@ struct b200mpc_lmpc {
     double* workspace = nullptr;
     size_t ws_stride = 0;
     int* counter = nullptr;
+    int* order = nullptr;          // drawing order of the next solve (history ordering), [batch]
+    int history_order = getenv("B200MPC_HISTORY_ORDER") ? atoi(getenv("B200MPC_HISTORY_ORDER")) : 1;
     int warps_per_cta = 0, ctas_per_sm = 0, grid = 0, num_sms = 0;
     int req_wpc = 0, req_cps = 0;
     size_t smem_cta = 0;
@@ -146,6 +148,7 @@ extern "C" int b200mpc_lmpc_create(const b200mpc_lmpc_dims* dims, int batch, int
     if ((rc = dalloc(&h->rho_updates, Bn))) return rc;
     if ((rc = dalloc(&h->polish, Bn))) return rc;
     if ((rc = dalloc(&h->counter, 1))) return rc;
+    if ((rc = dalloc(&h->order, (size_t)batch))) return rc;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
@@ -353,8 +356,13 @@ static int configure_t(b200mpc_lmpc* h) {
 template <class DM>
 static int launch_t(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
     DM dm; dm.from(h->d);
+    const int* order = nullptr;
+    if (h->history_order && h->has_iters && h->batch > h->warps_per_cta) {      // needs a previous solve of this handle
+        order_by_history_kernel<<<1, 1024, 0, h->stream>>>(h->iters, h->batch, h->p.check_termination > 0 ? h->p.check_termination : 25, h->order);
+        order = h->order;
+    }
     lmpc_solve_kernel<DM><<<h->grid, h->warps_per_cta * 32, h->smem_cta, h->stream>>>(dm, h->p, pr, o, h->batch, h->workspace,
-                                                                                      h->ws_stride, h->counter, h->model_shared, h->gang);
+                                                                                      h->ws_stride, h->counter, h->model_shared, h->gang, order);
     CK(cudaGetLastError());
     return B200MPC_OK;
 }
@@ -373,6 +381,11 @@ static int launch(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
 extern "C" int b200mpc_lmpc_set_schedule(b200mpc_lmpc_t h, int schedule) {
     if (!h || schedule < 0 || schedule > 8) return fail(B200MPC_EINVAL, "bad schedule");
     h->gang = schedule;
+    return B200MPC_OK;
+}
+extern "C" int b200mpc_lmpc_set_history_order(b200mpc_lmpc_t h, int enable) {
+    if (!h) return fail(B200MPC_EINVAL, "null handle");
+    h->history_order = enable ? 1 : 0;
     return B200MPC_OK;
 }
 extern "C" int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm) {
@@ -412,6 +425,7 @@ extern "C" int b200mpc_lmpc_solve(b200mpc_lmpc_t h, const double* x0, const doub
     if ((rc = launch(h, pr, o))) return rc;
     h->launches += 1;
     h->has_prev = true;   // optimal_prev_x / optimal_prev_y now hold a solution (LOptimizer.hpp:295-296)
+    h->has_iters = true;
     return B200MPC_OK;
 }
 

@@ -1432,7 +1432,7 @@ template <class DM>
 __global__ void __launch_bounds__(B200_MAX_THREADS, 1) lmpc_solve_kernel(const __grid_constant__ DM d, const __grid_constant__ Params p,
                                                         const __grid_constant__ Prob pr, const __grid_constant__ Out o,
                                                         int batch, double* workspace, size_t ws_stride, int* counter, int model_shared,
-                                                        int gang) {
+                                                        int gang, const int* order) {
     __shared__ int gang_base, gang_take;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -1498,11 +1498,28 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, 1) lmpc_solve_kernel(const _
             if (inst >= batch) break;
         }
         if (inst < batch) {
-            c.inst = inst;
+            c.inst = order ? order[inst] : inst;      // drawing order (longest-expected first), see order_by_history_kernel
             solve_instance(c, o);
         }
         __syncwarp();
     }
+}
+
+// Drawing order for the next solve: instances sorted by the iteration count of their PREVIOUS solve, longest first
+// (counting sort on iters / check_termination; one CTA).  Consecutive MPC steps of a controller need similar iteration
+// counts, so (i) the members of a gang finish together instead of waiting for one straggler and (ii) the long instances
+// start first (longest-processing-time-first).  Results do not depend on the order.
+__global__ void order_by_history_kernel(const int* iters, int batch, int bucket, int* order) {
+    constexpr int NB = 1024;
+    __shared__ int hist[NB];
+    for (int k = threadIdx.x; k < NB; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    auto key = [&](int it) { int b = (it < 0 ? 0 : it) / bucket; return NB - 1 - (b >= NB ? NB - 1 : b); };    // descending
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) atomicAdd(&hist[key(iters[i])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { int acc = 0; for (int k = 0; k < NB; ++k) { int v = hist[k]; hist[k] = acc; acc += v; } }
+    __syncthreads();
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) order[atomicAdd(&hist[key(iters[i])], 1)] = i;
 }
 
 }  // namespace b200mpc

@@ -194,6 +194,10 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
     const int nz = ph * nx + ch * nu + 1;
     auto SX = [&](int j) { return sx ? sx[j] : 1.0; };
     auto SU = [&](int j) { return su ? su[j] : 1.0; };
+    // no FP64 division on the unscaled path (it is the common one and these sit in the innermost loops)
+    auto DIVX = [&](double v, int j) { return sx ? v / sx[j] : v; };
+    auto RXX = [&](int q, int r) { return sx ? sx[q] / sx[r] : 1.0; };
+    auto RUX = [&](int qu, int r) { return sx ? SU(qu) / sx[r] : SU(qu); };
     const double dv = 1.4901161193847656e-08;     // sqrt(DBL_EPSILON)  (Objective.hpp:283)
     // unwrapVector: X row 0 = x0, rows 1..ph from z; U row i = block min(i, ch-1), last row repeated
     for (int e = g_.tid; e < (ph + 1) * nx; e += G::nt) {
@@ -253,10 +257,10 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
             for (int j = 0; j < nu; ++j) uk[j] = U[i * nu + j];
             if (S::continuous) {
                 S::f(fk, xk, uk, i, p); S::f(fk1, xk1, uk, i, p);
-                for (int j = 0; j < nx; ++j) c[i * nx + j] = (xk[j] + (h * (fk[j] + fk1[j])) - xk1[j]) / SX(j);
+                for (int j = 0; j < nx; ++j) c[i * nx + j] = DIVX(xk[j] + (h * (fk[j] + fk1[j])) - xk1[j], j);
             } else {
                 S::f(fk, xk, uk, i, p);
-                for (int j = 0; j < nx; ++j) c[i * nx + j] = (xk1[j] - fk[j]) / SX(j);
+                for (int j = 0; j < nx; ++j) c[i * nx + j] = DIVX(xk1[j] - fk[j], j);
             }
         }
         if (J) {
@@ -273,14 +277,14 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
                     xk[q] = keep - dx; S::f(fm, xk, uk, i, p);
                     xk[q] = keep;
                     if (S::continuous) {
-                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = (r == q ? 1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx)) * (SX(q) / SX(r));
+                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = (r == q ? 1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx)) * RXX(q, r);
                         double dx1 = dv * fmax(fabs(xk1[q]), 1.0), keep1 = xk1[q];
                         xk1[q] = keep1 + dx1; S::f(fp, xk1, uk, i, p);
                         xk1[q] = keep1 - dx1; S::f(fm, xk1, uk, i, p);
                         xk1[q] = keep1;
-                        for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? -1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx1)) * (SX(q) / SX(r));
+                        for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? -1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx1)) * RXX(q, r);
                     } else {
-                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = -((fp[r] - fm[r]) / (2 * dx)) * (SX(q) / SX(r));
+                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = -((fp[r] - fm[r]) / (2 * dx)) * RXX(q, r);
                         for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? 1.0 : 0.0);
                     }
                 } else {
@@ -295,9 +299,9 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
                         uk[qu] = keep + du; S::f(fp, xk1, uk, i, p);
                         uk[qu] = keep - du; S::f(fm, xk1, uk, i, p);
                         uk[qu] = keep;
-                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], h * (Bk[r] + (fp[r] - fm[r]) / (2 * du)) * (SU(qu) / SX(r)));
+                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], h * (Bk[r] + (fp[r] - fm[r]) / (2 * du)) * RUX(qu, r));
                     } else {
-                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], -Bk[r] * (SU(qu) / SX(r)));
+                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], -Bk[r] * RUX(qu, r));
                     }
                 }
             }

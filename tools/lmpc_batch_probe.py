@@ -16,6 +16,7 @@ for B in [int(v) for v in sys.argv[1:]] or [1776, 3552, 4096, 32768]:
     f, c = build_controller(L, PH, B, MAXIT)
     import os
     if os.environ.get('GENERIC'): c.set_launch(-int(os.environ['GENERIC']), 0)
+    if os.environ.get('NOHIST'): c.set_history_order(False)
     if os.environ.get('WPC'): c.set_launch(int(os.environ['WPC']), int(os.environ.get('CPS', 0)))
     x0, r = synth_inputs(0, B)
     yref = np.zeros((B, 12, PH)); yref[:, 2, :] = r[:, None]
