@@ -52,6 +52,19 @@ extern "C" int b200mpc_nlmpc_system_neq(int system, int ph, int* neq) {
     return B200MPC_OK;
 }
 
+// Temporaries come from the stream-ordered allocator with a pool that keeps its memory: after the first call a solve does no
+// cudaMalloc / cudaFree (each costs up to milliseconds and cudaFree synchronises the device).
+static void keep_pool(int dev) {
+    static bool done[64] = {false};
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
 // state / input scaling vectors are tiny host arrays: stage them with stream-ordered allocations
 static int stage_scaling(const b200mpc_nlmpc_scaling* sc, int nx, int nu, const double** dsx, const double** dsu, cudaStream_t stream,
                          std::vector<void*>& async_free) {
@@ -84,6 +97,7 @@ extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, cons
     if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
     int nx, nu, np, ni, nue, rc0;
     if ((rc0 = nl_dims(system, &nx, &nu, &np, ph, &ni, &nue))) return rc0;
+    { int cur = 0; if (cudaGetDevice(&cur) == cudaSuccess) keep_pool(cur); }
     if (ph < 1 || ch < 1 || ch > ph || batch < 1 || !z || !x0 || !params) return fail(B200MPC_EINVAL, "bad arguments");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int nz = ph * nx + ch * nu + 1;
@@ -93,7 +107,7 @@ extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, cons
     auto in = [&](const double* h, size_t n, const double** d) -> int {
         if (dev) { *d = h; return 0; }
         double* p = nullptr;
-        CK(cudaMalloc(&p, n * sizeof(double))); tofree.push_back(p);
+        CK(cudaMallocAsync(&p, n * sizeof(double), stream)); tofree.push_back(p);
         CK(cudaMemcpyAsync(p, h, n * sizeof(double), cudaMemcpyHostToDevice, stream));
         *d = p; return 0;
     };
@@ -101,7 +115,7 @@ extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, cons
         if (!h) { *d = nullptr; return 0; }
         if (dev) { *d = h; return 0; }
         double* p = nullptr;
-        CK(cudaMalloc(&p, n * sizeof(double))); tofree.push_back(p);
+        CK(cudaMallocAsync(&p, n * sizeof(double), stream)); tofree.push_back(p);
         *d = p; return 0;
     };
     int rc;
@@ -138,7 +152,7 @@ extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, cons
         if (nue && (rc = back(cue, a.cue, (size_t)batch * nue))) return rc;
         if (nue && (rc = back(Jue, a.Jue, (size_t)batch * nue * nz))) return rc;
         CK(cudaStreamSynchronize(stream));
-        for (void* p : tofree) cudaFree(p);
+        for (void* p : tofree) cudaFreeAsync(p, stream);
     }
     return B200MPC_OK;
 }
@@ -175,6 +189,7 @@ extern "C" int b200mpc_nlmpc_solve_ex(int system, int ph, int ch, int batch, con
     if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
     int nx, nu, np, ni, nue, rc0;
     if ((rc0 = nl_dims(system, &nx, &nu, &np, ph, &ni, &nue))) return rc0;
+    { int cur = 0; if (cudaGetDevice(&cur) == cudaSuccess) keep_pool(cur); }
     if (ph < 1 || ch < 1 || ch > ph || batch < 1 || !z0 || !x0 || !sys_params || !lb || !ub || !z) return fail(B200MPC_EINVAL, "bad arguments");
     b200mpc_nlmpc_params q;
     if (prm) q = *prm; else b200mpc_nlmpc_default_params(&q);
@@ -185,18 +200,18 @@ extern "C" int b200mpc_nlmpc_solve_ex(int system, int ph, int ch, int batch, con
     a.ph = ph; a.ch = ch; a.batch = batch; a.param_stride = params_per_instance ? np : 0;
     a.max_sqp = q.max_sqp; a.max_qp = q.max_qp; a.tol = q.tol; a.ftol = q.ftol; a.qp_eps = q.qp_eps; a.rho0 = q.rho;
     std::vector<void*> tofree;
-    struct Free { std::vector<void*>& v; ~Free() { for (void* p : v) cudaFree(p); } } freer{tofree};
+    struct Free { std::vector<void*>& v; cudaStream_t s; ~Free() { for (void* p : v) cudaFreeAsync(p, s); } } freer{tofree, stream};
     auto in = [&](const double* h, size_t n, const double** d) -> int {
         if (dev) { *d = h; return 0; }
         double* p = nullptr;
-        CK(cudaMalloc(&p, n * sizeof(double))); tofree.push_back(p);
+        CK(cudaMallocAsync(&p, n * sizeof(double), stream)); tofree.push_back(p);
         CK(cudaMemcpyAsync(p, h, n * sizeof(double), cudaMemcpyHostToDevice, stream));
         *d = p; return 0;
     };
     auto out = [&](void* h, size_t bytes, void** d) -> int {
         if (dev && h) { *d = h; return 0; }
         void* p = nullptr;
-        CK(cudaMalloc(&p, bytes)); tofree.push_back(p);
+        CK(cudaMallocAsync(&p, bytes, stream)); tofree.push_back(p);
         *d = p; return 0;
     };
     int rc;

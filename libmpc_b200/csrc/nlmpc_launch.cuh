@@ -35,7 +35,7 @@ int nl_launch_t(NlSolveArgs& a, size_t smem_per_group, int groups_per_cta, size_
     a.mat_ws = nullptr;
     if (MODE) {
         void* ws = nullptr;
-        CK(cudaMalloc(&ws, (size_t)grid * groups_per_cta * gmem_doubles * sizeof(double)));
+        CK(cudaMallocAsync(&ws, (size_t)grid * groups_per_cta * gmem_doubles * sizeof(double), stream));
         tofree.push_back(ws);
         a.mat_ws = (double*)ws;
     }

@@ -77,7 +77,13 @@ struct NlWs {
     __host__ __device__ static size_t gmem_doubles(int mode, int n, int me, int mi) {
         return (mode >= 1 ? mat_doubles(n, me, mi, true) : 0) + (mode == 2 ? h_doubles(n) : 0);
     }
+    // what carve() was called with: the shared subroutines take this by value and rebuild their own NlWs, so that the caller's
+    // copy never has its address taken and stays in registers (an NlWs passed by reference lives in local memory and every
+    // pointer field becomes a local load)
+    struct Key { double* sm; double* gm; int mode, n, me, mi, mii, ph, ch, nx, nu; };
+    Key key;
     __device__ void carve(int mode, double* sm, double* gm, int n_, int me_, int mi_, int ph_, int ch_, int nx_, int nu_) {
+        key = Key{sm, gm, mode, n_, me_, mi_, mi_, ph_, ch_, nx_, nu_};
         n = n_; me = me_; mi = mi_; m = me + mi + n; ld = ldim(n, mode >= 1); nx = nx_; nu = nu_; ph = ph_; ch = ch_;
         double*& pm = mode >= 1 ? gm : sm;
         B = pm; pm += (size_t)n * ld; Je = pm; pm += (size_t)me * ld; Ji = pm; pm += (size_t)mi * ld;
@@ -178,16 +184,19 @@ __device__ __forceinline__ bool nl_factor_impl(const G& g, NlWs& w, double c, do
 }
 
 template <class G>
-__device__ __noinline__ bool nl_factor_call(const G& g, NlWs& w, double c, double sigma) { return nl_factor_impl(g, w, c, sigma); }
+__device__ __noinline__ bool nl_factor_call(G g, NlWs::Key k, double c, double sigma) {
+    NlWs w; w.carve(k.mode, k.sm, k.gm, k.n, k.me, k.mi, k.ph, k.ch, k.nx, k.nu); w.mii = k.mii;
+    return nl_factor_impl(g, w, c, sigma);
+}
 // a warp per controller inlines (tiny problems, measured 82k vs 60k solves/s on vanderpol_ex); CTA groups share one copy
 template <class G>
 __device__ __forceinline__ bool nl_factor(const G& g, NlWs& w, double c, double sigma) {
-    if constexpr (G::nt == 32) return nl_factor_impl(g, w, c, sigma); else return nl_factor_call(g, w, c, sigma);
+    if constexpr (G::nt == 32) return nl_factor_impl(g, w, c, sigma); else { NlWs::Key k = w.key; k.mii = w.mii; return nl_factor_call(g, k, c, sigma); }
 }
 
 // xt = (Linv' Linv) rhs ; optionally dxt = D .* xt (the input nl_As_core wants)
 template <class G>
-__device__ void nl_kkt_apply(const G& g, NlWs& w, double* dxt = nullptr) {
+__device__ __forceinline__ void nl_kkt_apply(const G& g, NlWs& w, double* dxt = nullptr) {
     const int n = w.n;
     for (int i = g.tid; i < n; i += G::nt) {            // row walk: conflict-free across consecutive rows (packed storage)
         const double* hrow = w.H + NlWs::tri(i);
@@ -213,7 +222,7 @@ __device__ void nl_kkt_apply(const G& g, NlWs& w, double* dxt = nullptr) {
 // out_r = E_r * (A dx)_r for all m rows, dx = D.*x already formed: J_eq rows by their two column runs, J_in rows one
 // warp per row.  Ends with a barrier.
 template <class G>
-__device__ void nl_As_core(const G& g, NlWs& w, const double* dx, double* out) {
+__device__ __forceinline__ void nl_As_core(const G& g, NlWs& w, const double* dx, double* out) {
     const int n = w.n, me = w.me, mc = w.me + w.mi, ld = w.ld;
     for (int r = g.tid; r < me; r += G::nt) {
         int c0, c1, u0; w.je_cols(r, c0, c1, u0);
@@ -234,14 +243,14 @@ __device__ void nl_As_core(const G& g, NlWs& w, const double* dx, double* out) {
     g.sync();
 }
 template <class G>
-__device__ void nl_As(const G& g, NlWs& w, const double* x, double* out) {
+__device__ __forceinline__ void nl_As(const G& g, NlWs& w, const double* x, double* out) {
     for (int i = g.tid; i < w.n; i += G::nt) w.tmp[i] = w.D[i] * x[i];
     g.sync();
     nl_As_core(g, w, w.tmp, out);
 }
 // out_j = D_j * (A' (E.v))_j
 template <class G>
-__device__ void nl_Ats(const G& g, NlWs& w, const double* v, double* out) {
+__device__ __forceinline__ void nl_Ats(const G& g, NlWs& w, const double* v, double* out) {
     const int n = w.n, mc = w.me + w.mi;
     for (int r = g.tid; r < w.m; r += G::nt) w.w[r] = w.E[r] * v[r];
     g.sync();
@@ -250,7 +259,7 @@ __device__ void nl_Ats(const G& g, NlWs& w, const double* v, double* out) {
 }
 // out_i = (c D B D x)_i ; B symmetric, read down its columns
 template <class G>
-__device__ void nl_Ps(const G& g, NlWs& w, double c, const double* x, double* out) {
+__device__ __forceinline__ void nl_Ps(const G& g, NlWs& w, double c, const double* x, double* out) {
     const int n = w.n, ld = w.ld;
     for (int i = g.tid; i < n; i += G::nt) w.tmp[i] = w.D[i] * x[i];
     g.sync();
@@ -265,7 +274,7 @@ __device__ void nl_Ps(const G& g, NlWs& w, double c, const double* x, double* ou
 
 // max bound violation of A x and max |P x + q + A' y| in the scaled problem (uses pt, rhs, zt2)
 template <class G>
-__device__ void nl_qp_residuals(const G& g, NlWs& w, double c, const double* x, const double* y, double& pri, double& dua) {
+__device__ __forceinline__ void nl_qp_residuals(const G& g, NlWs& w, double c, const double* x, const double* y, double& pri, double& dua) {
     nl_As(g, w, x, w.pt);
     double p = 0, d = 0;
     for (int r = g.tid; r < w.m; r += G::nt) p = fmax(p, fmax(fmax(w.ls[r] - w.pt[r], w.pt[r] - w.us[r]), 0.0));
@@ -321,16 +330,19 @@ __device__ __forceinline__ bool nl_qp_polish_impl(const G& g, NlWs& w, double c)
 }
 
 template <class G>
-__device__ __noinline__ bool nl_qp_polish_call(const G& g, NlWs& w, double c) { return nl_qp_polish_impl(g, w, c); }
+__device__ __noinline__ bool nl_qp_polish_call(G g, NlWs::Key k, double c) {
+    NlWs w; w.carve(k.mode, k.sm, k.gm, k.n, k.me, k.mi, k.ph, k.ch, k.nx, k.nu); w.mii = k.mii;
+    return nl_qp_polish_impl(g, w, c);
+}
 template <class G>
 __device__ __forceinline__ bool nl_qp_polish(const G& g, NlWs& w, double c) {
-    if constexpr (G::nt == 32) return nl_qp_polish_impl(g, w, c); else return nl_qp_polish_call(g, w, c);
+    if constexpr (G::nt == 32) return nl_qp_polish_impl(g, w, c); else { NlWs::Key k = w.key; k.mii = w.mii; return nl_qp_polish_call(g, k, c); }
 }
 
 // Dense OSQP-style ADMM for the QP subproblem.  In: B, g, Je, Ji, ce, ci, z, lb, ub; warm dual yq (if have_y).
 // Out: d (step), yq (multipliers, unscaled).  Returns ADMM iterations.
 template <class G>
-__device__ int nl_qp_solve(const G& g, NlWs& w, const NlSolveArgs& a, bool have_y) {
+__device__ __forceinline__ int nl_qp_solve(const G& g, NlWs& w, const NlSolveArgs& a, bool have_y) {
     const int n = w.n, me = w.me, mi = w.mi, mc = me + mi, m = w.m, ld = w.ld;
     const double sigma = 1e-6, alpha = 1.6;
     // ---- Ruiz equilibration (10 passes) with cost normalisation
