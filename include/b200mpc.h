@@ -191,8 +191,8 @@ int b200mpc_nlmpc_system_neq(int system, int ph, int* neq);
  *     __device__ static void f(double* out, const double* x, const double* u, int stage, const double* p);   // model
  *     __device__ static double cost(const Acc& a, double slack, int ph, const double* p);                    // objective
  *     __device__ static double ineq(int r, const Acc& a, double slack, int ph, const double* p);             // c_r <= 0
- *   optionally a sparsity hint  __device__ static int ineq_stage(int r, int ph);  // the one row of (X,U) inequality r reads, -1 = any
- *   (rows that do not read the perturbed variable have an exactly-zero finite difference and are skipped),
+ *   optionally a sparsity hint  static constexpr int ineq_per_stage = K;   // inequality r reads only row r / K of (X, U)
+ *   (rows that do not read the perturbed variable have an exactly-zero finite difference and are not evaluated),
  *   and optionally (user equality constraints)
  *     __host__ __device__ static int neq(int ph);   __device__ static double eq(int r, const Acc& a, int ph, const double* p);
  * where a.x(i,j) / a.u(i,j) read the unwrapped state / input sequences ((ph+1) rows, Mapping::unwrapVector) and

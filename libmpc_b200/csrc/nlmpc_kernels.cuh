@@ -28,13 +28,15 @@ namespace b200mpc {
 template <class S, class = void> struct NlHasEq { static constexpr bool value = false; };
 template <class S> struct NlHasEq<S, decltype((void)S::neq(1))> { static constexpr bool value = true; };
 template <class S> __host__ __device__ inline int nl_neq(int ph) { if constexpr (NlHasEq<S>::value) return S::neq(ph); else return 0; }
-// Optional sparsity hint:  __device__ static int ineq_stage(int r, int ph)  returns the ONE row i of (X, U) that inequality r
-// reads (-1: any).  The reference re-evaluates the whole constraint vector for every perturbed variable
-// (Constraints.hpp:641-721: 2 ph (nx+nu) evaluations of all Tineq rows); a row that does not read the perturbed variable
-// gives (c - c) / (2 dx) = 0 exactly, so skipping it changes nothing but the cost (ugv Tph=30: 22 320 -> 744 evaluations).
-template <class S, class = void> struct NlHasIneqStage { static constexpr bool value = false; };
-template <class S> struct NlHasIneqStage<S, decltype((void)S::ineq_stage(0, 1))> { static constexpr bool value = true; };
-template <class S> __device__ __forceinline__ int nl_ineq_stage(int r, int ph) { if constexpr (NlHasIneqStage<S>::value) return S::ineq_stage(r, ph); else return -1; }
+// Optional sparsity hint:  static constexpr int ineq_per_stage = K  declares that inequality r reads only row r / K of (X, U)
+// (K rows per stage, stage-major: true of every per-stage bound or obstacle constraint).  The reference re-evaluates the
+// whole constraint vector for every perturbed variable (Constraints.hpp:641-721: 2 ph (nx+nu) evaluations of all Tineq
+// rows); a row that does not read the perturbed variable gives (c - c) / (2 dx) = 0 exactly, so evaluating only the K rows
+// of the perturbed stage changes nothing but the cost (ugv Tph=30: 22 320 -> 720 evaluations).  The loop over those K
+// rows has the same trip count on every lane (a per-row `skip` test instead made the warp walk all rows anyway, one lane
+// at a time: measured 3.5x slower on vanderpol_ex).
+template <class S, class = void> struct NlIneqPerStage { static constexpr int value = 0; };
+template <class S> struct NlIneqPerStage<S, decltype((void)S::ineq_per_stage)> { static constexpr int value = S::ineq_per_stage; };
 
 // X [(ph+1) x nx], U [(ph+1) x nu] row-major in shared memory + one (or a pair of) perturbed entries
 struct Acc {
@@ -69,7 +71,7 @@ struct SysVanDerPol {
         return sx + su;
     }
     __device__ static double ineq(int r, const Acc& a, double, int, const double*) { return a.u(r, 0) - 0.5; }
-    __device__ static int ineq_stage(int r, int) { return r; }
+    static constexpr int ineq_per_stage = 1;
 };
 
 // examples/networked_oscillators_ex.cpp:5-72 -- params: [Ts, mu, k]
@@ -96,7 +98,7 @@ struct SysOscNet {
         return sx + su;
     }
     __device__ static double ineq(int r, const Acc& a, double, int, const double*) { return a.u(r / nu, r % nu) - 0.5; }
-    __device__ static int ineq_stage(int r, int) { return r / nu; }
+    static constexpr int ineq_per_stage = nu;
 };
 
 // examples/ugv_ex.cpp:12-126 -- discrete double integrator, 2 circular obstacles, soft constraints.
@@ -132,7 +134,7 @@ struct SysUgv {
         double dx = a.x(i, 0) - p[26 + 3 * j], dy = a.x(i, 1) - p[26 + 3 * j + 1];
         return p[26 + 3 * j + 2] - sqrt(dx * dx + dy * dy);
     }
-    __device__ static int ineq_stage(int r, int) { return r / nobs; }
+    static constexpr int ineq_per_stage = nobs;
 };
 
 // ---- the threads that cooperate on one controller -------------------------------------------------------------------
@@ -331,11 +333,10 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
                 double dx = dv * fmax(fabs(X[lr * nx + lc]), 1.0);
                 Acc ap = base; ap.kind = 1; ap.row = i + 1; ap.col = j; ap.d = dx;
                 Acc am = ap; am.d = -dx;
-                for (int r = 0; r < ni; ++r) {
-                    const int st = nl_ineq_stage<S>(r, ph);
-                    if (st >= 0 && st != i + 1) continue;                 // row does not read X(i+1, .): exactly 0 (pre-zeroed)
+                constexpr int K = NlIneqPerStage<S>::value;             // K > 0: only the rows of stage i+1 read X(i+1, .)
+                const int rlo = K ? (i + 1) * K : 0, rhi = K ? (i + 2) * K : ni;
+                for (int r = rlo; r < rhi && r < ni; ++r)
                     J[(size_t)r * ldj + i * nx + j] = (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * dx) * SX(j);
-                }
             }
             for (int t = g_.tid; t < ph * nu; t += G::nt) {     // every one of the ph rows alone (row ph is never perturbed)
                 int i = t / nu, j = t - i * nu;
@@ -344,11 +345,10 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
                 Acc ap = base; ap.kind = 2; ap.row = i; ap.col = j; ap.d = du;
                 Acc am = ap; am.d = -du;
                 int blk = i < ch ? i : ch - 1;
-                for (int r = 0; r < ni; ++r) {
-                    const int st = nl_ineq_stage<S>(r, ph);
-                    if (st >= 0 && st != i) continue;                     // row does not read U(i, .)
+                constexpr int K = NlIneqPerStage<S>::value;             // K > 0: only the rows of stage i read U(i, .)
+                const int rlo = K ? i * K : 0, rhi = K ? (i + 1) * K : ni;
+                for (int r = rlo; r < rhi && r < ni; ++r)
                     atomicAdd(&J[(size_t)r * ldj + ph * nx + blk * nu + j], (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * du) * SU(j));
-                }
             }
             {
                 double ea = fmax(dv, fabs(slack)), de = ea * dv;
