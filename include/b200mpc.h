@@ -162,6 +162,12 @@ int b200mpc_lmpc_set_history_order(b200mpc_lmpc_t h, int enable);
 int b200mpc_lmpc_profile(b200mpc_lmpc_t h, long long* out_host);
 int b200mpc_sync(b200mpc_lmpc_t h);
 
+/* ---- set-up helper: mpc::discretization<nx,nu>(A,B,Ts,Ad,Bd) (include/mpc/Utils.hpp:23-47) for `batch`
+ * systems in one launch -- zero-order-hold c2d through exp([[A,B],[0,0]] Ts).  A[nx*nx], B[nx*nu] row-major (one copy, or
+ * `batch` copies with model_per_instance), Ts one value or `batch` values; outputs Ad[batch*nx*nx], Bd[batch*nx*nu]. */
+int b200mpc_c2d(int nx, int nu, int batch, const double* A, const double* B, int model_per_instance, const double* Ts,
+                int ts_per_instance, double* Ad, double* Bd, int dev, void* stream);
+
 /* ---- NLMPC: batched evaluation of everything libmpc++ hands to its NLP solver for a decision vector z --------------
  * (SURVEY.md kernel K5).  Replaces, for `batch` controllers at once, the four NLopt callbacks of NLOptimizer
  * (include/mpc/NLMPC/NLOptimizer.hpp:760-997): Objective::evaluate (NLMPC/Objective.hpp:91-265),

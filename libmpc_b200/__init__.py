@@ -83,6 +83,7 @@ def load_library():
     lib.b200mpc_lmpc_set_history_order.argtypes = [H, C.c_int]
     lib.b200mpc_lmpc_profile.argtypes = [H, C.c_void_p]
     lib.b200mpc_sync.argtypes = [H]
+    lib.b200mpc_c2d.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.b200mpc_nlmpc_system_dims.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
     lib.b200mpc_nlmpc_eval.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
     lib.b200mpc_nlmpc_system_neq.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
@@ -107,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_set_input_bounds", "b200mpc_lmpc_set_output_bounds", "b200mpc_lmpc_set_scalar_constraint",
     "b200mpc_lmpc_set_references", "b200mpc_lmpc_set_exogenous_inputs", "b200mpc_lmpc_set_warm_start",
     "b200mpc_lmpc_get_warm_start", "b200mpc_lmpc_solve", "b200mpc_lmpc_closed_loop", "b200mpc_lmpc_get_result", "b200mpc_lmpc_get_sequence",
-    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_set_schedule", "b200mpc_lmpc_set_history_order", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
+    "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_set_schedule", "b200mpc_lmpc_set_history_order", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_c2d", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
     "b200mpc_nlmpc_default_params", "b200mpc_nlmpc_solve_smem_bytes", "b200mpc_nlmpc_solve",
     "b200mpc_nlmpc_system_neq", "b200mpc_nlmpc_register_system", "b200mpc_nlmpc_compile_check", "b200mpc_nlmpc_eval_ex",
     "b200mpc_nlmpc_solve_ex",
@@ -516,6 +517,23 @@ class LMPC:
         """Device-to-device copy of results into caller-owned device buffers (async on the handle's stream)."""
         v = lambda p: C.c_void_p(int(p)) if p else None
         _check(self.lib.b200mpc_lmpc_get_result(self._h, v(cmd_ptr), None, v(status_ptr), None, None, v(iters_ptr), None, None, 1))
+
+
+def discretization(A, B, Ts):
+    """mpc::discretization (include/mpc/Utils.hpp:23-47) on the device: A [nx,nx] or [batch,nx,nx], B likewise, Ts scalar or
+    [batch].  Returns (Ad, Bd) with the batch axis of the inputs (none when everything is a single system)."""
+    lib = load_library()
+    A = np.ascontiguousarray(A, dtype=np.float64); B = np.ascontiguousarray(B, dtype=np.float64)
+    Ts = np.ascontiguousarray(Ts, dtype=np.float64)
+    nx, nu = A.shape[-1], B.shape[-1]
+    mpi, tpi = A.ndim == 3, Ts.ndim == 1
+    batch = A.shape[0] if mpi else (Ts.shape[0] if tpi else 1)
+    if A.shape[-2:] != (nx, nx) or B.shape[-2:] != (nx, nu) or (mpi and B.shape[0] != batch) or (mpi and tpi and Ts.shape[0] != batch):
+        raise ValueError("discretization: inconsistent shapes")
+    Ad, Bd = np.empty((batch, nx, nx)), np.empty((batch, nx, nu))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _check(lib.b200mpc_c2d(nx, nu, batch, vp(A), vp(B), int(mpi), vp(Ts.reshape(-1)), int(tpi), vp(Ad), vp(Bd), 0, None))
+    return (Ad, Bd) if (mpi or tpi) else (Ad[0], Bd[0])
 
 
 # ---- NLMPC problem evaluation (SURVEY.md K5) ------------------------------------------------------------------------
