@@ -110,6 +110,16 @@ inline void check(int rc) {
 constexpr int dimp1(int d) { return d == Dynamic ? Dynamic : d + 1; }
 }  // namespace detail
 
+// mpc::discretization<nx,nu>(A, B, Ts, Ad, Bd)  (include/mpc/Utils.hpp:23-47): zero-order-hold c2d, on the device
+template <int nx, int nu>
+void discretization(const mat<nx, nx>& A, const mat<nx, nu>& B, const double& Ts, mat<nx, nx>& Ad, mat<nx, nu>& Bd) {
+    const int n = A.rows(), m = B.cols();
+    std::vector<double> a = A.rowMajor(), b = B.rowMajor(), ad((size_t)n * n), bd((size_t)n * m);
+    detail::check(b200mpc_c2d(n, m, 1, a.data(), b.data(), 0, &Ts, 0, ad.data(), bd.data(), 0, nullptr));
+    Ad.resize(n, n); Bd.resize(n, m);
+    for (int i = 0; i < n; ++i) { for (int j = 0; j < n; ++j) Ad(i, j) = ad[(size_t)i * n + j]; for (int j = 0; j < m; ++j) Bd(i, j) = bd[(size_t)i * m + j]; }
+}
+
 // ---- mpc::LMPC<Tnx,Tnu,Tndu,Tny,Tph,Tch>  (include/mpc/LMPC.hpp:23-26) ------------------------------------------------
 template <int Tnx = Dynamic, int Tnu = Dynamic, int Tndu = Dynamic, int Tny = Dynamic, int Tph = Dynamic, int Tch = Dynamic>
 class LMPC {
@@ -253,6 +263,15 @@ public:
             r.cost = cost[b]; r.status = (ResultStatus)st[b]; r.solver_status = sst[b]; r.is_feasible = feas[b] != 0;
         }
         return last_;
+    }
+    // `steps` control steps on the device (optimize -> apply cmd -> x+ = A x + B u with the controller's own model): the loop
+    // every example wraps around optimize().  traj_x[(steps+1)*batch*nx], traj_u[steps*batch*nu], row-major per instance.
+    void closedLoop(const double* x0, const double* lastU, int steps, std::vector<double>& traj_x, std::vector<double>& traj_u,
+                    std::vector<int32_t>* status = nullptr) {
+        traj_x.assign((size_t)(steps + 1) * batch_ * nx_, 0.0); traj_u.assign((size_t)steps * batch_ * nu_, 0.0);
+        if (status) status->assign((size_t)steps * batch_, 0);
+        detail::check(b200mpc_lmpc_closed_loop(h_, x0, lastU, steps, nullptr, nullptr, 0, traj_x.data(), traj_u.data(),
+                                               status ? status->data() : nullptr, nullptr, 0));
     }
     Result<Tnu> getLastResult() { return last_.empty() ? Result<Tnu>() : last_[0]; }
     OptSequence<Tnx, Tny, Tnu, detail::dimp1(Tph)> getOptimalSequence(int instance = 0) {

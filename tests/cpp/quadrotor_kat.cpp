@@ -88,6 +88,22 @@ int main() {
         if (std::sqrt(num) > 1e-4 * std::sqrt(den)) return 2;      // Eigen isApprox(…, 1e-4)
         if (res.status != mpc::SUCCESS || !res.is_feasible) return 2;
         if (std::fabs(seq.input(0, 1) - res.cmd(1)) > 1e-15) return 2;
+
+        // the loop of examples/quadrotor_ex.cpp on the device: the first command of the trajectory is the golden one, and the
+        // plant follows x+ = A x + B u
+        std::vector<double> tx, tu, xinit(Tnx, 0.0), uinit(Tnu, 0.0);
+        optsolver.closedLoop(xinit.data(), uinit.data(), 3, tx, tu);
+        for (int k = 0; k < 4; ++k) if (std::fabs(tu[k] - res.cmd(k)) > 1e-9) return 2;
+        double x1_2 = 0;                                            // row 2 of A x0 + B u0 with x0 = 0
+        for (int k = 0; k < 4; ++k) x1_2 += Bd(2, k) * tu[k];
+        if (std::fabs(tx[Tnx + 2] - x1_2) > 1e-12) return 2;
+
+        // mpc::discretization (test/test_utils.cpp:10-63): 2-dof double integrator, Ts = 0.02
+        mpc::mat<4, 4> Ac, Adz; mpc::mat<4, 2> Bc, Bdz;
+        Ac(0, 2) = 1; Ac(1, 3) = 1; Bc(2, 0) = 1; Bc(3, 1) = 1;
+        mpc::discretization<4, 2>(Ac, Bc, 0.02, Adz, Bdz);
+        if (std::fabs(Adz(0, 2) - 0.02) > 1e-15 || std::fabs(Adz(0, 0) - 1) > 1e-15 || std::fabs(Bdz(0, 0) - 0.0002) > 1e-15 ||
+            std::fabs(Bdz(2, 0) - 0.02) > 1e-15) return 2;
         return 0;
     } catch (const std::exception& e) {
         std::printf("exception: %s\n", e.what());
