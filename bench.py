@@ -337,7 +337,8 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": config,
             "value_cold_order": (world * B / (cold_ms * 1e-3)) if cold_ms else None,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": a.steps,
+            # per step: the solve kernel, plus the one-CTA ordering kernel when history ordering is on (profiles/r01_launches.csv)
+            "gpu_launches": a.steps * (1 if a.no_history_order else 2),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "note": "algorithmic bytes/solve (SURVEY 8d) x batch / kernel time; the solve is bound by instruction issue / "
