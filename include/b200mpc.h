@@ -155,7 +155,9 @@ enum { B200MPC_SCHEDULE_FREE = 0, B200MPC_SCHEDULE_GANG = 1 };
 int b200mpc_lmpc_set_schedule(b200mpc_lmpc_t h, int schedule);
 /* History ordering (default on): from the second solve of a handle on, instances are drawn in the order of the iteration
  * counts of their previous solve, longest first.  Consecutive MPC steps of a controller take similar iteration counts, so
- * the members of a gang finish together and the long solves start first.  Affects scheduling only, never results. */
+ * the members of a gang finish together and the long solves start first.  Affects scheduling only, never results.
+ * (Experiment knobs: the environment variables B200MPC_GANG=<0|1|k> and B200MPC_HISTORY_ORDER=<0|1>, read when a handle is
+ * created, set the initial value of these two switches.) */
 int b200mpc_lmpc_set_history_order(b200mpc_lmpc_t h, int enable);
 /* Profiling aid: first call (out_host ignored) enables per-instance phase cycle counters; later calls copy
  * batch*8 counters [setup, factorize, admm sweeps, info, polish prep, polish factor, polish solve, unpack] to the host. */
