@@ -203,8 +203,9 @@ int b200mpc_nlmpc_system_neq(int system, int ph, int* neq);
  *   (rows that do not read the perturbed variable have an exactly-zero finite difference and are not evaluated),
  *   and optionally (user equality constraints)
  *     __host__ __device__ static int neq(int ph);   __device__ static double eq(int r, const Acc& a, int ph, const double* p);
- * where a.x(i,j) / a.u(i,j) read the unwrapped state / input sequences ((ph+1) rows, Mapping::unwrapVector) and
- * y = x (systems with an output map apply it inside cost/ineq).  Returns a system id >= B200MPC_SYS_USER_BASE usable
+ * where a.x(i,j) / a.u(i,j) read the unwrapped state / input sequences ((ph+1) rows, Mapping::unwrapVector).  An output
+ * map (setOutputFunction, NLMPC.hpp:202) is  __device__ static void out(double* y, const double* x, const double* u, int i,
+ * const double* p);  cost / ineq read it as  b200mpc::nl_y<Self>(a, i, j, p)  (OptSequence::output still reports the state).  Returns a system id >= B200MPC_SYS_USER_BASE usable
  * wherever a built-in id is.  Kernels are compiled on first use and cached per device.  Compile errors are returned as
  * B200MPC_EINVAL with the NVRTC log in b200mpc_last_error(). */
 #define B200MPC_SYS_USER_BASE 100

@@ -52,6 +52,20 @@ struct Acc {
     }
 };
 
+// Output map (NLMPC::setOutputFunction, NLMPC.hpp:202-215 -> Model::getOutput, Model.hpp:72-96): the reference hands the
+// objective and the inequality constraints Y(i,:) = out(X(i,:), U(i,:), i) next to X and U.  A system that has an output map
+// defines   __device__ static void out(double* y, const double* x, const double* u, int i, const double* p)   and reads
+// nl_y<Self>(a, i, j, p) inside cost / ineq: the map is applied to the (perturbed) row on the fly, exactly what the reference's
+// re-evaluation of getOutput inside every finite-difference perturbation computes.
+template <class S>
+__device__ __forceinline__ double nl_y(const Acc& a, int i, int j, const double* p) {
+    double x[S::nx], u[S::nu], y[S::ny];
+    for (int k = 0; k < S::nx; ++k) x[k] = a.x(i, k);
+    for (int k = 0; k < S::nu; ++k) u[k] = a.u(i, k);
+    S::out(y, x, u, i, p);
+    return y[j];
+}
+
 // ---- built-in systems ---------------------------------------------------------------------------------------------
 // examples/vanderpol_ex.cpp:9-71 -- params: [Ts]
 struct SysVanDerPol {

@@ -3,7 +3,7 @@ setIneqConFunction / setEqConFunction) compile with NVRTC for sm_100a into the e
 the compile step.  The run-time behaviour is covered by tests/test_gpu_user_systems.py."""
 import pytest
 
-from user_systems import BROKEN_SRC, PENDULUM_SRC, VANDERPOL_SRC
+from user_systems import BROKEN_SRC, OUTPUT_MAP_SRC, PENDULUM_SRC, VANDERPOL_SRC
 
 
 def test_user_system_compiles_eval_kernel():
@@ -15,6 +15,12 @@ def test_user_system_with_equality_constraints_compiles_solve_kernel():
     import libmpc_b200 as L
     assert L.compile_check(PENDULUM_SRC, "UserPendulum", 0) > 10_000
     assert L.compile_check(PENDULUM_SRC, "UserPendulum", 1) > 50_000       # warp-per-controller solve variant
+
+
+def test_user_system_with_output_map_compiles():
+    """setOutputFunction: cost / ineq read y = out(x, u) through nl_y (the map is re-applied inside every perturbation)."""
+    import libmpc_b200 as L
+    assert L.compile_check(OUTPUT_MAP_SRC, "UserWithOutput", 0) > 10_000
 
 
 def test_compile_error_is_reported_with_the_nvrtc_log():

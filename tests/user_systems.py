@@ -57,6 +57,27 @@ struct UserPendulum {
 };
 """
 
+# A system with an OUTPUT MAP (NLMPC::setOutputFunction): the cost and the constraint read y = out(x, u), not x.
+OUTPUT_MAP_SRC = r"""
+struct UserWithOutput {
+    static constexpr int nx = 2, nu = 1, ny = 1, nparam = 1;
+    static constexpr bool continuous = false;
+    __device__ static double Ts(const double*) { return 0.0; }
+    __host__ __device__ static int nineq(int ph) { return ph + 1; }
+    __device__ static void f(double* xn, const double* x, const double* u, int, const double* p) {
+        xn[0] = x[0] + p[0] * x[1];
+        xn[1] = x[1] + p[0] * u[0];
+    }
+    __device__ static void out(double* y, const double* x, const double* u, int, const double*) { y[0] = x[0] + 0.5 * x[1] * x[1]; }
+    __device__ static double cost(const Acc& a, double, int ph, const double* p) {
+        double c = 0;
+        for (int i = 0; i <= ph; ++i) { double y = b200mpc::nl_y<UserWithOutput>(a, i, 0, p); c += (y - 1.0) * (y - 1.0) + 0.01 * a.u(i, 0) * a.u(i, 0); }
+        return c;
+    }
+    __device__ static double ineq(int r, const Acc& a, double, int, const double* p) { return b200mpc::nl_y<UserWithOutput>(a, r, 0, p) - 1.5; }
+};
+"""
+
 BROKEN_SRC = "struct Broken { static constexpr int nx = 2; int oops( };"
 
 
