@@ -105,3 +105,14 @@ def pendulum_formulation(ph=10, ch=5, Ts=0.1, damping=0.3, target=0.4):
     f.eq = lambda X, U: np.array([(X[ph, 0] - target) + 0.5 * X[ph, 1], X[ph // 2, 0] * X[ph // 2, 0] + X[ph // 2, 1] - 0.1])
     f.params = np.array([Ts, damping, target])
     return f
+
+
+def output_map_formulation(ph=6, ch=3, Ts=0.1):
+    f = NLMPCFormulation(2, 1, 1, ph, ch, nineq=ph + 1)
+    f.continuous = False
+    f.f = lambda x, u, i=0: np.array([x[0] + Ts * x[1], x[1] + Ts * u[0]])
+    f.out = lambda x, u, i=0: np.array([x[0] + 0.5 * x[1] * x[1]])
+    f.obj = lambda X, Y, U, e: float(((Y[:, 0] - 1.0) ** 2).sum() + 0.01 * (U[:, 0] ** 2).sum())
+    f.ineq = lambda X, Y, U, e: Y[:, 0] - 1.5
+    f.params = np.array([Ts])
+    return f
