@@ -3,7 +3,7 @@ setIneqConFunction / setEqConFunction) compile with NVRTC for sm_100a into the e
 the compile step.  The run-time behaviour is covered by tests/test_gpu_user_systems.py."""
 import pytest
 
-from user_systems import BROKEN_SRC, OUTPUT_MAP_SRC, PENDULUM_SRC, VANDERPOL_SRC
+from user_systems import BROKEN_SRC, OUTPUT_MAP_SRC, PENDULUM_SRC, UNICYCLE_SRC, VANDERPOL_SRC
 
 
 def test_user_system_compiles_eval_kernel():
@@ -21,6 +21,13 @@ def test_user_system_with_output_map_compiles():
     """setOutputFunction: cost / ineq read y = out(x, u) through nl_y (the map is re-applied inside every perturbation)."""
     import libmpc_b200 as L
     assert L.compile_check(OUTPUT_MAP_SRC, "UserWithOutput", 0) > 10_000
+
+
+def test_baseline_unicycle_shape_compiles_for_the_kernel_it_would_run():
+    """BASELINE.json configs[2] at its stated shape (nx3 nu2 Tph30, 62 obstacle inequalities): nz = 151 does not fit shared
+    memory with its matrices, so the launch policy picks the packed-factor variant (kernel index 3)."""
+    import libmpc_b200 as L
+    assert L.compile_check(UNICYCLE_SRC, "UserUnicycle", 3) > 50_000
 
 
 def test_compile_error_is_reported_with_the_nvrtc_log():

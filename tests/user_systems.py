@@ -78,6 +78,39 @@ struct UserWithOutput {
 };
 """
 
+# BASELINE.json configs[2] at its stated shape (SURVEY.md 8d row 3b): unicycle x = [px, py, theta], u = [v, omega], discrete
+# x+ = x + Ts [v cos(theta), v sin(theta), omega], Tph = Tch = 30, two circular obstacles on (px, py) -> Tineq = 62, soft
+# constraints; cost 10 |p - p_goal|^2 + 1e-2 |u|^2 + 1e-5 e^2.  The model is NOT in the reference (its ugv_ex is a double
+# integrator with nx = 4), so this shape exists only as a user-defined system.  params = [Ts, goal(2), obs0(x,y,r), obs1(x,y,r)].
+UNICYCLE_SRC = r"""
+struct UserUnicycle {
+    static constexpr int nx = 3, nu = 2, ny = 3, nparam = 9, nobs = 2;
+    static constexpr bool continuous = false;
+    static constexpr int ineq_per_stage = nobs;
+    __device__ static double Ts(const double*) { return 0.0; }
+    __host__ __device__ static int nineq(int ph) { return (ph + 1) * nobs; }
+    __device__ static void f(double* xn, const double* x, const double* u, int, const double* p) {
+        xn[0] = x[0] + p[0] * (u[0] * cos(x[2]));
+        xn[1] = x[1] + p[0] * (u[0] * sin(x[2]));
+        xn[2] = x[2] + p[0] * u[1];
+    }
+    __device__ static double cost(const Acc& a, double e, int ph, const double* p) {
+        double c = 0;
+        for (int i = 0; i <= ph; ++i) {
+            double d0 = a.x(i, 0) - p[1], d1 = a.x(i, 1) - p[2], u0 = a.u(i, 0), u1 = a.u(i, 1);
+            c += 1e1 * (d0 * d0 + d1 * d1);
+            c += 1e-2 * (u0 * u0 + u1 * u1);
+        }
+        return c + 1e-5 * e * e;
+    }
+    __device__ static double ineq(int r, const Acc& a, double, int, const double* p) {
+        int i = r / nobs, j = r % nobs;
+        double dx = a.x(i, 0) - p[3 + 3 * j], dy = a.x(i, 1) - p[3 + 3 * j + 1];
+        return p[3 + 3 * j + 2] - sqrt(dx * dx + dy * dy);
+    }
+};
+"""
+
 BROKEN_SRC = "struct Broken { static constexpr int nx = 2; int oops( };"
 
 
@@ -115,4 +148,30 @@ def output_map_formulation(ph=6, ch=3, Ts=0.1):
     f.obj = lambda X, Y, U, e: float(((Y[:, 0] - 1.0) ** 2).sum() + 0.01 * (U[:, 0] ** 2).sum())
     f.ineq = lambda X, Y, U, e: Y[:, 0] - 1.5
     f.params = np.array([Ts])
+    return f
+
+
+def unicycle_formulation(ph=30, ch=30, Ts=0.1, goal=(2.0, 2.0), obstacles=((1.0, 0.6, 0.3), (1.4, 1.7, 0.3))):
+    """Oracle side of UNICYCLE_SRC (BASELINE.json configs[2] shape)."""
+    obs = np.asarray(obstacles, float); goal = np.asarray(goal, float)
+    f = NLMPCFormulation(3, 2, 3, ph, ch, nineq=(ph + 1) * len(obs))
+    f.continuous = False
+    f.f = lambda x, u, i=0: np.array([x[0] + Ts * (u[0] * np.cos(x[2])), x[1] + Ts * (u[0] * np.sin(x[2])), x[2] + Ts * u[1]])
+
+    def cost(X, Y, U, e):
+        c = 0.0
+        for i in range(ph + 1):
+            d0, d1 = X[i, 0] - goal[0], X[i, 1] - goal[1]
+            c += 1e1 * (d0 * d0 + d1 * d1)
+            c += 1e-2 * (U[i, 0] * U[i, 0] + U[i, 1] * U[i, 1])
+        return c + 1e-5 * e * e
+
+    def ineq(X, Y, U, e):
+        out = np.zeros((ph + 1) * len(obs))
+        for i in range(ph + 1):
+            for j in range(len(obs)):
+                out[i * len(obs) + j] = obs[j, 2] - np.sqrt((X[i, 0] - obs[j, 0]) ** 2 + (X[i, 1] - obs[j, 1]) ** 2)
+        return out
+    f.obj, f.ineq = cost, ineq
+    f.params = np.concatenate([[Ts], goal, obs.ravel()])
     return f
