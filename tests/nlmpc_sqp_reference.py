@@ -108,7 +108,24 @@ class QPADMM:
         return D * xs, E * ys / c, it
 
 
-def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, verbose=False):
+def stage_groups(f):
+    """Index groups of a per-stage block-diagonal quasi-Newton matrix: stage s holds X_{s+1} and, when s opens a control
+    block, that block; the slack is its own group."""
+    ph, ch, nx, nu = f.ph, f.ch, f.nx, f.nu
+    G = []
+    for s in range(ph):
+        idx = list(range(s * nx, (s + 1) * nx))
+        if s < ch:
+            idx += list(range(ph * nx + s * nu, ph * nx + (s + 1) * nu))
+        G.append(np.array(idx))
+    G.append(np.array([f.nz - 1]))
+    return G
+
+
+def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, verbose=False, bfgs_groups=None):
+    """bfgs_groups=None: the dense damped BFGS the CUDA kernel implements.  bfgs_groups=stage_groups(f): the same update applied
+    block by block (B stays block diagonal, so the QP's reduced KKT matrix is block tridiagonal over the stages) -- the
+    specification of the stage-structured kernel planned next."""
     qp = qp or QPADMM()
     x0 = np.asarray(x0, float)
     z = np.clip(np.array(z0, float), lb, ub)
@@ -175,13 +192,20 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
         gl_new = g_new + Je_new.T @ lam_e + Ji_new.T @ lam_i
         gl_old = g + Je.T @ lam_e + Ji.T @ lam_i
         yk = gl_new - gl_old
-        Bs = B @ s
-        sBs = s @ Bs
-        sy = s @ yk
-        if sBs > 1e-300:
-            theta = 1.0 if sy >= 0.2 * sBs else 0.8 * sBs / (sBs - sy)
-            r = theta * yk + (1 - theta) * Bs
-            B = B - np.outer(Bs, Bs) / sBs + np.outer(r, r) / (s @ r)
+        def damped_bfgs(Bm, sv, yv):
+            Bs = Bm @ sv
+            sBs = sv @ Bs
+            sy = sv @ yv
+            if sBs > 1e-300:
+                theta = 1.0 if sy >= 0.2 * sBs else 0.8 * sBs / (sBs - sy)
+                r = theta * yv + (1 - theta) * Bs
+                return Bm - np.outer(Bs, Bs) / sBs + np.outer(r, r) / (sv @ r)
+            return Bm
+        if bfgs_groups is None:
+            B = damped_bfgs(B, s, yk)
+        else:
+            for G in bfgs_groups:
+                B[np.ix_(G, G)] = damped_bfgs(B[np.ix_(G, G)], s[G], yk[G])
         step = np.abs(d).max()            # the full QP step: small only at a KKT point (t*d can be small far from one)
         hist.append((k, f_new, v0, step, t, qit))
         if verbose:

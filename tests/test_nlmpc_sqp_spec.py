@@ -37,3 +37,17 @@ def test_ugv_example_optimum():
     assert np.abs(got["z"] - ref["z"]).max() < 1e-4
     assert abs(got["cost"] - ref["cost"]) < 1e-6 * max(1.0, abs(ref["cost"]))
     assert got["viol"] < 1e-8
+
+
+def test_block_diagonal_bfgs_variant_reaches_the_same_optimum():
+    """Groundwork for the stage-structured kernel: with a per-stage block-diagonal damped BFGS the SQP reaches the
+    optimum of the dense variant (and of SLSQP) in no more major iterations (profiles/r01_block_bfgs_experiment.txt)."""
+    from nlmpc_sqp_reference import stage_groups
+    f = vanderpol_formulation()
+    lb, ub = S.default_bounds(f, True)
+    for x0 in (np.array([0.0, 1.0]), np.array([0.8, -0.4])):
+        z0 = S.initial_guess(f, x0, np.zeros(1), lb=lb, ub=ub)
+        dense = sqp_solve(f, x0, z0, lb, ub)
+        block = sqp_solve(f, x0, z0, lb, ub, bfgs_groups=stage_groups(f))
+        assert np.abs(block["z"] - dense["z"]).max() < 5e-6 and abs(block["cost"] - dense["cost"]) < 1e-8 * max(1.0, abs(dense["cost"]))
+        assert block["viol"] < 1e-8 and block["nit"] <= dense["nit"]
