@@ -17,9 +17,18 @@ class QPADMM:
     """Dense OSQP-style ADMM: Jacobi equilibration, rho_eq = 1e3 rho, alpha = 1.6, residual test + adaptive rho (OSQP's
     estimate, refactor when it moves by more than 5x) every `check` iterations."""
 
-    def __init__(self, rho=0.1, sigma=1e-6, alpha=1.6, max_iter=200, eps=1e-5, check=25, polish=True, delta=1e-6, refine=5):
+    def __init__(self, rho=0.1, sigma=1e-6, alpha=1.6, max_iter=200, eps=1e-5, check=25, polish=True, delta=1e-6, refine=5,
+                 spd_factor=None):
         self.rho, self.sigma, self.alpha, self.max_iter, self.eps, self.check = rho, sigma, alpha, max_iter, eps, check
         self.polish, self.delta, self.refine = polish, delta, refine
+        # H -> (rhs -> H^-1 rhs).  Default: dense Cholesky (what the CUDA kernel does today); the stage-structured kernel
+        # plugs in the bordered block-tridiagonal factorisation of tests/nlmpc_structured_kkt_reference.py.
+        self.spd_factor = spd_factor or self._dense_factor
+
+    @staticmethod
+    def _dense_factor(H):
+        L = np.linalg.cholesky(H)
+        return lambda rhs: np.linalg.solve(L.T, np.linalg.solve(L, rhs))
 
     def solve(self, B, g, A, l, u, x=None, y=None):
         n, m = B.shape[0], A.shape[0]
@@ -45,15 +54,15 @@ class QPADMM:
         def factor(rho0):
             rho = np.where(loose, 1e-6, np.where(eq, 1e3 * rho0, rho0))
             H = Bs + self.sigma * np.eye(n) + As.T @ (rho[:, None] * As)
-            return rho, np.linalg.cholesky(H)
-        rho, L = factor(rho0)
+            return rho, self.spd_factor(H)
+        rho, kkt_solve = factor(rho0)
         xs = np.zeros(n) if x is None else x / D
         ys = np.zeros(m) if y is None else c * y / E
         zs = np.clip(As @ xs, ls, us)
         it = 0
         for it in range(1, self.max_iter + 1):
             rhs = self.sigma * xs - gs + As.T @ (rho * zs - ys)
-            xt = np.linalg.solve(L.T, np.linalg.solve(L, rhs))
+            xt = kkt_solve(rhs)
             zt = As @ xt
             xn = self.alpha * xt + (1 - self.alpha) * xs
             zr = self.alpha * zt + (1 - self.alpha) * zs
@@ -73,7 +82,7 @@ class QPADMM:
                 est = min(max(rho0 * np.sqrt(pn / (dn + 1e-10)), 1e-6), 1e6)
                 if est > 5 * rho0 or est < rho0 / 5:
                     rho0 = est
-                    rho, L = factor(rho0)
+                    rho, kkt_solve = factor(rho0)
         if self.polish:
             # OSQP polish.c: guess the active set from (z, y), solve the equality-constrained QP on it through the same
             # reduced system (rho = 1/delta on active rows, sigma = delta) with iterative refinement, keep it if both
@@ -85,9 +94,9 @@ class QPADMM:
             Aa = As[act]
             dl = self.delta
             Hp = Bs + dl * np.eye(n) + Aa.T @ Aa / dl
-            Lp = np.linalg.cholesky(Hp)
+            polish_solve = self.spd_factor(Hp)
             def kkt(r1, r2):           # [Bs+dl I, Aa'; Aa, -dl I] [x; y] = [r1; r2]
-                x = np.linalg.solve(Lp.T, np.linalg.solve(Lp, r1 + Aa.T @ r2 / dl))
+                x = polish_solve(r1 + Aa.T @ r2 / dl)
                 return x, (Aa @ x - r2) / dl
             xp, yp = kkt(-gs, b)
             for _ in range(self.refine):

@@ -84,3 +84,24 @@ def assemble_blocks(H, groups, border):
     sub = [H[np.ix_(groups[s + 1], groups[s])] for s in range(len(groups) - 1)]
     C = [H[np.ix_(g, border)] for g in groups]
     return diag, sub, C, H[np.ix_(border, border)], outside
+
+
+def structured_factor(f):
+    """spd_factor hook for tests/nlmpc_sqp_reference.QPADMM: factor H through its stage blocks only."""
+    groups, border = stage_partition(f)
+
+    def factor(H):
+        diag, sub, C, D, outside = assemble_blocks(H, groups, border)
+        if outside != 0.0:
+            raise ValueError(f"H is not bordered block tridiagonal (largest outside entry {outside})")
+        F = BorderedBlockTridiagonal(diag, sub, C, D)
+
+        def solve(rhs):
+            xT, xb = F.solve([rhs[g] for g in groups], rhs[border])
+            x = np.empty_like(rhs)
+            for g, v in zip(groups, xT):
+                x[g] = v
+            x[border] = xb
+            return x
+        return solve
+    return factor
