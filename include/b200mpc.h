@@ -59,6 +59,11 @@ typedef struct b200mpc_lmpc_params {
     int check_termination;        /* 25                                                                      */
     int adaptive_rho_interval;    /* 25: v0.6.3 derives it from wall-clock time; pinned      */
     int polish_refine_iter;       /* 3                                                                       */
+    double time_limit;            /* Parameters::time_limit = 0 (off), seconds (LOptimizer.hpp:256): OSQP checks its run time
+                                     (set-up included) at the top of every ADMM iteration; when it is exceeded the solve stops
+                                     with OSQP_TIME_LIMIT_REACHED (-6), which LOptimizer::convertToResultStatus maps to UNKNOWN
+                                     (LOptimizer.hpp:386-415).  Per controller, measured with the GPU's global timer from the
+                                     moment its solve starts; honoured by the CTA-per-controller engine               */
 } b200mpc_lmpc_params;
 
 /* mpc::ResultStatus (include/mpc/Types.hpp:84-91) */
@@ -96,6 +101,10 @@ int b200mpc_lmpc_set_weights(b200mpc_lmpc_t h, const double* OW, const double* U
 int b200mpc_lmpc_set_state_bounds(b200mpc_lmpc_t h, const double* XMin, const double* XMax, int per_instance, int dev);
 int b200mpc_lmpc_set_input_bounds(b200mpc_lmpc_t h, const double* UMin, const double* UMax, int per_instance, int dev);
 int b200mpc_lmpc_set_output_bounds(b200mpc_lmpc_t h, const double* YMin, const double* YMax, int per_instance, int dev);
+/* The reference's INTERNAL input-bound matrices minU/maxU [nu x ph] as they stand after any mix of the matrix setter (which
+ * replicates column ch-1 into the tail, ProblemBuilder.hpp:397-413) and the per-index setter (which writes one column and does
+ * NOT touch the tail, ProblemBuilder.hpp:469-477): UMin/UMax[ph*nu], all ph columns taken verbatim. */
+int b200mpc_lmpc_set_input_bounds_full(b200mpc_lmpc_t h, const double* UMin, const double* UMax, int per_instance, int dev);
 /* LMPC::setScalarConstraint(min,max,X,U,slice all) (LMPC.hpp:355-407) -> ProblemBuilder::setScalarConstraint
  * (:347-365).  SMin/SMax[ph], X[nx], U[nu].  As in the reference the multiplier applies to every stage. */
 int b200mpc_lmpc_set_scalar_constraint(b200mpc_lmpc_t h, const double* SMin, const double* SMax, const double* X,
@@ -144,7 +153,14 @@ int b200mpc_lmpc_cmd_device_ptr(b200mpc_lmpc_t h, double** cmd_dev);
 /* Engine introspection used by bench.py / profiles: resident warp slots, workspace bytes per slot, kernel
  * launches issued so far, algorithmic FP64 flop estimate of the last solve (sum over instances). */
 int b200mpc_lmpc_info(b200mpc_lmpc_t h, int* warp_slots, size_t* workspace_bytes_per_slot, long long* launches);
-/* Override launch geometry (0 = auto): warps per CTA and CTAs per SM of the persistent solve kernel. */
+/* Solve engine.  0 = automatic; 2 = one thread block per controller with its whole state (factor, vectors, iterates) in shared
+ * memory, a persistent grid of one block per SM (the default whenever the vectors fit: batch 1 -- a single mpc::LMPC<> object --
+ * up to any batch); 1 = one warp per controller, state streamed from HBM through TMA rings (any size).  cta_threads: 0 (auto), 256
+ * or 512.  Results do not depend on the engine (tests/test_gpu_lmpc_properties.py).  Environment: B200MPC_ENGINE, B200MPC_CTA_THREADS. */
+int b200mpc_lmpc_set_engine(b200mpc_lmpc_t h, int engine, int cta_threads);
+int b200mpc_lmpc_get_engine(b200mpc_lmpc_t h, int* engine, int* threads_per_cta, int* factor_in_shared_memory);
+/* Override launch geometry of engine 1 (0 = auto): warps per CTA and CTAs per SM of the persistent warp-per-controller kernel
+ * (a non-zero value selects engine 1). */
 int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int ctas_per_sm);
 /* How the persistent warps draw instances.  GANG (default): the warps of a CTA draw and start their instances together
  * and wait for the slowest before drawing again -- they run the same phase of the program at the same time and share its
@@ -187,6 +203,8 @@ enum { B200MPC_SYS_VANDERPOL = 0,  /* examples/vanderpol_ex.cpp: params [Ts]    
 int b200mpc_nlmpc_system_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq);
 /* number of user equality constraints Teq of the system (NLMPC<...,Tineq,Teq>, NLMPC.hpp:26-30); 0 for the built-ins */
 int b200mpc_nlmpc_system_neq(int system, int ph, int* neq);
+/* Tny of the system and whether it defines an output map (NLMPC::setOutputFunction, NLMPC.hpp:202-215) */
+int b200mpc_nlmpc_system_ny(int system, int ph, int* ny, int* has_output_map);
 
 /* ---- user-defined systems: NLMPC::setStateSpaceFunction / setObjectiveFunction / setIneqConFunction / setEqConFunction
  * (NLMPC.hpp:165,139,228,261; callback typedefs IDimensionable.hpp:94-149).  The reference takes host std::function
@@ -205,7 +223,8 @@ int b200mpc_nlmpc_system_neq(int system, int ph, int* neq);
  *     __host__ __device__ static int neq(int ph);   __device__ static double eq(int r, const Acc& a, int ph, const double* p);
  * where a.x(i,j) / a.u(i,j) read the unwrapped state / input sequences ((ph+1) rows, Mapping::unwrapVector).  An output
  * map (setOutputFunction, NLMPC.hpp:202) is  __device__ static void out(double* y, const double* x, const double* u, int i,
- * const double* p);  cost / ineq read it as  b200mpc::nl_y<Self>(a, i, j, p)  (OptSequence::output still reports the state).  Returns a system id >= B200MPC_SYS_USER_BASE usable
+ * const double* p);  cost / ineq read it as  b200mpc::nl_y<Self>(a, i, j, p); b200mpc_nlmpc_output applies it to a solution
+ * (OptSequence::output).  Returns a system id >= B200MPC_SYS_USER_BASE usable
  * wherever a built-in id is.  Kernels are compiled on first use and cached per device.  Compile errors are returned as
  * B200MPC_EINVAL with the NVRTC log in b200mpc_last_error(). */
 #define B200MPC_SYS_USER_BASE 100
@@ -249,6 +268,11 @@ int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, const double* z
                           int params_per_instance, const b200mpc_nlmpc_scaling* scaling, double* fval, double* grad,
                           double* ceq, double* Jeq, double* cin, double* Jin, double* cue, double* Jue, int dev,
                           void* stream);
+/* OptSequence::output as NLOptimizer::run fills it (NLOptimizer.hpp:596-611): Model::getOutput (NLMPC/Model.hpp:72-96) applied
+ * to every row of the sequences Mapping::unwrapVector gives for z.  y[batch*(ph+1)*ny]; all zeros for a system without an
+ * output map, exactly as the reference (Model.hpp:82-84). */
+int b200mpc_nlmpc_output(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
+                         int params_per_instance, const b200mpc_nlmpc_scaling* scaling, double* y, int dev, void* stream);
 void b200mpc_nlmpc_default_params(b200mpc_nlmpc_params* p);
 long long b200mpc_nlmpc_solve_smem_bytes(int system, int ph, int ch);
 int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* params, const double* z0,

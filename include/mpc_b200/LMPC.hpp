@@ -145,6 +145,7 @@ public:
         q.maximum_iteration = lp->maximum_iteration; q.enable_warm_start = lp->enable_warm_start;
         q.alpha = lp->alpha; q.rho = lp->rho; q.eps_rel = lp->eps_rel; q.eps_abs = lp->eps_abs;
         q.eps_prim_inf = lp->eps_prim_inf; q.eps_dual_inf = lp->eps_dual_inf; q.adaptive_rho = lp->adaptive_rho; q.polish = lp->polish;
+        q.time_limit = lp->time_limit;                                                       // LOptimizer.hpp:256
         detail::check(b200mpc_lmpc_set_params(h_, &q));
     }
 
@@ -310,8 +311,8 @@ private:
     bool pushWeights() { detail::check(b200mpc_lmpc_set_weights(h_, ow_.data(), uw_.data(), duw_.data(), 0, 0)); return sync(); }
     bool pushState() { detail::check(b200mpc_lmpc_set_state_bounds(h_, xmin_.data(), xmax_.data(), 0, 0)); return sync(); }
     bool pushOutput() { detail::check(b200mpc_lmpc_set_output_bounds(h_, ymin_.data(), ymax_.data(), 0, 0)); return sync(); }
-    bool pushInput() {   // the ABI takes the first ch columns and replicates the tail exactly like ProblemBuilder.hpp:406-410
-        detail::check(b200mpc_lmpc_set_input_bounds(h_, umin_.data(), umax_.data(), 0, 0)); return sync();
+    bool pushInput() {   // all ph internal columns verbatim: the per-index setter never re-replicates the tail (ProblemBuilder.hpp:469-477)
+        detail::check(b200mpc_lmpc_set_input_bounds_full(h_, umin_.data(), umax_.data(), 0, 0)); return sync();
     }
     bool pushRefs() { detail::check(b200mpc_lmpc_set_references(h_, yref_.data(), uref_.data(), duref_.data(), 0, 0)); return sync(); }
     bool pushMeas() { detail::check(b200mpc_lmpc_set_exogenous_inputs(h_, umeas_.data(), 0, 0)); return sync(); }

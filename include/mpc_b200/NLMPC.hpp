@@ -140,6 +140,14 @@ public:
             detail::check(b200mpc_nlmpc_eval_ex(system_, ph_, ch_, batch_, opt_.data(), x0, params_.data(), per_instance_ ? 1 : 0, &sc,
                                                 nullptr, nullptr, nullptr, nullptr, ni > 0 ? cin.data() : nullptr, nullptr,
                                                 neq_ > 0 ? cue.data() : nullptr, nullptr, 0, nullptr));
+        // OptSequence::output = Model::getOutput(Xmat, Umat) (NLOptimizer.hpp:611, Model.hpp:72-96), on the device
+        int sys_ny = 0;
+        detail::check(b200mpc_nlmpc_system_ny(system_, ph_, &sys_ny, nullptr));
+        yseq_.assign((size_t)batch_ * (ph_ + 1) * std::max(sys_ny, 1), 0.0);
+        sys_ny_ = sys_ny;
+        if (sys_ny > 0)
+            detail::check(b200mpc_nlmpc_output(system_, ph_, ch_, batch_, opt_.data(), x0, params_.data(), per_instance_ ? 1 : 0, &sc,
+                                               yseq_.data(), 0, nullptr));
         last_.assign(batch_, Result<Tnu>());
         x0_.assign(x0, x0 + (size_t)batch_ * nx_);
         for (int b = 0; b < batch_; ++b) {
@@ -170,7 +178,8 @@ public:
                 q.state(t, k) = (t == 0 ? x0_[(size_t)instance * nx_ + k] : z[(t - 1) * nx_ + k]) / (sx_.empty() ? 1.0 : sx_[k]);
             int blk = std::min(std::min(t, ph_ - 1), ch_ - 1);
             for (int k = 0; k < nu_; ++k) q.input(t, k) = (su_.empty() ? 1.0 : su_[k]) * z[ph_ * nx_ + blk * nu_ + k];
-            for (int k = 0; k < ny_ && k < nx_; ++k) q.output(t, k) = q.state(t, k);      // built-in systems: y = x
+            for (int k = 0; k < ny_; ++k)                                                     // the system's output map (zeros without one)
+                q.output(t, k) = k < sys_ny_ ? yseq_[((size_t)instance * (ph_ + 1) + t) * sys_ny_ + k] : 0.0;
         }
         return q;
     }
@@ -222,7 +231,8 @@ private:
     double ineq_tol_ = 1e-10, eq_tol_ = 1e-10;
     std::vector<double> sx_, su_;
     NLParameters p_;
-    std::vector<double> params_, lb_, ub_, opt_, slack_, x0_;
+    std::vector<double> params_, lb_, ub_, opt_, slack_, x0_, yseq_;
+    int sys_ny_ = 0;
     std::vector<Result<Tnu>> last_;
 };
 

@@ -36,7 +36,8 @@ class _Params(C.Structure):
                 ("rho", C.c_double), ("eps_rel", C.c_double), ("eps_abs", C.c_double), ("eps_prim_inf", C.c_double),
                 ("eps_dual_inf", C.c_double), ("adaptive_rho", C.c_int), ("polish", C.c_int), ("sigma", C.c_double),
                 ("delta", C.c_double), ("adaptive_rho_tolerance", C.c_double), ("scaling", C.c_int),
-                ("check_termination", C.c_int), ("adaptive_rho_interval", C.c_int), ("polish_refine_iter", C.c_int)]
+                ("check_termination", C.c_int), ("adaptive_rho_interval", C.c_int), ("polish_refine_iter", C.c_int),
+                ("time_limit", C.c_double)]
 
 
 _lib = None
@@ -67,7 +68,7 @@ def load_library():
     lib.b200mpc_lmpc_set_stream.argtypes = [H, C.c_void_p]
     lib.b200mpc_lmpc_set_params.argtypes = [H, C.POINTER(_Params)]
     for name, nptr in (("set_model", 3), ("set_disturbances", 2), ("set_weights", 3), ("set_state_bounds", 2),
-                       ("set_input_bounds", 2), ("set_output_bounds", 2), ("set_scalar_constraint", 4),
+                       ("set_input_bounds", 2), ("set_input_bounds_full", 2), ("set_output_bounds", 2), ("set_scalar_constraint", 4),
                        ("set_references", 3), ("set_exogenous_inputs", 1)):
         getattr(lib, "b200mpc_lmpc_" + name).argtypes = [H] + [C.c_void_p] * nptr + [C.c_int, C.c_int]
     lib.b200mpc_lmpc_set_warm_start.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int]
@@ -79,6 +80,8 @@ def load_library():
     lib.b200mpc_lmpc_cmd_device_ptr.argtypes = [H, C.POINTER(C.c_void_p)]
     lib.b200mpc_lmpc_info.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_longlong)]
     lib.b200mpc_lmpc_set_launch.argtypes = [H, C.c_int, C.c_int]
+    lib.b200mpc_lmpc_set_engine.argtypes = [H, C.c_int, C.c_int]
+    lib.b200mpc_lmpc_get_engine.argtypes = [H] + [C.POINTER(C.c_int)] * 3
     lib.b200mpc_lmpc_set_schedule.argtypes = [H, C.c_int]
     lib.b200mpc_lmpc_set_history_order.argtypes = [H, C.c_int]
     lib.b200mpc_lmpc_profile.argtypes = [H, C.c_void_p]
@@ -87,6 +90,8 @@ def load_library():
     lib.b200mpc_nlmpc_system_dims.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
     lib.b200mpc_nlmpc_eval.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
     lib.b200mpc_nlmpc_system_neq.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.b200mpc_nlmpc_system_ny.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.b200mpc_nlmpc_output.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]
     lib.b200mpc_nlmpc_register_system.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
     lib.b200mpc_nlmpc_compile_check.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_size_t)]
     lib.b200mpc_nlmpc_eval_ex.argtypes = ([C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] + [C.c_void_p] * 8 +
@@ -111,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_set_schedule", "b200mpc_lmpc_set_history_order", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_c2d", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
     "b200mpc_nlmpc_default_params", "b200mpc_nlmpc_solve_smem_bytes", "b200mpc_nlmpc_solve",
     "b200mpc_nlmpc_system_neq", "b200mpc_nlmpc_register_system", "b200mpc_nlmpc_compile_check", "b200mpc_nlmpc_eval_ex",
-    "b200mpc_nlmpc_solve_ex",
+    "b200mpc_nlmpc_solve_ex", "b200mpc_nlmpc_system_ny", "b200mpc_nlmpc_output", "b200mpc_lmpc_set_input_bounds_full", "b200mpc_lmpc_set_engine", "b200mpc_lmpc_get_engine",
 ]
 
 
@@ -258,6 +263,7 @@ class LMPC:
         q.alpha, q.rho, q.eps_rel, q.eps_abs = p.alpha, p.rho, p.eps_rel, p.eps_abs
         q.eps_prim_inf, q.eps_dual_inf = p.eps_prim_inf, p.eps_dual_inf
         q.adaptive_rho, q.polish = int(bool(p.adaptive_rho)), int(bool(p.polish))
+        q.time_limit = float(p.time_limit)                        # LOptimizer.hpp:256
         _check(self.lib.b200mpc_lmpc_set_params(self._h, C.byref(q)))
 
     def setStateSpaceModel(self, A, B, Cm):
@@ -338,7 +344,6 @@ class LMPC:
                                            np.repeat(v1[..., :, None], self.ch, axis=-1))
             if not self._group(("UMin", "UMax"), (UMin, UMax), sl, (self.nu, self.nu), self.ph, validate_ctrl=True):
                 return False
-        # the C setter takes the [ch] columns and replicates the tail itself; pass internal columns directly by using ch=ph view
         self._push_input_bounds()
         return True
 
@@ -399,13 +404,10 @@ class LMPC:
         _check(self.lib.b200mpc_sync(self._h))
 
     def _push_input_bounds(self):
-        # host mirror holds the internal [nu x ph] matrices; the C entry point wants [ch] columns + tail rule.  The
-        # internal columns beyond ch can differ from column ch-1 only through per-index setters, which the reference
-        # restricts to index < ch, so sending the first ch columns reproduces the internal state exactly.
-        lo, hi = self._st["UMin"][..., :, :self.ch], self._st["UMax"][..., :, :self.ch]
-        (a, b), pi = self._bcast_pi([self._hz(lo, (self.nu, self.ch)), self._hz(hi, (self.nu, self.ch))])
-        _check(self.lib.b200mpc_lmpc_set_input_bounds(self._h, self._p(a), self._p(b), pi, 0))
-        _check(self.lib.b200mpc_sync(self._h))
+        # The host mirror holds the reference's internal [nu x ph] matrices.  The per-index setter writes ONE column and never
+        # re-replicates the tail (ProblemBuilder.hpp:469-477), so after a slice set at ch-1 the tail columns ch..ph-1 keep what
+        # the last matrix call put there: all ph columns are pushed verbatim.
+        self._push2("b200mpc_lmpc_set_input_bounds_full", "UMin", "UMax", (self.nu, self.ph))
 
     # ---- warm start accessors (LMPC.hpp:677-722) -------------------------------------------------
     def getSolverWarmStartPrimal(self):
@@ -430,6 +432,15 @@ class LMPC:
 
     def set_launch(self, warps_per_cta=0, ctas_per_sm=0):
         _check(self.lib.b200mpc_lmpc_set_launch(self._h, warps_per_cta, ctas_per_sm))
+
+    def set_engine(self, engine=0, cta_threads=0):
+        """0 auto, 1 warp per controller (TMA-streamed state), 2 CTA per controller (state in shared memory); include/b200mpc.h."""
+        _check(self.lib.b200mpc_lmpc_set_engine(self._h, int(engine), int(cta_threads)))
+
+    def get_engine(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _check(self.lib.b200mpc_lmpc_get_engine(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(engine=a.value, threads_per_cta=b.value, factor_in_shared_memory=bool(c.value))
 
     def set_schedule(self, gang=True):
         """Gang (default) or free scheduling of the persistent warps (include/b200mpc.h); results are identical."""
@@ -545,7 +556,10 @@ def nlmpc_system_dims(system, ph):
     v = [C.c_int() for _ in range(5)]
     _check(lib.b200mpc_nlmpc_system_dims(system, ph, *[C.byref(x) for x in v[:4]]))
     _check(lib.b200mpc_nlmpc_system_neq(system, ph, C.byref(v[4])))
-    return dict(nx=v[0].value, nu=v[1].value, nparam=v[2].value, nineq=v[3].value, neq=v[4].value)
+    ny, ho = C.c_int(), C.c_int()
+    _check(lib.b200mpc_nlmpc_system_ny(system, ph, C.byref(ny), C.byref(ho)))
+    return dict(nx=v[0].value, nu=v[1].value, nparam=v[2].value, nineq=v[3].value, neq=v[4].value, ny=ny.value,
+                has_output_map=bool(ho.value))
 
 
 def register_system(cuda_source, type_name):
@@ -620,6 +634,28 @@ def nlmpc_eval(system, ph, ch, z, x0, params, want=("f", "grad", "ceq", "Jeq", "
                                      ptr["cin"], ptr["Jin"], ptr["cue"], ptr["Jue"], 0, None))
     del keep
     return out
+
+
+def nlmpc_output(system, ph, ch, z, x0, params, state_scale=None, input_scale=None):
+    """OptSequence::output of NLOptimizer::run (NLOptimizer.hpp:596-611): Model::getOutput (Model.hpp:72-96) of the unwrapped
+    sequences of z on the GPU -> [B, ph+1, ny]; zeros when the system has no output map (as the reference)."""
+    lib = load_library()
+    d = nlmpc_system_dims(system, ph)
+    z = np.ascontiguousarray(np.atleast_2d(z), dtype=np.float64)
+    B, nz = z.shape
+    if nz != ph * d["nx"] + ch * d["nu"] + 1:
+        raise ValueError("z has the wrong length")
+    x0 = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(x0), (B, d["nx"])), dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    ppi = 1 if params.ndim == 2 else 0
+    y = np.zeros((B, ph + 1, d["ny"]))
+    if d["ny"] == 0:
+        return y
+    sc, keep = _scaling_arg(d, state_scale, input_scale)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _check(lib.b200mpc_nlmpc_output(system, ph, ch, B, vp(z), vp(x0), vp(params), ppi, sc, vp(y), 0, None))
+    del keep
+    return y
 
 
 # ---- NLMPC solve (SURVEY.md K6/K7) -----------------------------------------------------------------------------------
@@ -820,7 +856,8 @@ class NLMPC:
         solver_status = np.where(r["status"] == 0, 4, 5).astype(np.int32)     # nlopt::XTOL_REACHED / MAXEVAL_REACHED
         self.result = Result(U[:, 0].copy(), r["cost"], status, solver_status, feas, r["iters"], r["qp_iters"], np.zeros(B, np.int32))
         self.result.viol = r["viol"]
-        self.sequence = OptSequence(X, U, X.copy())               # built-in systems use the identity output map
+        Y = nlmpc_output(self.system, ph, ch, z, x0, self.params, state_scale=self.state_scale, input_scale=self.input_scale)
+        self.sequence = OptSequence(X, U, Y)                      # sequence.output = model->getOutput(Xmat, Umat) (NLOptimizer.hpp:611)
         return self.result
 
     step = optimize

@@ -5,6 +5,7 @@
 // that would compute returns B200MPC_ENOGPU.
 #include "capi_common.h"
 #include "lmpc_kernels.cuh"
+#include "lmpc_cta_launch.h"
 
 #include <cstdio>
 #include <cstring>
@@ -51,6 +52,12 @@ struct b200mpc_lmpc {
     int gang = getenv("B200MPC_GANG") ? atoi(getenv("B200MPC_GANG")) : 1;     // B200MPC_SCHEDULE_GANG unless overridden
     int model_shared = 0;
     long long launches = 0;
+    // engine 2 (CTA per controller, lmpc_cta_kernels.cuh)
+    int engine_req = getenv("B200MPC_ENGINE") ? atoi(getenv("B200MPC_ENGINE")) : 0;   // 0 auto, 1 warp per controller, 2 CTA per controller
+    int engine = 0;                // what configure_launch selected
+    CtaLaunchCfg ctacfg;
+    int req_cta_threads = getenv("B200MPC_CTA_THREADS") ? atoi(getenv("B200MPC_CTA_THREADS")) : 0;
+    double time_limit = 0.0;
     std::vector<double> stage;   // host staging
 };
 
@@ -69,6 +76,7 @@ extern "C" void b200mpc_lmpc_default_params(b200mpc_lmpc_params* p) {
     p->adaptive_rho = 1; p->polish = 1;
     p->sigma = 1e-6; p->delta = 1e-6; p->adaptive_rho_tolerance = 5.0; p->scaling = 10; p->check_termination = 25;
     p->adaptive_rho_interval = 25; p->polish_refine_iter = 3;
+    p->time_limit = 0.0;
 }
 
 static int fill_const(b200mpc_lmpc* h, DevBuf& b, size_t count, double v) {
@@ -166,7 +174,7 @@ extern "C" int b200mpc_lmpc_destroy(b200mpc_lmpc_t h) {
                       &h->UMin, &h->UMax, &h->SMin, &h->SMax, &h->SX, &h->SU, &h->yRef, &h->uRef, &h->duRef, &h->uMeas};
     for (DevBuf* b : bufs) free_buf(*b);
     void* ptrs[] = {h->x0, h->u0, h->cmd, h->prev_cmd, h->cost, h->seq_state, h->seq_input, h->seq_output, h->sol_x, h->sol_y,
-                    h->status, h->solver_status, h->feasible, h->iters, h->rho_updates, h->polish, h->counter, h->workspace, h->prof};
+                    h->status, h->solver_status, h->feasible, h->iters, h->rho_updates, h->polish, h->counter, h->order, h->workspace, h->prof};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
     return B200MPC_OK;
@@ -188,6 +196,7 @@ extern "C" int b200mpc_lmpc_set_params(b200mpc_lmpc_t h, const b200mpc_lmpc_para
     p.alpha = q->alpha; p.rho = q->rho; p.sigma = q->sigma; p.delta = q->delta; p.eps_abs = q->eps_abs; p.eps_rel = q->eps_rel;
     p.eps_prim_inf = q->eps_prim_inf; p.eps_dual_inf = q->eps_dual_inf; p.adaptive_rho_tolerance = q->adaptive_rho_tolerance;
     h->enable_warm_start = q->enable_warm_start;
+    h->time_limit = q->time_limit > 0.0 ? q->time_limit : 0.0;
     return B200MPC_OK;
 }
 
@@ -273,6 +282,14 @@ extern "C" int b200mpc_lmpc_set_input_bounds(b200mpc_lmpc_t h, const double* lo,
     int rc;
     if ((rc = upload_input_bounds(h, h->UMin, lo, pi, dev))) return rc;
     return upload_input_bounds(h, h->UMax, hi, pi, dev);
+}
+// ProblemBuilder::setInputBounds(index, ...) (ProblemBuilder.hpp:469-477) writes ONE internal column and never re-replicates
+// the tail: the host mirrors keep the reference's internal [nu x ph] matrices and push all ph columns through this entry.
+extern "C" int b200mpc_lmpc_set_input_bounds_full(b200mpc_lmpc_t h, const double* lo, const double* hi, int pi, int dev) {
+    HCHECK();
+    int rc;
+    if ((rc = upload(h, h->UMin, lo, pi, dev))) return rc;
+    return upload(h, h->UMax, hi, pi, dev);
 }
 extern "C" int b200mpc_lmpc_set_scalar_constraint(b200mpc_lmpc_t h, const double* SMin, const double* SMax, const double* X,
                                                   const double* U, int pi, int dev) {
@@ -361,6 +378,9 @@ static int launch_t(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
         order_by_history_kernel<<<1, 1024, 0, h->stream>>>(h->iters, h->batch, h->p.check_termination > 0 ? h->p.check_termination : 25, h->order);
         order = h->order;
     }
+    // the attribute belongs to the kernel function, not to the handle: another handle of the same instantiation may have
+    // lowered it since this one was configured
+    CK(cudaFuncSetAttribute(lmpc_solve_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cta));
     lmpc_solve_kernel<DM><<<h->grid, h->warps_per_cta * 32, h->smem_cta, h->stream>>>(dm, h->p, pr, o, h->batch, h->workspace,
                                                                                       h->ws_stride, h->counter, h->model_shared, h->gang, order);
     CK(cudaGetLastError());
@@ -368,14 +388,58 @@ static int launch_t(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
 }
 static bool is_quad(const Dm& d) { return d.nx == 12 && d.nu == 4 && d.ndu == 4 && d.ny == 12; }
 
+// Engine selection.  Engine 2 (one CTA per controller, everything in shared memory: lmpc_cta_kernels.cuh) is used whenever
+// the controller's vectors fit the shared memory of an SM; engine 1 (one warp per controller, state streamed through TMA rings:
+// lmpc_kernels.cuh) otherwise, or when asked for (b200mpc_lmpc_set_engine / B200MPC_ENGINE).
 static int configure_launch(b200mpc_lmpc* h) {
     if (h->workspace) return B200MPC_OK;
-    if (!h->force_generic && is_quad(h->d)) return configure_t<DmQuad>(h);
+    const bool quad = !h->force_generic && is_quad(h->d);
+    const bool mshared = !h->A.per_instance && !h->B.per_instance && !h->C.per_instance && !h->SX.per_instance && !h->SU.per_instance;
+    if (h->engine_req != 1) {
+        CtaLaunchCfg cfg;
+        int rc = cta_configure(h->d, quad, h->device, h->num_sms, h->batch, h->req_cta_threads, &cfg);
+        if (rc == B200MPC_OK) {
+            h->ctacfg = cfg; h->engine = 2; h->model_shared = mshared ? 1 : 0;
+            CK(cudaMalloc(&h->workspace, (size_t)cfg.grid * (size_t)cfg.L.gtotal * sizeof(double)));
+            h->warps_per_cta = cfg.threads / 32; h->ctas_per_sm = 1; h->grid = cfg.grid; h->smem_cta = cfg.smem_bytes;
+            h->ws_stride = (size_t)cfg.L.gtotal;
+            return B200MPC_OK;
+        }
+        if (h->engine_req == 2) return rc;
+    }
+    h->engine = 1;
+    if (quad) return configure_t<DmQuad>(h);
     return configure_t<Dm>(h);
 }
 static int launch(b200mpc_lmpc* h, const Prob& pr, const Out& o) {
+    if (h->engine == 2) {
+        const int* order = nullptr;
+        if (h->history_order && h->has_iters && h->batch > h->grid) {      // longest-expected first (LPT over the persistent CTAs)
+            order_by_history_kernel<<<1, 1024, 0, h->stream>>>(h->iters, h->batch, h->p.check_termination > 0 ? h->p.check_termination : 25, h->order);
+            order = h->order;
+        }
+        return cta_launch(h->ctacfg, h->d, h->p, pr, o, h->batch, h->workspace, h->counter, h->model_shared, order, h->time_limit, h->stream);
+    }
     if (!h->force_generic && is_quad(h->d)) return launch_t<DmQuad>(h, pr, o);
     return launch_t<Dm>(h, pr, o);
+}
+
+extern "C" int b200mpc_lmpc_set_engine(b200mpc_lmpc_t h, int engine, int cta_threads) {
+    HCHECK();
+    if (engine < 0 || engine > 2 || (cta_threads != 0 && cta_threads != 256 && cta_threads != 384)) return fail(B200MPC_EINVAL, "bad engine");
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->workspace) { cudaFree(h->workspace); h->workspace = nullptr; }
+    h->engine_req = engine; h->req_cta_threads = cta_threads;
+    return configure_launch(h);
+}
+extern "C" int b200mpc_lmpc_get_engine(b200mpc_lmpc_t h, int* engine, int* threads_per_cta, int* factor_in_shared_memory) {
+    HCHECK();
+    int rc = configure_launch(h);
+    if (rc) return rc;
+    if (engine) *engine = h->engine;
+    if (threads_per_cta) *threads_per_cta = h->warps_per_cta * 32;
+    if (factor_in_shared_memory) *factor_in_shared_memory = h->engine == 2 ? h->ctacfg.L.fac_shared : 0;
+    return B200MPC_OK;
 }
 
 extern "C" int b200mpc_lmpc_set_schedule(b200mpc_lmpc_t h, int schedule) {
@@ -393,6 +457,7 @@ extern "C" int b200mpc_lmpc_set_launch(b200mpc_lmpc_t h, int warps_per_cta, int 
     if (warps_per_cta < -(B200_MAX_THREADS / 32) || warps_per_cta > B200_MAX_THREADS / 32 || ctas_per_sm < 0) return fail(B200MPC_EINVAL, "bad launch geometry");
     h->force_generic = warps_per_cta < 0;   // negative: use the runtime-dimension kernel (parity testing of both instantiations)
     if (warps_per_cta < 0) warps_per_cta = -warps_per_cta;
+    if (warps_per_cta > 0 || ctas_per_sm > 0) h->engine_req = 1;      // an explicit warp geometry is a request for the warp-per-controller engine
     CK(cudaStreamSynchronize(h->stream));
     if (h->workspace) { cudaFree(h->workspace); h->workspace = nullptr; }
     h->req_wpc = warps_per_cta; h->req_cps = ctas_per_sm;

@@ -18,7 +18,7 @@ extern template int nl_solve_t<SysOscNet<6>>(NlSolveArgs&, cudaStream_t, std::ve
 extern template int nl_solve_t<SysUgv>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);
 // user-defined systems (b200mpc_nlmpc_rtc.cu)
 bool rtc_is_user(int system);
-int rtc_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq, int* neq);
+int rtc_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq, int* neq, int* ny = nullptr, int* has_out = nullptr);
 int rtc_eval(int system, const NlEvalArgs& a, cudaStream_t stream);
 int rtc_solve(int system, NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree);
 }
@@ -42,6 +42,23 @@ extern "C" int b200mpc_nlmpc_system_dims(int system, int ph, int* nx, int* nu, i
     int rc = nl_dims(system, &a, &b, &c, ph, &d, &e);
     if (rc) return rc;
     if (nx) *nx = a; if (nu) *nu = b; if (nparam) *nparam = c; if (nineq) *nineq = d;
+    return B200MPC_OK;
+}
+// Tny of the system and whether it defines an output map (NLMPC::setOutputFunction, NLMPC.hpp:202)
+extern "C" int b200mpc_nlmpc_system_ny(int system, int ph, int* ny, int* has_output_map) {
+    int v = 0, ho = 0;
+    switch (system) {
+    case B200MPC_SYS_VANDERPOL: v = 2; break;
+    case B200MPC_SYS_OSCNET4: v = 8; break;
+    case B200MPC_SYS_OSCNET6: v = 12; break;
+    case B200MPC_SYS_UGV: v = 4; ho = 1; break;
+    default: {
+        if (!rtc_is_user(system)) return fail(B200MPC_EINVAL, "unknown system id");
+        int rc = rtc_dims(system, ph, nullptr, nullptr, nullptr, nullptr, nullptr, &v, &ho);
+        if (rc) return rc;
+    }
+    }
+    if (ny) *ny = v; if (has_output_map) *has_output_map = ho;
     return B200MPC_OK;
 }
 extern "C" int b200mpc_nlmpc_system_neq(int system, int ph, int* neq) {
@@ -90,10 +107,32 @@ extern "C" int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const d
                                  nullptr, nullptr, dev, stream_);
 }
 
+static int nl_eval_impl(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
+                        int params_per_instance, const b200mpc_nlmpc_scaling* scaling, double* fval, double* grad,
+                        double* ceq, double* Jeq, double* cin, double* Jin, double* cue, double* Jue, double* yout, int dev,
+                        void* stream_);
+
 extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
                                      int params_per_instance, const b200mpc_nlmpc_scaling* scaling, double* fval, double* grad,
                                      double* ceq, double* Jeq, double* cin, double* Jin, double* cue, double* Jue, int dev,
                                      void* stream_) {
+    return nl_eval_impl(system, ph, ch, batch, z, x0, params, params_per_instance, scaling, fval, grad, ceq, Jeq, cin, Jin, cue, Jue,
+                        nullptr, dev, stream_);
+}
+
+// OptSequence::output of NLOptimizer::run (NLOptimizer.hpp:596-611): Model::getOutput (Model.hpp:72-96) of the unwrapped
+// sequences of z, y[batch*(ph+1)*ny]; zeros for a system without an output map, exactly as the reference.
+extern "C" int b200mpc_nlmpc_output(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
+                                    int params_per_instance, const b200mpc_nlmpc_scaling* scaling, double* y, int dev, void* stream_) {
+    if (!y) return fail(B200MPC_EINVAL, "null output pointer");
+    return nl_eval_impl(system, ph, ch, batch, z, x0, params, params_per_instance, scaling, nullptr, nullptr, nullptr, nullptr, nullptr,
+                        nullptr, nullptr, nullptr, y, dev, stream_);
+}
+
+static int nl_eval_impl(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
+                        int params_per_instance, const b200mpc_nlmpc_scaling* scaling, double* fval, double* grad,
+                        double* ceq, double* Jeq, double* cin, double* Jin, double* cue, double* Jue, double* yout, int dev,
+                        void* stream_) {
     if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
     int nx, nu, np, ni, nue, rc0;
     if ((rc0 = nl_dims(system, &nx, &nu, &np, ph, &ni, &nue))) return rc0;
@@ -103,7 +142,11 @@ extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, cons
     const int nz = ph * nx + ch * nu + 1;
     NlEvalArgs a;
     a.ph = ph; a.ch = ch; a.batch = batch; a.param_stride = params_per_instance ? np : 0;
+    int ny = 0;
+    if (yout && (rc0 = b200mpc_nlmpc_system_ny(system, ph, &ny, nullptr))) return rc0;
     std::vector<void*> tofree;
+    // every temporary is released on every exit path (stream-ordered: after the work enqueued so far)
+    struct Free { std::vector<void*>& v; cudaStream_t s; ~Free() { for (void* p : v) cudaFreeAsync(p, s); } } freer{tofree, stream};
     auto in = [&](const double* h, size_t n, const double** d) -> int {
         if (dev) { *d = h; return 0; }
         double* p = nullptr;
@@ -130,8 +173,8 @@ extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, cons
     if ((rc = out(Jin, (size_t)batch * ni * nz, &a.Jin))) return rc;
     if ((rc = out(nue ? cue : nullptr, (size_t)batch * nue, &a.cue))) return rc;
     if ((rc = out(nue ? Jue : nullptr, (size_t)batch * nue * nz, &a.Jue))) return rc;
-    std::vector<void*> async_free;
-    if ((rc = stage_scaling(scaling, nx, nu, &a.sx, &a.su, stream, async_free))) return rc;
+    if ((rc = out(ny ? yout : nullptr, (size_t)batch * (ph + 1) * ny, &a.yout))) return rc;
+    if ((rc = stage_scaling(scaling, nx, nu, &a.sx, &a.su, stream, tofree))) return rc;
     switch (system) {
     case B200MPC_SYS_VANDERPOL: rc = nl_eval_t<SysVanDerPol>(a, stream); break;
     case B200MPC_SYS_OSCNET4: rc = nl_eval_t<SysOscNet<4>>(a, stream); break;
@@ -139,7 +182,6 @@ extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, cons
     case B200MPC_SYS_UGV: rc = nl_eval_t<SysUgv>(a, stream); break;
     default: rc = rtc_eval(system, a, stream); break;
     }
-    for (void* p : async_free) cudaFreeAsync(p, stream);
     if (rc) return rc;
     if (!dev) {
         auto back = [&](double* h, const double* d, size_t n) -> int { if (h) CK(cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, stream)); return 0; };
@@ -151,8 +193,8 @@ extern "C" int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, cons
         if ((rc = back(Jin, a.Jin, (size_t)batch * ni * nz))) return rc;
         if (nue && (rc = back(cue, a.cue, (size_t)batch * nue))) return rc;
         if (nue && (rc = back(Jue, a.Jue, (size_t)batch * nue * nz))) return rc;
+        if (ny && (rc = back(yout, a.yout, (size_t)batch * (ph + 1) * ny))) return rc;
         CK(cudaStreamSynchronize(stream));
-        for (void* p : tofree) cudaFreeAsync(p, stream);
     }
     return B200MPC_OK;
 }

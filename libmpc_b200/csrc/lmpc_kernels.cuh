@@ -1509,7 +1509,7 @@ __global__ void __launch_bounds__(B200_MAX_THREADS, 1) lmpc_solve_kernel(const _
 // (counting sort on iters / check_termination; one CTA).  Consecutive MPC steps of a controller need similar iteration
 // counts, so (i) the members of a gang finish together instead of waiting for one straggler and (ii) the long instances
 // start first (longest-processing-time-first).  Results do not depend on the order.
-__global__ void order_by_history_kernel(const int* iters, int batch, int bucket, int* order) {
+static __global__ void order_by_history_kernel(const int* iters, int batch, int bucket, int* order) {
     constexpr int NB = 1024;
     __shared__ int hist[NB];
     for (int k = threadIdx.x; k < NB; k += blockDim.x) hist[k] = 0;

@@ -38,6 +38,11 @@ template <class S> __host__ __device__ inline int nl_neq(int ph) { if constexpr 
 template <class S, class = void> struct NlIneqPerStage { static constexpr int value = 0; };
 template <class S> struct NlIneqPerStage<S, decltype((void)S::ineq_per_stage)> { static constexpr int value = S::ineq_per_stage; };
 
+// Optional output map (NLMPC::setOutputFunction, NLMPC.hpp:202): a system may define
+//   __device__ static void out(double* y, const double* x, const double* u, int i, const double* p);
+template <class S, class = void> struct NlHasOut { static constexpr bool value = false; };
+template <class S> struct NlHasOut<S, decltype((void)&S::out)> { static constexpr bool value = true; };
+
 // X [(ph+1) x nx], U [(ph+1) x nu] row-major in shared memory + one (or a pair of) perturbed entries
 struct Acc {
     const double* X; const double* U; int nx, nu;
@@ -132,6 +137,9 @@ struct SysUgv {
             xn[r] = v + w;
         }
     }
+    __device__ static void out(double* y, const double* x, const double*, int, const double*) {      // ugv_ex.cpp:69-77, Cd = I, Dd = 0
+        for (int r = 0; r < 4; ++r) y[r] = x[r];
+    }
     __device__ static double cost(const Acc& a, double e, int ph, const double* p) {
         double cost = 0;
         for (int i = 0; i <= ph; ++i) {
@@ -202,6 +210,7 @@ struct NlEvalArgs {
     double* Jue;            // [batch, neq, nz]
     const double* sx;       // [nx] state scaling  (NLMPC::setStateScale, Mapping.hpp:108-130); null = 1
     const double* su;       // [nu] input scaling  (NLMPC::setInputScale); null = 1
+    double* yout;           // [batch, ph+1, ny]  Model::getOutput of the unwrapped sequences (Model.hpp:72-96); may be null
 };
 
 // ---- evaluation of one instance by one thread group (shared by the evaluation kernel and by the SQP kernel) ----------
@@ -436,6 +445,19 @@ __global__ void __launch_bounds__(128) nlmpc_eval_kernel(const NlEvalArgs a) {
                             a.ceq ? a.ceq + (size_t)inst * ph * nx : nullptr, a.Jeq ? a.Jeq + (size_t)inst * ph * nx * nz : nullptr,
                             a.cin ? a.cin + (size_t)inst * ni : nullptr, a.Jin ? a.Jin + (size_t)inst * ni * nz : nullptr, nz, a.sx, a.su,
                             a.cue ? a.cue + (size_t)inst * nue : nullptr, a.Jue ? a.Jue + (size_t)inst * nue * nz : nullptr);
+        if (a.yout) {
+            // OptSequence::output = Model::getOutput(Xmat, Umat) (NLOptimizer.hpp:596-611, Model.hpp:72-96): the output map of
+            // every row of the unwrapped sequences; all zeros when the system has no output map, as in the reference.
+            constexpr int ny = S::ny;
+            double* Y = a.yout + (size_t)inst * (ph + 1) * ny;
+            for (int i = lane; i <= ph; i += 32) {
+                double y[ny > 0 ? ny : 1];
+                for (int r = 0; r < ny; ++r) y[r] = 0.0;
+                if constexpr (NlHasOut<S>::value) S::out(y, X + i * nx, U + i * nu, i, a.params + (size_t)inst * a.param_stride);
+                for (int r = 0; r < ny; ++r) Y[i * ny + r] = y[r];
+            }
+            __syncwarp();
+        }
     }
 }
 

@@ -123,7 +123,55 @@ def nlmpc_solve_fixture():
     np.savez_compressed(os.path.join(HERE, "nlmpc_solve.npz"), x0=x0, z=z, cmd=cmd, cost=cost, success=ok)
 
 
+def nlmpc_unicycle_fixture(B=8):
+    """BASELINE.json configs[2] at its stated shape (unicycle nx3 nu2 Tph=Tch=30, 2 obstacles): the first B
+    instances of the bench workload (libmpc_b200.workloads.unicycle_inputs, seed 30), cold start, SLSQP-oracle optimum."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from user_systems import unicycle_formulation
+    from libmpc_b200.workloads import unicycle_inputs, cold_start, soft_bounds
+    x0, params = unicycle_inputs(0, B)
+    f0 = unicycle_formulation(params=params[0])
+    lb, ub = soft_bounds(f0.nz)
+    z0 = cold_start(x0, np.zeros(2), 30, 30)
+    z = np.zeros((B, f0.nz)); cmd = np.zeros((B, 2)); cost = np.zeros(B); ok = np.zeros(B, dtype=np.int64); nit = np.zeros(B, dtype=np.int64)
+    for b in range(B):
+        f = unicycle_formulation(params=params[b])
+        r = S.solve(f, x0[b], z0[b], lb, ub, maxiter=600)
+        z[b] = r["z"]; cmd[b] = r["cmd"]; cost[b] = r["cost"]; ok[b] = int(r["success"]); nit[b] = r["nit"]
+        print("unicycle", b, r["success"], r["nit"], r["cost"], flush=True)
+    np.savez_compressed(os.path.join(HERE, "nlmpc_unicycle.npz"), x0=x0, params=params, z0=z0, z=z, cmd=cmd, cost=cost, success=ok, nit=nit)
+
+
+def nlmpc_output_fixture():
+    """A system with an output map (NLMPC::setOutputFunction): evaluation through Y and OptSequence::output of the optimum."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from user_systems import output_map_formulation
+    f = output_map_formulation()
+    rng = np.random.default_rng(5)
+    B = 4
+    z = rng.standard_normal((B, f.nz)) * 0.6; z[:, -1] = 0.0
+    x0 = rng.uniform(-0.5, 0.5, (B, 2))
+    out = dict(z=z, x0=x0, params=f.params)
+    fv = np.zeros(B); g = np.zeros((B, f.nz)); ci = np.zeros((B, f.nineq)); Ji = np.zeros((B, f.nineq, f.nz)); Y = np.zeros((B, f.ph + 1, f.ny))
+    for b in range(B):
+        fv[b], g[b] = f.objective(z[b], x0[b]); ci[b], Ji[b] = f.ineq_con(z[b], x0[b])
+        X, U, e = f.unwrap(z[b], x0[b]); Y[b] = f.output(X, U)
+    out.update(f=fv, grad=g, cin=ci, Jin=Ji, Y=Y)
+    lb, ub = S.default_bounds(f, True)
+    zs = np.zeros((B, f.nz)); Ys = np.zeros((B, f.ph + 1, f.ny)); cost = np.zeros(B); ok = np.zeros(B, dtype=np.int64)
+    for b in range(B):
+        z0 = S.initial_guess(f, x0[b], np.zeros(1), lb=lb, ub=ub)
+        r = S.solve(f, x0[b], z0, lb, ub, maxiter=400)
+        zs[b] = r["z"]; cost[b] = r["cost"]; ok[b] = int(r["success"]); Ys[b] = f.output(r["state"], r["input"])
+    out.update(sol_z=zs, sol_Y=Ys, sol_cost=cost, sol_success=ok)
+    np.savez_compressed(os.path.join(HERE, "nlmpc_output_map.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--unicycle" in sys.argv:
+        nlmpc_unicycle_fixture(); sys.exit(0)
+    if "--output-map" in sys.argv:
+        nlmpc_output_fixture(); sys.exit(0)
     with open(os.path.join(HERE, "reference_kats.json"), "w") as fh:
         json.dump(REFERENCE_KATS, fh, indent=1)
     lmpc_fixture()

@@ -1,0 +1,124 @@
+"""GPU: the BASELINE.json configurations that had never touched a GPU.
+
+* configs[2] AT ITS STATED SHAPE: unicycle nx=3 nu=2 Tph=Tch=30 with two obstacle inequalities per stage
+  (Tineq=62), soft constraints, registered as a user-defined system (the model is not in the reference: its ugv_ex is a double
+  integrator -- examples/ugv_ex.cpp:79-115 gives the shape of the cost / obstacle constraint).  Evaluation level vs the numpy
+  oracle, solve level vs the committed SLSQP-oracle fixture (tests/golden/nlmpc_unicycle.npz; NLopt's LD_SLSQP call that has no
+  upstream pin: NLOptimizer.hpp:519) at command 1e-5 / cost 1e-7.
+* the output map on the device (NLMPC::setOutputFunction -> Model::getOutput, Model.hpp:72-96, used by NLOptimizer.hpp:596-611
+  to fill OptSequence::output).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+from libmpc_b200 import workloads as W
+from user_systems import OUTPUT_MAP_SRC, output_map_formulation, unicycle_formulation
+
+_ids = {}
+
+
+def _sys(src, name):
+    import libmpc_b200 as L
+    if name not in _ids:
+        _ids[name] = L.register_system(src, name)
+    return _ids[name]
+
+
+def test_unicycle_cfg2_evaluation_matches_oracle():
+    import libmpc_b200 as L
+    sid = _sys(W.UNICYCLE_SRC, W.UNICYCLE_TYPE)
+    d = L.nlmpc_system_dims(sid, 30)
+    assert (d["nx"], d["nu"], d["nparam"], d["nineq"], d["neq"], d["ny"]) == (3, 2, 9, 62, 0, 3)
+    x0, params = W.unicycle_inputs(0, 3)
+    rng = np.random.default_rng(31)
+    z = rng.standard_normal((3, 151)) * 0.8
+    z[:, -1] = np.abs(z[:, -1]) * 0.1
+    out = L.nlmpc_eval(sid, 30, 30, z, x0, params)
+    for b in range(3):
+        f = unicycle_formulation(params=params[b])
+        fv, g = f.objective(z[b], x0[b]); c, J = f.state_eq(z[b], x0[b]); ci, Ji = f.ineq_con(z[b], x0[b])
+        assert abs(out["f"][b] - fv) <= 1e-12 * max(1, abs(fv))
+        assert np.allclose(out["ceq"][b], c, rtol=1e-12, atol=1e-13)
+        assert np.allclose(out["cin"][b], ci, rtol=1e-12, atol=1e-13)
+        assert np.allclose(out["grad"][b], g, rtol=1e-6, atol=5e-7 * max(1.0, abs(fv)))
+        assert np.allclose(out["Jeq"][b], J, rtol=1e-6, atol=5e-7)
+        assert np.allclose(out["Jin"][b], Ji, rtol=1e-6, atol=5e-7)
+        assert np.array_equal(out["Jeq"][b] != 0, J != 0)
+
+
+def test_unicycle_cfg2_solve_batch64_matches_slsqp_fixture():
+    """Batch 64 of the bench workload; the first 8 instances are pinned by the SLSQP-oracle fixture (cold start, soft
+    constraints).  Tolerances: first command 1e-5 relative, cost 1e-7 relative."""
+    import libmpc_b200 as L
+    sid = _sys(W.UNICYCLE_SRC, W.UNICYCLE_TYPE)
+    g = np.load(os.path.join(GOLD, "nlmpc_unicycle.npz"))
+    B, ph, ch, nx, nu = 64, 30, 30, 3, 2
+    x0, params = W.unicycle_inputs(0, B)
+    assert np.array_equal(x0[:8], g["x0"]) and np.array_equal(params[:8], g["params"])
+    z0 = W.cold_start(x0, np.zeros(nu), ph, ch)
+    lb, ub = W.soft_bounds(ph * nx + ch * nu + 1)
+    out = L.nlmpc_solve(sid, ph, ch, z0, x0, params, lb, ub, max_sqp=300)
+    assert (out["status"] == 0).all(), np.unique(out["status"], return_counts=True)
+    assert (out["viol"] < 1e-6).all(), out["viol"].max()
+    ok = g["success"].astype(bool)
+    assert ok.all()
+    cmd = out["z"][:8, ph * nx:ph * nx + nu]
+    rel_cost = np.abs(out["cost"][:8] - g["cost"]) / np.maximum(1.0, np.abs(g["cost"]))
+    rel_cmd = np.abs(cmd - g["cmd"]).max(axis=1) / np.maximum(1.0, np.abs(g["cmd"]).max(axis=1))
+    assert rel_cost.max() < 1e-7, rel_cost
+    assert rel_cmd.max() < 1e-5, rel_cmd
+    # the other 56: a feasible stationary point no worse than the cold start's cost scale (size-independent sanity)
+    assert np.isfinite(out["cost"]).all() and (out["cost"] > 0).all() and (out["cost"] < 400).all()
+
+
+def test_output_map_evaluation_and_sequence_output():
+    """cost / ineq read Y = out(X, U); OptSequence::output = Model::getOutput of the optimum."""
+    import libmpc_b200 as L
+    g = np.load(os.path.join(GOLD, "nlmpc_output_map.npz"))
+    f = output_map_formulation()
+    sid = _sys(OUTPUT_MAP_SRC, "UserWithOutput")
+    d = L.nlmpc_system_dims(sid, f.ph)
+    assert d["ny"] == 1 and d["has_output_map"]
+    z, x0 = g["z"], g["x0"]
+    out = L.nlmpc_eval(sid, f.ph, f.ch, z, x0, g["params"])
+    assert np.allclose(out["f"], g["f"], rtol=1e-12, atol=0)
+    assert np.allclose(out["cin"], g["cin"], rtol=1e-12, atol=1e-13)
+    assert np.allclose(out["grad"], g["grad"], rtol=1e-6, atol=5e-7 * max(1.0, np.abs(g["f"]).max()))
+    assert np.allclose(out["Jin"], g["Jin"], rtol=1e-6, atol=5e-7)
+    Y = L.nlmpc_output(sid, f.ph, f.ch, z, x0, g["params"])
+    assert Y.shape == (4, f.ph + 1, 1)
+    assert np.allclose(Y, g["Y"], rtol=1e-13, atol=1e-14)
+    # through the NLMPC mirror: optimize() -> getOptimalSequence().output
+    ctl = L.NLMPC(sid, f.ph, f.ch, batch=4)
+    ctl.setSystemParameters(g["params"])
+    res = ctl.optimize(x0, np.zeros((4, 1)))
+    seq = ctl.getOptimalSequence()
+    ok = g["sol_success"].astype(bool)
+    assert ok.sum() >= 3
+    assert np.abs(res.cost[ok] - g["sol_cost"][ok]).max() < 1e-7 * max(1.0, np.abs(g["sol_cost"][ok]).max())
+    assert np.abs(seq.output[ok] - g["sol_Y"][ok]).max() < 1e-5
+    for b in range(4):                                        # and it is exactly the map of the returned sequences
+        X, U = seq.state[b], seq.input[b]
+        assert np.allclose(seq.output[b, :, 0], X[:, 0] + 0.5 * X[:, 1] ** 2, rtol=1e-13, atol=1e-14)
+
+
+def test_builtin_systems_output_follows_the_reference():
+    """ugv_ex sets y = Cd x + Dd u with Cd = I, Dd = 0 (ugv_ex.cpp:69-77); vanderpol_ex sets no output function, so
+    Model::getOutput returns zeros (Model.hpp:82-84)."""
+    import libmpc_b200 as L
+    from oracle.nlmpc_formulation import ugv_formulation
+    f = ugv_formulation(10, 10, v_pref=(0.6, 0.8))
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((2, f.nz)); x0 = rng.uniform(-0.5, 0.5, (2, 4))
+    Y = L.nlmpc_output(L.SYS_UGV, 10, 10, z, x0, f.params)
+    for b in range(2):
+        X, U, _ = f.unwrap(z[b], x0[b])
+        assert np.array_equal(Y[b], X)
+    zv = rng.standard_normal((2, 26)); xv = rng.uniform(-1, 1, (2, 2))
+    assert (L.nlmpc_output(L.SYS_VANDERPOL, 10, 5, zv, xv, np.array([0.1])) == 0).all()

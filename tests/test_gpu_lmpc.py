@@ -201,3 +201,69 @@ def test_no_fallback_symbols_loaded():
     lib = L.load_library()
     assert lib.b200mpc_device_count() >= 1
     assert L.LIB_PATH.endswith("libmpc_b200/libb200mpc.so")
+
+
+def test_input_bound_tail_after_slice_set_with_ch_lt_ph():
+    """the matrix setter replicates column ch-1 into the tail ch..ph-1 (ProblemBuilder.hpp:397-413) but the per-index
+    setter writes ONE column and leaves the tail alone (ProblemBuilder.hpp:469-477).  Tight bounds everywhere, then step ch-1
+    loosened through the slice setter: the tail must stay tight on the device, as in the reference."""
+    import libmpc_b200 as L
+    nx, nu, ph, ch = 2, 1, 6, 3
+    Ad, Bdm = discretization(np.array([[0, 1.0], [0, 0.0]]), np.array([[0.0], [1.0]]), 0.1)
+    f = LMPCFormulation(nx, nu, 0, nx, ph, ch)
+    f.set_state_space_model(Ad, Bdm, np.eye(nx))
+    f.set_objective_weights(np.array([10.0, 1.0]), np.array([0.01]), np.array([0.0]))
+    f.set_input_bounds(np.full((nu, ch), -0.2), np.full((nu, ch), 0.2))
+    f.set_input_bounds_at(ch - 1, np.array([-5.0]), np.array([5.0]))
+    f.set_references(np.array([1.0, 0.0]), np.zeros(nu), np.zeros(nu))
+    c = L.LMPC(nx, nu, 0, nx, ph, ch, batch=2)
+    assert c.setStateSpaceModel(Ad, Bdm, np.eye(nx))
+    assert c.setObjectiveWeights(np.array([10.0, 1.0]), np.array([0.01]), np.array([0.0]), L.HorizonSlice.all())
+    assert c.setInputBounds(np.full((nu, ch), -0.2), np.full((nu, ch), 0.2))
+    assert c.setInputBounds(np.array([-5.0]), np.array([5.0]), (ch - 1, ch))
+    assert c.setReferences(np.array([1.0, 0.0]), np.zeros(nu), np.zeros(nu), L.HorizonSlice.all())
+    assert np.array_equal(c._st["UMin"][..., 0, :], f.minU[0]) and np.array_equal(c._st["UMax"][..., 0, :], f.maxU[0])
+    assert f.maxU[0, ch - 1] == 5.0 and (f.maxU[0, ch:] == 0.2).all()
+    c.setOptimizerParameters(L.LParameters(maximum_iteration=2000))
+    x0 = np.array([[0.0, 0.0], [0.3, -0.1]]); u0 = np.zeros((2, nu))
+    res = c.optimize(x0, u0)
+    seq = c.getOptimalSequence()
+    for b in range(2):
+        r = lmpc_optimize(f, x0[b], u0[b], Settings(max_iter=2000))
+        assert res.solver_status[b] == r["solver_status"] and res.iterations[b] == r["iter"]
+        assert _relerr(res.cmd[b], r["cmd"]) < REL
+        assert np.abs(seq.input[b] - r["input"]).max() < 1e-6
+    # the tail obeys the TIGHT bound (it would reach 5 if the device had re-replicated column ch-1)
+    # (an un-polished ADMM solution honours a bound to ~eps_abs = 1e-4, hence the 1e-3)
+    assert np.abs(seq.input[:, ch + 1:, 0]).max() <= 0.2 + 1e-3 and np.abs(seq.input[:, :, 0]).max() > 0.25
+
+
+def test_two_live_handles_of_different_sizes_interleaved():
+    """the dynamic-shared-memory attribute belongs to the kernel function, not to a handle; a second, smaller handle
+    must not break the first one's next launch."""
+    import libmpc_b200 as L
+    rng = np.random.default_rng(5)
+
+    def make(ph, B):
+        nx, nu = 3, 2
+        A = np.eye(nx) + 0.1 * rng.standard_normal((nx, nx)); Bm = rng.standard_normal((nx, nu))
+        f = LMPCFormulation(nx, nu, 0, nx, ph, ph)
+        f.set_state_space_model(A, Bm, np.eye(nx)); f.set_objective_weights(np.ones(nx), 0.1 * np.ones(nu), np.zeros(nu))
+        f.set_input_bounds(np.full(nu, -1.0), np.full(nu, 1.0)); f.set_references(np.ones(nx) * 0.2, np.zeros(nu), np.zeros(nu))
+        c = L.LMPC(nx, nu, 0, nx, ph, ph, batch=B)
+        c.setStateSpaceModel(A, Bm, np.eye(nx)); c.setObjectiveWeights(np.ones(nx), 0.1 * np.ones(nu), np.zeros(nu), L.HorizonSlice.all())
+        c.setInputBounds(np.full(nu, -1.0), np.full(nu, 1.0), L.HorizonSlice.all())
+        c.setReferences(np.ones(nx) * 0.2, np.zeros(nu), np.zeros(nu), L.HorizonSlice.all())
+        c.setOptimizerParameters(L.LParameters(maximum_iteration=1000))
+        return f, c, rng.uniform(-0.3, 0.3, (B, nx))
+    fa, ca, xa = make(12, 5)
+    ra0 = ca.optimize(xa, np.zeros((5, 2)))
+    fb, cb, xb = make(2, 3)                                   # much smaller shared-memory footprint
+    rb = cb.optimize(xb, np.zeros((3, 2)))
+    ra1 = ca.optimize(xa, np.zeros((5, 2)))                   # the older handle again
+    rb1 = cb.optimize(xb, np.zeros((3, 2)))
+    assert np.array_equal(ra0.cmd, ra1.cmd) and np.array_equal(rb.cmd, rb1.cmd)
+    for f, res, x in ((fa, ra1, xa), (fb, rb1, xb)):
+        for b in range(len(x)):
+            r = lmpc_optimize(f, x[b], np.zeros(2), Settings(max_iter=1000))
+            assert res.iterations[b] == r["iter"] and _relerr(res.cmd[b], r["cmd"]) < REL

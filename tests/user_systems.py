@@ -78,38 +78,9 @@ struct UserWithOutput {
 };
 """
 
-# BASELINE.json configs[2] at its stated shape (SURVEY.md 8d row 3b): unicycle x = [px, py, theta], u = [v, omega], discrete
-# x+ = x + Ts [v cos(theta), v sin(theta), omega], Tph = Tch = 30, two circular obstacles on (px, py) -> Tineq = 62, soft
-# constraints; cost 10 |p - p_goal|^2 + 1e-2 |u|^2 + 1e-5 e^2.  The model is NOT in the reference (its ugv_ex is a double
-# integrator with nx = 4), so this shape exists only as a user-defined system.  params = [Ts, goal(2), obs0(x,y,r), obs1(x,y,r)].
-UNICYCLE_SRC = r"""
-struct UserUnicycle {
-    static constexpr int nx = 3, nu = 2, ny = 3, nparam = 9, nobs = 2;
-    static constexpr bool continuous = false;
-    static constexpr int ineq_per_stage = nobs;
-    __device__ static double Ts(const double*) { return 0.0; }
-    __host__ __device__ static int nineq(int ph) { return (ph + 1) * nobs; }
-    __device__ static void f(double* xn, const double* x, const double* u, int, const double* p) {
-        xn[0] = x[0] + p[0] * (u[0] * cos(x[2]));
-        xn[1] = x[1] + p[0] * (u[0] * sin(x[2]));
-        xn[2] = x[2] + p[0] * u[1];
-    }
-    __device__ static double cost(const Acc& a, double e, int ph, const double* p) {
-        double c = 0;
-        for (int i = 0; i <= ph; ++i) {
-            double d0 = a.x(i, 0) - p[1], d1 = a.x(i, 1) - p[2], u0 = a.u(i, 0), u1 = a.u(i, 1);
-            c += 1e1 * (d0 * d0 + d1 * d1);
-            c += 1e-2 * (u0 * u0 + u1 * u1);
-        }
-        return c + 1e-5 * e * e;
-    }
-    __device__ static double ineq(int r, const Acc& a, double, int, const double* p) {
-        int i = r / nobs, j = r % nobs;
-        double dx = a.x(i, 0) - p[3 + 3 * j], dy = a.x(i, 1) - p[3 + 3 * j + 1];
-        return p[3 + 3 * j + 2] - sqrt(dx * dx + dy * dy);
-    }
-};
-"""
+# BASELINE.json configs[2] at its stated shape (SURVEY.md 8d row 3b): the CUDA source lives with the workload definitions
+# (bench.py measures it); the oracle-side formulation is unicycle_formulation below.
+from libmpc_b200.workloads import UNICYCLE_SRC  # noqa: E402,F401
 
 BROKEN_SRC = "struct Broken { static constexpr int nx = 2; int oops( };"
 
@@ -151,8 +122,12 @@ def output_map_formulation(ph=6, ch=3, Ts=0.1):
     return f
 
 
-def unicycle_formulation(ph=30, ch=30, Ts=0.1, goal=(2.0, 2.0), obstacles=((1.0, 0.6, 0.3), (1.4, 1.7, 0.3))):
-    """Oracle side of UNICYCLE_SRC (BASELINE.json configs[2] shape)."""
+def unicycle_formulation(ph=30, ch=30, Ts=0.1, goal=(2.0, 2.0), obstacles=((1.0, 0.6, 0.3), (1.4, 1.7, 0.3)), params=None):
+    """Oracle side of UNICYCLE_SRC (BASELINE.json configs[2] shape).  `params` = one row of
+    libmpc_b200.workloads.unicycle_inputs ([Ts, goal(2), obs0(3), obs1(3)]) overrides the keyword values."""
+    if params is not None:
+        params = np.asarray(params, float)
+        Ts, goal, obstacles = float(params[0]), params[1:3], params[3:9].reshape(2, 3)
     obs = np.asarray(obstacles, float); goal = np.asarray(goal, float)
     f = NLMPCFormulation(3, 2, 3, ph, ch, nineq=(ph + 1) * len(obs))
     f.continuous = False
