@@ -1,13 +1,17 @@
 #!/usr/bin/env python
-"""bench.py -- batched LMPC solves/s on B200 (BASELINE.json metric), one process per GPU.
+"""bench.py -- batched MPC solves/s on B200 (BASELINE.json metric), one process per GPU.
 
   python bench.py --gpus 1 --steps K --warmup W            # our CUDA engine
   python bench.py --impl reference ...                     # the CPU oracle (restated reference path) on host cores
-  torchrun --nproc-per-node N bench.py --gpus N ...        # weak scaling: every rank owns `--batch` instances
+  torchrun --nproc-per-node N bench.py --gpus N ...        # weak scaling: every rank owns `--batch` controllers
+  ... --global-batch 65536 --ph 50                         # strong scaling: a fixed global batch split over the ranks (configs[4])
 
-A "step" is one batched IOptimizer::run over all instances of the workload configs[1] of BASELINE.json:
-quadrotor LMPC nx=12 nu=4 ny=12 ph=ch=20, batch 4096 per GPU, maximum_iteration=250, synthetic x0 / yRef (seed 20,
-instance b drawn from PCG64(seed+b)).  Prints ONE JSON line (rank 0).
+A "step" is one batched IOptimizer::run over all controllers of BASELINE.json configs[1]: quadrotor LMPC nx=12 nu=4 ny=12
+ph=ch=20, batch 4096 per GPU, maximum_iteration=250, synthetic x0 / yRef (seed 20, controller b drawn from PCG64(seed+b);
+SURVEY.md 8d).  The timed steps form a CLOSED LOOP: after every solve the plant advances, x+ = A x + B u, u0 <- cmd
+(examples/quadrotor_ex.cpp), so every step solves a new batch and the scheduling history is real, not replayed.
+Prints ONE JSON line (rank 0).  The same line carries `nlmpc`: BASELINE configs[2] (unicycle nx3 nu2 Tph30, batch 1024) and
+configs[3] (networked oscillators nx8 nu4 Tph15, batch 8192 globally) with their own CPU baselines.
 """
 import argparse
 import json
@@ -22,25 +26,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NX, NU, NDU, NY = 12, 4, 4, 12
-X0_SCALE = np.array([0.2, 0.2, 0.5, 0.5, 0.5, 0.5] + [0.3] * 6)
+from libmpc_b200 import workloads as W      # noqa: E402  (data only: no oracle, no CUDA)
 
-
-def synth_inputs(first, count, seed=20):
-    """x0 ~ U(-1,1)*scale clipped into the state box, u0 = 0, yRef = [0,0,r,0..], r ~ U(0.5,1.5)."""
-    x0 = np.empty((count, NX))
-    r = np.empty(count)
-    for k in range(count):
-        g = np.random.Generator(np.random.PCG64(seed + first + k))
-        x0[k] = g.uniform(-1, 1, NX) * X0_SCALE
-        r[k] = g.uniform(0.5, 1.5)
-    x0[:, 0:2] = np.clip(x0[:, 0:2], -np.pi / 6, np.pi / 6)
-    x0[:, 5] = np.maximum(x0[:, 5], -1.0)
-    return x0, r
+NX, NU, NDU, NY = W.QUAD_NX, W.QUAD_NU, W.QUAD_NDU, W.QUAD_NY
 
 
 def algorithmic_bytes(ph, shared_model):
-    """per-instance model + weights + bounds + (x0,u0) + references over the horizon + outputs; the
+    """per-controller model + weights + bounds + (x0,u0) + references over the horizon + outputs; the
     shared-model variant drops the model/weights/bounds term (3 296 B for the quadrotor)."""
     nx, nu, ny = NX, NU, NY
     model = 8 * (nx * nx + nx * nu + ny * nx + (ny + 2 * nu) + 2 * (nx + nu + ny))
@@ -88,57 +80,124 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def build_controller(L, ph, batch, max_iter, per_instance_model=False):
-    from oracle.lmpc_formulation import quadrotor_formulation, quadrotor_model
-    f = quadrotor_formulation(ph)
-    c = L.LMPC(NX, NU, NDU, NY, ph, ph, batch=batch, device=int(os.environ.get("LOCAL_RANK", 0)))
-    Ad, Bd = quadrotor_model()
-    if per_instance_model:   # batch copies of A,B,C (the per-instance-model variant of SURVEY 8d)
-        c.setStateSpaceModel(np.broadcast_to(Ad, (batch, NX, NX)), np.broadcast_to(Bd, (batch, NX, NU)),
-                             np.broadcast_to(np.eye(NX), (batch, NY, NX)))
-    else:                    # the quadrotor_ex model/weights/bounds, per-instance x0 / yRef
-        c.setStateSpaceModel(Ad, Bd, np.eye(NX))
-    c.setObjectiveWeights(f.wOutput[:, 1], f.wU[:, 1], f.wDeltaU[:, 0], (0, ph))
-    c.setStateBounds(f.minX[:, 1], f.maxX[:, 1], (0, ph))
-    c.setInputBounds(f.minU[:, 0], f.maxU[:, 0], (0, ph))
-    c.setOptimizerParameters(L.LParameters(maximum_iteration=max_iter))
-    return f, c
-
-
-def cpu_oracle_solve(args):
-    ph, x0, r, max_iter = args
-    from oracle.lmpc_formulation import quadrotor_formulation
-    from oracle.osqp_restated import Settings, lmpc_optimize
-    f = quadrotor_formulation(ph)
-    yr = np.zeros(NY)
-    yr[2] = r
-    f.set_references(yr, np.zeros(NU), np.zeros(NU))
-    t = time.perf_counter()
-    res = lmpc_optimize(f, x0, np.zeros(NU), Settings(max_iter=max_iter))
-    return time.perf_counter() - t, res["cmd"]
-
-
+# ---- CPU baselines (the restated reference path, oracle/): ONLY here and in --impl reference -----------------------------------
 def cpu_baseline(ph, max_iter, n_solves, cores):
     """Times the CPU oracle (the restated reference path) on a bounded sample of the same workload."""
-    x0, r = synth_inputs(0, n_solves)
-    try:
-        from oracle import c_oracle   # C port (oracle/Makefile), preferred when built
-        c_oracle.lib()
-        return c_oracle.time_batch(ph, x0, r, max_iter, cores)
-    except RuntimeError:
-        pass
-    jobs = [(ph, x0[k], r[k], max_iter) for k in range(n_solves)]
+    from oracle import c_oracle
+    x0, r = W.quadrotor_inputs(0, n_solves)
+    c_oracle.lib()
+    return c_oracle.time_batch(ph, x0, r, max_iter, cores)
+
+
+def cpu_latency_p50(ph, max_iter, n=24):
+    """p50 of single solves (one controller, one core) through the C port: what one mpc::LMPC<>::optimize costs on the host."""
+    from oracle import c_oracle
+    x0, r = W.quadrotor_inputs(0, n)
+    ts = []
+    for k in range(n):
+        t = time.perf_counter()
+        c_oracle.time_batch(ph, x0[k:k + 1], r[k:k + 1], max_iter, 1)
+        ts.append(time.perf_counter() - t)
+    return float(np.median(ts[2:])) * 1e3
+
+
+def _nlmpc_cpu_one(k):
+    """One cold-start solve of BASELINE configs[2] (unicycle) through the numpy restatement + SciPy SLSQP."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import nlmpc_slsqp as S
+    from user_systems import unicycle_formulation
+    x0, params = W.unicycle_inputs(k, 1)
+    f = unicycle_formulation(params=params[0])
+    lb, ub = W.soft_bounds(f.nz)
+    z0 = W.cold_start(x0, np.zeros(2), 30, 30)[0]
     t = time.perf_counter()
-    if cores > 1:
+    r = S.solve(f, x0[0], z0, lb, ub, maxiter=300)
+    return time.perf_counter() - t, bool(r["success"])
+
+
+def nlmpc_cpu_baseline(name, cores):
+    """SLSQP (SciPy's compiled Kraft core: the algorithm NLopt's LD_SLSQP implements) on the restated formulation, finite differences
+    included, one solve stream per core; a bounded sample of the same cold-start workload (a single solve takes 10-25 s)."""
+    n = max(1, min(cores, 16))
+    t = time.perf_counter()
+    if name == "unicycle":                       # user-defined system: numpy restatement (tests/user_systems.py)
         import multiprocessing as mp
-        with mp.get_context("fork").Pool(cores) as pool:
-            pool.map(cpu_oracle_solve, jobs)
-    else:
-        for j in jobs:
-            cpu_oracle_solve(j)
-    dt = time.perf_counter() - t
-    return {"value": n_solves / dt, "unit": "solves/s", "cores": cores, "kind": "port",
-            "sample": f"{n_solves} solves of the same workload through oracle/osqp_restated.py (numpy, dense KKT LU)"}
+        with mp.get_context("fork").Pool(n) as pool:
+            res = pool.map(_nlmpc_cpu_one, list(range(n)))
+        dt = time.perf_counter() - t
+        conv, how = int(sum(1 for _, ok in res if ok)), "oracle/nlmpc_formulation.py (numpy) callbacks"
+    else:                                        # built-in system: the C restatement of the callbacks (oracle/nlmpc_oracle.c)
+        from oracle import nlmpc_c_oracle as CO
+        x0, params = W.oscnet4_inputs(0, n)
+        lb, ub = W.hard_bounds(15 * 8 + 8 * 4 + 1)
+        z0 = W.cold_start(x0, np.zeros(4), 15, 8)
+        r = CO.time_batch(1, 15, 8, x0, z0, params, lb, ub, cores=n)
+        dt = time.perf_counter() - t
+        conv, how = int(r["converged"]), "oracle/nlmpc_oracle.c (C) callbacks"
+    return {"value": n / dt, "unit": "solves/s", "cores": n, "kind": "port",
+            "sample": f"{n} cold-start solves of the same workload, one per core: SciPy SLSQP (Kraft's algorithm, as NLopt LD_SLSQP) with {how} "
+                      "-- the reference's finite-difference objective / constraints restated", "converged": conv}
+
+
+def nlmpc_flops(nx, nu, ph, nz, me, mi, sqp_it, qp_it):
+    """SURVEY 8d NLMPC: sqp_iters x [model evaluations + QP]; the QP here is a dense reduced-KKT ADMM: per SQP iteration one H
+    build + Cholesky (nz^3/3 + nz^2 (me+mi)) and per ADMM iteration two triangular solves + two A products."""
+    per_sqp = nz ** 3 / 3.0 + nz * nz * (me + mi) + (ph * (nx + nu) + 3) * 2 * ph * (nx + nu) * 10
+    per_qp = 2 * nz * nz + 4 * nz * (me + mi)
+    return 2.0 * (sqp_it * per_sqp + qp_it * per_qp)
+
+
+def bench_nlmpc(L, torch, rank, world, steps, fp64_peak, with_cpu):
+    """BASELINE configs[2] and configs[3] through the C ABI with host buffers (cold start, as the first optimize() of a controller)."""
+    out = {}
+    cfgs = [("unicycle", "configs[2]: unicycle NLMPC nx=3 nu=2 Tph=Tch=30, 2 obstacle inequalities per stage (Tineq=62), soft constraints, "
+             "cold start; batch 1024 per GPU (user-defined system, NVRTC)", 1024, True),
+            ("oscnet4", "configs[3]: networked oscillators N=4 NLMPC nx=8 nu=4 Tph=15 Tch=8, u<=0.5 (Tineq=64), cold start; global batch "
+             "8192 sharded over the GPUs", 8192 // world, False)]
+    for name, desc, B, per_gpu in cfgs:
+        first = rank * B
+        if name == "unicycle":
+            sid = L.register_system(W.UNICYCLE_SRC, W.UNICYCLE_TYPE)
+            ph, ch, nx, nu = 30, 30, 3, 2
+            x0, params = W.unicycle_inputs(first, B)
+            lb, ub = W.soft_bounds(ph * nx + ch * nu + 1)
+            kw = dict(max_sqp=300)
+            mi = 62
+        else:
+            sid = L.SYS_OSCNET4
+            ph, ch, nx, nu = 15, 8, 8, 4
+            x0, params = W.oscnet4_inputs(first, B)
+            lb, ub = W.hard_bounds(ph * nx + ch * nu + 1)
+            kw = {}
+            mi = 64
+        nz = ph * nx + ch * nu + 1
+        z0 = W.cold_start(x0, np.zeros(nu), ph, ch)
+        L.nlmpc_solve(sid, ph, ch, z0[:8], x0[:8], params if params.ndim == 1 else params[:8], lb, ub, **kw)      # compile / warm up
+        ts = []
+        for _ in range(steps):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            r = L.nlmpc_solve(sid, ph, ch, z0, x0, params, lb, ub, **kw)
+            ts.append(time.perf_counter() - t)
+        ms = float(np.mean(ts)) * 1e3
+        if world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        flops = float(sum(nlmpc_flops(nx, nu, ph, nz, ph * nx, mi, int(a), int(b)) for a, b in zip(r["iters"], r["qp_iters"])))
+        tfl = flops * world / (ms * 1e-3) / 1e12
+        out[name] = {"workload": desc, "value": world * B / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms, "batch_per_gpu": B,
+                     "e2e": "host buffers in, results out, inside the timed call",
+                     "converged": int((r["status"] == 0).sum()), "sqp_iterations_mean": float(r["iters"].mean()),
+                     "qp_iterations_mean": float(r["qp_iters"].mean()), "viol_max": float(r["viol"].max()),
+                     "roofline": {"bound": "fp64", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak}}
+        if with_cpu and rank == 0:
+            try:
+                out[name]["cpu_baseline"] = nlmpc_cpu_baseline(name, os.cpu_count() or 1)
+            except Exception as e:                                        # noqa: BLE001
+                out[name]["cpu_baseline"] = {"error": repr(e)[:200]}
+    return out
 
 
 def main():
@@ -147,29 +206,28 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (weak scaling)")
+    ap.add_argument("--batch", type=int, default=4096, help="controllers per GPU (weak scaling)")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: this many controllers in total, split over the ranks")
     ap.add_argument("--ph", type=int, default=20)
     ap.add_argument("--max-iter", type=int, default=250)
     ap.add_argument("--cpu-sample", type=int, default=0, help="solves in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--per-instance-model", action="store_true", help="give every instance its own copy of A,B,C")
-    ap.add_argument("--schedule", default="gang", choices=["gang", "free"], help="persistent-warp scheduling (include/b200mpc.h)")
-    ap.add_argument("--no-history-order", action="store_true",
-                    help="do not draw instances in the order of their previous solve's iteration counts (include/b200mpc.h)")
-    ap.add_argument("--warps-per-cta", type=int, default=0)
-    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--no-nlmpc", action="store_true", help="skip the NLMPC configurations (configs[2], configs[3])")
+    ap.add_argument("--per-instance-model", action="store_true", help="give every controller its own copy of A,B,C")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 warp per controller, 2 CTA per controller (include/b200mpc.h)")
+    ap.add_argument("--no-history-order", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    ph, B = a.ph, a.batch
+    ph = a.ph
+    strong = a.global_batch > 0
+    B = (a.global_batch + world - 1) // world if strong else a.batch
     config = {"workload": f"quadrotor LMPC nx=12 nu=4 ny=12 ph=ch={ph}, batch={B} per GPU, maximum_iteration={a.max_iter}, "
-                          f"{'per-instance' if a.per_instance_model else 'shared'} model, per-instance x0/yRef synthetic seed 20 (BASELINE.json configs[1])",
+                          f"{'per-instance' if a.per_instance_model else 'shared'} model, per-controller x0/yRef synthetic seed 20 (BASELINE.json "
+                          f"configs[{4 if strong else 1}]); closed loop: every timed step solves from the state the previous command produced",
               "batch_per_gpu": B, "global_batch": B * world, "ph": ph, "parallelism": f"dp{world}",
-              "schedule": a.schedule + ("" if a.no_history_order else ", instances drawn longest-first by the iteration counts of the handle's "
-                                         "previous solve (every timed step repeats the same batch, so that history is exact here; "
-                                         "value_cold_order is the same measurement without it)"),
-              "l2": "L2 flushed (512 MiB write) between timed steps; each step timed by its own CUDA-event pair"}
+              "l2": "L2 flushed (512 MiB write) between timed steps; each step timed by its own CUDA-event pair on the solve stream"}
 
     if a.impl == "reference":
         # the reference's own CPU implementation of the path, restated (oracle/): rank 0 only
@@ -186,7 +244,7 @@ def main():
         cb["value"] = v
         line = {"impl": "reference", "metric": "LMPC solves/sec (batched)", "value": v, "unit": "solves/s", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * per_step / v, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": cb, "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -199,28 +257,33 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    f, c = build_controller(L, ph, B, a.max_iter, a.per_instance_model)
-    if a.warps_per_cta or a.ctas_per_sm:
-        c.set_launch(a.warps_per_cta, a.ctas_per_sm)
-    c.set_schedule(a.schedule == "gang")
+    c = W.build_quadrotor_controller(L, ph, B, a.max_iter, a.per_instance_model, device=local_rank)
+    if a.engine:
+        c.set_engine(a.engine)
     c.set_history_order(not a.no_history_order)
     stream = torch.cuda.current_stream()
     c.set_stream(stream.cuda_stream)
-    x0_h, r = synth_inputs(rank * B, B)
+    x0_h, r = W.quadrotor_inputs(rank * B, B)
     yref = np.zeros((B, NY, ph))
     yref[:, 2, :] = r[:, None]
     c.setReferences(yref, np.zeros((NU, ph)), np.zeros((NU, ph)))
-    x0_d = torch.from_numpy(x0_h).cuda()
-    u0_d = torch.zeros((B, NU), dtype=torch.float64, device="cuda")
+    x_d = torch.from_numpy(x0_h).cuda()
+    x_init = x_d.clone()
+    u_d = torch.zeros((B, NU), dtype=torch.float64, device="cuda")
     cmd_d = torch.empty((B, NU), dtype=torch.float64, device="cuda")
     cmd_all = torch.empty((world * B, NU), dtype=torch.float64, device="cuda") if world > 1 else None
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    launches = {"n": 0}
 
-    def step():
-        c.solve_async(x0_d.data_ptr(), u0_d.data_ptr(), dev=True)      # ONE kernel launch
+    def step(advance=True):
+        c.solve_async(x_d.data_ptr(), u_d.data_ptr(), dev=True)          # history ordering (1 CTA) + ONE solve kernel
+        launches["n"] += 2 if (not a.no_history_order) else 1
         if world > 1:
             c.get_result_into(cmd_ptr=cmd_d.data_ptr())
-            dist.all_gather_into_tensor(cmd_all, cmd_d)                  # the one exchange step
+            dist.all_gather_into_tensor(cmd_all, cmd_d)                    # the one exchange step
+        if advance:
+            c.advance(x_d.data_ptr(), u_d.data_ptr())                      # x+ = A x + B u, u0 <- cmd (our plant-step kernel)
+            launches["n"] += 1
 
     for _ in range(a.warmup):
         step()
@@ -231,12 +294,15 @@ def main():
     sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     torch.cuda.synchronize()
+    launches["n"] = 0
+    iters_acc, rho_acc, pol_acc = [], [], []
     for s in range(a.steps):
         flush.zero_()
         evs[s][0].record(stream)
         step()
         evs[s][1].record(stream)
     torch.cuda.synchronize()
+    n_launch = launches["n"]
     if world > 1:
         dist.barrier()
     sampler.stop_flag = True
@@ -246,35 +312,46 @@ def main():
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    res = c.fetch_result()
+    res = c.fetch_result()                       # counters of the LAST timed step (the flop estimate below uses them)
     value = world * B / (ms * 1e-3)
-    # the same measurement with history ordering off (what the FIRST solve of a handle, or a batch of unrelated problems, gets)
-    cold_ms = None
-    if not a.no_history_order:
-        c.set_history_order(False)
-        step(); torch.cuda.synchronize()
-        cevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(a.steps, 5))]
-        for e0, e1 in cevs:
-            flush.zero_()
-            e0.record(stream); step(); e1.record(stream)
-        torch.cuda.synchronize()
-        cold_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in cevs]))
-        if world > 1:
-            t = torch.tensor([cold_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            cold_ms = float(t.item())
-        c.set_history_order(True)
 
-    # end-to-end through the public API with host buffers (pinned), H2D + D2H inside the timed region
-    x0_pin = torch.from_numpy(x0_h).pin_memory()
-    u0_pin = torch.zeros((B, NU), dtype=torch.float64).pin_memory()
+    # the exchange step on its own (N > 1): all-gather of the command block, timed with events
+    coll_ms = None
+    if world > 1:
+        cevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for e0, e1 in cevs:
+            e0.record(stream); c.get_result_into(cmd_ptr=cmd_d.data_ptr()); dist.all_gather_into_tensor(cmd_all, cmd_d); e1.record(stream)
+        torch.cuda.synchronize()
+        coll_ms = float(np.median([e0.elapsed_time(e1) for e0, e1 in cevs[5:]]))
+
+    # the first solve of a handle on a fresh batch: no scheduling history, nothing warm (what a batch of unrelated problems gets)
+    cold_ms = None
+    c.set_history_order(False)
+    x_d.copy_(x_init); u_d.zero_()
+    step(advance=False); torch.cuda.synchronize()
+    cevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(a.steps, 5))]
+    for e0, e1 in cevs:
+        flush.zero_()
+        e0.record(stream); step(advance=False); e1.record(stream)
+    torch.cuda.synchronize()
+    cold_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in cevs]))
+    if world > 1:
+        t = torch.tensor([cold_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cold_ms = float(t.item())
+    c.set_history_order(not a.no_history_order)
+
+    # end-to-end through the public API with host buffers (pinned), H2D + D2H inside the timed region; closed loop on the host
+    x_pin = torch.from_numpy(x0_h.copy()).pin_memory()
+    u_pin = torch.zeros((B, NU), dtype=torch.float64).pin_memory()
+    Ad, Bd = W.quadrotor_model()
     e2e_t = []
     for s in range(a.warmup + a.steps):
         torch.cuda.synchronize()
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out = c.optimize(x0_pin.numpy(), u0_pin.numpy())      # H2D x0,u0 -> solve -> D2H cmd,cost,status...
+        out = c.optimize(x_pin.numpy(), u_pin.numpy())      # H2D x0,u0 -> solve -> D2H cmd,cost,status...
         if world > 1:
             c.get_result_into(cmd_ptr=cmd_d.data_ptr())
             dist.all_gather_into_tensor(cmd_all, cmd_d)
@@ -282,6 +359,8 @@ def main():
         dt = time.perf_counter() - t0
         if s >= a.warmup:
             e2e_t.append(dt)
+        xn = x_pin.numpy() @ Ad.T + out.cmd @ Bd.T            # the plant (host side of the loop, outside the timed region)
+        x_pin.numpy()[:] = xn; u_pin.numpy()[:] = out.cmd
     e2e_ms = float(np.mean(e2e_t)) * 1e3
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
@@ -290,75 +369,92 @@ def main():
     h2d = B * (NX + NU) * 8
     d2h = B * (NU * 8 + 8 + 6 * 4)
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fp64_peak, fp64_src = 37.0, "nominal B200 FP64 vector (no FP64 entry in MEASURED_PEAKS.json)"
+    try:
+        fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["fp64_tflops"]
+        fp64_src = ("DFMA throughput measured on this pool by tools/ubench.cu (profiles/fp64_peak.json); MEASURED_PEAKS.json has no FP64 "
+                    "entry; nominal 37")
+    except Exception:
+        pass
+
+    nl = None
+    if not a.no_nlmpc:
+        nl = bench_nlmpc(L, torch, rank, world, max(1, min(a.steps, 2)), fp64_peak, with_cpu=(world == 1 and not a.no_cpu_baseline))
+
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        kernel_ms = ms  # one kernel per step; at N>1 the all-gather is inside the step time too
         abytes = algorithmic_bytes(ph, not a.per_instance_model) * B
-        achieved = abytes / (kernel_ms * 1e-3) / 1e9
+        achieved = abytes / (ms * 1e-3) / 1e9
         flops = sum(algorithmic_flops(ph, int(i), int(u), int(p == 1)) for i, u, p in zip(res.iterations, res.rho_updates, res.status_polish))
-        tfl = flops / (kernel_ms * 1e-3) / 1e12
-        fp64_peak, fp64_src = 37.0, "nominal B200 FP64 vector"
-        try:
-            fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["fp64_tflops"]
-            fp64_src = "measured DFMA throughput on this pool (tools/ubench.cu -> profiles/fp64_peak.json)"
-        except Exception:
-            pass
+        tfl = flops / (ms * 1e-3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if tj.get("batch") == B and tj.get("ph", 20) == ph:      # the capture is of the default launch only
+                if tj.get("batch") == B and tj.get("ph", 20) == ph and tj.get("engine") == c.get_engine()["engine"]:
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        # per-solve latency of ONE controller (batch = 1: what a single mpc::LMPC<> object sees), host buffers, p50 of 15
-        lat1 = None
+        # BASELINE's second metric: p50 per-solve latency of ONE controller (batch 1 = one mpc::LMPC<> object) through the public
+        # API with host buffers, over 200 timed solves on successive closed-loop states, next to the CPU port's p50
+        lat = None
         if world == 1:
-            f1, c1 = build_controller(L, ph, 1, a.max_iter, False)
+            c1 = W.build_quadrotor_controller(L, ph, 1, a.max_iter, False)
             yr1 = np.zeros((1, NY, ph)); yr1[:, 2, :] = r[0]
             c1.setReferences(yr1, np.zeros((NU, ph)), np.zeros((NU, ph)))
+            x1 = x0_h[:1].copy(); u1 = np.zeros((1, NU))
             ts1 = []
-            for s in range(18):
+            for s in range(210):
                 t0 = time.perf_counter()
-                c1.optimize(x0_h[:1], np.zeros((1, NU)))
+                o1 = c1.optimize(x1, u1)
                 ts1.append(time.perf_counter() - t0)
-            lat1 = float(np.median(ts1[3:])) * 1e3
+                if s % 30 == 29:
+                    x1 = x0_h[(s // 30) % B: (s // 30) % B + 1].copy(); u1 = np.zeros((1, NU))   # a new transient every 30 steps
+                else:
+                    x1 = x1 @ Ad.T + o1.cmd @ Bd.T; u1 = o1.cmd.copy()
+            ts1 = np.array(ts1[10:]) * 1e3
+            lat = {"single_controller_p50_ms": float(np.percentile(ts1, 50)), "single_controller_p95_ms": float(np.percentile(ts1, 95)),
+                   "solves_timed": int(ts1.size), "engine": c1.get_engine(),
+                   "note": "batch 1 through the public API with host buffers (one mpc::LMPC<> object), closed loop"}
             del c1
         line = {
             "metric": "LMPC solves/sec (batched)", "value": value, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
             "value_cold_order": (world * B / (cold_ms * 1e-3)) if cold_ms else None,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            # per step: the solve kernel, plus the one-CTA ordering kernel when history ordering is on (profiles/r01_launches.csv)
-            "gpu_launches": a.steps * (1 if a.no_history_order else 2),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "note": "algorithmic bytes/solve (SURVEY 8d) x batch / kernel time; the solve is bound by instruction issue / "
-                                 "dependent latency of the stage recurrence, not by HBM: see roofline_fp64, DESIGN.md 5, profiles/r01_icache.md"},
-            "roofline_fp64": {"bound": "fp64-pipe", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak,
-                              "peak_source": fp64_src,
-                              "flops_per_solve_mean": flops / B},
+            # per step: the one-CTA ordering kernel, the solve kernel, the plant-step kernel (profiles/*launches.csv)
+            "gpu_launches": n_launch,
+            "collective_ms": coll_ms,
+            # the governing bound of an on-chip solver is the FP64 pipe; HBM (algorithmic bytes and measured traffic) is secondary
+            "roofline": {"bound": "fp64", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak,
+                         "traffic": traffic, "peak_source": fp64_src, "flops_per_solve_mean": flops / B,
+                         "note": "algorithmic flops (SURVEY 8d formulae with the kernel's own per-controller iteration / rho-update / polish "
+                                 "counters of the last timed step) / step time"},
+            "roofline_hbm": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                             "traffic": traffic, "peak_source": peak_src,
+                             "note": "algorithmic bytes/solve (SURVEY 8d) x batch / step time; traffic = dram bytes per launch from the ncu "
+                                     "capture of this launch (profiles/traffic.json)"},
             "solver": {"iterations_mean": float(res.iterations.mean()), "iterations_max": int(res.iterations.max()),
                        "rho_updates_mean": float(res.rho_updates.mean()), "solved": int((res.solver_status == 1).sum()),
-                       "polished": int((res.status_polish == 1).sum()), **c.info()},
-            "p50_latency_us_per_solve": 1e3 * ms / B,
-            "latency": {"amortised_us_per_solve": 1e3 * ms / B, "single_controller_p50_ms": lat1,
-                        "note": "single_controller = batch 1 through the public API with host buffers (one mpc::LMPC<> object)"},
+                       "polished": int((res.status_polish == 1).sum()), "engine": c.get_engine(), **c.info()},
+            "latency": lat,
             "clocks": sampler.summary(),
         }
+        if nl is not None:
+            line["nlmpc"] = nl
         if world == 1 and not a.no_cpu_baseline:
-            cores = 1
             n = a.cpu_sample or 2048
-            line["cpu_baseline"] = cpu_baseline(ph, a.max_iter, n, cores)
-            line["latency"]["cpu_port_ms_per_solve"] = 1e3 / line["cpu_baseline"]["value"]
+            line["cpu_baseline"] = cpu_baseline(ph, a.max_iter, n, 1)
+            if lat is not None:
+                lat["cpu_port_p50_ms"] = cpu_latency_p50(ph, a.max_iter)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

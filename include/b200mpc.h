@@ -137,6 +137,10 @@ int b200mpc_lmpc_closed_loop(b200mpc_lmpc_t h, const double* x0, const double* u
                              const double* Bp, int plant_per_instance, double* traj_x, double* traj_u,
                              int32_t* traj_status, int32_t* traj_iters, int dev);
 
+/* One plant step of that loop on its own: x <- A x + B cmd with the controller's model (x_dev [batch*nx], updated in place) and
+ * u_out_dev [batch*nu] <- cmd, asynchronous on the handle's stream (solve / advance pairs enqueue back to back). */
+int b200mpc_lmpc_advance(b200mpc_lmpc_t h, double* x_dev, double* u_out_dev);
+
 /* mpc::Result<nu> fields (Types.hpp:168-182), one entry per instance.  Any pointer may be NULL.
  *   cmd[batch*nu], cost[batch], status[batch] (ResultStatus), solver_status[batch] (OSQP status_val),
  *   is_feasible[batch] (0/1), iterations[batch], rho_updates[batch], status_polish[batch]

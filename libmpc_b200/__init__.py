@@ -80,6 +80,7 @@ def load_library():
     lib.b200mpc_lmpc_cmd_device_ptr.argtypes = [H, C.POINTER(C.c_void_p)]
     lib.b200mpc_lmpc_info.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_longlong)]
     lib.b200mpc_lmpc_set_launch.argtypes = [H, C.c_int, C.c_int]
+    lib.b200mpc_lmpc_advance.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.b200mpc_lmpc_set_engine.argtypes = [H, C.c_int, C.c_int]
     lib.b200mpc_lmpc_get_engine.argtypes = [H] + [C.POINTER(C.c_int)] * 3
     lib.b200mpc_lmpc_set_schedule.argtypes = [H, C.c_int]
@@ -116,7 +117,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_lmpc_cmd_device_ptr", "b200mpc_lmpc_info", "b200mpc_lmpc_set_launch", "b200mpc_lmpc_set_schedule", "b200mpc_lmpc_set_history_order", "b200mpc_lmpc_profile", "b200mpc_sync", "b200mpc_c2d", "b200mpc_nlmpc_system_dims", "b200mpc_nlmpc_eval",
     "b200mpc_nlmpc_default_params", "b200mpc_nlmpc_solve_smem_bytes", "b200mpc_nlmpc_solve",
     "b200mpc_nlmpc_system_neq", "b200mpc_nlmpc_register_system", "b200mpc_nlmpc_compile_check", "b200mpc_nlmpc_eval_ex",
-    "b200mpc_nlmpc_solve_ex", "b200mpc_nlmpc_system_ny", "b200mpc_nlmpc_output", "b200mpc_lmpc_set_input_bounds_full", "b200mpc_lmpc_set_engine", "b200mpc_lmpc_get_engine",
+    "b200mpc_nlmpc_solve_ex", "b200mpc_nlmpc_system_ny", "b200mpc_nlmpc_output", "b200mpc_lmpc_set_input_bounds_full", "b200mpc_lmpc_set_engine", "b200mpc_lmpc_get_engine", "b200mpc_lmpc_advance",
 ]
 
 
@@ -473,6 +474,10 @@ class LMPC:
         u0 = np.ascontiguousarray(np.broadcast_to(np.asarray(u0, float), (self.batch, self.nu)))
         self._keep = [x0, u0]
         _check(self.lib.b200mpc_lmpc_solve(self._h, self._p(x0), self._p(u0), 0))
+
+    def advance(self, x_dev_ptr, u_out_dev_ptr):
+        """x <- A x + B cmd on the device (raw device pointers), asynchronous: the plant step between two optimize() calls."""
+        _check(self.lib.b200mpc_lmpc_advance(self._h, C.c_void_p(int(x_dev_ptr)), C.c_void_p(int(u_out_dev_ptr))))
 
     def fetch_result(self):
         B = self.batch

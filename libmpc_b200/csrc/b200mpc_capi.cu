@@ -33,7 +33,7 @@ struct b200mpc_lmpc {
     int enable_warm_start = 0;
     bool has_prev = false, model_set = false, has_iters = false;
     DevBuf A, B, C, Bd, Dd, OW, UW, DUW, XMin, XMax, YMin, YMax, UMin, UMax, SMin, SMax, SX, SU, yRef, uRef, duRef, uMeas;
-    double *x0 = nullptr, *u0 = nullptr;
+    double *x0 = nullptr, *u0 = nullptr, *xnext = nullptr;
     // results
     double *cmd = nullptr, *prev_cmd = nullptr, *cost = nullptr, *seq_state = nullptr, *seq_input = nullptr, *seq_output = nullptr;
     double *sol_x = nullptr, *sol_y = nullptr;
@@ -174,7 +174,7 @@ extern "C" int b200mpc_lmpc_destroy(b200mpc_lmpc_t h) {
                       &h->UMin, &h->UMax, &h->SMin, &h->SMax, &h->SX, &h->SU, &h->yRef, &h->uRef, &h->duRef, &h->uMeas};
     for (DevBuf* b : bufs) free_buf(*b);
     void* ptrs[] = {h->x0, h->u0, h->cmd, h->prev_cmd, h->cost, h->seq_state, h->seq_input, h->seq_output, h->sol_x, h->sol_y,
-                    h->status, h->solver_status, h->feasible, h->iters, h->rho_updates, h->polish, h->counter, h->order, h->workspace, h->prof};
+                    h->status, h->solver_status, h->feasible, h->iters, h->rho_updates, h->polish, h->counter, h->order, h->workspace, h->prof, h->xnext};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
     return B200MPC_OK;
@@ -395,7 +395,11 @@ static int configure_launch(b200mpc_lmpc* h) {
     if (h->workspace) return B200MPC_OK;
     const bool quad = !h->force_generic && is_quad(h->d);
     const bool mshared = !h->A.per_instance && !h->B.per_instance && !h->C.per_instance && !h->SX.per_instance && !h->SU.per_instance;
-    if (h->engine_req != 1) {
+    // automatic choice: the CTA engine runs one controller per SM at a time (best latency, no HBM streaming); the warp engine
+    // keeps ~12 controllers per SM in flight and wins on throughput once the batch is several times the SM count
+    static const int kAutoMax = getenv("B200MPC_ENGINE2_MAX_BATCH") ? atoi(getenv("B200MPC_ENGINE2_MAX_BATCH")) : 0;
+    const int auto_max = kAutoMax > 0 ? kAutoMax : 4 * h->num_sms;
+    if (h->engine_req == 2 || (h->engine_req == 0 && h->batch <= auto_max)) {
         CtaLaunchCfg cfg;
         int rc = cta_configure(h->d, quad, h->device, h->num_sms, h->batch, h->req_cta_threads, &cfg);
         if (rc == B200MPC_OK) {
@@ -566,6 +570,23 @@ extern "C" int b200mpc_lmpc_closed_loop(b200mpc_lmpc_t h, const double* x0, cons
         if (traj_iters) CK(cudaMemcpyAsync(traj_iters, dI, steps * Bn * 4, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));      // temporaries are freed on return
+    return B200MPC_OK;
+}
+
+// One plant step on the device with the controller's own model: x <- A x + B cmd (in place, device pointer), u_out <- cmd.
+// The piece of the examples' control loop between two optimize() calls (examples/quadrotor_ex.cpp), asynchronous on the
+// handle's stream: solve / advance pairs can be enqueued back to back without a host round trip.
+extern "C" int b200mpc_lmpc_advance(b200mpc_lmpc_t h, double* x_dev, double* u_out_dev) {
+    HCHECK();
+    if (!x_dev || !u_out_dev) return fail(B200MPC_EINVAL, "null pointer");
+    const Dm& d = h->d;
+    const size_t nX = (size_t)h->batch * d.nx;
+    if (!h->xnext) CK(cudaMalloc(&h->xnext, (nX ? nX : 1) * sizeof(double)));
+    const long long sA = h->A.per_instance ? (long long)d.nx * d.nx : 0, sB = h->B.per_instance ? (long long)d.nx * d.nu : 0;
+    plant_step_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, h->stream>>>(h->batch, d.nx, d.nu, h->A.p, sA, h->B.p, sB, x_dev, h->cmd, h->xnext,
+                                                                          u_out_dev, h->status, h->iters, nullptr, nullptr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(x_dev, h->xnext, nX * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     return B200MPC_OK;
 }
 

@@ -1,5 +1,6 @@
 // the CTA-per-controller LMPC engine: configuration, dispatch, and the kernels with run-time dimensions
 #include "lmpc_cta_launch_impl.cuh"
+#include <cstdlib>
 
 namespace b200mpc {
 
@@ -12,14 +13,16 @@ int cta_configure(const Dm& d, bool quad, int device, int num_sms, int batch, in
     int max_smem = 0;
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     const size_t stat = 64;                               // static shared memory of the kernel (the drawn index)
-    CtaLayout L = cta_layout(d, 1);
-    if ((size_t)L.total * sizeof(double) + stat > (size_t)max_smem) L = cta_layout(d, 0);
+    const int generic_scratch = quad ? 0 : 1;           // the run-time-dimension path eliminates in shared memory
+    CtaLayout L = cta_layout(d, 1, generic_scratch);
+    if ((size_t)L.total * sizeof(double) + stat > (size_t)max_smem) L = cta_layout(d, 0, generic_scratch);
     if ((size_t)L.total * sizeof(double) + stat > (size_t)max_smem)
         return fail(B200MPC_EINVAL, "controller vectors exceed the shared memory of an SM");
     if (d.b + d.ne >= 32768) return fail(B200MPC_EINVAL, "stage too large for the elimination table");
     cfg->L = L;
     cfg->threads = req_threads == 384 ? 384 : 256;
     cfg->quad = quad ? 1 : 0;
+    cfg->pipelined = getenv("B200MPC_CTA_PIPE") ? atoi(getenv("B200MPC_CTA_PIPE")) : 0;
     cfg->smem_bytes = (size_t)L.total * sizeof(double);
     cfg->grid = batch < num_sms ? batch : num_sms;       // one CTA per SM: the whole SM works on one controller
     return B200MPC_OK;

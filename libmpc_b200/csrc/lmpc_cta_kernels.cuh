@@ -17,8 +17,14 @@
 //                   x_i = [xe_i ; s_i[ne:] - W_i[:, ne:]^T xe_{i+1}]                     (parallel)
 //     which is algebraically the block forward / backward substitution of lmpc_kernels.cuh (tests/structured_reference.py)
 //     with the two dependent mat-vecs per stage fused into one.
-//   * The factorisation is an LDL' elimination of the augmented block [S_i Hc_i'; Hc_i 0] by the whole block (one barrier per
-//     pivot): it yields L_i^-1, Lc_i and the Schur complement for stage i+1 in the same b steps.
+//   * L_i^-1 and W_i are stored as zero-padded rectangles with an even leading dimension whose half is odd: every dot product
+//     has a compile-time length (no triangular predicates), rows are read with 128-bit loads and both the row walk and the
+//     column walk are bank-conflict free.
+//   * The factorisation of a stage is a register-resident LDL' by ONE warp (lane r = row r of the pivot block, lane q = column
+//     q of the accumulated inverse; the pivot column is the only thing that goes through shared memory), followed by
+//     stage-parallel dot products for Lc_i, the Schur complement of stage i+1 and W_i.
+//   * The ADMM iteration is warp-specialised: warp 0 runs the two serial recurrences, the other warps run per-stage jobs
+//     behind it, ordered by shared-memory progress flags (pipelined_iteration).
 //   * A x / A' y / P x never touch a matrix: rows and columns are evaluated from A, B, C, the weights and the scalar row.
 //
 // Used for batch sizes from 1 (a single mpc::LMPC<> object: the whole SM works on it) to any; the warp-per-controller engine
@@ -33,49 +39,59 @@ constexpr int OSQP_TIME_LIMIT_REACHED = -6;   // constants.h of OSQP v0.6.3; LOp
 
 struct CtaLayout {
     // offsets (doubles) into dynamic shared memory
-    int oG, oC, oSV, oW, oD, oQ, oX, oT, oR, oE, oLO, oUP, oZ, oY, oV, oRT, oGT, oCAR, oYV, oRED, oAUG, oM, oLCS, oTB, oTAB, oV2, oXE, oFLAG, oFAC;
-    int lda;         // leading dimension of the augmented elimination matrix ((b+ne) | 1)
-    int n_ent;       // entries of the elimination (lower triangle of the augmented matrix + strict lower triangle of M)
-    int n_aug;       // of which augmented-matrix entries (they come first in the table)
-    int total;       // doubles of dynamic shared memory
-    int fac_shared;  // factor records in shared memory (else in the CTA's global scratch)
+    int oG, oC, oSV, oW, oD, oQ, oX, oT, oR, oE, oLO, oUP, oZ, oY, oV, oRT, oGT, oCAR, oYV, oRED, oAUG, oM, oLCS, oTB, oTAB, oXE, oFLAG, oFAC;
+    int ldG, ldC, LD;    // leading dimensions of G (ne x b), C (ny x nx) and of the factor blocks: even, half odd
+    int oWm, FS2;        // factor record of a stage: L^-1 (b x LD, zero above the diagonal) then W (ne x LD)
+    int nP;              // padded length of the stage-major variable vectors, (ph+1) b (the last stage has no du block)
+    int lda;             // leading dimension of the elimination matrix of the run-time-dimension path
+    int n_ent, n_aug;    // elimination table of the run-time-dimension path
+    int total;           // doubles of dynamic shared memory
+    int fac_shared;      // factor records in shared memory (else in the CTA's global scratch)
     // global scratch of a CTA (doubles)
     int gVA, gPX, gRA, gRB, gRC;
     long long gFAC, gtotal;
 };
 
+// even leading dimension >= n whose half is odd: 16-byte aligned rows for 128-bit loads, and both a walk down the rows
+// (stride ld) and across a row touch every bank group once
+__host__ __device__ constexpr int cta_evld(int n) { int h = (n + 1) / 2; if ((h & 1) == 0) ++h; return 2 * h; }
+
 template <class DM>
-inline CtaLayout cta_layout(const DM& d, int fac_shared) {
+inline CtaLayout cta_layout(const DM& d, int fac_shared, int generic_scratch) {
     CtaLayout L;
     int o = 0;
     auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
-    L.oG = take(d.ne * d.ldG); L.oC = take(d.ny * d.ldC); L.oSV = take(d.ne);
+    L.ldG = cta_evld(d.b); L.ldC = cta_evld(d.nx); L.LD = cta_evld(d.b);
+    L.oWm = d.b * L.LD; L.FS2 = (d.b + d.ne) * L.LD;
+    L.nP = (d.ph + 1) * d.b;
+    L.oG = take(d.ne * L.ldG); L.oC = take(d.ny * L.ldC); L.oSV = take(d.ne);
     L.oW = take((d.ph + 1) * (d.ny + 2 * d.nu));
-    L.oD = take(d.n); L.oQ = take(d.n); L.oX = take(d.n); L.oT = take(d.n); L.oR = take(d.n);
+    L.oD = take(L.nP); L.oQ = take(L.nP); L.oX = take(L.nP); L.oT = take(L.nP); L.oR = take(L.nP + d.b);
     L.oE = take(d.m); L.oLO = take(d.m); L.oUP = take(d.m); L.oZ = take(d.m); L.oY = take(d.m); L.oV = take(d.m);
     L.oRT = take((d.m + 7) / 8);
-    L.oGT = take((d.ph + 1) * d.ne); L.oCAR = take((d.ph + 1) * d.ne);
+    L.oGT = take((d.ph + 1) * d.ne); L.oCAR = take((d.ph + 2) * d.ne); L.oXE = take((d.ph + 2) * d.ne);
     L.oYV = take((d.ph + 1) * d.ny);
-    L.oRED = take(16 * 32);
-    L.lda = (d.b + d.ne) | 1;
-    L.oAUG = take((d.b + d.ne) * L.lda);
-    L.oM = take(d.b * d.ldb);
-    L.oLCS = take(d.ne * d.ldb);
-    L.oTB = take(d.ne * d.ldb);
-    L.n_aug = (d.b + d.ne) * (d.b + d.ne + 1) / 2;
+    L.oRED = take(16 * 16);
+    L.oLCS = take(d.ne * L.LD);
+    L.oTB = take(d.ne * L.LD);
+    L.oFLAG = take((6 * (d.ph + 2) + 1) / 2);        // int32 progress flags of the pipelined sweep
+    L.lda = d.b | 1;
+    L.n_aug = d.b * (d.b + 1) / 2;
     L.n_ent = L.n_aug + d.b * (d.b - 1) / 2;
-    L.oTAB = take((L.n_ent + 1) / 2);               // int32 table, 2 per double
-    L.oV2 = take(d.m);
-    L.oXE = take((d.ph + 1) * d.ne);
-    L.oFLAG = take((6 * (d.ph + 2) + 1) / 2);         // int32 progress flags of the pipelined sweep
+    L.oAUG = L.oM = L.oTAB = o;
+    if (generic_scratch) {
+        L.oAUG = take(d.b * L.lda);
+        L.oM = take(d.b * L.LD);
+        L.oTAB = take((L.n_ent + 1) / 2);            // int32 table, 2 per double
+    }
     L.oFAC = o;
     L.fac_shared = fac_shared;
-    if (fac_shared) o += (d.ph + 1) * d.FS;
+    if (fac_shared) o += (d.ph + 1) * L.FS2;
     L.total = o;
     long long g = 0;
     auto gt = [&](long long cnt) { long long r = g; g += (cnt + 3) & ~3ll; return r; };
-    L.gVA = (int)gt(d.n); L.gPX = (int)gt(d.n); L.gRA = (int)gt(d.m); L.gRB = (int)gt(d.m); L.gRC = (int)gt(d.m);
-    L.gFAC = gt((long long)(d.ph + 1) * d.FS);      // also the Ruiz scratch (P blocks of all stages)
+    L.gVA = (int)gt(L.nP); L.gPX = (int)gt(L.nP); L.gRA = (int)gt(d.m); L.gRB = (int)gt(d.m); L.gRC = (int)gt(d.m);
+    L.gFAC = gt((long long)(d.ph + 1) * L.FS2);     // also the Ruiz scratch (P blocks of all stages)
     L.gtotal = g;
     return L;
 }
@@ -88,28 +104,73 @@ __device__ __forceinline__ void cta_static_for(Fn&& fn) {
     if constexpr (K < N) { fn(std::integral_constant<int, K>{}); cta_static_for<K + 1, N>(fn); }
 }
 
-// entries of the stage elimination (lower triangle of the augmented block + strict lower triangle of M), compile-time dims
-template <class DM, bool S = DM::is_static> struct CtaEntCount { static constexpr int value = 1; };
-template <class DM> struct CtaEntCount<DM, true> {
-    static constexpr int value = (DM::b + DM::ne) * (DM::b + DM::ne + 1) / 2 + DM::b * (DM::b - 1) / 2;
+// compile-time dimensions of a dimension policy (0 = run-time): lengths of the unrolled dot products
+template <class DM, bool S = DM::is_static> struct CtaDims { static constexpr int b = 0, ne = 0, nx = 0, ny = 0, LD = 0, ldG = 0, ldC = 0; };
+template <class DM> struct CtaDims<DM, true> {
+    static constexpr bool even = (DM::b % 2 == 0) && (DM::ne % 2 == 0) && (DM::nx % 2 == 0) && (DM::ny % 2 == 0);
+    static constexpr int b = even ? DM::b : 0, ne = even ? DM::ne : 0, nx = even ? DM::nx : 0, ny = even ? DM::ny : 0;
+    static constexpr int LD = cta_evld(DM::b), ldG = cta_evld(DM::b), ldC = cta_evld(DM::nx);   // immediates in every strided address
 };
+
+// dot product  sum_q a[q*sa] x[q].  NS > 0: compile-time length, fully unrolled, four accumulators, all loads issued ahead of
+// the multiply-adds.  MODE 0: `a` is a contiguous 16-byte aligned row and `x` is 16-byte aligned (128-bit loads of both);
+// MODE 1: `a` strided, `x` aligned;  MODE 2: `a` strided, `x` unaligned.  NS == 0: run-time length n.
+template <int NS, int MODE>
+__device__ __forceinline__ double cta_dot(const double* __restrict__ a, int sa, const double* __restrict__ x, int n) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if constexpr (NS > 0) {
+        if constexpr (MODE == 0) {
+            const double2* a2 = reinterpret_cast<const double2*>(a); const double2* x2 = reinterpret_cast<const double2*>(x);
+#pragma unroll
+            for (int j = 0; j < NS / 2; ++j) {
+                const double2 av = a2[j], xv = x2[j];
+                if (j & 1) { s2 = fma(av.x, xv.x, s2); s3 = fma(av.y, xv.y, s3); } else { s0 = fma(av.x, xv.x, s0); s1 = fma(av.y, xv.y, s1); }
+            }
+        } else if constexpr (MODE == 1) {
+            const double2* x2 = reinterpret_cast<const double2*>(x);
+#pragma unroll
+            for (int j = 0; j < NS / 2; ++j) {
+                const double2 xv = x2[j];
+                const double alo = a[(2 * j) * sa], ahi = a[(2 * j + 1) * sa];
+                if (j & 1) { s2 = fma(alo, xv.x, s2); s3 = fma(ahi, xv.y, s3); } else { s0 = fma(alo, xv.x, s0); s1 = fma(ahi, xv.y, s1); }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS / 2; ++j) {
+                const double alo = a[(2 * j) * sa], ahi = a[(2 * j + 1) * sa], xlo = x[2 * j], xhi = x[2 * j + 1];
+                if (j & 1) { s2 = fma(alo, xlo, s2); s3 = fma(ahi, xhi, s3); } else { s0 = fma(alo, xlo, s0); s1 = fma(ahi, xhi, s1); }
+            }
+        }
+    } else {
+        int q = 0;
+        for (; q + 1 < n; q += 2) { s0 = fma(a[q * sa], x[q], s0); s1 = fma(a[(q + 1) * sa], x[q + 1], s1); }
+        if (q < n) s0 = fma(a[q * sa], x[q], s0);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
 
 template <class DM, int NT, bool FSH>
 struct CtaSolver {
     static constexpr int NW = NT / 32;
+    static constexpr int SB = CtaDims<DM>::b, SNE = CtaDims<DM>::ne, SNX = CtaDims<DM>::nx, SNY = CtaDims<DM>::ny;
     const DM& d; const Params& p; const Prob& pr; const CtaLayout& L;
+    // leading dimensions: compile-time for static dimension policies (the host layout computes the same values)
+    __device__ __forceinline__ int fLD() const { if constexpr (DM::is_static) return CtaDims<DM>::LD; else return L.LD; }
+    __device__ __forceinline__ int fldG() const { if constexpr (DM::is_static) return CtaDims<DM>::ldG; else return L.ldG; }
+    __device__ __forceinline__ int fWm() const { return d.b * fLD(); }
+    __device__ __forceinline__ int fldC() const { if constexpr (DM::is_static) return CtaDims<DM>::ldC; else return L.ldC; }
     int inst, tid, lane, warp;
     double* gws;
     double c;
     double rsel[3], rinv[3];
     double time_limit; long long t_start;
-    long long sp[8]; long long sq0;   // sub-phase cycle counters of the ADMM iteration (profiling aid)
-    int prof_on;
+    int pipelined;       // ADMM iteration schedule: 1 warp-specialised pipeline, 0 bulk-synchronous phases
+    long long pw[8];     // profiling aid: [0] chain fwd, [1] chain bwd, [2] this warp's flag waits, [3] fwd jobs, [4] bwd jobs, [5] sweep total
 
     __device__ CtaSolver(const DM& d_, const Params& p_, const Prob& pr_, const CtaLayout& L_) : d(d_), p(p_), pr(pr_), L(L_) {}
 
     __device__ __forceinline__ double* fac(int i) const {
-        if constexpr (FSH) return smem + L.oFAC + i * d.FS; else return gws + L.gFAC + (size_t)i * d.FS;
+        if constexpr (FSH) return smem + L.oFAC + i * L.FS2; else return gws + L.gFAC + (size_t)i * L.FS2;
     }
     __device__ __forceinline__ double* pblk() const { if constexpr (FSH) return smem + L.oFAC; else return gws + L.gFAC; }
     __device__ __forceinline__ int jcol(int i) const { return i > 0 ? i - 1 : 0; }
@@ -154,20 +215,22 @@ struct CtaSolver {
     // ---- model to shared memory: G = [A B B; 0 I I] (ne x b), C, scalar row -------------------------------------------------
     __device__ void load_model() {
         double* G = CSM(G); double* Cm = CSM(C); double* sv = CSM(SV);
-        for (int e = tid; e < d.ne * d.b; e += NT) {
-            int r = e / d.b, k = e - r * d.b;
-            double v;
-            if (r < d.nx) {
-                if (k < d.nx) v = ldp(pr.A, inst, r * d.nx + k);
-                else if (k < d.ne) v = ldp(pr.B, inst, r * d.nu + (k - d.nx));
-                else v = ldp(pr.B, inst, r * d.nu + (k - d.ne));
-            } else {
-                int j = r - d.nx;
-                v = ((k >= d.nx && k < d.ne && k - d.nx == j) || (k >= d.ne && k - d.ne == j)) ? 1.0 : 0.0;
+        for (int e = tid; e < d.ne * L.ldG; e += NT) {
+            int r = e / L.ldG, k = e - r * L.ldG;
+            double v = 0.0;
+            if (k < d.b) {
+                if (r < d.nx) {
+                    if (k < d.nx) v = ldp(pr.A, inst, r * d.nx + k);
+                    else if (k < d.ne) v = ldp(pr.B, inst, r * d.nu + (k - d.nx));
+                    else v = ldp(pr.B, inst, r * d.nu + (k - d.ne));
+                } else {
+                    int j = r - d.nx;
+                    v = ((k >= d.nx && k < d.ne && k - d.nx == j) || (k >= d.ne && k - d.ne == j)) ? 1.0 : 0.0;
+                }
             }
-            G[r * d.ldG + k] = v;
+            G[e] = v;
         }
-        for (int e = tid; e < d.ny * d.nx; e += NT) { int r = e / d.nx, k = e - r * d.nx; Cm[r * d.ldC + k] = ldp(pr.C, inst, e); }
+        for (int e = tid; e < d.ny * L.ldC; e += NT) { int r = e / L.ldC, k = e - r * L.ldC; Cm[e] = k < d.nx ? ldp(pr.C, inst, r * d.nx + k) : 0.0; }
         for (int k = tid; k < d.ne; k += NT) sv[k] = k < d.nx ? ldp(pr.SX, inst, k) : ldp(pr.SU, inst, k - d.nx);
         __syncthreads();
     }
@@ -215,7 +278,7 @@ struct CtaSolver {
         double* G = CSM(G); double* Cm = CSM(C); double* sv = CSM(SV); double* Wr = CSM(W);
         double* D = CSM(D); double* Q = CSM(Q); double* E = CSM(E); double* YV = CSM(YV);
         double* Dt = CSM(T); double* Et = CSM(V);
-        const int nw = d.ny + 2 * d.nu;
+        const int nw = d.ny + 2 * d.nu, ldG = fldG(), ldC = fldC();
         for (int e = tid; e < (d.ph + 1) * nw; e += NT) {
             int i = e / nw, r = e - i * nw;
             Wr[e] = r < d.ny ? wO(i, r) : (r < d.ny + d.nu ? wU(i, r - d.ny) : (i < d.ph ? wDU(i, r - d.ny - d.nu) : 0.0));
@@ -226,11 +289,16 @@ struct CtaSolver {
             for (int q = 0; q < d.ndu; ++q) acc += ldp(pr.Dd, inst, r * d.ndu + q) * ldp(pr.uMeas, inst, j * d.ndu + q);
             YV[e] = wO(i, r) * acc;
         }
+        // the du slots of the last stage do not exist: keep them zero in every stage-major vector
+        for (int kg = d.n + tid; kg < L.nP + d.b; kg += NT) {
+            if (kg < L.nP) { D[kg] = 0.0; Q[kg] = 0.0; CSM(X)[kg] = 0.0; CSM(T)[kg] = 0.0; }
+            CSM(R)[kg] = 0.0;
+        }
         __syncthreads();
         for (int kg = tid; kg < d.n; kg += NT) {
             int i = kg / d.b, k = kg - i * d.b, j = jcol(i);
             double v;
-            if (k < d.nx) { v = 0; for (int r = 0; r < d.ny; ++r) v += Cm[r * d.ldC + k] * YV[i * d.ny + r]; }
+            if (k < d.nx) { v = 0; for (int r = 0; r < d.ny; ++r) v += Cm[r * ldC + k] * YV[i * d.ny + r]; }
             else if (k < d.ne) { int q = k - d.nx; v = Wr[i * nw + d.ny + q] * (-ldp(pr.uRef, inst, j * d.nu + q)); }
             else { int q = k - d.ne; v = -(Wr[i * nw + d.ny + d.nu + q] * ldp(pr.duRef, inst, j * d.nu + q)); }
             Q[kg] = v; D[kg] = 1.0;
@@ -242,7 +310,7 @@ struct CtaSolver {
             for (int e = tid; e < (d.ph + 1) * nn; e += NT) {
                 int i = e / nn, rem = e - i * nn, a = rem / d.nx, k = rem - a * d.nx;
                 double acc = 0;
-                for (int r = 0; r < d.ny; ++r) acc += Cm[r * d.ldC + a] * Wr[i * nw + r] * Cm[r * d.ldC + k];
+                for (int r = 0; r < d.ny; ++r) acc += Cm[r * ldC + a] * Wr[i * nw + r] * Cm[r * ldC + k];
                 P[e] = acc;
             }
         }
@@ -259,10 +327,10 @@ struct CtaSolver {
                 if (k < d.ne) {
                     cn = fmax(cn, eprev[k] * dk);
                     cn = fmax(cn, erow[d.oBOX + k] * dk);
-                    if (k < d.nx) for (int r = 0; r < d.ny; ++r) cn = fmax(cn, erow[d.oOUT + r] * fabs(Cm[r * d.ldC + k]) * dk);
+                    if (k < d.nx) for (int r = 0; r < d.ny; ++r) cn = fmax(cn, erow[d.oOUT + r] * fabs(Cm[r * ldC + k]) * dk);
                     cn = fmax(cn, erow[d.oSC] * fabs(sv[k]) * dk);
                 } else cn = fmax(cn, erow[d.oDU + k - d.ne] * dk);
-                if (i < d.ph) for (int r = 0; r < d.ne; ++r) cn = fmax(cn, erow[d.oEQ + r] * fabs(G[r * d.ldG + k]) * dk);
+                if (i < d.ph) for (int r = 0; r < d.ne; ++r) cn = fmax(cn, erow[d.oEQ + r] * fabs(G[r * ldG + k]) * dk);
                 Dt[kg] = 1.0 / sqrt(lim_scaling(cn));
             }
             for (int g = tid; g < d.m; g += NT) {
@@ -272,9 +340,9 @@ struct CtaSolver {
                 else {
                     const double* dcur = D + i * d.b;
                     if (r < d.oOUT) rn = e * dcur[r];
-                    else if (r < d.oSC) { rn = 0; int q = r - d.oOUT; for (int k = 0; k < d.nx; ++k) rn = fmax(rn, e * fabs(Cm[q * d.ldC + k]) * dcur[k]); }
+                    else if (r < d.oSC) { rn = 0; int q = r - d.oOUT; for (int k = 0; k < d.nx; ++k) rn = fmax(rn, e * fabs(Cm[q * ldC + k]) * dcur[k]); }
                     else if (r < d.oEQ) { rn = 0; for (int k = 0; k < d.ne; ++k) rn = fmax(rn, e * fabs(sv[k]) * dcur[k]); }
-                    else if (r < d.oDU) { int q = r - d.oEQ; rn = e * dcur[d.b + q]; for (int k = 0; k < d.b; ++k) rn = fmax(rn, e * fabs(G[q * d.ldG + k]) * dcur[k]); }
+                    else if (r < d.oDU) { int q = r - d.oEQ; rn = e * dcur[d.b + q]; for (int k = 0; k < d.b; ++k) rn = fmax(rn, e * fabs(G[q * ldG + k]) * dcur[k]); }
                     else rn = e * dcur[d.ne + r - d.oDU];
                 }
                 Et[g] = 1.0 / sqrt(lim_scaling(rn));
@@ -302,6 +370,7 @@ struct CtaSolver {
         double* LO = CSM(LO); double* UP = CSM(UP);
         int8_t* rt = reinterpret_cast<int8_t*>(smem + L.oRT);
         for (int kg = tid; kg < d.n; kg += NT) Q[kg] *= pending_c;
+        for (int kg = d.n + tid; kg < L.nP; kg += NT) CSM(T)[kg] = 0.0;      // (T served as scratch)
         for (int g = tid; g < d.m; g += NT) {
             int i, r; row_of(g, i, r);
             double e = E[g];
@@ -321,29 +390,16 @@ struct CtaSolver {
     }
 
     // ---- structured products ---------------------------------------------------------------------------------------------
-    // unscaled (A' v)[kg] for the E-weighted row values V
+    // unscaled (A' v)[kg] for the E-weighted row values Vs
     __device__ __forceinline__ double col_atv(int i, int k, const double* Vs) const {
-        const double* G = CSM(G); const double* Cm = CSM(C); const double* sv = CSM(SV);
         const double* vj = Vs + d.roff(i);
         const double* vprev = i == 0 ? Vs : Vs + d.roff(i - 1) + d.oEQ;
         double au;
         if (k < d.ne) {
-            au = vj[d.oBOX + k] - vprev[k] + sv[k] * vj[d.oSC];
-            if (k < d.nx) {
-                double a0 = 0, a1 = 0;
-                int r = 0;
-                for (; r + 1 < d.ny; r += 2) { a0 = fma(Cm[r * d.ldC + k], vj[d.oOUT + r], a0); a1 = fma(Cm[(r + 1) * d.ldC + k], vj[d.oOUT + r + 1], a1); }
-                if (r < d.ny) a0 = fma(Cm[r * d.ldC + k], vj[d.oOUT + r], a0);
-                au += a0 + a1;
-            }
+            au = vj[d.oBOX + k] - vprev[k] + CSM(SV)[k] * vj[d.oSC];
+            if (k < d.nx) au += cta_dot<SNY, 2>(CSM(C) + k, fldC(), vj + d.oOUT, d.ny);
         } else au = vj[d.oDU + k - d.ne];
-        if (i < d.ph) {
-            double a0 = 0, a1 = 0;
-            int r = 0;
-            for (; r + 1 < d.ne; r += 2) { a0 = fma(G[r * d.ldG + k], vj[d.oEQ + r], a0); a1 = fma(G[(r + 1) * d.ldG + k], vj[d.oEQ + r + 1], a1); }
-            if (r < d.ne) a0 = fma(G[r * d.ldG + k], vj[d.oEQ + r], a0);
-            au += a0 + a1;
-        }
+        if (i < d.ph) au += cta_dot<SNE, 2>(CSM(G) + k, fldG(), vj + d.oEQ, d.ne);
         return au;
     }
     // row tasks are ordered by row class so that the lanes of a warp run the same dot-product length:
@@ -360,55 +416,30 @@ struct CtaSolver {
     }
     // a_g . u for the unscaled variable values u = D x in R
     __device__ __forceinline__ double row_dot(int i, int r) const {
-        const double* G = CSM(G); const double* Cm = CSM(C); const double* sv = CSM(SV);
         const double* U = CSM(R);
         if (i < 0) return -U[r];
         const double* u = U + i * d.b;
         if (r < d.oOUT) return u[r];
-        if (r < d.oSC) {
-            const double* cp = Cm + (r - d.oOUT) * d.ldC;
-            double a0 = 0, a1 = 0; int k = 0;
-            for (; k + 1 < d.nx; k += 2) { a0 = fma(cp[k], u[k], a0); a1 = fma(cp[k + 1], u[k + 1], a1); }
-            if (k < d.nx) a0 = fma(cp[k], u[k], a0);
-            return a0 + a1;
-        }
-        if (r < d.oEQ) {
-            double a0 = 0, a1 = 0; int k = 0;
-            for (; k + 1 < d.ne; k += 2) { a0 = fma(sv[k], u[k], a0); a1 = fma(sv[k + 1], u[k + 1], a1); }
-            if (k < d.ne) a0 = fma(sv[k], u[k], a0);
-            return a0 + a1;
-        }
-        if (r < d.oDU) {
-            int q = r - d.oEQ;
-            const double* gp = G + q * d.ldG;
-            double a0 = 0, a1 = 0, a2 = 0, a3 = 0; int k = 0;
-            for (; k + 3 < d.b; k += 4) {
-                a0 = fma(gp[k], u[k], a0); a1 = fma(gp[k + 1], u[k + 1], a1); a2 = fma(gp[k + 2], u[k + 2], a2); a3 = fma(gp[k + 3], u[k + 3], a3);
-            }
-            for (; k < d.b; ++k) a0 = fma(gp[k], u[k], a0);
-            return ((a0 + a1) + (a2 + a3)) - u[d.b + q];
-        }
+        if (r < d.oSC) return cta_dot<SNX, 0>(CSM(C) + (r - d.oOUT) * fldC(), 1, u, d.nx);
+        if (r < d.oEQ) return cta_dot<SNE, 0>(CSM(SV), 1, u, d.ne);
+        if (r < d.oDU) { const int q = r - d.oEQ; return cta_dot<SB, 0>(CSM(G) + q * fldG(), 1, u, d.b) - u[d.b + q]; }
         return u[d.ne + r - d.oDU];
     }
     // c D_k (P u)_k of variable (i,k); needs YV_i = wO_i .* (C u_x) for k < nx
     __device__ __forceinline__ double col_pu(int i, int k) const {
-        const double* Cm = CSM(C); const double* Wst = CSM(W) + i * (d.ny + 2 * d.nu);
-        const double* U = CSM(R) + i * d.b; const double* yv = CSM(YV) + i * d.ny;
+        const double* Wst = CSM(W) + i * (d.ny + 2 * d.nu);
+        const double* U = CSM(R) + i * d.b;
         double pu;
-        if (k < d.nx) { pu = 0; for (int r = 0; r < d.ny; ++r) pu = fma(Cm[r * d.ldC + k], yv[r], pu); }
+        if (k < d.nx) pu = cta_dot<SNY, 1>(CSM(C) + k, fldC(), CSM(YV) + i * d.ny, d.ny);
         else if (k < d.ne) pu = Wst[d.ny + k - d.nx] * U[k];
         else pu = Wst[d.ny + d.nu + k - d.ne] * U[k];
         return pu * c * CSM(D)[i * d.b + k];
     }
     __device__ __forceinline__ void fill_yv() {      // YV_i = wO_i .* (C u_x,i)
-        const double* Cm = CSM(C); const double* U = CSM(R); double* YV = CSM(YV);
         const int nw = d.ny + 2 * d.nu;
         for (int e = tid; e < (d.ph + 1) * d.ny; e += NT) {
             int i = e / d.ny, r = e - i * d.ny;
-            const double* u = U + i * d.b;
-            double acc = 0;
-            for (int k = 0; k < d.nx; ++k) acc = fma(Cm[r * d.ldC + k], u[k], acc);
-            YV[e] = CSM(W)[i * nw + r] * acc;
+            CSM(YV)[e] = CSM(W)[i * nw + r] * cta_dot<SNX, 0>(CSM(C) + r * fldC(), 1, CSM(R) + i * d.b, d.nx);
         }
     }
     __device__ __forceinline__ void refresh_V() {    // V = E (rho z - y): the row weights of the next right-hand side
@@ -418,62 +449,60 @@ struct CtaSolver {
         __syncthreads();
     }
 
-    // ---- elimination table: (kind, row, col) of every entry the factorisation updates, built once per launch -------------------
+    // ---- elimination table of the run-time-dimension path: (kind, row, col) of every entry, built once per launch ------------
     __device__ void build_table() {
-        int* tab = reinterpret_cast<int*>(smem + L.oTAB);
-        const int na = d.b + d.ne;
-        for (int e = tid; e < L.n_ent; e += NT) {
-            int kind = e < L.n_aug ? 0 : 1;
-            int pidx = kind ? e - L.n_aug : e;
-            int r = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
-            while ((r + 1) * (r + 2) / 2 <= pidx) ++r;
-            while (r * (r + 1) / 2 > pidx) --r;
-            int k = pidx - r * (r + 1) / 2;
-            if (kind) r += 1;                       // strict lower triangle of M: (r+1, k)
-            tab[e] = (kind << 30) | (r << 15) | k;
+        if constexpr (!DM::is_static) {
+            int* tab = reinterpret_cast<int*>(smem + L.oTAB);
+            for (int e = tid; e < L.n_ent; e += NT) {
+                int kind = e < L.n_aug ? 0 : 1;
+                int pidx = kind ? e - L.n_aug : e;
+                int r = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
+                while ((r + 1) * (r + 2) / 2 <= pidx) ++r;
+                while (r * (r + 1) / 2 > pidx) --r;
+                int k = pidx - r * (r + 1) / 2;
+                if (kind) r += 1;                       // strict lower triangle of M: (r+1, k)
+                tab[e] = (kind << 30) | (r << 15) | k;
+            }
         }
-        (void)na;
         __syncthreads();
     }
 
     // ---- block-tridiagonal factorisation of H = D (c P + A' R A) D + sigma I ---------------------------------------------------
-    // Per stage i: S_i = H_ii - Lc_{i-1} Lc_{i-1}',  S_i = L_i L_i',  Lc_i = H_{i+1,i} L_i^-T.  Stored: L_i^-1 (packed lower
-    // triangle) and W_i = Lc_i L_i^-1.  The stage is eliminated as the LDL' of the augmented block [S_i Hc_i'; Hc_i 0] by the
-    // whole thread block, one barrier per pivot; the unit-lower inverse is accumulated by the same row operations.
+    // Per stage i: S_i = H_ii - Lc_{i-1} Lc_{i-1}',  S_i = L_i L_i',  Lc_i = H_{i+1,i} L_i^-T.  Stored: L_i^-1 (b x LD, zero above
+    // the diagonal and in the rows / columns a short last stage does not have) and W_i = Lc_i L_i^-1 (ne x LD).
     __device__ bool factorize(double sigma) {
         const double* G = CSM(G); const double* Cm = CSM(C); const double* sv = CSM(SV); const double* Wr = CSM(W);
         const double* D = CSM(D); const double* E = CSM(E);
         double* RW = CSM(V);                         // rho' = rho E^2 per row (V is rebuilt afterwards)
         double* YV = CSM(YV);
-        double* AUG = CSM(AUG); double* M = CSM(M); double* LCS = CSM(LCS); double* TB = CSM(TB);
-        const int* tab = reinterpret_cast<const int*>(smem + L.oTAB);
+        double* LCS = CSM(LCS); double* TB = CSM(TB);
         const int8_t* rt = rtp();
-        const int nw = d.ny + 2 * d.nu, NP = d.b * (d.b + 1) / 2, lda = L.lda, ldb = d.ldb;
+        const int nw = d.ny + 2 * d.nu, LD = fLD(), ldG = fldG(), ldC = fldC();
         for (int g = tid; g < d.m; g += NT) { double e = E[g]; RW[g] = rho_of(rt[g]) * e * e; }
         __syncthreads();
         for (int e = tid; e < (d.ph + 1) * d.ny; e += NT) { int i = e / d.ny, r = e - i * d.ny; YV[e] = c * Wr[i * nw + r] + RW[d.roff(i) + d.oOUT + r]; }
         __syncthreads();
-        // H_ii of every stage (stage-parallel), packed into the L^-1 slot of the stage's record
-        for (int t = tid; t < (d.ph + 1) * NP; t += NT) {
-            int i = t / NP, pidx = t - i * NP;
-            int r = (tab[pidx] >> 15) & 0x7fff, k = tab[pidx] & 0x7fff;
-            if (r >= d.bcount(i)) continue;
-            const double* rw = RW + d.roff(i);
-            const double* rwp = i == 0 ? RW : RW + d.roff(i - 1) + d.oEQ;
-            const double* wst = Wr + i * nw; const double* yv = YV + i * d.ny;
+        // H_ii of every stage (stage-parallel) into the L^-1 slot of the stage's record: lower triangle, zero elsewhere
+        for (int t = tid; t < (d.ph + 1) * d.b * d.b; t += NT) {
+            const int i = t / (d.b * d.b), rem = t - i * d.b * d.b, r = rem / d.b, k = rem - r * d.b;
             double v = 0;
-            if (i < d.ph) for (int j = 0; j < d.ne; ++j) v += G[j * d.ldG + r] * rw[d.oEQ + j] * G[j * d.ldG + k];
-            if (r < d.ne) {
-                v += rw[d.oSC] * sv[r] * sv[k];
-                if (r < d.nx) for (int j = 0; j < d.ny; ++j) v += Cm[j * d.ldC + r] * yv[j] * Cm[j * d.ldC + k];
-                if (r == k) {
-                    v += rwp[k] + rw[d.oBOX + k];
-                    if (k >= d.nx) v += c * wst[d.ny + k - d.nx];
-                }
-            } else if (r == k) v += c * wst[d.ny + d.nu + k - d.ne] + rw[d.oDU + k - d.ne];
-            v = D[i * d.b + r] * v * D[i * d.b + k];
-            if (r == k) v += sigma;
-            fac(i)[pidx] = v;
+            if (k <= r && r < d.bcount(i)) {
+                const double* rw = RW + d.roff(i);
+                const double* rwp = i == 0 ? RW : RW + d.roff(i - 1) + d.oEQ;
+                const double* wst = Wr + i * nw; const double* yv = YV + i * d.ny;
+                if (i < d.ph) for (int j = 0; j < d.ne; ++j) v += G[j * ldG + r] * rw[d.oEQ + j] * G[j * ldG + k];
+                if (r < d.ne) {
+                    v += rw[d.oSC] * sv[r] * sv[k];
+                    if (r < d.nx) for (int j = 0; j < d.ny; ++j) v += Cm[j * ldC + r] * yv[j] * Cm[j * ldC + k];
+                    if (r == k) {
+                        v += rwp[k] + rw[d.oBOX + k];
+                        if (k >= d.nx) v += c * wst[d.ny + k - d.nx];
+                    }
+                } else if (r == k) v += c * wst[d.ny + d.nu + k - d.ne] + rw[d.oDU + k - d.ne];
+                v = D[i * d.b + r] * v * D[i * d.b + k];
+                if (r == k) v += sigma;
+            }
+            fac(i)[r * LD + k] = v;
         }
         __syncthreads();
         bool ok = true;
@@ -493,7 +522,7 @@ struct CtaSolver {
                     cta_static_for<0, B>([&](auto qc) {
                         constexpr int q = decltype(qc)::value;
                         double v = 0.0;
-                        if (r < bi && q <= r) { v = F[r * (r + 1) / 2 + q]; if (i > 0 && r < d.ne) v += TB[r * ldb + q]; }
+                        if (r < bi && q <= r) { v = F[r * LD + q]; if (i > 0 && r < d.ne) v += TB[r * LD + q]; }
                         a[q] = v; m[q] = (q == r) ? 1.0 : 0.0;           // m[x]: entry (row x, column = lane)
                     });
                     cta_static_for<0, B>([&](auto kc) {
@@ -516,22 +545,25 @@ struct CtaSolver {
                             __syncwarp();
                         }
                     });
-                    // row scales 1/sqrt(d_r), then L^-1(r, q) = m_q[r] rs_r : lane q writes column q
+                    // row scales 1/sqrt(d_r), then L^-1(x, q) = m_q[x] rs_x : lane q writes column q (zeros where L^-1 has none)
                     COL[32 + lane] = rsqrt(dsave);
                     __syncwarp();
                     cta_static_for<0, B>([&](auto xc) {
                         constexpr int x = decltype(xc)::value;
-                        if (x >= lane && x < bi && lane < bi) F[x * (x + 1) / 2 + lane] = m[x] * COL[32 + x];
+                        if (lane < B) F[x * LD + lane] = (x >= lane && x < bi && lane < bi) ? m[x] * COL[32 + x] : 0.0;
                     });
                 }
                 __syncthreads();
             } else {
                 // run-time dimensions: the same elimination by the whole block on shared memory, one barrier per pivot
+                double* AUG = CSM(AUG); double* M = CSM(M);
+                const int* tab = reinterpret_cast<const int*>(smem + L.oTAB);
+                const int lda = L.lda;
                 for (int e = tid; e < L.n_ent; e += NT) {
                     const int te = tab[e];
                     const int r = (te >> 15) & 0x7fff, k = te & 0x7fff;
-                    if (te >> 30) M[r * ldb + k] = 0.0;
-                    else if (r < bi) { double v = F[r * (r + 1) / 2 + k]; if (i > 0 && r < d.ne) v += TB[r * ldb + k]; AUG[r * lda + k] = v; }
+                    if (te >> 30) M[r * LD + k] = 0.0;
+                    else if (r < bi) { double v = F[r * LD + k]; if (i > 0 && r < d.ne) v += TB[r * LD + k]; AUG[r * lda + k] = v; }
                 }
                 __syncthreads();
                 for (int k = 0; k < bi; ++k) {
@@ -543,45 +575,43 @@ struct CtaSolver {
                         const int r = (te >> 15) & 0x7fff, q = te & 0x7fff;
                         if (r >= bi) continue;
                         if (te >> 30) {      // M(r,q), strict lower: active for q <= k < r
-                            if (q <= k && k < r) M[r * ldb + q] -= (AUG[r * lda + k] * rd) * ((k == q) ? 1.0 : M[k * ldb + q]);
+                            if (q <= k && k < r) M[r * LD + q] -= (AUG[r * lda + k] * rd) * ((k == q) ? 1.0 : M[k * LD + q]);
                         } else if (q > k) AUG[r * lda + q] -= (AUG[r * lda + k] * rd) * AUG[q * lda + k];
                     }
                     __syncthreads();
                 }
-                for (int e = tid; e < L.n_ent; e += NT) {
-                    const int te = tab[e];
-                    const int r = (te >> 15) & 0x7fff, q = te & 0x7fff;
-                    if (r >= bi) continue;
-                    if (te >> 30) F[r * (r + 1) / 2 + q] = M[r * ldb + q] * rsqrt(AUG[r * lda + r]);
-                    else if (r == q) F[r * (r + 1) / 2 + r] = rsqrt(AUG[r * lda + r]);
+                for (int e = tid; e < d.b * d.b; e += NT) {
+                    const int r = e / d.b, q = e - r * d.b;
+                    double v = 0.0;
+                    if (r < bi && q <= r) v = (q == r ? 1.0 : M[r * LD + q]) * rsqrt(AUG[r * lda + r]);
+                    F[r * LD + q] = v;
                 }
                 __syncthreads();
             }
             if (i == d.ph) break;
             // ---- Lc_i = Hc_i L_i^-T,  Hc_i = -(D_e(i+1) rho'_eq(i+1)) G D_i   (ne x b, stage-parallel dot products) ----
-            for (int e = tid; e < d.ne * bi; e += NT) {
-                int h = e / bi, k = e - h * bi;
+            for (int e = tid; e < d.ne * d.b; e += NT) {
+                const int h = e / d.b, k = e - h * d.b;
                 const double hs = -(D[(i + 1) * d.b + h] * RW[d.roff(i) + d.oEQ + h]);
-                const double* gp = G + h * d.ldG; const double* dp = D + i * d.b; const double* li = F + k * (k + 1) / 2;
-                double acc = 0;
-                for (int q = 0; q <= k; ++q) acc = fma(gp[q] * dp[q], li[q], acc);
-                LCS[h * ldb + k] = hs * acc;
+                const double* gp = G + h * ldG; const double* dp = D + i * d.b; const double* li = F + k * LD;
+                double a0 = 0, a1 = 0;
+                if constexpr (SB > 0) {
+#pragma unroll
+                    for (int q = 0; q < SB; q += 2) { a0 = fma(gp[q] * dp[q], li[q], a0); a1 = fma(gp[q + 1] * dp[q + 1], li[q + 1], a1); }
+                } else for (int q = 0; q <= k; ++q) a0 = fma(gp[q] * dp[q], li[q], a0);
+                LCS[h * LD + k] = hs * (a0 + a1);
             }
             __syncthreads();
-            // ---- TB = -Lc Lc' for the next stage's pivot block;  W_i = Lc_i L_i^-1 ----
+            // ---- TB = -Lc Lc' (full symmetric ne x ne) for the next stage's pivot block;  W_i = Lc_i L_i^-1 ----
             {
-                const int nT = d.ne * (d.ne + 1) / 2;
-                for (int e = tid; e < nT + d.ne * bi; e += NT) {
+                const int nT = d.ne * d.ne;
+                for (int e = tid; e < nT + d.ne * d.b; e += NT) {
                     if (e < nT) {
-                        int r = (tab[e] >> 15) & 0x7fff, k = tab[e] & 0x7fff;
-                        double acc = 0;
-                        for (int q = 0; q < bi; ++q) acc = fma(LCS[r * ldb + q], LCS[k * ldb + q], acc);
-                        TB[r * ldb + k] = -acc;
+                        const int r = e / d.ne, k = e - r * d.ne;
+                        TB[r * LD + k] = -cta_dot<SB, 0>(LCS + r * LD, 1, LCS + k * LD, d.b);
                     } else {
-                        int e2 = e - nT, h = e2 / bi, cc = e2 - h * bi;
-                        double acc = 0;
-                        for (int q = cc; q < bi; ++q) acc = fma(LCS[h * ldb + q], F[q * (q + 1) / 2 + cc], acc);
-                        F[d.oLc + h * ldb + cc] = acc;
+                        const int e2 = e - nT, h = e2 / d.b, cc = e2 - h * d.b;
+                        F[fWm() + h * LD + cc] = cta_dot<SB, 1>(F + cc, LD, LCS + h * LD, d.b);
                     }
                 }
             }
@@ -590,118 +620,46 @@ struct CtaSolver {
         return !__syncthreads_or(ok ? 0 : 1);
     }
 
-    // ---- reduced KKT solve: in R = right-hand side (stage-major), out T = solution (scaled), R = D .* solution ------------------
-#define SPROF(slot) do { if (prof_on) { long long q1_ = clock64(); sp[slot] += q1_ - sq0; sq0 = q1_; } } while (0)
+    // ---- reduced KKT solve, bulk-synchronous (polish): in R = right-hand side, out T = solution (scaled), R = D .* solution ----
     template <class Epi>
     __device__ __forceinline__ void kkt_solve(Epi epilogue) {
-        double* R = CSM(R); double* T = CSM(T); double* GT = CSM(GT); double* CAR = CSM(CAR); const double* D = CSM(D);
-        const int ldb = d.ldb, nWr = d.ph * d.ne;
-        // forward, parallel part: g_i = W_i r_i, rhat_i = L_i^-1 r_i
-        for (int t = tid; t < nWr + d.n; t += NT) {
-            if (t < nWr) {
-                int i = t / d.ne, r = t - i * d.ne;
-                const double* w = fac(i) + d.oLc + r * ldb; const double* x = R + i * d.b;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0; int q = 0;
-                for (; q + 3 < d.b; q += 4) { a0 = fma(w[q], x[q], a0); a1 = fma(w[q + 1], x[q + 1], a1); a2 = fma(w[q + 2], x[q + 2], a2); a3 = fma(w[q + 3], x[q + 3], a3); }
-                for (; q < d.b; ++q) a0 = fma(w[q], x[q], a0);
-                GT[t] = (a0 + a1) + (a2 + a3);
-            } else {
-                int kg = t - nWr, i = kg / d.b, r = kg - i * d.b;
-                const double* li = fac(i) + r * (r + 1) / 2; const double* x = R + i * d.b;
-                double a0 = 0, a1 = 0; int q = 0;
-                for (; q + 1 <= r; q += 2) { a0 = fma(li[q], x[q], a0); a1 = fma(li[q + 1], x[q + 1], a1); }
-                if (q <= r) a0 = fma(li[q], x[q], a0);
-                T[kg] = a0 + a1;
-            }
-        }
+        double* R = CSM(R); double* T = CSM(T); double* GT = CSM(GT); double* CAR = CSM(CAR); double* XE = CSM(XE); const double* D = CSM(D);
+        const int LD = fLD();
+        for (int j = warp; j <= d.ph; j += NW) stage_p3(j);
         __syncthreads();
-        SPROF(1);
-        // forward, serial part: c_{i+1} = g_i - W_i[:, :ne] c_i
         if (warp == 0) {
             for (int r = lane; r < d.ne; r += 32) CAR[r] = 0.0;
             __syncwarp();
             for (int i = 0; i < d.ph; ++i) {
-                const double* cp = CAR + i * d.ne;
-                for (int r = lane; r < d.ne; r += 32) {
-                    const double* w = fac(i) + d.oLc + r * ldb;
-                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0; int q = 0;
-                    for (; q + 3 < d.ne; q += 4) { a0 = fma(w[q], cp[q], a0); a1 = fma(w[q + 1], cp[q + 1], a1); a2 = fma(w[q + 2], cp[q + 2], a2); a3 = fma(w[q + 3], cp[q + 3], a3); }
-                    for (; q < d.ne; ++q) a0 = fma(w[q], cp[q], a0);
-                    CAR[(i + 1) * d.ne + r] = GT[i * d.ne + r] - ((a0 + a1) + (a2 + a3));
-                }
+                for (int r = lane; r < d.ne; r += 32) CAR[(i + 1) * d.ne + r] = GT[i * d.ne + r] - cta_dot<SNE, 0>(fac(i) + fWm() + r * LD, 1, CAR + i * d.ne, d.ne);
                 __syncwarp();
             }
         }
         __syncthreads();
-        SPROF(2);
-        // t_i = rhat_i - L_i^-1[:, :ne] c_i
-        for (int kg = tid; kg < d.n; kg += NT) {
-            int i = kg / d.b, r = kg - i * d.b;
-            if (i == 0) continue;
-            const double* li = fac(i) + r * (r + 1) / 2; const double* cp = CAR + i * d.ne;
-            const int cnt = r < d.ne ? r + 1 : d.ne;
-            double a0 = 0, a1 = 0; int q = 0;
-            for (; q + 1 < cnt; q += 2) { a0 = fma(li[q], cp[q], a0); a1 = fma(li[q + 1], cp[q + 1], a1); }
-            if (q < cnt) a0 = fma(li[q], cp[q], a0);
-            T[kg] -= a0 + a1;
-        }
+        for (int j = warp; j <= d.ph; j += NW) stage_fwd(j);
         __syncthreads();
-        SPROF(3);
-        // backward, parallel part: s_i = L_i^-T t_i  -> R
-        for (int kg = tid; kg < d.n; kg += NT) {
-            int i = kg / d.b, k = kg - i * d.b;
-            const int bi = d.bcount(i);
-            if (k >= bi) continue;
-            const double* F = fac(i); const double* t = T + i * d.b;
-            double a0 = 0, a1 = 0; int r = k;
-            for (; r + 1 < bi; r += 2) { a0 = fma(F[r * (r + 1) / 2 + k], t[r], a0); a1 = fma(F[(r + 1) * (r + 2) / 2 + k], t[r + 1], a1); }
-            if (r < bi) a0 = fma(F[r * (r + 1) / 2 + k], t[r], a0);
-            R[kg] = a0 + a1;
-        }
-        __syncthreads();
-        SPROF(4);
-        // backward, serial part: xe_i = s_i[:ne] - W_i[:, :ne]' xe_{i+1}
         if (warp == 0) {
-            for (int r = lane; r < d.ne; r += 32) CAR[d.ph * d.ne + r] = R[d.ph * d.b + r];
+            for (int r = lane; r < d.ne; r += 32) XE[d.ph * d.ne + r] = R[d.ph * d.b + r];
             __syncwarp();
             for (int i = d.ph - 1; i >= 0; --i) {
-                const double* xn = CAR + (i + 1) * d.ne;
-                const double* w = fac(i) + d.oLc;
-                for (int cc = lane; cc < d.ne; cc += 32) {
-                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0; int r = 0;
-                    for (; r + 3 < d.ne; r += 4) {
-                        a0 = fma(w[r * ldb + cc], xn[r], a0); a1 = fma(w[(r + 1) * ldb + cc], xn[r + 1], a1);
-                        a2 = fma(w[(r + 2) * ldb + cc], xn[r + 2], a2); a3 = fma(w[(r + 3) * ldb + cc], xn[r + 3], a3);
-                    }
-                    for (; r < d.ne; ++r) a0 = fma(w[r * ldb + cc], xn[r], a0);
-                    CAR[i * d.ne + cc] = R[i * d.b + cc] - ((a0 + a1) + (a2 + a3));
-                }
+                for (int cc = lane; cc < d.ne; cc += 32) XE[i * d.ne + cc] = R[i * d.b + cc] - cta_dot<SNE, 1>(fac(i) + fWm() + cc, LD, XE + (i + 1) * d.ne, d.ne);
                 __syncwarp();
             }
         }
         __syncthreads();
-        SPROF(5);
-        // x_i = [xe_i ; s_i[ne:] - W_i[:, ne:]' xe_{i+1}]
         for (int kg = tid; kg < d.n; kg += NT) {
-            int i = kg / d.b, k = kg - i * d.b;
+            const int i = kg / d.b, k = kg - i * d.b;
             double xt;
-            if (k < d.ne) xt = CAR[i * d.ne + k];
-            else {
-                const double* xn = CAR + (i + 1) * d.ne; const double* w = fac(i) + d.oLc + k;
-                double a0 = 0, a1 = 0; int r = 0;
-                for (; r + 1 < d.ne; r += 2) { a0 = fma(w[r * ldb], xn[r], a0); a1 = fma(w[(r + 1) * ldb], xn[r + 1], a1); }
-                if (r < d.ne) a0 = fma(w[r * ldb], xn[r], a0);
-                xt = R[kg] - (a0 + a1);
-            }
+            if (k < d.ne) xt = XE[i * d.ne + k];
+            else xt = R[kg] - cta_dot<SNE, 1>(fac(i) + fWm() + k, LD, XE + (i + 1) * d.ne, d.ne);
             T[kg] = xt;
             R[kg] = D[kg] * xt;
             epilogue(kg, xt);
         }
         __syncthreads();
-        SPROF(6);
     }
 
-    // ================= pipelined ADMM sweep (warp-specialised) =================================================================
+    // ================= per-stage jobs (one warp each) and the pipelined ADMM sweep ===============================================
     // The serial recurrences of the KKT solve take ~40 dependent ne x ne mat-vecs per iteration; a bulk-synchronous schedule
     // leaves all but one warp idle meanwhile.  Here warp 0 runs ONLY the two recurrences and the other warps run per-stage
     // jobs behind it, ordered by shared-memory progress flags (value = sweep number, monotone, never reset):
@@ -713,14 +671,19 @@ struct CtaSolver {
     __device__ __forceinline__ volatile int* flagp(int which, int i) const { return reinterpret_cast<volatile int*>(smem + L.oFLAG) + which * (d.ph + 2) + i; }
     enum { FG = 0, FC = 1, FS = 2, FX = 3, FU = 4, FV = 5 };
     __device__ __forceinline__ void wait_flag(int which, int i, int stamp) const {
+#ifdef B200_CTA_PROF
+        const long long q0 = clock64();
+#endif
         if (lane == 0) { volatile int* f = flagp(which, i); while (*f < stamp) { } }
         __syncwarp();
         asm volatile("" ::: "memory");
+#ifdef B200_CTA_PROF
+        const_cast<CtaSolver*>(this)->pw[2] += clock64() - q0;
+#endif
     }
-    // Data and flag are both shared memory written by the same warp in program order (the data by warp-wide stores BEFORE
-    // the flag store); the shared-memory pipeline of an SM keeps a warp's accesses in order and has no per-thread cache, so a
-    // warp that observes the flag observes the data.  (A membar.cta here costs several hundred cycles per post: measured 2x
-    // on the whole iteration.)
+    // Data and flag are both shared memory written by the same warp in program order (the data by warp-wide stores BEFORE the
+    // flag store); the shared-memory pipeline of an SM keeps a warp's accesses in order and has no per-thread cache, so a warp
+    // that observes the flag observes the data (a membar.cta per post was measured and changes nothing but the cost).
     __device__ __forceinline__ void post_flag(int which, int i, int stamp) const {
         __syncwarp();
         asm volatile("" ::: "memory");
@@ -733,69 +696,41 @@ struct CtaSolver {
     }
     // rhat_j = L_j^-1 r_j -> T,  g_j = W_j r_j -> GT  (one warp; r_j in R)
     __device__ __forceinline__ void stage_p3(int j) {
-        const int bj = d.bcount(j), nt = bj + (j < d.ph ? d.ne : 0), ldb = d.ldb;
+        const int nt = d.b + (j < d.ph ? d.ne : 0), LD = fLD();
         const double* x = CSM(R) + j * d.b;
         for (int t = lane; t < nt; t += 32) {
-            if (t < bj) {
-                const double* li = fac(j) + t * (t + 1) / 2;
-                double a0 = 0, a1 = 0; int q = 0;
-                for (; q + 1 <= t; q += 2) { a0 = fma(li[q], x[q], a0); a1 = fma(li[q + 1], x[q + 1], a1); }
-                if (q <= t) a0 = fma(li[q], x[q], a0);
-                CSM(T)[j * d.b + t] = a0 + a1;
-            } else {
-                const int r = t - bj;
-                const double* w = fac(j) + d.oLc + r * ldb;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0; int q = 0;
-                for (; q + 3 < d.b; q += 4) { a0 = fma(w[q], x[q], a0); a1 = fma(w[q + 1], x[q + 1], a1); a2 = fma(w[q + 2], x[q + 2], a2); a3 = fma(w[q + 3], x[q + 3], a3); }
-                for (; q < d.b; ++q) a0 = fma(w[q], x[q], a0);
-                CSM(GT)[j * d.ne + r] = (a0 + a1) + (a2 + a3);
-            }
+            const double v = cta_dot<SB, 0>(fac(j) + t * LD, 1, x, d.b);      // rows 0..b-1: L^-1, rows b..b+ne-1: W
+            if (t < d.b) CSM(T)[j * d.b + t] = v; else CSM(GT)[j * d.ne + (t - d.b)] = v;
         }
     }
     __device__ __forceinline__ void stage_rhs(int j) {
         const double sigma = p.sigma;
-        const int bj = d.bcount(j);
-        for (int k = lane; k < bj; k += 32) { const int kg = j * d.b + k; CSM(R)[kg] = sigma * CSM(X)[kg] - CSM(Q)[kg] + CSM(D)[kg] * col_atv(j, k, CSM(V)); }
+        for (int k = lane; k < d.b; k += 32) {
+            const int kg = j * d.b + k;
+            CSM(R)[kg] = k < d.bcount(j) ? sigma * CSM(X)[kg] - CSM(Q)[kg] + CSM(D)[kg] * col_atv(j, k, CSM(V)) : 0.0;
+        }
     }
     // job F_i
     __device__ __forceinline__ void stage_fwd(int i) {
         double* T = CSM(T) + i * d.b; double* R = CSM(R) + i * d.b; const double* F = fac(i);
-        const double* cp = CSM(CAR) + i * d.ne;
-        const int bi = d.bcount(i);
+        const int LD = fLD();
         if (i > 0) {
-            for (int r = lane; r < bi; r += 32) {
-                const double* li = F + r * (r + 1) / 2;
-                const int cnt = r < d.ne ? r + 1 : d.ne;
-                double a0 = 0, a1 = 0; int q = 0;
-                for (; q + 1 < cnt; q += 2) { a0 = fma(li[q], cp[q], a0); a1 = fma(li[q + 1], cp[q + 1], a1); }
-                if (q < cnt) a0 = fma(li[q], cp[q], a0);
-                T[r] -= a0 + a1;
-            }
+            const double* cp = CSM(CAR) + i * d.ne;
+            for (int r = lane; r < d.b; r += 32) T[r] -= cta_dot<SNE, 0>(F + r * LD, 1, cp, d.ne);
         }
         __syncwarp();
-        for (int k = lane; k < bi; k += 32) {
-            double a0 = 0, a1 = 0; int r = k;
-            for (; r + 1 < bi; r += 2) { a0 = fma(F[r * (r + 1) / 2 + k], T[r], a0); a1 = fma(F[(r + 1) * (r + 2) / 2 + k], T[r + 1], a1); }
-            if (r < bi) a0 = fma(F[r * (r + 1) / 2 + k], T[r], a0);
-            R[k] = a0 + a1;
-        }
+        for (int k = lane; k < d.b; k += 32) R[k] = cta_dot<SB, 1>(F + k, LD, T, d.b);
     }
     // x_i = [xe_i ; s_i[ne:] - W_i[:, ne:]' xe_{i+1}],  u_i = D x_i -> R,  x-update (update_x of osqp.c)
     __device__ __forceinline__ void stage_x(int i, bool store_delta) {
-        const int bi = d.bcount(i), ldb = d.ldb;
+        const int bi = d.bcount(i), LD = fLD();
         const double alpha = p.alpha;
         double* va = gws + L.gVA;
         for (int k = lane; k < bi; k += 32) {
             const int kg = i * d.b + k;
             double xt;
             if (k < d.ne) xt = CSM(XE)[i * d.ne + k];
-            else {
-                const double* xn = CSM(XE) + (i + 1) * d.ne; const double* w = fac(i) + d.oLc + k;
-                double a0 = 0, a1 = 0; int r = 0;
-                for (; r + 1 < d.ne; r += 2) { a0 = fma(w[r * ldb], xn[r], a0); a1 = fma(w[(r + 1) * ldb], xn[r + 1], a1); }
-                if (r < d.ne) a0 = fma(w[r * ldb], xn[r], a0);
-                xt = CSM(R)[kg] - (a0 + a1);
-            }
+            else xt = CSM(R)[kg] - cta_dot<SNE, 1>(fac(i) + fWm() + k, LD, CSM(XE) + (i + 1) * d.ne, d.ne);
             CSM(R)[kg] = CSM(D)[kg] * xt;
             const double xo = CSM(X)[kg];
             const double xnw = alpha * xt + (1.0 - alpha) * xo;
@@ -833,64 +768,64 @@ struct CtaSolver {
     // the two recurrences (warp 0).  Static dimensions: the K rows / columns of the next stage are prefetched into registers
     // while the current stage's flag is awaited, so only the broadcast of the carried vector sits between two steps.
     __device__ __forceinline__ void chain_sweeps(int S) {
-        const int ldb = d.ldb;
+        const int LD = fLD();
+        const long long qc0 = clock64();
         double* CAR = CSM(CAR); double* XE = CSM(XE); const double* GT = CSM(GT); const double* R = CSM(R);
-        if constexpr (DM::is_static) {
-            constexpr int NE = DM::ne;
+        if constexpr (SNE > 0) {
+            constexpr int NE = SNE;
             const int r = lane < NE ? lane : NE - 1;
             double kr[NE], kn[NE];
+            auto ld_row = [&](double (&dst)[NE], int st) {
+                const double2* w2 = reinterpret_cast<const double2*>(fac(st) + fWm() + r * LD);
+                cta_static_for<0, NE / 2>([&](auto jc) { constexpr int j = decltype(jc)::value; const double2 v = w2[j]; dst[2 * j] = v.x; dst[2 * j + 1] = v.y; });
+            };
+            auto ld_col = [&](double (&dst)[NE], int st) {
+                const double* w = fac(st) + fWm() + r;
+                cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; dst[q] = w[q * LD]; });
+            };
+            auto dotk = [&](const double (&kk)[NE], const double* x) {
+                const double2* x2 = reinterpret_cast<const double2*>(x);
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                cta_static_for<0, NE / 2>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    const double2 xv = x2[j];
+                    if constexpr (j & 1) { a2 = fma(kk[2 * j], xv.x, a2); a3 = fma(kk[2 * j + 1], xv.y, a3); } else { a0 = fma(kk[2 * j], xv.x, a0); a1 = fma(kk[2 * j + 1], xv.y, a1); }
+                });
+                return (a0 + a1) + (a2 + a3);
+            };
             if (lane < NE) CAR[lane] = 0.0;
-            cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; kr[q] = fac(0)[d.oLc + r * ldb + q]; });
+            ld_row(kr, 0);
             for (int i = 0; i < d.ph; ++i) {
-                const int inx = i + 1 < d.ph ? i + 1 : i;
-                cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; kn[q] = fac(inx)[d.oLc + r * ldb + q]; });
+                ld_row(kn, i + 1 < d.ph ? i + 1 : i);
                 wait_flag(FG, i, S);
                 const double g = GT[i * NE + r];
-                const double* cp = CAR + i * NE;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                cta_static_for<0, NE / 4>([&](auto qc) {
-                    constexpr int q = 4 * decltype(qc)::value;
-                    a0 = fma(kr[q], cp[q], a0); a1 = fma(kr[q + 1], cp[q + 1], a1); a2 = fma(kr[q + 2], cp[q + 2], a2); a3 = fma(kr[q + 3], cp[q + 3], a3);
-                });
-                cta_static_for<(NE / 4) * 4, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; a0 = fma(kr[q], cp[q], a0); });
-                if (lane < NE) CAR[(i + 1) * NE + lane] = g - ((a0 + a1) + (a2 + a3));
+                const double v = g - dotk(kr, CAR + i * NE);
+                if (lane < NE) CAR[(i + 1) * NE + lane] = v;
                 post_flag(FC, i + 1, S);
                 cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; kr[q] = kn[q]; });
             }
+            pw[0] += clock64() - qc0;
             // backward: lane = column c of K_i
+            if (d.ph >= 1) ld_col(kr, d.ph - 1);
             wait_flag(FS, d.ph, S);
             if (lane < NE) XE[d.ph * NE + lane] = R[d.ph * d.b + lane];
             post_flag(FX, d.ph, S);
-            if (d.ph >= 1) cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; kr[q] = fac(d.ph - 1)[d.oLc + q * ldb + r]; });
             for (int i = d.ph - 1; i >= 0; --i) {
-                const int inx = i > 0 ? i - 1 : 0;
-                cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; kn[q] = fac(inx)[d.oLc + q * ldb + r]; });
+                ld_col(kn, i > 0 ? i - 1 : 0);
                 wait_flag(FS, i, S);
                 const double sv_ = R[i * d.b + r];
-                const double* xn = XE + (i + 1) * NE;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                cta_static_for<0, NE / 4>([&](auto qc) {
-                    constexpr int q = 4 * decltype(qc)::value;
-                    a0 = fma(kr[q], xn[q], a0); a1 = fma(kr[q + 1], xn[q + 1], a1); a2 = fma(kr[q + 2], xn[q + 2], a2); a3 = fma(kr[q + 3], xn[q + 3], a3);
-                });
-                cta_static_for<(NE / 4) * 4, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; a0 = fma(kr[q], xn[q], a0); });
-                if (lane < NE) XE[i * NE + lane] = sv_ - ((a0 + a1) + (a2 + a3));
+                const double v = sv_ - dotk(kr, XE + (i + 1) * NE);
+                if (lane < NE) XE[i * NE + lane] = v;
                 post_flag(FX, i, S);
                 cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; kr[q] = kn[q]; });
             }
+            pw[1] += clock64() - qc0;
         } else {
             for (int r = lane; r < d.ne; r += 32) CAR[r] = 0.0;
             __syncwarp();
             for (int i = 0; i < d.ph; ++i) {
                 wait_flag(FG, i, S);
-                const double* cp = CAR + i * d.ne;
-                for (int r = lane; r < d.ne; r += 32) {
-                    const double* w = fac(i) + d.oLc + r * ldb;
-                    double a0 = 0, a1 = 0; int q = 0;
-                    for (; q + 1 < d.ne; q += 2) { a0 = fma(w[q], cp[q], a0); a1 = fma(w[q + 1], cp[q + 1], a1); }
-                    if (q < d.ne) a0 = fma(w[q], cp[q], a0);
-                    CAR[(i + 1) * d.ne + r] = GT[i * d.ne + r] - (a0 + a1);
-                }
+                for (int r = lane; r < d.ne; r += 32) CAR[(i + 1) * d.ne + r] = GT[i * d.ne + r] - cta_dot<0, 0>(fac(i) + fWm() + r * LD, 1, CAR + i * d.ne, d.ne);
                 post_flag(FC, i + 1, S);
             }
             wait_flag(FS, d.ph, S);
@@ -898,13 +833,7 @@ struct CtaSolver {
             post_flag(FX, d.ph, S);
             for (int i = d.ph - 1; i >= 0; --i) {
                 wait_flag(FS, i, S);
-                const double* xn = XE + (i + 1) * d.ne; const double* w = fac(i) + d.oLc;
-                for (int cc = lane; cc < d.ne; cc += 32) {
-                    double a0 = 0, a1 = 0; int r = 0;
-                    for (; r + 1 < d.ne; r += 2) { a0 = fma(w[r * ldb + cc], xn[r], a0); a1 = fma(w[(r + 1) * ldb + cc], xn[r + 1], a1); }
-                    if (r < d.ne) a0 = fma(w[r * ldb + cc], xn[r], a0);
-                    XE[i * d.ne + cc] = R[i * d.b + cc] - (a0 + a1);
-                }
+                for (int cc = lane; cc < d.ne; cc += 32) XE[i * d.ne + cc] = R[i * d.b + cc] - cta_dot<0, 1>(fac(i) + fWm() + cc, LD, XE + (i + 1) * d.ne, d.ne);
                 post_flag(FX, i, S);
             }
         }
@@ -912,6 +841,7 @@ struct CtaSolver {
     // One ADMM iteration.  Needs T = rhat, GT = g of this iteration (flags FG >= S) on entry; leaves them for iteration S + 1.
     __device__ __forceinline__ void pipelined_iteration(int S, bool store_delta) {
         constexpr int NH = NW - 1;
+        const long long q0 = clock64();
         if (warp == 0) chain_sweeps(S);
         else {
             const int h = warp - 1;
@@ -921,6 +851,7 @@ struct CtaSolver {
                 stage_fwd(i);
                 post_flag(FS, i, S);
             }
+            pw[3] += clock64() - q0;
             int itop = h + ((d.ph - h) / NH) * NH;
             if (h > d.ph) itop = -1;
             for (int i = itop; i >= 0; i -= NH) {
@@ -944,12 +875,29 @@ struct CtaSolver {
                     post_flag(FG, 0, S + 1);
                 }
             }
+            pw[4] += clock64() - q0;
         }
+        __syncthreads();
+        pw[5] += clock64() - q0;
+    }
+    // The same iteration, bulk-synchronous: every phase by all warps, the recurrences by warp 0 between barriers.
+    __device__ __forceinline__ void bulk_iteration(bool store_delta) {
+        for (int j = warp; j <= d.ph; j += NW) stage_rhs(j);
+        __syncthreads();
+        const double alpha = p.alpha;
+        double* va = gws + L.gVA;
+        kkt_solve([&](int kg, double xt) {
+            const double xo = CSM(X)[kg];
+            const double xn = alpha * xt + (1.0 - alpha) * xo;
+            CSM(X)[kg] = xn;
+            if (store_delta) va[kg] = xn - xo;
+        });
+        for (int t = tid; t < d.m; t += NT) { int i, r; const int g = row_task(t, i, r); row_update(g, i, r, store_delta); }
         __syncthreads();
     }
     // bulk right-hand side + rhat / g of every stage (first iteration, and after a refactorisation); marks them ready for sweep S
     __device__ void prologue(int S) {
-        for (int kg = tid; kg < d.n; kg += NT) { int i = kg / d.b, k = kg - i * d.b; CSM(R)[kg] = p.sigma * CSM(X)[kg] - CSM(Q)[kg] + CSM(D)[kg] * col_atv(i, k, CSM(V)); }
+        for (int j = warp; j <= d.ph; j += NW) stage_rhs(j);
         __syncthreads();
         for (int j = warp; j <= d.ph; j += NW) stage_p3(j);
         __syncthreads();
@@ -959,10 +907,10 @@ struct CtaSolver {
 
     // ---- update_info (auxil.c): residuals and the norms of the termination test / rho estimate ---------------------------------
     // XSRC 0: x = X (ADMM iterate), 1: x = px (polish iterate, global).  ZY 0: (z, y) = (Z, Y); 1: polish pair
-    // z = clip(Ax + pnu), y = Ax + pnu - z (project_normalcone).  Leaves V2 = E y (and rc = E y in global scratch); clobbers R, YV.
+    // z = clip(Ax + pnu), y = Ax + pnu - z (project_normalcone).  Leaves rc = E y (global scratch: V, the row weights of the next right-hand side, must survive); clobbers R, YV.
     template <int XSRC, int ZYM>
     __device__ InfoNorms info_pass() {
-        const double* D = CSM(D); const double* E = CSM(E); double* R = CSM(R); double* V = CSM(V2);
+        const double* D = CSM(D); const double* E = CSM(E); double* R = CSM(R);
         const double* LO = CSM(LO); const double* UP = CSM(UP); const double* Q = CSM(Q);
         const double* xs = XSRC ? gws + L.gPX : CSM(X);
         double* rc = gws + L.gRC; const double* rb = gws + L.gRB;
@@ -978,7 +926,7 @@ struct CtaSolver {
             double Ax = e * row_dot(i, r), z, y;
             if (ZYM == 0) { z = CSM(Z)[g]; y = CSM(Y)[g]; }
             else { double tt = Ax + rb[g]; z = fmin(fmax(tt, LO[g]), UP[g]); y = tt - z; }
-            V[g] = e * y; rc[g] = e * y;
+            rc[g] = e * y;
             double pv = Ax - z;
             a[3] = fmax(a[3], fabs(pv)); a[4] = fmax(a[4], fabs(z)); a[5] = fmax(a[5], fabs(Ax));
             a[0] = fmax(a[0], fabs(einv * pv)); a[1] = fmax(a[1], fabs(einv * z)); a[2] = fmax(a[2], fabs(einv * Ax));
@@ -987,7 +935,7 @@ struct CtaSolver {
         for (int kg = tid; kg < d.n; kg += NT) {
             int i = kg / d.b, k = kg - i * d.b;
             double dk = D[kg], dinv = 1.0 / dk;
-            double aty = dk * col_atv(i, k, V), px = col_pu(i, k), q = Q[kg];
+            double aty = dk * col_atv(i, k, rc), px = col_pu(i, k), q = Q[kg];
             double dv = q + px + aty;
             a[10] = fmax(a[10], fabs(dv)); a[11] = fmax(a[11], fabs(q)); a[12] = fmax(a[12], fabs(aty)); a[13] = fmax(a[13], fabs(px));
             a[6] = fmax(a[6], fabs(dinv * dv)); a[7] = fmax(a[7], fabs(dinv * q)); a[8] = fmax(a[8], fabs(dinv * aty)); a[9] = fmax(a[9], fabs(dinv * px));
@@ -1002,10 +950,10 @@ struct CtaSolver {
         return I;
     }
 
-    // is_primal_infeasible (auxil.c); delta_y in ra (global).  Clobbers V2.
+    // is_primal_infeasible (auxil.c); delta_y in ra (global).  Clobbers rb (global).
     __device__ bool primal_infeasible(double eps) {
-        const double* E = CSM(E); const double* LO = CSM(LO); const double* UP = CSM(UP); double* V = CSM(V2);
-        double* ra = gws + L.gRA;
+        const double* E = CSM(E); const double* LO = CSM(LO); const double* UP = CSM(UP);
+        double* ra = gws + L.gRA; double* V = gws + L.gRB;      // E dy: global scratch (the polish multipliers are not live here)
         double a[2] = {0.0, 0.0};      // [nd (max), lhs (sum)]
         for (int g = tid; g < d.m; g += NT) {
             double dy = ra[g], l = LO[g], u = UP[g];
@@ -1079,9 +1027,7 @@ struct CtaSolver {
         const double* D = CSM(D); const double* Q = CSM(Q); const double* E = CSM(E); const double* LO = CSM(LO); const double* UP = CSM(UP);
         double* va = gws + L.gVA; double* px = gws + L.gPX; double* ra = gws + L.gRA; double* rb = gws + L.gRB; double* rc = gws + L.gRC;
         long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        prof_on = o.prof != nullptr;
-        for (int k = 0; k < 8; ++k) sp[k] = 0;
-        sq0 = 0;
+        for (int k = 0; k < 8; ++k) pw[k] = 0;
         long long t0 = clock64(), t1;
 #define PROF(slot) do { t1 = clock64(); pt[slot] += t1 - t0; t0 = t1; } while (0)
         bool valid = setup_and_scale();
@@ -1141,9 +1087,11 @@ struct CtaSolver {
             can_check = p.check_termination && (it % p.check_termination == 0);
             const bool can_adapt = p.adaptive_rho && p.adaptive_rho_interval && (it % p.adaptive_rho_interval == 0);
             const bool store_delta = can_check || it == p.max_iter;
-            if (need_prologue) { prologue(sweep); need_prologue = false; }
-            pipelined_iteration(sweep, store_delta);
-            ++sweep;
+            if (pipelined) {
+                if (need_prologue) { prologue(sweep); need_prologue = false; }
+                pipelined_iteration(sweep, store_delta);
+                ++sweep;
+            } else bulk_iteration(store_delta);
             PROF(2);
             if (can_check || can_adapt) {
                 I = info_pass<0, 0>();
@@ -1272,7 +1220,7 @@ struct CtaSolver {
         if (o.seq_output) for (int e = tid; e < (d.ph + 1) * d.ny; e += NT) {
             int i = e / d.ny, r = e - i * d.ny, j = i > 0 ? i - 1 : 0;
             double acc = 0;
-            for (int k = 0; k < d.nx; ++k) acc += CSM(C)[r * d.ldC + k] * xu[i * d.b + k];
+            for (int k = 0; k < d.nx; ++k) acc += CSM(C)[r * fldC() + k] * xu[i * d.b + k];
             for (int q = 0; q < d.ndu; ++q) acc += ldp(pr.Dd, inst, r * d.ndu + q) * ldp(pr.uMeas, inst, j * d.ndu + q);
             o.seq_output[ib * (d.ph + 1) * d.ny + e] = acc;
         }
@@ -1282,7 +1230,8 @@ struct CtaSolver {
             o.iters[inst] = iters; o.rho_updates[inst] = rho_updates; o.polish[inst] = status_polish;
         }
         PROF(7);
-        if (o.prof && tid == 0) { for (int k = 0; k < 8; ++k) { o.prof[ib * 16 + k] = pt[k]; o.prof[ib * 16 + 8 + k] = sp[k]; } }
+        if (o.prof && tid == 0) { for (int k = 0; k < 8; ++k) o.prof[ib * 16 + k] = pt[k]; o.prof[ib * 16 + 8] = pw[0]; o.prof[ib * 16 + 9] = pw[1]; o.prof[ib * 16 + 10] = pw[2]; o.prof[ib * 16 + 11] = pw[5]; o.prof[ib * 16 + 12] = 0; }
+        if (o.prof && warp == 1 && lane == 0) { o.prof[ib * 16 + 13] = pw[3]; o.prof[ib * 16 + 14] = pw[2]; o.prof[ib * 16 + 15] = pw[4]; }
 #undef PROF
         __syncthreads();
     }
@@ -1293,12 +1242,13 @@ template <class DM, int NT, bool FSH>
 __global__ void __launch_bounds__(NT, 1) lmpc_cta_kernel(const __grid_constant__ DM d, const __grid_constant__ Params p,
                                                          const __grid_constant__ Prob pr, const __grid_constant__ Out o,
                                                          const __grid_constant__ CtaLayout L, int batch, double* gscratch, int* counter,
-                                                         int model_shared, const int* order, double time_limit) {
+                                                         int model_shared, const int* order, double time_limit, int pipelined) {
     __shared__ int s_next;
     CtaSolver<DM, NT, FSH> S(d, p, pr, L);
     S.tid = threadIdx.x; S.lane = threadIdx.x & 31; S.warp = threadIdx.x >> 5;
     S.gws = gscratch + (size_t)blockIdx.x * L.gtotal;
     S.time_limit = time_limit;
+    S.pipelined = (pipelined && NT >= 64) ? 1 : 0;
     S.inst = 0;
     S.build_table();
     if (model_shared) S.load_model();
