@@ -272,6 +272,12 @@ def main():
     u_d = torch.zeros((B, NU), dtype=torch.float64, device="cuda")
     cmd_d = torch.empty((B, NU), dtype=torch.float64, device="cuda")
     cmd_all = torch.empty((world * B, NU), dtype=torch.float64, device="cuda") if world > 1 else None
+    comm = None
+    if world > 1:
+        # the engine's own communicator (include/b200mpc.h: b200mpc_comm_*): torch.distributed only carries the 128-byte id
+        uid = [L.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = L.Comm(world, rank, uid[0], local_rank)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
     launches = {"n": 0}
 
@@ -279,8 +285,8 @@ def main():
         c.solve_async(x_d.data_ptr(), u_d.data_ptr(), dev=True)          # history ordering (1 CTA) + ONE solve kernel
         launches["n"] += 2 if (not a.no_history_order) else 1
         if world > 1:
-            c.get_result_into(cmd_ptr=cmd_d.data_ptr())
-            dist.all_gather_into_tensor(cmd_all, cmd_d)                    # the one exchange step
+            c.allgather_cmd(comm, cmd_all.data_ptr())                      # the one exchange step, through the C ABI
+            launches["n"] += 1
         if advance:
             c.advance(x_d.data_ptr(), u_d.data_ptr())                      # x+ = A x + B u, u0 <- cmd (our plant-step kernel)
             launches["n"] += 1
@@ -320,7 +326,7 @@ def main():
     if world > 1:
         cevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
         for e0, e1 in cevs:
-            e0.record(stream); c.get_result_into(cmd_ptr=cmd_d.data_ptr()); dist.all_gather_into_tensor(cmd_all, cmd_d); e1.record(stream)
+            e0.record(stream); c.allgather_cmd(comm, cmd_all.data_ptr()); e1.record(stream)
         torch.cuda.synchronize()
         coll_ms = float(np.median([e0.elapsed_time(e1) for e0, e1 in cevs[5:]]))
 
@@ -353,8 +359,7 @@ def main():
         t0 = time.perf_counter()
         out = c.optimize(x_pin.numpy(), u_pin.numpy())      # H2D x0,u0 -> solve -> D2H cmd,cost,status...
         if world > 1:
-            c.get_result_into(cmd_ptr=cmd_d.data_ptr())
-            dist.all_gather_into_tensor(cmd_all, cmd_d)
+            c.allgather_cmd(comm, cmd_all.data_ptr())
             torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if s >= a.warmup:
@@ -457,6 +462,7 @@ def main():
                 lat["cpu_port_p50_ms"] = cpu_latency_p50(ph, a.max_iter)
         print(json.dumps(line))
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 

@@ -154,6 +154,22 @@ int b200mpc_lmpc_get_sequence(b200mpc_lmpc_t h, double* state, double* input, do
 /* Device pointer of the command block cmd[batch*nu] (for a fused NCCL all-gather on the same stream). */
 int b200mpc_lmpc_cmd_device_ptr(b200mpc_lmpc_t h, double** cmd_dev);
 
+/* ---- multi-GPU: the batch shards across ranks (one process per GPU, rank r owns a contiguous block of
+ * controllers) with no data-path collective; the ONE exchange step is an all-gather of the command blocks.  The reference is a
+ * single-threaded, single-controller library and has no counterpart; the contract is SURVEY.md 8b's b200mpc_comm_init /
+ * _allgather_cmd.  NCCL is loaded at run time (the copy already in the process when there is one).
+ *   b200mpc_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId, the caller broadcasts it by any means;
+ *   b200mpc_comm_init_rank: every rank joins (ncclCommInitRank on `device`);   b200mpc_comm_init: wrap an existing ncclComm_t;
+ *   b200mpc_lmpc_allgather_cmd: cmd[batch*nu] of every rank -> cmd_all_dev[nranks*batch*nu] (device memory, rank-major),
+ *   enqueued on the handle's stream directly behind the solve (send buffer = the kernel's output block; no host sync). */
+typedef struct b200mpc_comm* b200mpc_comm_t;
+int b200mpc_comm_unique_id(void* id128);
+int b200mpc_comm_init_rank(int nranks, int rank, const void* id128, int device, b200mpc_comm_t* out);
+int b200mpc_comm_init(void* nccl_comm, int nranks, int rank, b200mpc_comm_t* out);
+int b200mpc_comm_destroy(b200mpc_comm_t c);
+int b200mpc_comm_size(b200mpc_comm_t c, int* nranks, int* rank);
+int b200mpc_lmpc_allgather_cmd(b200mpc_lmpc_t h, b200mpc_comm_t c, double* cmd_all_dev);
+
 /* Engine introspection used by bench.py / profiles: resident warp slots, workspace bytes per slot, kernel
  * launches issued so far, algorithmic FP64 flop estimate of the last solve (sum over instances). */
 int b200mpc_lmpc_info(b200mpc_lmpc_t h, int* warp_slots, size_t* workspace_bytes_per_slot, long long* launches);
@@ -233,7 +249,7 @@ int b200mpc_nlmpc_system_ny(int system, int ph, int* ny, int* has_output_map);
  * B200MPC_EINVAL with the NVRTC log in b200mpc_last_error(). */
 #define B200MPC_SYS_USER_BASE 100
 int b200mpc_nlmpc_register_system(const char* cuda_source, const char* type_name, int* system_id);
-/* Compile-only check, needs no GPU: kernel 0 = evaluation kernel, 1..4 = the four solve-kernel variants. */
+/* Compile-only check, needs no GPU: kernel 0 = evaluation kernel, 1..4 = the four solve-kernel variants, 5 = plant step / RK4. */
 int b200mpc_nlmpc_compile_check(const char* cuda_source, const char* type_name, int kernel, size_t* cubin_bytes);
 
 /* NLMPC::setStateScale / setInputScale (NLMPC.hpp:108-130 -> Mapping::setStateScaling / setInputScaling,
@@ -291,6 +307,30 @@ int b200mpc_nlmpc_solve_ex(int system, int ph, int ch, int batch, const b200mpc_
                            const b200mpc_nlmpc_scaling* scaling, const double* lb, const double* ub, double* z,
                            double* cost, double* viol, int32_t* status, int32_t* iters, int32_t* qp_iters, int dev,
                            void* stream);
+
+/* ---- set-up helper: mpc::RK4<N>::run(t, in, h, integration_step) (include/mpc/Integrator.hpp:16-56) for `batch`
+ * states in one launch.  The vector field is the system's model with the input held over the step, dx/dt = f(x, u, stage, params);
+ * as in the reference the time argument (`stage` here) is not advanced between the sub-steps.  x[batch*nx], u[batch*nu],
+ * x_out[batch*nx]. */
+int b200mpc_nlmpc_rk4(int system, int batch, int stage, const double* x, const double* u, const double* sys_params,
+                      int params_per_instance, double h, int integration_steps, double* x_out, int dev, void* stream);
+
+/* ---- NLMPC closed loop on the device: the loop the examples wrap around optimize()
+ * (examples/vanderpol_ex.cpp:76-85, ugv_ex.cpp:143-166) for `steps` control steps without leaving the GPU.  Step k:
+ *   1. NLOptimizer::run's initial guess (NLOptimizer.hpp:425-510) built by a kernel: cold tile of (x_k, u_{k-1}) on the first step
+ *      or when enable_warm_start == 0, else the previous optimum; fixOptimalSolution (:705-716); one-stage left shift of the state
+ *      rows and of the per-stage controls through Iz2u / Iu2z (move blocking); slack carry-over;
+ *   2. the batched solve (as b200mpc_nlmpc_solve_ex);
+ *   3. cmd = first control block (x input scaling) applied to the plant = the system's own model:
+ *      plant_mode 0: x+ = f(x,u) (discrete systems); 1: x+ = x + plant_h f(x,u) (the Euler step of vanderpol_ex.cpp:80-81);
+ *      2: plant_substeps RK4 steps of size plant_h (Integrator.hpp).
+ * Outputs: traj_x[(steps+1)*batch*nx], traj_u[steps*batch*nu]; traj_status / traj_iters[steps*batch], traj_cost[steps*batch] may be
+ * NULL.  No host round trip between the steps; synchronises at the end. */
+int b200mpc_nlmpc_closed_loop(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* params, const double* x0,
+                              const double* u0, const double* sys_params, int params_per_instance,
+                              const b200mpc_nlmpc_scaling* scaling, const double* lb, const double* ub, int steps,
+                              int enable_warm_start, int plant_mode, int plant_substeps, double plant_h, double* traj_x,
+                              double* traj_u, int32_t* traj_status, int32_t* traj_iters, double* traj_cost, int dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,12 @@ def load_library():
     lib.b200mpc_lmpc_set_history_order.argtypes = [H, C.c_int]
     lib.b200mpc_lmpc_profile.argtypes = [H, C.c_void_p]
     lib.b200mpc_sync.argtypes = [H]
+    lib.b200mpc_comm_unique_id.argtypes = [C.c_void_p]
+    lib.b200mpc_comm_init_rank.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(H)]
+    lib.b200mpc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(H)]
+    lib.b200mpc_comm_destroy.argtypes = [H]
+    lib.b200mpc_comm_size.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.b200mpc_lmpc_allgather_cmd.argtypes = [H, H, C.c_void_p]
     lib.b200mpc_c2d.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.b200mpc_nlmpc_system_dims.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
     lib.b200mpc_nlmpc_eval.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
@@ -100,6 +106,9 @@ def load_library():
     lib.b200mpc_nlmpc_solve_ex.argtypes = ([C.c_int] * 4 + [C.POINTER(_NLParams)] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] +
                                            [C.c_void_p] * 8 + [C.c_int, C.c_void_p])
     lib.b200mpc_nlmpc_default_params.argtypes = [C.POINTER(_NLParams)]
+    lib.b200mpc_nlmpc_rk4.argtypes = [C.c_int] * 3 + [C.c_void_p] * 3 + [C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.b200mpc_nlmpc_closed_loop.argtypes = ([C.c_int] * 4 + [C.POINTER(_NLParams)] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 +
+                                              [C.c_int] * 4 + [C.c_double] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p])
     lib.b200mpc_nlmpc_solve_smem_bytes.argtypes = [C.c_int] * 3
     lib.b200mpc_nlmpc_solve_smem_bytes.restype = C.c_longlong
     lib.b200mpc_nlmpc_solve.argtypes = [C.c_int] * 4 + [C.POINTER(_NLParams)] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p]
@@ -118,6 +127,8 @@ EXPORTED_SYMBOLS = [
     "b200mpc_nlmpc_default_params", "b200mpc_nlmpc_solve_smem_bytes", "b200mpc_nlmpc_solve",
     "b200mpc_nlmpc_system_neq", "b200mpc_nlmpc_register_system", "b200mpc_nlmpc_compile_check", "b200mpc_nlmpc_eval_ex",
     "b200mpc_nlmpc_solve_ex", "b200mpc_nlmpc_system_ny", "b200mpc_nlmpc_output", "b200mpc_lmpc_set_input_bounds_full", "b200mpc_lmpc_set_engine", "b200mpc_lmpc_get_engine", "b200mpc_lmpc_advance",
+    "b200mpc_comm_unique_id", "b200mpc_comm_init_rank", "b200mpc_comm_init", "b200mpc_comm_destroy", "b200mpc_comm_size",
+    "b200mpc_lmpc_allgather_cmd", "b200mpc_nlmpc_rk4", "b200mpc_nlmpc_closed_loop",
 ]
 
 
@@ -529,10 +540,47 @@ class LMPC:
         _check(self.lib.b200mpc_lmpc_cmd_device_ptr(self._h, C.byref(p)))
         return p.value
 
+    def allgather_cmd(self, comm, cmd_all_dev_ptr):
+        """The one exchange step of the sharded batch: cmd[batch,nu] of every rank -> cmd_all[nranks*batch,nu] (raw device
+        pointer) on every rank; NCCL all-gather enqueued on this controller's stream right behind the solve."""
+        _check(self.lib.b200mpc_lmpc_allgather_cmd(self._h, comm._c, C.c_void_p(int(cmd_all_dev_ptr))))
+
     def get_result_into(self, cmd_ptr=None, status_ptr=None, iters_ptr=None):
         """Device-to-device copy of results into caller-owned device buffers (async on the handle's stream)."""
         v = lambda p: C.c_void_p(int(p)) if p else None
         _check(self.lib.b200mpc_lmpc_get_result(self._h, v(cmd_ptr), None, v(status_ptr), None, None, v(iters_ptr), None, None, 1))
+
+
+class Comm:
+    """The multi-GPU exchange context of the engine (include/b200mpc.h): one NCCL communicator over the ranks that
+    share a sharded batch.  `Comm.unique_id()` on rank 0 -> broadcast the 128 bytes by any means (torch.distributed, MPI, a file)
+    -> `Comm(nranks, rank, uid, device)` on every rank.  The only collective of the path is LMPC.allgather_cmd."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        _check(load_library().b200mpc_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, nranks, rank, uid, device=0):
+        self.lib = load_library()
+        self._c = C.c_void_p()
+        if len(uid) != 128:
+            raise ValueError("unique id must be 128 bytes")
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        _check(self.lib.b200mpc_comm_init_rank(int(nranks), int(rank), buf, int(device), C.byref(self._c)))
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    def close(self):
+        if getattr(self, "_c", None):
+            self.lib.b200mpc_comm_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def discretization(A, B, Ts):
@@ -707,6 +755,55 @@ def nlmpc_solve(system, ph, ch, z0, x0, params, lb, ub, max_sqp=100, max_qp=200,
     sc, keep = _scaling_arg(d, state_scale, input_scale)
     _check(lib.b200mpc_nlmpc_solve_ex(system, ph, ch, B, C.byref(q), vp(z0), vp(x0), vp(params), ppi, sc, vp(lb), vp(ub), vp(out["z"]),
                                       vp(out["cost"]), vp(out["viol"]), vp(out["status"]), vp(out["iters"]), vp(out["qp_iters"]), 0, None))
+    del keep
+    return out
+
+
+def nlmpc_rk4(system, x, u, params, h, integration_steps=1, stage=0):
+    """mpc::RK4<N>::run (include/mpc/Integrator.hpp:38-56) for a batch of states on the GPU: the system's model with the input held,
+    `integration_steps` classical Runge-Kutta steps of size h.  x [B,nx], u [B,nu] -> [B,nx]."""
+    lib = load_library()
+    d = nlmpc_system_dims(system, 1)
+    x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+    B = x.shape[0]
+    u = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(u), (B, d["nu"])), dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    ppi = 1 if params.ndim == 2 else 0
+    if x.shape[1] != d["nx"] or params.shape[-1] != d["nparam"]:
+        raise ValueError("nlmpc_rk4: wrong shapes")
+    out = np.empty_like(x)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _check(lib.b200mpc_nlmpc_rk4(system, B, int(stage), vp(x), vp(u), vp(params), ppi, float(h), int(integration_steps), vp(out), 0, None))
+    return out
+
+
+PLANT_DISCRETE, PLANT_EULER, PLANT_RK4 = 0, 1, 2
+
+
+def nlmpc_closed_loop(system, ph, ch, x0, u0, params, lb, ub, steps, warm_start=True, plant_mode=PLANT_DISCRETE, plant_substeps=1,
+                      plant_h=0.0, max_sqp=100, max_qp=200, tol=1e-7, ftol=1e-12, qp_eps=1e-5, rho=0.1, state_scale=None, input_scale=None):
+    """`steps` control steps of the NLMPC examples' loop on the device (include/b200mpc.h: b200mpc_nlmpc_closed_loop): guess /
+    repair / shift (NLOptimizer.hpp:425-510) -> solve -> apply cmd -> plant step, no host round trip.
+    Returns dict(x [steps+1,B,nx], u [steps,B,nu], status, iterations [steps,B], cost [steps,B])."""
+    lib = load_library()
+    d = nlmpc_system_dims(system, ph)
+    x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+    B = x0.shape[0]
+    u0 = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(u0), (B, d["nu"])), dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    ppi = 1 if params.ndim == 2 else 0
+    nz = ph * d["nx"] + ch * d["nu"] + 1
+    lb = np.ascontiguousarray(lb, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
+    if lb.shape != (nz,) or ub.shape != (nz,) or x0.shape[1] != d["nx"]:
+        raise ValueError("nlmpc_closed_loop: wrong shapes")
+    q = _NLParams(int(max_sqp), int(max_qp), float(tol), float(ftol), float(qp_eps), float(rho))
+    out = dict(x=np.empty((steps + 1, B, d["nx"])), u=np.empty((steps, B, d["nu"])), status=np.empty((steps, B), np.int32),
+               iterations=np.empty((steps, B), np.int32), cost=np.empty((steps, B)))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    sc, keep = _scaling_arg(d, state_scale, input_scale)
+    _check(lib.b200mpc_nlmpc_closed_loop(system, ph, ch, B, C.byref(q), vp(x0), vp(u0), vp(params), ppi, sc, vp(lb), vp(ub), int(steps),
+                                         int(bool(warm_start)), int(plant_mode), int(plant_substeps), float(plant_h), vp(out["x"]),
+                                         vp(out["u"]), vp(out["status"]), vp(out["iterations"]), vp(out["cost"]), 0, None))
     del keep
     return out
 

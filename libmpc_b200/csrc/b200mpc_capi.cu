@@ -656,3 +656,99 @@ extern "C" int b200mpc_sync(b200mpc_lmpc_t h) {
     CK(cudaStreamSynchronize(h->stream));
     return B200MPC_OK;
 }
+
+// ---- the exchange step: one all-gather of the command block over NCCL, inside the product ------------
+// The batch shards across ranks with no data-path collective; the single exchange is cmd[batch*nu] of every rank ->
+// cmd_all[nranks*batch*nu] on every rank, enqueued on the handle's stream right behind the solve kernel (no host sync, no
+// staging copy: the send buffer is the kernel's own output block).  NCCL is dlopen'ed (the process's already-loaded copy when
+// there is one, e.g. torch's), so the library still loads on a box without it.
+#include <dlfcn.h>
+namespace {
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUid*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) if ((lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL))) break;      // the copy already in the process
+        if (!lib) for (const char* n : names) if ((lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!lib) { err = "cannot load libnccl.so.2 (needed for the multi-GPU command all-gather)"; return false; }
+#define SYM(f) f = (decltype(f))dlsym(lib, "nccl" #f); if (!f) { err = "libnccl lacks nccl" #f; lib = nullptr; return false; }
+        SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllGather) SYM(GetErrorString)
+#undef SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+int ncfail(int r, const char* what) { return fail(B200MPC_ECUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error")); }
+}  // namespace
+
+struct b200mpc_comm {
+    void* comm = nullptr;      // ncclComm_t
+    int nranks = 1, rank = 0;
+    bool owned = false;
+};
+
+extern "C" int b200mpc_comm_unique_id(void* id128) {
+    if (!id128) return fail(B200MPC_EINVAL, "null pointer");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(B200MPC_ESTATE, err);
+    NcclUid id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r) return ncfail(r, "ncclGetUniqueId");
+    memcpy(id128, &id, sizeof id);
+    return B200MPC_OK;
+}
+extern "C" int b200mpc_comm_init_rank(int nranks, int rank, const void* id128, int device, b200mpc_comm_t* out) {
+    if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks) return fail(B200MPC_EINVAL, "bad arguments");
+    if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(B200MPC_ESTATE, err);
+    CK(cudaSetDevice(device));
+    NcclUid id;
+    memcpy(&id, id128, sizeof id);
+    void* comm = nullptr;
+    int r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (r) return ncfail(r, "ncclCommInitRank");
+    b200mpc_comm* c = new (std::nothrow) b200mpc_comm();
+    if (!c) return fail(B200MPC_EINVAL, "out of host memory");
+    c->comm = comm; c->nranks = nranks; c->rank = rank; c->owned = true;
+    *out = c;
+    return B200MPC_OK;
+}
+extern "C" int b200mpc_comm_init(void* nccl_comm, int nranks, int rank, b200mpc_comm_t* out) {
+    if (!nccl_comm || !out || nranks < 1 || rank < 0 || rank >= nranks) return fail(B200MPC_EINVAL, "bad arguments");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(B200MPC_ESTATE, err);
+    b200mpc_comm* c = new (std::nothrow) b200mpc_comm();
+    if (!c) return fail(B200MPC_EINVAL, "out of host memory");
+    c->comm = nccl_comm; c->nranks = nranks; c->rank = rank; c->owned = false;
+    *out = c;
+    return B200MPC_OK;
+}
+extern "C" int b200mpc_comm_destroy(b200mpc_comm_t c) {
+    if (!c) return B200MPC_OK;
+    if (c->owned && c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+    return B200MPC_OK;
+}
+extern "C" int b200mpc_comm_size(b200mpc_comm_t c, int* nranks, int* rank) {
+    if (!c) return fail(B200MPC_EINVAL, "null communicator");
+    if (nranks) *nranks = c->nranks;
+    if (rank) *rank = c->rank;
+    return B200MPC_OK;
+}
+extern "C" int b200mpc_lmpc_allgather_cmd(b200mpc_lmpc_t h, b200mpc_comm_t c, double* cmd_all_dev) {
+    HCHECK();
+    if (!c || !cmd_all_dev) return fail(B200MPC_EINVAL, "null argument");
+    const size_t count = (size_t)h->batch * h->d.nu;
+    int r = g_nccl.AllGather(h->cmd, cmd_all_dev, count, /* ncclFloat64 */ 8, c->comm, h->stream);
+    if (r) return ncfail(r, "ncclAllGather");
+    h->launches += 1;
+    return B200MPC_OK;
+}

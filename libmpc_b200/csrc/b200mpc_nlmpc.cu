@@ -12,6 +12,11 @@ extern template int nl_eval_t<SysVanDerPol>(const NlEvalArgs&, cudaStream_t);
 extern template int nl_eval_t<SysOscNet<4>>(const NlEvalArgs&, cudaStream_t);
 extern template int nl_eval_t<SysOscNet<6>>(const NlEvalArgs&, cudaStream_t);
 extern template int nl_eval_t<SysUgv>(const NlEvalArgs&, cudaStream_t);
+template <class S> int nl_plant_t(const NlPlantArgs& a, cudaStream_t stream);
+extern template int nl_plant_t<SysVanDerPol>(const NlPlantArgs&, cudaStream_t);
+extern template int nl_plant_t<SysOscNet<4>>(const NlPlantArgs&, cudaStream_t);
+extern template int nl_plant_t<SysOscNet<6>>(const NlPlantArgs&, cudaStream_t);
+extern template int nl_plant_t<SysUgv>(const NlPlantArgs&, cudaStream_t);
 extern template int nl_solve_t<SysVanDerPol>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);
 extern template int nl_solve_t<SysOscNet<4>>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);
 extern template int nl_solve_t<SysOscNet<6>>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);
@@ -21,6 +26,7 @@ bool rtc_is_user(int system);
 int rtc_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq, int* neq, int* ny = nullptr, int* has_out = nullptr);
 int rtc_eval(int system, const NlEvalArgs& a, cudaStream_t stream);
 int rtc_solve(int system, NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree);
+int rtc_plant(int system, const NlPlantArgs& a, cudaStream_t stream);
 }
 
 // ---- NLMPC problem evaluation (K5) --------------------------------------------------------------------------------
@@ -223,11 +229,27 @@ extern "C" int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const 
                                   status, iters, qp_iters, dev, stream_);
 }
 
+static int nl_solve_impl(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* prm, const double* z0,
+                         const double* x0, const double* sys_params, int params_per_instance,
+                         const b200mpc_nlmpc_scaling* scaling, const double* dsx, const double* dsu, const double* lb, const double* ub,
+                         double* z, double* cost, double* viol, int32_t* status, int32_t* iters, int32_t* qp_iters, int dev,
+                         void* stream_, bool sync);
+
 extern "C" int b200mpc_nlmpc_solve_ex(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* prm, const double* z0,
                                       const double* x0, const double* sys_params, int params_per_instance,
                                       const b200mpc_nlmpc_scaling* scaling, const double* lb, const double* ub, double* z,
                                       double* cost, double* viol, int32_t* status, int32_t* iters, int32_t* qp_iters, int dev,
                                       void* stream_) {
+    return nl_solve_impl(system, ph, ch, batch, prm, z0, x0, sys_params, params_per_instance, scaling, nullptr, nullptr, lb, ub, z, cost,
+                         viol, status, iters, qp_iters, dev, stream_, true);
+}
+
+// dsx / dsu: scaling vectors already on the device (closed loop), used instead of `scaling`
+static int nl_solve_impl(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* prm, const double* z0,
+                         const double* x0, const double* sys_params, int params_per_instance,
+                         const b200mpc_nlmpc_scaling* scaling, const double* dsx, const double* dsu, const double* lb, const double* ub,
+                         double* z, double* cost, double* viol, int32_t* status, int32_t* iters, int32_t* qp_iters, int dev,
+                         void* stream_, bool sync) {
     if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
     int nx, nu, np, ni, nue, rc0;
     if ((rc0 = nl_dims(system, &nx, &nu, &np, ph, &ni, &nue))) return rc0;
@@ -269,6 +291,8 @@ extern "C" int b200mpc_nlmpc_solve_ex(int system, int ph, int ch, int batch, con
     if ((rc = out(iters, (size_t)batch * 4, (void**)&a.iters))) return rc;
     if ((rc = out(qp_iters, (size_t)batch * 4, (void**)&a.qp_iters))) return rc;
     if ((rc = stage_scaling(scaling, nx, nu, &a.sx, &a.su, stream, tofree))) return rc;      // freed after the final synchronise
+    if (dsx) a.sx = dsx;
+    if (dsu) a.su = dsu;
     switch (system) {
     case B200MPC_SYS_VANDERPOL: rc = nl_solve_t<SysVanDerPol>(a, stream, tofree); break;
     case B200MPC_SYS_OSCNET4: rc = nl_solve_t<SysOscNet<4>>(a, stream, tofree); break;
@@ -286,6 +310,133 @@ extern "C" int b200mpc_nlmpc_solve_ex(int system, int ph, int ch, int batch, con
         if ((rc = back(iters, a.iters, (size_t)batch * 4))) return rc;
         if ((rc = back(qp_iters, a.qp_iters, (size_t)batch * 4))) return rc;
     }
-    CK(cudaStreamSynchronize(stream));     // temporaries are freed on return
+    if (sync || !dev) CK(cudaStreamSynchronize(stream));     // (temporaries are released in stream order either way)
+    return B200MPC_OK;
+}
+
+// ---- plant step / RK4 and the closed loop on the device ---------------------------------------------
+static int nl_plant_dispatch(int system, const NlPlantArgs& a, cudaStream_t stream) {
+    switch (system) {
+    case B200MPC_SYS_VANDERPOL: return nl_plant_t<SysVanDerPol>(a, stream);
+    case B200MPC_SYS_OSCNET4: return nl_plant_t<SysOscNet<4>>(a, stream);
+    case B200MPC_SYS_OSCNET6: return nl_plant_t<SysOscNet<6>>(a, stream);
+    case B200MPC_SYS_UGV: return nl_plant_t<SysUgv>(a, stream);
+    default: return rtc_plant(system, a, stream);
+    }
+}
+
+// mpc::RK4<N>::run(t, in, h, integration_step) (include/mpc/Integrator.hpp:38-56) for `batch` states at once; the vector field is
+// the system's model with the input held: dx/dt = f(x, u, stage, params).
+extern "C" int b200mpc_nlmpc_rk4(int system, int batch, int stage, const double* x, const double* u, const double* sys_params,
+                                 int params_per_instance, double h, int integration_steps, double* x_out, int dev, void* stream_) {
+    if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
+    int nx, nu, np, ni, nue, rc;
+    if ((rc = nl_dims(system, &nx, &nu, &np, 1, &ni, &nue))) return rc;
+    if (batch < 1 || !x || (!u && nu) || !sys_params || !x_out || integration_steps < 0) return fail(B200MPC_EINVAL, "bad arguments");
+    { int cur = 0; if (cudaGetDevice(&cur) == cudaSuccess) keep_pool(cur); }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    std::vector<void*> tofree;
+    struct Free { std::vector<void*>& v; cudaStream_t s; ~Free() { for (void* p : v) cudaFreeAsync(p, s); } } freer{tofree, stream};
+    auto in = [&](const double* h_, size_t n, const double** d) -> int {
+        if (dev) { *d = h_; return 0; }
+        double* p = nullptr;
+        CK(cudaMallocAsync(&p, (n ? n : 1) * sizeof(double), stream)); tofree.push_back(p);
+        if (n) CK(cudaMemcpyAsync(p, h_, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        *d = p; return 0;
+    };
+    NlPlantArgs a{};
+    a.batch = batch; a.mode = 2; a.substeps = integration_steps; a.stage = stage; a.h = h;
+    a.param_stride = params_per_instance ? np : 0;
+    if ((rc = in(x, (size_t)batch * nx, &a.x))) return rc;
+    if ((rc = in(u, (size_t)batch * nu, &a.u_in))) return rc;
+    if ((rc = in(sys_params, (size_t)(params_per_instance ? batch : 1) * np, &a.params))) return rc;
+    double* dout = x_out;
+    if (!dev) { CK(cudaMallocAsync(&dout, (size_t)batch * nx * sizeof(double), stream)); tofree.push_back(dout); }
+    a.x_out = dout;
+    if ((rc = nl_plant_dispatch(system, a, stream))) return rc;
+    if (!dev) {
+        CK(cudaMemcpyAsync(x_out, dout, (size_t)batch * nx * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    return B200MPC_OK;
+}
+
+// The control loop of the NLMPC examples (examples/vanderpol_ex.cpp:76-85, ugv_ex.cpp:143-166) for `steps` control steps without
+// leaving the GPU: every step builds NLOptimizer::run's initial guess on the device (cold tile or previous optimum, bound repair,
+// one-stage shift, slack carry-over: NLOptimizer.hpp:425-510), solves, applies cmd = first control block and steps the plant.
+extern "C" int b200mpc_nlmpc_closed_loop(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* prm, const double* x0,
+                                         const double* u0, const double* sys_params, int params_per_instance,
+                                         const b200mpc_nlmpc_scaling* scaling, const double* lb, const double* ub, int steps,
+                                         int enable_warm_start, int plant_mode, int plant_substeps, double plant_h, double* traj_x,
+                                         double* traj_u, int32_t* traj_status, int32_t* traj_iters, double* traj_cost, int dev,
+                                         void* stream_) {
+    if (b200mpc_device_count() <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
+    int nx, nu, np, ni, nue, rc;
+    if ((rc = nl_dims(system, &nx, &nu, &np, ph, &ni, &nue))) return rc;
+    if (ph < 1 || ch < 1 || ch > ph || batch < 1 || steps < 1 || !x0 || !u0 || !sys_params || !lb || !ub || !traj_x || !traj_u ||
+        plant_mode < 0 || plant_mode > 2 || (plant_mode == 2 && plant_substeps < 1))
+        return fail(B200MPC_EINVAL, "bad arguments");
+    { int cur = 0; if (cudaGetDevice(&cur) == cudaSuccess) keep_pool(cur); }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int nz = ph * nx + ch * nu + 1;
+    const size_t Bn = (size_t)batch, nX = Bn * nx, nU = Bn * nu, nZ = Bn * nz;
+    std::vector<void*> tofree;
+    struct Free { std::vector<void*>& v; cudaStream_t s; ~Free() { for (void* p : v) cudaFreeAsync(p, s); } } freer{tofree, stream};
+    auto dbuf = [&](void** p, size_t bytes) -> int { CK(cudaMallocAsync(p, bytes ? bytes : 8, stream)); tofree.push_back(*p); return 0; };
+    auto in = [&](const double* h_, size_t n, const double** d) -> int {
+        if (dev) { *d = h_; return 0; }
+        double* p = nullptr;
+        if (dbuf((void**)&p, n * sizeof(double))) return B200MPC_ECUDA;
+        CK(cudaMemcpyAsync(p, h_, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        *d = p; return 0;
+    };
+    const double *dx0, *du0, *dpar, *dlb, *dub, *dsx = nullptr, *dsu = nullptr;
+    if ((rc = in(x0, nX, &dx0)) || (rc = in(u0, nU, &du0)) || (rc = in(sys_params, (size_t)(params_per_instance ? batch : 1) * np, &dpar)) ||
+        (rc = in(lb, nz, &dlb)) || (rc = in(ub, nz, &dub)))
+        return rc;
+    if ((rc = stage_scaling(scaling, nx, nu, &dsx, &dsu, stream, tofree))) return rc;
+    double *dX = traj_x, *dU = traj_u, *dC = traj_cost; int *dS = traj_status, *dI = traj_iters;
+    if (!dev) {
+        if ((rc = dbuf((void**)&dX, (steps + 1) * nX * 8)) || (rc = dbuf((void**)&dU, steps * nU * 8))) return rc;
+        if (traj_status && (rc = dbuf((void**)&dS, steps * Bn * 4))) return rc;
+        if (traj_iters && (rc = dbuf((void**)&dI, steps * Bn * 4))) return rc;
+        if (traj_cost && (rc = dbuf((void**)&dC, steps * Bn * 8))) return rc;
+    }
+    double *zprev, *zguess, *dviol; int* dqp; int* dstat_tmp = nullptr; int* dit_tmp = nullptr; double* dcost_tmp = nullptr;
+    if ((rc = dbuf((void**)&zprev, nZ * 8)) || (rc = dbuf((void**)&zguess, nZ * 8)) || (rc = dbuf((void**)&dviol, Bn * 8)) ||
+        (rc = dbuf((void**)&dqp, Bn * 4)))
+        return rc;
+    if (!dS && (rc = dbuf((void**)&dstat_tmp, Bn * 4))) return rc;
+    if (!dI && (rc = dbuf((void**)&dit_tmp, Bn * 4))) return rc;
+    if (!dC && (rc = dbuf((void**)&dcost_tmp, Bn * 8))) return rc;
+    CK(cudaMemcpyAsync(dX, dx0, nX * 8, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemsetAsync(zprev, 0, nZ * 8, stream));
+    const unsigned gblocks = (unsigned)((nZ + 255) / 256);
+    for (int k = 0; k < steps; ++k) {
+        const double* xk = dX + (size_t)k * nX;
+        const double* uk = k == 0 ? du0 : dU + (size_t)(k - 1) * nU;
+        const int first = k == 0, cold = (first || !enable_warm_start) ? 1 : 0;
+        nlmpc_guess_kernel<0><<<gblocks, 256, 0, stream>>>(batch, nx, nu, ph, ch, cold, xk, uk, zprev, first ? nullptr : zprev + (nz - 1), dlb,
+                                                        dub, zguess);
+        CK(cudaGetLastError());
+        if ((rc = nl_solve_impl(system, ph, ch, batch, prm, zguess, xk, dpar, params_per_instance, nullptr, dsx, dsu, dlb, dub, zprev,
+                                dC ? dC + (size_t)k * Bn : dcost_tmp, dviol, dS ? dS + (size_t)k * Bn : dstat_tmp,
+                                dI ? dI + (size_t)k * Bn : dit_tmp, dqp, 1, stream_, false)))
+            return rc;
+        NlPlantArgs a{};
+        a.batch = batch; a.mode = plant_mode; a.substeps = plant_substeps; a.stage = 0; a.h = plant_h;
+        a.x = xk; a.u_in = nullptr; a.z = zprev; a.u_off = ph * nx; a.nz = nz; a.su = dsu; a.params = dpar;
+        a.param_stride = params_per_instance ? np : 0;
+        a.x_out = dX + (size_t)(k + 1) * nX; a.u_out = dU + (size_t)k * nU;
+        if ((rc = nl_plant_dispatch(system, a, stream))) return rc;
+    }
+    if (!dev) {
+        CK(cudaMemcpyAsync(traj_x, dX, (steps + 1) * nX * 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(traj_u, dU, steps * nU * 8, cudaMemcpyDeviceToHost, stream));
+        if (traj_status) CK(cudaMemcpyAsync(traj_status, dS, steps * Bn * 4, cudaMemcpyDeviceToHost, stream));
+        if (traj_iters) CK(cudaMemcpyAsync(traj_iters, dI, steps * Bn * 4, cudaMemcpyDeviceToHost, stream));
+        if (traj_cost) CK(cudaMemcpyAsync(traj_cost, dC, steps * Bn * 8, cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaStreamSynchronize(stream));
     return B200MPC_OK;
 }

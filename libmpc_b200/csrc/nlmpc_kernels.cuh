@@ -461,4 +461,95 @@ __global__ void __launch_bounds__(128) nlmpc_eval_kernel(const NlEvalArgs a) {
     }
 }
 
+// ---- plant step / RK4 (SURVEY.md 8f N1 + N3) ---------------------------------------------------------------------------
+// One thread per controller: x_out = step(x, u) with the system's own model S::f and u held over the step.
+//   mode 0  discrete:   x+ = f(x, u)                                   (ugv_ex.cpp:143-166: the loop steps its discrete model)
+//   mode 1  Euler:      x+ = x + h f(x, u)                             (vanderpol_ex.cpp:76-85: modelX += modeldX * ts)
+//   mode 2  RK4:        `substeps` classical Runge-Kutta steps of size h (mpc::RK4<N>::run, Integrator.hpp:38-56; like the
+//                       reference the time argument is NOT advanced between sub-steps: `stage` is passed unchanged)
+// u is either given (u_in [batch, nu]) or read from a solved decision vector z (first control block x input scaling = row 0 of
+// Umat = Result::cmd, NLOptimizer.hpp:596-606); u_out / status bookkeeping serve the closed loop.
+struct NlPlantArgs {
+    int batch, mode, substeps, stage;
+    double h;
+    const double* x;        // [batch, nx]
+    const double* u_in;     // [batch, nu] or null
+    const double* z;        // [batch, nz] or null (u = su * z[ph*nx .. +nu])
+    int u_off, nz;
+    const double* su;       // input scaling or null
+    const double* params; long long param_stride;
+    double* x_out;          // [batch, nx]
+    double* u_out;          // [batch, nu] or null
+};
+template <class S>
+__global__ void nlmpc_plant_kernel(const NlPlantArgs a) {
+    constexpr int nx = S::nx, nu = S::nu;
+    for (int inst = blockIdx.x * blockDim.x + threadIdx.x; inst < a.batch; inst += gridDim.x * blockDim.x) {
+        const double* p = a.params + (size_t)inst * a.param_stride;
+        double x[nx], u[nu > 0 ? nu : 1], k1[nx], k2[nx], k3[nx], k4[nx], t[nx];
+        for (int j = 0; j < nx; ++j) x[j] = a.x[(size_t)inst * nx + j];
+        for (int j = 0; j < nu; ++j) {
+            double v = a.u_in ? a.u_in[(size_t)inst * nu + j] : a.z[(size_t)inst * a.nz + a.u_off + j] * (a.su ? a.su[j] : 1.0);
+            u[j] = v;
+            if (a.u_out) a.u_out[(size_t)inst * nu + j] = v;
+        }
+        if (a.mode == 0) {
+            S::f(k1, x, u, a.stage, p);
+            for (int j = 0; j < nx; ++j) x[j] = k1[j];
+        } else if (a.mode == 1) {
+            S::f(k1, x, u, a.stage, p);
+            for (int j = 0; j < nx; ++j) x[j] += k1[j] * a.h;
+        } else {
+            const double h = a.h;
+            for (int s = 0; s < a.substeps; ++s) {
+                S::f(k1, x, u, a.stage, p);
+                for (int j = 0; j < nx; ++j) t[j] = x[j] + (h / 2.0) * k1[j];
+                S::f(k2, t, u, a.stage, p);
+                for (int j = 0; j < nx; ++j) t[j] = x[j] + (h / 2.0) * k2[j];
+                S::f(k3, t, u, a.stage, p);
+                for (int j = 0; j < nx; ++j) t[j] = x[j] + h * k3[j];
+                S::f(k4, t, u, a.stage, p);
+                for (int j = 0; j < nx; ++j) x[j] += h * (k1[j] + 2.0 * k2[j] + 2.0 * k3[j] + k4[j]) / 6.0;
+            }
+        }
+        for (int j = 0; j < nx; ++j) a.x_out[(size_t)inst * nx + j] = x[j];
+    }
+}
+
+// ---- NLOptimizer::run's initial guess on the device (NLOptimizer.hpp:425-510) ---------------------------------------------
+// zprev [batch, nz] is the optimisation vector the previous optimize() left (opt_vector); cold (first iteration or warm start
+// off) tiles x0 / u0 over the horizons first; fixOptimalSolution (:705-716) replaces out-of-bound entries by (ub - lb) / 2;
+// then the state rows and the per-stage controls (through Iz2u, move blocking) shift left by one stage, the last repeats,
+// Iu2z picks the first stage of every block, and the slack entry carries currentSlack.  System independent: one thread per
+// (controller, entry).
+template <int UNUSED = 0>
+__global__ void nlmpc_guess_kernel(int batch, int nx, int nu, int ph, int ch, int cold, const double* x0, const double* u0,
+                                   const double* zprev, const double* slack, const double* lb, const double* ub, double* z0) {
+    const int nz = ph * nx + ch * nu + 1;
+    const long long total = (long long)batch * nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int inst = (int)(t / nz), e = (int)(t - (long long)inst * nz);
+        auto src = [&](int k) -> double {                 // entry k of the repaired (cold-tiled or previous) vector
+            double v;
+            if (k == nz - 1) v = cold ? 0.0 : zprev[(size_t)inst * nz + k];
+            else if (cold) v = k < ph * nx ? x0[(size_t)inst * nx + k % nx] : u0[(size_t)inst * nu + (k - ph * nx) % nu];
+            else v = zprev[(size_t)inst * nz + k];
+            if (v < lb[k] || v > ub[k]) v = (ub[k] - lb[k]) / 2.0;
+            return v;
+        };
+        double v;
+        if (e == nz - 1) v = slack ? slack[(size_t)inst * nz] : 0.0;     // `slack` points at entry nz-1 of controller 0's previous vector
+        else if (e < ph * nx) {
+            int i = e / nx, j = e - i * nx;
+            v = src((i == ph - 1 ? i : i + 1) * nx + j);
+        } else {
+            int c = (e - ph * nx) / nu, j = (e - ph * nx) - c * nu;      // block c <- stage c (Iu2z), shifted stage c+1 (last repeats)
+            int st = c == ph - 1 ? c : c + 1;
+            int blk = st < ch ? st : ch - 1;                             // Iz2u
+            v = src(ph * nx + blk * nu + j);
+        }
+        z0[t] = v;
+    }
+}
+
 }  // namespace b200mpc

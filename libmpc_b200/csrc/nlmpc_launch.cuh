@@ -65,8 +65,17 @@ int nl_solve_t(NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree) 
     return nl_launch_t<S, 2, 256>(a, sm(2), 1, NlWs::gmem_doubles(2, n, me, ni), sms, stream, tofree);
 }
 
+template <class S>
+int nl_plant_t(const NlPlantArgs& a, cudaStream_t stream) {
+    int grid = (a.batch + 127) / 128;
+    nlmpc_plant_kernel<S><<<grid, 128, 0, stream>>>(a);
+    CK(cudaGetLastError());
+    return B200MPC_OK;
+}
+
 #define B200MPC_INSTANTIATE_NL_SYSTEM(S)                                                         \
     template int nl_eval_t<S>(const NlEvalArgs&, cudaStream_t);                                   \
-    template int nl_solve_t<S>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);
+    template int nl_solve_t<S>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);          \
+    template int nl_plant_t<S>(const NlPlantArgs&, cudaStream_t);
 
 }  // namespace b200mpc

@@ -34,3 +34,10 @@ def test_compile_error_is_reported_with_the_nvrtc_log():
     import libmpc_b200 as L
     with pytest.raises(RuntimeError, match="NVRTC could not compile"):
         L.compile_check(BROKEN_SRC, "Broken", 0)
+
+
+def test_user_system_compiles_plant_kernel():
+    """The plant-step / RK4 kernel of the device closed loop (b200mpc_nlmpc_closed_loop, b200mpc_nlmpc_rk4) for a user system."""
+    import libmpc_b200 as L
+    assert L.compile_check(VANDERPOL_SRC, "UserVanDerPol", 5) > 2_000
+    assert L.compile_check(UNICYCLE_SRC, "UserUnicycle", 5) > 2_000
