@@ -276,7 +276,7 @@ int b200mpc_nlmpc_eval(int system, int ph, int ch, int batch, const double* z, c
  * ones keep the matrices in a per-warp HBM workspace (L2-resident) and only the vectors in shared memory. */
 typedef struct {
     int32_t max_sqp;      /* major iterations (NLParameters::maximum_iteration, default 100)                 */
-    int32_t max_qp;       /* ADMM iterations per QP subproblem                                               */
+    int32_t max_qp;       /* ADMM iteration cap per QP subproblem (200; raised 5x once a line search fails)        */
     double tol;           /* relative step tolerance (NLParameters::relative_xtol plays this role)           */
     double ftol;          /* stop when |g'd| < ftol*max(1,|f|) and feasible (NLParameters::relative_ftol)   */
     double qp_eps;        /* QP residual tolerance                                                            */
@@ -294,6 +294,12 @@ int b200mpc_nlmpc_eval_ex(int system, int ph, int ch, int batch, const double* z
 int b200mpc_nlmpc_output(int system, int ph, int ch, int batch, const double* z, const double* x0, const double* params,
                          int params_per_instance, const b200mpc_nlmpc_scaling* scaling, double* y, int dev, void* stream);
 void b200mpc_nlmpc_default_params(b200mpc_nlmpc_params* p);
+/* Which solve kernel b200mpc_nlmpc_solve* / _closed_loop launch (process-wide).  0 (default): automatic -- the STAGE-STRUCTURED
+ * kernel (libmpc_b200/csrc/nlmpc_structured.cuh: per-stage block BFGS, compact Jacobians, bordered block-tridiagonal KKT
+ * factorisation, everything of a controller in shared memory) whenever the system declares `ineq_per_stage`, has no user equality
+ * constraints and fits shared memory, else the dense kernel (nlmpc_sqp.cuh); 1: dense; 2: structured (EINVAL when it does not
+ * apply).  Both reach the same optimum (tests/test_gpu_nlmpc_structured.py); the iteration paths differ (dense vs block BFGS). */
+int b200mpc_nlmpc_set_solver(int solver);
 long long b200mpc_nlmpc_solve_smem_bytes(int system, int ph, int ch);
 int b200mpc_nlmpc_solve(int system, int ph, int ch, int batch, const b200mpc_nlmpc_params* params, const double* z0,
                         const double* x0, const double* sys_params, int params_per_instance, const double* lb,

@@ -128,7 +128,7 @@ EXPORTED_SYMBOLS = [
     "b200mpc_nlmpc_system_neq", "b200mpc_nlmpc_register_system", "b200mpc_nlmpc_compile_check", "b200mpc_nlmpc_eval_ex",
     "b200mpc_nlmpc_solve_ex", "b200mpc_nlmpc_system_ny", "b200mpc_nlmpc_output", "b200mpc_lmpc_set_input_bounds_full", "b200mpc_lmpc_set_engine", "b200mpc_lmpc_get_engine", "b200mpc_lmpc_advance",
     "b200mpc_comm_unique_id", "b200mpc_comm_init_rank", "b200mpc_comm_init", "b200mpc_comm_destroy", "b200mpc_comm_size",
-    "b200mpc_lmpc_allgather_cmd", "b200mpc_nlmpc_rk4", "b200mpc_nlmpc_closed_loop",
+    "b200mpc_lmpc_allgather_cmd", "b200mpc_nlmpc_rk4", "b200mpc_nlmpc_closed_loop", "b200mpc_nlmpc_set_solver",
 ]
 
 
@@ -757,6 +757,14 @@ def nlmpc_solve(system, ph, ch, z0, x0, params, lb, ub, max_sqp=100, max_qp=200,
                                       vp(out["cost"]), vp(out["viol"]), vp(out["status"]), vp(out["iters"]), vp(out["qp_iters"]), 0, None))
     del keep
     return out
+
+
+NL_SOLVER_AUTO, NL_SOLVER_DENSE, NL_SOLVER_STRUCTURED = 0, 1, 2
+
+
+def nlmpc_set_solver(solver):
+    """Select the NLMPC solve kernel (include/b200mpc.h: b200mpc_nlmpc_set_solver): automatic / dense / stage-structured."""
+    _check(load_library().b200mpc_nlmpc_set_solver(int(solver)))
 
 
 def nlmpc_rk4(system, x, u, params, h, integration_steps=1, stage=0):

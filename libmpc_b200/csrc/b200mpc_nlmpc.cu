@@ -2,6 +2,7 @@
 // The kernels themselves are instantiated per system in nlmpc_sys_*.cu.
 #include "capi_common.h"
 #include "nlmpc_sqp.cuh"
+#include "nlmpc_launch_choice.h"
 
 using namespace b200mpc;
 
@@ -23,10 +24,19 @@ extern template int nl_solve_t<SysOscNet<6>>(NlSolveArgs&, cudaStream_t, std::ve
 extern template int nl_solve_t<SysUgv>(NlSolveArgs&, cudaStream_t, std::vector<void*>&);
 // user-defined systems (b200mpc_nlmpc_rtc.cu)
 bool rtc_is_user(int system);
-int rtc_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq, int* neq, int* ny = nullptr, int* has_out = nullptr);
+int rtc_dims(int system, int ph, int* nx, int* nu, int* nparam, int* nineq, int* neq, int* ny = nullptr, int* has_out = nullptr,
+             int* struct_ok = nullptr, int* K = nullptr);
 int rtc_eval(int system, const NlEvalArgs& a, cudaStream_t stream);
 int rtc_solve(int system, NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree);
 int rtc_plant(int system, const NlPlantArgs& a, cudaStream_t stream);
+}
+
+static int g_nl_solver = 0;
+int b200mpc::nl_solver_override() { return g_nl_solver; }
+extern "C" int b200mpc_nlmpc_set_solver(int solver) {
+    if (solver < 0 || solver > 2) return fail(B200MPC_EINVAL, "solver must be 0 (automatic), 1 (dense) or 2 (stage-structured)");
+    g_nl_solver = solver;
+    return B200MPC_OK;
 }
 
 // ---- NLMPC problem evaluation (K5) --------------------------------------------------------------------------------

@@ -14,14 +14,31 @@
 // Lanes parallelise over the finite-difference perturbations: every lane evaluates the whole cost / one constraint
 // component through an accessor that adds its own perturbation on the fly, so X and U are never copied.
 #pragma once
+#if !defined(__CUDACC__) && !defined(__CUDACC_RTC__)
+// Host emulation (TEST INFRASTRUCTURE, tests/cpp/nl_structured_host.cpp): the per-controller device routines are written as
+// `for (i = g.tid; i < N; i += G::nt) ... g.sync()` loops over a thread group, so a "group" of ONE thread runs them
+// sequentially and exactly; plain g++ then compiles the same source and the CPU tests compare it with the Python specification
+// before anything touches a GPU.  Kernels (__global__) and the warp-shuffle group are compiled out.
+#define B200_HOST_EMU 1
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }
+#define B200_INF (INFINITY)
+using std::fabs; using std::fmax; using std::fmin; using std::sqrt; using std::fma;
+#else
 #ifndef __CUDACC_RTC__          // NVRTC (user-defined systems, b200mpc_nlmpc_register_system) has these built in
 #include <cuda_runtime.h>
 #include <math.h>
 #endif
+#define B200_INF (__longlong_as_double(0x7ff0000000000000LL))
+#endif
 
 namespace b200mpc {
-
-#define B200_INF (__longlong_as_double(0x7ff0000000000000LL))
 
 // Optional user equality constraints (NLMPC::setEqConFunction, NLMPC.hpp:261-281): a system may define
 //   __host__ __device__ static int neq(int ph);   __device__ static double eq(int r, const Acc&, int ph, const double* p);
@@ -161,6 +178,18 @@ struct SysUgv {
 
 // ---- the threads that cooperate on one controller -------------------------------------------------------------------
 // NT = 32: one warp (several controllers per CTA); NT > 32: the whole CTA works on one controller.
+#ifdef B200_HOST_EMU
+// a "thread group" of one: every cooperative loop runs sequentially (host emulation, see the top of this file)
+struct NlGrpHost {
+    static constexpr int nt = 1, nw = 1;
+    int tid = 0, lane = 0, wid = 0;
+    double* red = nullptr;
+    void sync() const {}
+    double sum(double v) const { return v; }
+    double max(double v) const { return v; }
+    bool any(bool b) const { return b; }
+};
+#else
 template <int NT>
 struct NlGrp {
     static constexpr int nt = NT, nw = NT / 32;
@@ -193,6 +222,40 @@ struct NlGrp {
     }
     __device__ __forceinline__ bool any(bool b) const { return NT == 32 ? __any_sync(0xffffffffu, b) : (bool)__syncthreads_or(b); }
 };
+#endif
+
+// Where nl_eval_instance puts a Jacobian entry.  Dense (the reference's layout): row-major with row stride ld.  Compact (the
+// stage-structured solver, nlmpc_structured.cuh): only the columns a row can touch are stored --
+//   dynamics row r of stage i = r / nx:      [ d/dX_i (nx) | d/dX_{i+1} (nx) | d/dU_i (nu) ]            (X_0 = x0: first run unused at i = 0)
+//   inequality row r of stage i = r / K:     [ d/dX_i (nx) | d/dU_i (nu) | d/dslack ]                   (needs ineq_per_stage = K)
+// with U_i standing for the control block stage i reads (move blocking, row ph duplicated).
+struct NlDenseMap {
+    int ld;
+    __device__ __forceinline__ size_t je(int r, int col) const { return (size_t)r * ld + col; }
+    __device__ __forceinline__ size_t ji(int r, int col) const { return (size_t)r * ld + col; }
+    __device__ __forceinline__ size_t je_total(int me) const { return (size_t)me * ld; }
+    __device__ __forceinline__ size_t ji_total(int mi) const { return (size_t)mi * ld; }
+};
+struct NlCompactMap {
+    int ph, ch, nx, nu, K;
+    __device__ __forceinline__ size_t je(int r, int col) const {
+        const int i = r / nx, we = 2 * nx + nu;
+        int q;
+        if (col >= ph * nx) q = 2 * nx + (col - ph * nx) % nu;          // the block stage i reads (the only one its rows touch)
+        else q = col - (i - 1) * nx;                                       // X_i -> [0, nx), X_{i+1} -> [nx, 2 nx)
+        return (size_t)r * we + q;
+    }
+    __device__ __forceinline__ size_t ji(int r, int col) const {
+        const int i = r / K, wi = nx + nu + 1;
+        int q;
+        if (col == ph * nx + ch * nu) q = nx + nu;                         // slack
+        else if (col >= ph * nx) q = (col - ph * nx) % nu + nx;
+        else q = col - (i - 1) * nx;                                       // X_i = z block i - 1
+        return (size_t)r * wi + q;
+    }
+    __device__ __forceinline__ size_t je_total(int me) const { return (size_t)me * (2 * nx + nu); }
+    __device__ __forceinline__ size_t ji_total(int mi) const { return (size_t)mi * (nx + nu + 1); }
+};
 
 struct NlEvalArgs {
     int ph, ch, batch;
@@ -221,10 +284,10 @@ struct NlEvalArgs {
 // state scaling (Constraints.hpp:528,588), forms the dynamics blocks as I + h Sx A Tx (Constraints.hpp:553-575), scales the
 // state columns of the user-constraint Jacobians but NOT of the objective gradient, and maps every input derivative
 // through Iz2u (x input scaling).  cue/Jue: user equality constraints, rows [0, neq).
-template <class S, class G>
-__device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
+template <class S, class G, class MAP>
+__device__ __forceinline__ void nl_eval_instance_map(const G& g_, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
                                  double* fval, double* grad, double* ceq, double* Jeq, double* cin, double* Jin, int ldj,
-                                 const double* sx, const double* su, double* cue, double* Jue) {
+                                 const double* sx, const double* su, double* cue, double* Jue, const MAP map) {
     constexpr int nx = S::nx, nu = S::nu;
     const int nz = ph * nx + ch * nu + 1;
     auto SX = [&](int j) { return sx ? sx[j] : 1.0; };
@@ -283,7 +346,7 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
     if (ceq) {
         double* c = ceq;
         double* J = Jeq;
-        if (J) for (int e = g_.tid; e < ph * nx * ldj; e += G::nt) J[e] = 0.0;
+        if (J) for (size_t e = g_.tid; e < map.je_total(ph * nx); e += G::nt) J[e] = 0.0;
         g_.sync();
         const double h = S::Ts(p) / 2.0;
         for (int i = g_.tid; i < ph; i += G::nt) {
@@ -312,15 +375,15 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
                     xk[q] = keep - dx; S::f(fm, xk, uk, i, p);
                     xk[q] = keep;
                     if (S::continuous) {
-                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = (r == q ? 1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx)) * RXX(q, r);
+                        if (i > 0) for (int r = 0; r < nx; ++r) J[map.je(i * nx + r, (i - 1) * nx + q)] = (r == q ? 1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx)) * RXX(q, r);
                         double dx1 = dv * fmax(fabs(xk1[q]), 1.0), keep1 = xk1[q];
                         xk1[q] = keep1 + dx1; S::f(fp, xk1, uk, i, p);
                         xk1[q] = keep1 - dx1; S::f(fm, xk1, uk, i, p);
                         xk1[q] = keep1;
-                        for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? -1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx1)) * RXX(q, r);
+                        for (int r = 0; r < nx; ++r) J[map.je(i * nx + r, i * nx + q)] = (r == q ? -1.0 : 0.0) + h * ((fp[r] - fm[r]) / (2 * dx1)) * RXX(q, r);
                     } else {
-                        if (i > 0) for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + (i - 1) * nx + q] = -((fp[r] - fm[r]) / (2 * dx)) * RXX(q, r);
-                        for (int r = 0; r < nx; ++r) J[(size_t)(i * nx + r) * ldj + i * nx + q] = (r == q ? 1.0 : 0.0);
+                        if (i > 0) for (int r = 0; r < nx; ++r) J[map.je(i * nx + r, (i - 1) * nx + q)] = -((fp[r] - fm[r]) / (2 * dx)) * RXX(q, r);
+                        for (int r = 0; r < nx; ++r) J[map.je(i * nx + r, i * nx + q)] = (r == q ? 1.0 : 0.0);
                     }
                 } else {
                     int qu = q - nx;
@@ -334,9 +397,9 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
                         uk[qu] = keep + du; S::f(fp, xk1, uk, i, p);
                         uk[qu] = keep - du; S::f(fm, xk1, uk, i, p);
                         uk[qu] = keep;
-                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], h * (Bk[r] + (fp[r] - fm[r]) / (2 * du)) * RUX(qu, r));
+                        for (int r = 0; r < nx; ++r) atomicAdd(&J[map.je(i * nx + r, ph * nx + blk * nu + qu)], h * (Bk[r] + (fp[r] - fm[r]) / (2 * du)) * RUX(qu, r));
                     } else {
-                        for (int r = 0; r < nx; ++r) atomicAdd(&J[(size_t)(i * nx + r) * ldj + ph * nx + blk * nu + qu], -Bk[r] * RUX(qu, r));
+                        for (int r = 0; r < nx; ++r) atomicAdd(&J[map.je(i * nx + r, ph * nx + blk * nu + qu)], -Bk[r] * RUX(qu, r));
                     }
                 }
             }
@@ -348,7 +411,7 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
         for (int r = g_.tid; r < ni; r += G::nt) c[r] = S::ineq(r, base, slack, ph, p);
         if (Jin) {
             double* J = Jin;
-            for (int e = g_.tid; e < ni * ldj; e += G::nt) J[e] = 0.0;
+            for (size_t e = g_.tid; e < map.ji_total(ni); e += G::nt) J[e] = 0.0;
             g_.sync();
             for (int t = g_.tid; t < ph * nx; t += G::nt) {
                 int i = t / nx, j = t - i * nx;
@@ -359,7 +422,7 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
                 constexpr int K = NlIneqPerStage<S>::value;             // K > 0: only the rows of stage i+1 read X(i+1, .)
                 const int rlo = K ? (i + 1) * K : 0, rhi = K ? (i + 2) * K : ni;
                 for (int r = rlo; r < rhi && r < ni; ++r)
-                    J[(size_t)r * ldj + i * nx + j] = (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * dx) * SX(j);
+                    J[map.ji(r, i * nx + j)] = (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * dx) * SX(j);
             }
             for (int t = g_.tid; t < ph * nu; t += G::nt) {     // every one of the ph rows alone (row ph is never perturbed)
                 int i = t / nu, j = t - i * nu;
@@ -371,11 +434,11 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
                 constexpr int K = NlIneqPerStage<S>::value;             // K > 0: only the rows of stage i read U(i, .)
                 const int rlo = K ? i * K : 0, rhi = K ? (i + 1) * K : ni;
                 for (int r = rlo; r < rhi && r < ni; ++r)
-                    atomicAdd(&J[(size_t)r * ldj + ph * nx + blk * nu + j], (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * du) * SU(j));
+                    atomicAdd(&J[map.ji(r, ph * nx + blk * nu + j)], (S::ineq(r, ap, slack, ph, p) - S::ineq(r, am, slack, ph, p)) / (2 * du) * SU(j));
             }
             {
                 double ea = fmax(dv, fabs(slack)), de = ea * dv;
-                for (int r = g_.tid; r < ni; r += G::nt) J[(size_t)r * ldj + nz - 1] = (S::ineq(r, base, slack + de, ph, p) - S::ineq(r, base, slack - de, ph, p)) / (2 * de);
+                for (int r = g_.tid; r < ni; r += G::nt) J[map.ji(r, nz - 1)] = (S::ineq(r, base, slack + de, ph, p) - S::ineq(r, base, slack - de, ph, p)) / (2 * de);
             }
         }
     }
@@ -413,6 +476,13 @@ __device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int c
 }
 
 template <class S, class G>
+__device__ __forceinline__ void nl_eval_instance_impl(const G& g_, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
+                                 double* fval, double* grad, double* ceq, double* Jeq, double* cin, double* Jin, int ldj,
+                                 const double* sx, const double* su, double* cue, double* Jue) {
+    nl_eval_instance_map<S>(g_, ph, ch, z, x0, p, X, U, fval, grad, ceq, Jeq, cin, Jin, ldj, sx, su, cue, Jue, NlDenseMap{ldj});
+}
+
+template <class S, class G>
 __device__ __noinline__ void nl_eval_instance_call(G g_, int ph, int ch, const double* z, const double* x0, const double* p, double* X, double* U,
                                  double* fval, double* grad, double* ceq, double* Jeq, double* cin, double* Jin, int ldj,
                                  const double* sx, const double* su, double* cue, double* Jue) {
@@ -428,6 +498,7 @@ __device__ __forceinline__ void nl_eval_instance(const G& g_, int ph, int ch, co
     else nl_eval_instance_call<S>(g_, ph, ch, z, x0, p, X, U, fval, grad, ceq, Jeq, cin, Jin, ldj, sx, su, cue, Jue);
 }
 
+#ifndef B200_HOST_EMU
 template <class S>
 __global__ void __launch_bounds__(128) nlmpc_eval_kernel(const NlEvalArgs a) {
     extern __shared__ __align__(16) double nl_smem[];
@@ -551,5 +622,6 @@ __global__ void nlmpc_guess_kernel(int batch, int nx, int nu, int ph, int ch, in
         z0[t] = v;
     }
 }
+#endif  // !B200_HOST_EMU
 
 }  // namespace b200mpc

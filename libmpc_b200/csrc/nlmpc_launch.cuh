@@ -3,6 +3,7 @@
 #pragma once
 #include "capi_common.h"
 #include "nlmpc_sqp.cuh"
+#include "nlmpc_launch_choice.h"
 
 namespace b200mpc {
 
@@ -47,12 +48,38 @@ int nl_launch_t(NlSolveArgs& a, size_t smem_per_group, int groups_per_cta, size_
 // Launch policy (NlWs residency modes): everything in shared memory when it fits (a warp per controller for tiny problems,
 // a 4-warp CTA otherwise); else the packed KKT factor in shared memory and B / J in a per-CTA HBM workspace (8 warps);
 // else everything in the workspace.
+template <class S, int NT>
+int nl_launch_structured_t(NlSolveArgs& a, size_t smem, int sms, cudaStream_t stream) {
+    auto kern = nlmpc_structured_kernel<S, NT>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) occ = 1;
+    int grid = a.batch < sms * occ ? a.batch : sms * occ;
+    a.mat_ws = nullptr;
+    kern<<<grid, NT, smem, stream>>>(a);
+    CK(cudaGetLastError());
+    return B200MPC_OK;
+}
+
 template <class S>
 int nl_solve_t(NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree) {
     int dev = 0, sms = 0, maxsm = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    {
+        constexpr int K = NlIneqPerStage<S>::value > 0 ? NlIneqPerStage<S>::value : 1;
+        const size_t ssm = NlSW::doubles(a.ph, a.ch, S::nx, S::nu, K) * sizeof(double);
+        int nt = 64;
+        const int choice = nl_structured_choice(nls_supported<S>(a.ph, a.ch), ssm, maxsm, &nt);
+        if (choice < 0) return fail(B200MPC_EINVAL, "the stage-structured NLMPC solver does not apply to this system / horizon");
+        if (choice > 0) {
+            if (nt == 32) return nl_launch_structured_t<S, 32>(a, ssm, sms, stream);
+            if (nt == 128) return nl_launch_structured_t<S, 128>(a, ssm, sms, stream);
+            return nl_launch_structured_t<S, 64>(a, ssm, sms, stream);
+        }
+    }
     const int n = a.ph * S::nx + a.ch * S::nu + 1, me = a.ph * S::nx;
     const int ni = S::nineq(a.ph) + nl_neq<S>(a.ph);
     auto sm = [&](int mode) { return NlWs::smem_doubles(mode, n, me, ni, a.ph, S::nx, S::nu) * sizeof(double); };

@@ -1,0 +1,25 @@
+// nlmpc_launch_choice.h -- dense vs stage-structured NLMPC solver selection, shared by the built-in and the NVRTC launch paths
+#pragma once
+#include <cstdlib>
+#include <cstring>
+
+namespace b200mpc {
+// Which solver a (system, horizon) gets: the stage-structured kernel (nlmpc_structured.cuh) whenever the system declares its
+// inequality sparsity and has no user equality constraints and one controller fits shared memory; the dense kernel otherwise.
+// B200MPC_NLMPC_SOLVER=dense|structured overrides (structured fails loudly when it is not applicable); B200MPC_NLS_THREADS=32|64|128.
+int nl_solver_override();          // b200mpc_nlmpc_set_solver: 0 automatic, 1 dense, 2 structured (b200mpc_nlmpc.cu)
+inline int nl_structured_choice(bool supported, size_t smem, int maxsm, int* nt) {
+    const char* e = getenv("B200MPC_NLMPC_SOLVER");
+    const int ov = nl_solver_override();
+    if (ov == 1) e = "dense";
+    if (ov == 2) e = "structured";
+    const char* t = getenv("B200MPC_NLS_THREADS");
+    *nt = t ? atoi(t) : 64;
+    if (*nt != 32 && *nt != 64 && *nt != 128) *nt = 64;
+    const bool fits = supported && smem <= (size_t)maxsm;
+    if (e && !strcmp(e, "dense")) return 0;
+    if (e && !strcmp(e, "structured")) return fits ? 1 : -1;
+    return fits ? 1 : 0;
+}
+
+}  // namespace b200mpc

@@ -15,6 +15,7 @@
 // large shapes; the stage-structured (block-tridiagonal) variant is the next step.
 #pragma once
 #include "nlmpc_kernels.cuh"
+#include "nlmpc_structured.cuh"
 
 namespace b200mpc {
 
@@ -62,13 +63,14 @@ struct NlWs {
     double *z, *g, *g2, *d, *xs, *xt, *D, *gs, *rhs, *tmp, *glo, *sv, *zt2;     // n
     double *E, *ls, *us, *zs, *ys, *rho, *yq, *w, *pr, *pt;                     // m
     double *ce, *ci, *cet, *cit;                                                // me, mi, me, mi
+    double *muv;                                                                // me + mi: L1-merit penalty per constraint row
     double *X, *U, *red;
     __host__ __device__ static int ldim(int n, bool global) { return global ? ((n + 3) & ~3) : (n | 1); }
     __host__ __device__ static size_t h_doubles(int n) { return ((size_t)n * (n + 1) / 2 + 1) & ~(size_t)1; }
     __host__ __device__ static size_t mat_doubles(int n, int me, int mi, bool global) { return (size_t)(n + me + mi) * ldim(n, global); }
     __host__ __device__ static size_t vec_doubles(int n, int me, int mi, int ph, int nx, int nu) {
         int m = me + mi + n;
-        return 13 * (size_t)n + 10 * (size_t)m + 2 * (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 16;
+        return 13 * (size_t)n + 10 * (size_t)m + 3 * (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 16;
     }
     // shared / global doubles one controller needs in each residency mode
     __host__ __device__ static size_t smem_doubles(int mode, int n, int me, int mi, int ph, int nx, int nu) {
@@ -94,7 +96,7 @@ struct NlWs {
         for (auto q : nv) { *q = p; p += n; }
         double** mv[] = {&E, &ls, &us, &zs, &ys, &rho, &yq, &w, &pr, &pt};
         for (auto q : mv) { *q = p; p += m; }
-        ce = p; p += me; ci = p; p += mi; cet = p; p += me; cit = p; p += mi;
+        ce = p; p += me; ci = p; p += mi; cet = p; p += me; cit = p; p += mi; muv = p; p += me + mi;
         X = p; p += (ph + 1) * nx; U = p; p += (ph + 1) * nu; red = p;
     }
     __device__ __forceinline__ static size_t tri(int i) { return (size_t)i * (i + 1) / 2; }
@@ -342,7 +344,7 @@ __device__ __forceinline__ bool nl_qp_polish(const G& g, NlWs& w, double c) {
 // Dense OSQP-style ADMM for the QP subproblem.  In: B, g, Je, Ji, ce, ci, z, lb, ub; warm dual yq (if have_y).
 // Out: d (step), yq (multipliers, unscaled).  Returns ADMM iterations.
 template <class G>
-__device__ __forceinline__ int nl_qp_solve(const G& g, NlWs& w, const NlSolveArgs& a, bool have_y) {
+__device__ __forceinline__ int nl_qp_solve(const G& g, NlWs& w, const NlSolveArgs& a, bool have_y, int max_qp) {
     const int n = w.n, me = w.me, mi = w.mi, mc = me + mi, m = w.m, ld = w.ld;
     const double sigma = 1e-6, alpha = 1.6;
     // ---- Ruiz equilibration (10 passes) with cost normalisation
@@ -421,7 +423,7 @@ __device__ __forceinline__ int nl_qp_solve(const G& g, NlWs& w, const NlSolveArg
     for (int r = g.tid; r < m; r += G::nt) { w.ys[r] = have_y ? c * w.yq[r] / w.E[r] : 0.0; w.zs[r] = fmin(fmax(0.0, w.ls[r]), w.us[r]); }
     g.sync();
     int it = 0;
-    for (it = 1; it <= a.max_qp; ++it) {
+    for (it = 1; it <= max_qp; ++it) {
         // rhs = sigma x - q + A'(rho z - y)  (scaled), 2 barriers
         for (int r = g.tid; r < m; r += G::nt) w.w[r] = w.E[r] * (w.rho[r] * w.zs[r] - w.ys[r]);
         g.sync();
@@ -456,7 +458,7 @@ __device__ __forceinline__ int nl_qp_solve(const G& g, NlWs& w, const NlSolveArg
             if (est > 5 * rho0 || est < rho0 / 5) { rho0 = est; set_rho(rho0); nl_factor(g, w, c, sigma); }
         }
     }
-    if (it > a.max_qp) it = a.max_qp;
+    if (it > max_qp) it = max_qp;
     nl_qp_polish(g, w, c);
     for (int i = g.tid; i < n; i += G::nt) w.d[i] = w.D[i] * w.xs[i];
     for (int r = g.tid; r < m; r += G::nt) w.yq[r] = w.E[r] * w.ys[r] / c;
@@ -490,27 +492,40 @@ __global__ void __launch_bounds__(NT == 32 ? 64 : NT) nlmpc_solve_kernel(const N
         nl_eval_instance<S>(g, ph, ch, w.z, x0, p, w.X, w.U, w.tmp, w.g, w.ce, w.Je, w.ci, w.Ji, ld, a.sx, a.su, w.ci + mii, w.Ji + (size_t)mii * ld);
         fval = w.tmp[0];
         g.sync();
-        double mu = 1.0;
         bool have_y = false;
         int k = 0, qp_total = 0, status = 1, resets = 0;
         bool just_reset = false;
+        int qp_cap = a.max_qp;             // ADMM iteration cap of the QP subproblems; raised once when a step fails (below)
         auto violation = [&](const double* ce, const double* ci) {
             double v = 0;
             for (int r = g.tid; r < me; r += NT) v += fabs(ce[r]);
             for (int r = g.tid; r < mi; r += NT) v += r < mii ? fmax(ci[r], 0.0) : fabs(ci[r]);
             return g.sum(v);
         };
+        // L1 merit with one penalty per constraint row, updated by Powell's rule as in Kraft's SLSQP:
+        // mu_r <- max(|lambda_r|, (mu_r + |lambda_r|) / 2).  (A single monotone penalty max_r |lambda_r| -- the first version --
+        // stays at the largest multiplier ever seen and forces tiny steps along curved dynamics: unicycle Tph=30, 300 iterations.)
+        auto merit_violation = [&](const double* ce, const double* ci) {
+            double v = 0;
+            for (int r = g.tid; r < me; r += NT) v += w.muv[r] * fabs(ce[r]);
+            for (int r = g.tid; r < mi; r += NT) v += w.muv[me + r] * (r < mii ? fmax(ci[r], 0.0) : fabs(ci[r]));
+            return g.sum(v);
+        };
         for (k = 0; k < a.max_sqp; ++k) {
-            qp_total += nl_qp_solve(g, w, a, have_y);
+            qp_total += nl_qp_solve(g, w, a, have_y, qp_cap);
             have_y = true;
             // L1 merit line search
             double v0 = violation(w.ce, w.ci);
-            double ymax = 0, gd = 0;
-            for (int r = g.tid; r < mc; r += NT) ymax = fmax(ymax, fabs(w.yq[r]));
+            double gd = 0;
+            for (int r = g.tid; r < mc; r += NT) {
+                const double lam = fabs(w.yq[r]);
+                w.muv[r] = (k == 0 || just_reset) ? lam : fmax(lam, 0.5 * (w.muv[r] + lam));
+            }
             for (int i = g.tid; i < n; i += NT) gd += w.g[i] * w.d[i];
-            ymax = g.max(ymax); gd = g.sum(gd);
-            mu = fmax(mu, 1.1 * ymax);
-            const double phi0 = fval + mu * v0, dphi = gd - mu * v0;
+            gd = g.sum(gd);
+            g.sync();
+            const double mv0 = merit_violation(w.ce, w.ci);
+            const double phi0 = fval + mv0, dphi = gd - mv0;
             // Kraft's first stopping test (|g'd| and the violation below the accuracy): nothing left to gain
             if (fabs(gd) < a.ftol * fmax(1.0, fabs(fval)) && v0 < 1e-8) { status = 0; ++k; break; }
             double t = 1.0, ft = fval;
@@ -521,13 +536,17 @@ __global__ void __launch_bounds__(NT == 32 ? 64 : NT) nlmpc_solve_kernel(const N
                 nl_eval_instance<S>(g, ph, ch, w.zt2, x0, p, w.X, w.U, w.tmp, nullptr, w.cet, nullptr, w.cit, nullptr, ld, a.sx, a.su, w.cit + mii, nullptr);
                 ft = w.tmp[0];
                 g.sync();
-                double vt = violation(w.cet, w.cit);
-                if (ft + mu * vt <= phi0 + 1e-4 * t * dphi) { ls_ok = true; break; }
+                const double mvt = merit_violation(w.cet, w.cit);
+                if (ft + mvt <= phi0 + 1e-4 * t * dphi) { ls_ok = true; break; }
                 t *= 0.5;
             }
             if (!ls_ok) {
                 // no decrease of the merit along d at any step length: restart the quasi-Newton matrix once (as SLSQP
                 // does); failing again straight after the restart is the finite-difference noise floor.
+                // First suspect: an inexact QP step (the ADMM stopped at its cap far from the QP's solution).  Re-solve this
+                // subproblem -- and every later one -- with a 5x cap before touching B (unicycle Tph=30: 2 of 64 cold starts need
+                // 650-1000 ADMM iterations in their first SQP iterations; a 1000 cap for everybody doubles the UGV solve time).
+                if (qp_cap == a.max_qp) { qp_cap = 5 * a.max_qp; continue; }
                 if (just_reset || resets >= 5) { status = v0 < 1e-8 ? 0 : 1; ++k; break; }
                 for (int e = g.tid; e < n * ld; e += NT) { int i = e / ld, j = e - i * ld; w.B[e] = (i == j) ? 1.0 : 0.0; }
                 g.sync();
@@ -581,6 +600,26 @@ __global__ void __launch_bounds__(NT == 32 ? 64 : NT) nlmpc_solve_kernel(const N
         if (g.tid == 0) {
             a.cost[inst] = fval; a.viol[inst] = vf; a.status[inst] = status; a.iters[inst] = k; a.qp_iters[inst] = qp_total;
         }
+        g.sync();
+    }
+}
+
+// ---- the stage-structured variant (nlmpc_structured.cuh): one CTA of NT threads per controller, everything in shared memory ----
+template <class S, int NT>
+__global__ void __launch_bounds__(NT) nlmpc_structured_kernel(const NlSolveArgs a) {
+    extern __shared__ __align__(16) double nls_smem2[];
+    constexpr int nx = S::nx, nu = S::nu, K = NlIneqPerStage<S>::value > 0 ? NlIneqPerStage<S>::value : 1;
+    NlSW w;
+    w.carve(nls_smem2, a.ph, a.ch, nx, nu, K);
+    const NlGrp<NT> g{(int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), w.red};
+    NlSParams sp;
+    sp.max_sqp = a.max_sqp; sp.max_qp = a.max_qp; sp.tol = a.tol; sp.ftol = a.ftol; sp.qp_eps = a.qp_eps; sp.rho0 = a.rho0;
+    sp.lb = a.lb; sp.ub = a.ub; sp.sx = a.sx; sp.su = a.su;
+    const int n = w.n;
+    for (int inst = blockIdx.x; inst < a.batch; inst += gridDim.x) {
+        NlSResult r = nls_solve_instance<S>(g, w, sp, a.z0 + (size_t)inst * n, a.x0 + (size_t)inst * nx, a.params + (size_t)inst * a.param_stride,
+                                            a.z_out + (size_t)inst * n);
+        if (g.tid == 0) { a.cost[inst] = r.cost; a.viol[inst] = r.viol; a.status[inst] = r.status; a.iters[inst] = r.iters; a.qp_iters[inst] = r.qp_iters; }
         g.sync();
     }
 }

@@ -7,8 +7,8 @@ central finite differences with the reference's step rules).  Each QP subproblem
     min 1/2 d'Bd + g'd   s.t.  J_eq d = -c_eq,  J_in d <= -c_in,  lb - z <= d <= ub - z
 is solved by a dense OSQP-style ADMM (Ruiz equilibration, rho by row class, over-relaxation 1.6, adaptive rho) run to a
 moderate accuracy and then polished (active-set guess + regularised KKT solve with iterative refinement, OSQP polish.c),
-warm started from the previous SQP iteration's multipliers; the step is globalised by an L1 merit function with
-backtracking; a failed line search restarts B = I once (as SLSQP does) and stops at the second failure in a row.
+warm started from the previous SQP iteration's multipliers; the step is globalised by an L1 merit function (one penalty
+per constraint row, Powell's update as in Kraft's SLSQP) with backtracking; a failed line search restarts B = I once (as SLSQP does) and stops at the second failure in a row.
 """
 import numpy as np
 
@@ -136,6 +136,7 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
     block by block (B stays block diagonal, so the QP's reduced KKT matrix is block tridiagonal over the stages) -- the
     specification of the stage-structured kernel planned next."""
     qp = qp or QPADMM()
+    qp_cap0 = qp.max_iter
     x0 = np.asarray(x0, float)
     z = np.clip(np.array(z0, float), lb, ub)
     n = z.size
@@ -152,7 +153,7 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
     mii = f.nineq if f.ineq is not None else 0
     ci, Ji = dense(z)
     me, mi = ce.size, ci.size
-    mu = 1.0
+    muv = None
     y_prev = None
     resets, just_reset = 0, False
     hist = []
@@ -164,10 +165,14 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
         y_prev = y
         lam_e, lam_i = y[:me], y[me:me + mi]
         viol = lambda ce_, ci_: np.abs(ce_).sum() + np.maximum(ci_[:mii], 0).sum() + np.abs(ci_[mii:]).sum()
+        rowv = lambda ce_, ci_: np.concatenate([np.abs(ce_), np.maximum(ci_[:mii], 0), np.abs(ci_[mii:])])
         v0 = viol(ce, ci)
-        mu = max(mu, 1.1 * (np.abs(y[:me + mi]).max() if me + mi else 0.0))
-        phi0 = fval + mu * v0
-        dphi = g @ d - mu * v0            # directional derivative bound of the L1 merit
+        # one penalty per constraint row, Powell's update as in Kraft's SLSQP: mu_r <- max(|lambda_r|, (mu_r + |lambda_r|) / 2)
+        lam = np.abs(y[:me + mi])
+        muv = lam.copy() if (k == 0 or just_reset) else np.maximum(lam, 0.5 * (muv + lam))
+        wv = lambda ce_, ci_: float(muv @ rowv(ce_, ci_))
+        phi0 = fval + wv(ce, ci)
+        dphi = g @ d - wv(ce, ci)         # directional derivative bound of the L1 merit
         # Kraft's first stopping test (SLSQP: |g'd| and the violation below the accuracy): nothing left to gain
         if abs(g @ d) < ftol * max(1.0, abs(fval)) and v0 < 1e-8:
             hist.append((k, fval, v0, np.abs(d).max(), 0.0, qit))
@@ -179,7 +184,7 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
             ft, _ = f.objective(zt, x0, want_grad=False)
             cet, _ = f.state_eq(zt, x0, want_jac=False)
             cit = dense(zt)[0]
-            if ft + mu * viol(cet, cit) <= phi0 + 1e-4 * t * dphi:
+            if ft + wv(cet, cit) <= phi0 + 1e-4 * t * dphi:
                 ls_ok = True
                 break
             t *= 0.5
@@ -187,6 +192,9 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
             # no decrease of the merit along d at any step length.  Like SLSQP, restart the quasi-Newton matrix once
             # (a poor B or an inexact QP step); failing again straight after the restart is the finite-difference noise floor.
             hist.append((k, fval, v0, np.abs(d).max(), 0.0, qit))
+            if qp.max_iter == qp_cap0:         # first suspect an inexact QP step: re-solve (and go on) with a 5x ADMM cap
+                qp.max_iter = 5 * qp_cap0
+                continue
             if just_reset or resets >= 5:
                 break
             B = np.eye(n); resets += 1; just_reset = True
@@ -222,6 +230,7 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
         z, fval, g, ce, Je, ci, Ji = z_new, f_new, g_new, ce_new, Je_new, ci_new, Ji_new
         if step < tol * max(1.0, np.abs(z).max()) and viol(ce, ci) < 1e-8:
             break
+    qp.max_iter = qp_cap0
     X, U, e = f.unwrap(z, x0)
     return dict(z=z, cmd=U[0].copy(), cost=fval, nit=k + 1,
                 viol=float(np.abs(ce).sum() + np.maximum(ci[:mii], 0).sum() + np.abs(ci[mii:]).sum()), hist=hist)

@@ -25,10 +25,10 @@ def test_full_size_optimality_certificate():
     """Every one of the 4096 returned (x,y) pairs of BASELINE configs[1] satisfies the KKT conditions of its own QP
     (primal feasibility, stationarity, complementarity), checked with dense numpy algebra -- no solver involved."""
     import libmpc_b200 as L
-    import bench
+    from libmpc_b200 import workloads as bench_w
     ph, B = 20, 4096
     f, c = _quad(L, ph, B)
-    x0, r = bench.synth_inputs(0, B)
+    x0, r = bench_w.quadrotor_inputs(0, B)
     yref = np.zeros((B, 12, ph)); yref[:, 2, :] = r[:, None]
     c.setReferences(yref, np.zeros((4, ph)), np.zeros((4, ph)))
     res = c.optimize(x0, np.zeros((B, 4)))
@@ -71,10 +71,10 @@ def test_batch_order_invariance_and_determinism():
     """The dynamic work queue must not leak between instances: permuting the batch permutes the results bit-for-bit,
     and two runs of the same batch are bit-identical."""
     import libmpc_b200 as L
-    import bench
+    from libmpc_b200 import workloads as bench_w
     ph, B = 20, 777
     f, c = _quad(L, ph, B)
-    x0, r = bench.synth_inputs(100, B)
+    x0, r = bench_w.quadrotor_inputs(100, B)
     yref = np.zeros((B, 12, ph)); yref[:, 2, :] = r[:, None]
     c.setReferences(yref, np.zeros((4, ph)), np.zeros((4, ph)))
     a = c.optimize(x0, np.zeros((B, 4)))

@@ -18,6 +18,16 @@ from oracle.nlmpc_formulation import oscnet_formulation, ugv_formulation, vander
 from nlmpc_sqp_reference import sqp_solve
 
 
+@pytest.fixture(autouse=True)
+def _dense_kernel():
+    """This module pins the DENSE solve kernel (nlmpc_sqp.cuh) to its specification; the stage-structured kernel that the
+    automatic choice now prefers for these systems has its own module (tests/test_gpu_nlmpc_structured.py)."""
+    import libmpc_b200 as L
+    L.nlmpc_set_solver(L.NL_SOLVER_DENSE)
+    yield
+    L.nlmpc_set_solver(L.NL_SOLVER_AUTO)
+
+
 def _cmd(f, z):
     return z[f.ph * f.nx:f.ph * f.nx + f.nu]
 
