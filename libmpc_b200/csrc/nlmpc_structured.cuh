@@ -50,12 +50,16 @@ struct NlSW {
     double *Bb, *Bsl;                        // ph blocks b x b (local order [U ; X], U slots live iff s < ch) ; slack entry
     double *Li, *Ls, *Wb, *LSi;              // factor: ph x (b x b) inverse diagonal blocks, ph x (b x b) sub-diagonal blocks,
                                              // ph x (nb x b) border rows, nb x nb inverse of the border's Cholesky factor
-    double *cy, *cs;                         // chain vectors ph x b (forward result), per-stage scalars 4 x (ph + 1)
+    double *Nb, *Vb;                         // solve-time products: N_s = Li_s' Lsub_s' (b x b), V_s = Li_s' Wb_s' (b x nb); after the
+                                             // factorisation Ls[s-1] holds M_s = Li_s Lsub_{s-1} (Lsub itself is no longer needed)
+    double *cy, *cq, *bp, *cs;               // chain vectors ph x b (y, then x), ph x b (gathered rhs / q), border partials nb x ph,
+                                             // per-stage scalars 4 x (ph + 1)
     __host__ __device__ static size_t doubles(int ph, int ch, int nx, int nu, int K) {
         const int b = nx + nu, nb = nu + 1, n = ph * nx + ch * nu + 1, me = ph * nx, mi = (ph + 1) * K, m = me + mi + n;
         size_t v = 13 * (size_t)n + 10 * (size_t)m + 2 * (size_t)(me + mi) + (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 16;
         size_t mats = (size_t)me * (2 * nx + nu) + (size_t)mi * (nx + nu + 1) + (size_t)ph * b * b + 2 + 2 * (size_t)ph * b * b +
-                      (size_t)ph * nb * b + (size_t)nb * nb + (size_t)ph * b + 4 * (size_t)(ph + 1) + 2 * (size_t)nb + 8;
+                      (size_t)ph * nb * b + (size_t)nb * nb + (size_t)ph * b + 4 * (size_t)(ph + 1) + 2 * (size_t)nb + 8 +
+                      (size_t)ph * b * b + (size_t)ph * b * nb + (size_t)ph * b + (size_t)nb * ph;
         return (v + mats + 1) & ~(size_t)1;
     }
     __device__ void carve(double* p, int ph_, int ch_, int nx_, int nu_, int K_) {
@@ -72,6 +76,7 @@ struct NlSW {
         Bb = p; p += (size_t)ph * b * b; Bsl = p; p += 2;
         Li = p; p += (size_t)ph * b * b; Ls = p; p += (size_t)ph * b * b; Wb = p; p += (size_t)ph * nb * b; LSi = p; p += nb * nb;
         cy = p; p += (size_t)ph * b; cs = p; p += 4 * (size_t)(ph + 1) + 2 * nb + 8;
+        Nb = p; p += (size_t)ph * b * b; Vb = p; p += (size_t)ph * b * nb; cq = p; p += (size_t)ph * b; bp = p; p += (size_t)nb * ph;
     }
     // ---- index algebra --------------------------------------------------------------------------------------------------
     __device__ __forceinline__ int blk(int i) const { int st = i < ph ? i : ph - 1; return st < ch ? st : ch - 1; }   // control block stage i reads
@@ -356,6 +361,33 @@ __device__ __forceinline__ bool nls_factor(const G& g, NlSW& w, double c, double
                 wsync();
                 for (int e = lane; e < nb * b; e += W) Wc[e] = Sc[e];
                 wsync();
+                // solve-time products (take the second mat-vec of every stage off the sequential chain, see nls_kkt_apply)
+                double* Vc = w.Vb + (size_t)s * b * nb;
+                for (int e = lane; e < b * nb; e += W) {
+                    const int l = e / nb, q = e - l * nb;
+                    double acc = 0; for (int k = l; k < b; ++k) acc = fma(A[k * b + l], Wc[q * b + k], acc);
+                    Vc[e] = acc;
+                }
+                if (s + 1 < ph) {
+                    const double* Lsb = w.Ls + (size_t)s * b * b;
+                    double* Nc = w.Nb + (size_t)s * b * b;
+                    for (int e = lane; e < b * b; e += W) {
+                        const int l = e / b, q = e - l * b;
+                        double acc = 0; for (int k = l; k < b; ++k) acc = fma(A[k * b + l], Lsb[q * b + k], acc);
+                        Nc[e] = acc;
+                    }
+                }
+                if (s > 0) {
+                    double* Lp = w.Ls + (size_t)(s - 1) * b * b;              // Lsub[s-1] -> M_s = Li_s Lsub[s-1]
+                    for (int e = lane; e < b * b; e += W) {
+                        const int l = e / b, q = e - l * b;
+                        double acc = 0; for (int k = 0; k <= l; ++k) acc = fma(A[l * b + k], Lp[k * b + q], acc);
+                        Sc[e] = acc;
+                    }
+                    wsync();
+                    for (int e = lane; e < b * b; e += W) Lp[e] = Sc[e];
+                }
+                wsync();
             }
         }
         // S = D_border - sum_s Wb[s] Wb[s]'  -> Cholesky -> inverse
@@ -395,68 +427,91 @@ __device__ __forceinline__ bool nls_factor(const G& g, NlSW& w, double c, double
     return !g.any(!ok);
 }
 
-// xt = H^-1 rhs through the factor; optionally dxt = D .* xt.  The block recurrences run on the group's first warp (lane = row).
-template <class G>
+// xt = H^-1 rhs through the factor; optionally dxt = D .* xt.
+//   forward   y_s = Li_s r_s - M_s y_{s-1}            (Li_s r_s for all stages in parallel first; one mat-vec per stage on the chain)
+//   border    y_b = LSi (r_b - sum_s Wb_s y_s),  x_b = LSi' y_b
+//   backward  x_s = (Li_s' y_s - V_s x_b) - N_s x_{s+1}   (the bracket in parallel; one mat-vec per stage on the chain)
+// The two recurrences run on the group's first warp, lane = row, one warp barrier per stage; everything else is group-parallel.
+template <int BS, class G>
 __device__ __forceinline__ void nls_kkt_apply(const G& g, NlSW& w, double* dxt = nullptr) {
-    const int ph = w.ph, b = w.b, nb = w.nb;
-    if (g.wid == 0) {
-        const int lane = g.lane;
-        constexpr int W = G::nt < 32 ? G::nt : 32;
-        auto wsync = [&]() {
+    const int ph = w.ph, nb = w.nb;
+    constexpr int b = BS;
+    constexpr int W = G::nt < 32 ? G::nt : 32;
+    auto wsync = [&]() {
 #ifndef B200_HOST_EMU
-            __syncwarp();
+        __syncwarp();
 #endif
-        };
-        double* yb = w.cs;                          // nb
-        double* xb = w.cs + nb;                     // nb
-        double* t = w.cs + 2 * nb;                  // b (needs 2 nb + b <= 4 (ph+1) + 2 nb + 8: checked by nls_fits)
-        // forward:  y_s = Li[s] (r_s - Lsub[s-1] y_{s-1})
-        for (int s = 0; s < ph; ++s) {
-            for (int l = lane; l < b; l += W) {
-                const int jz = w.gz(s, l);
-                double v = jz >= 0 ? w.rhs[jz] : 0.0;
-                if (s > 0) { const double* Lp = w.Ls + ((size_t)(s - 1) * b + l) * b; const double* yp = w.cy + (size_t)(s - 1) * b; for (int q = 0; q < b; ++q) v = fma(-Lp[q], yp[q], v); }
-                t[l] = v;
-            }
-            wsync();
-            for (int l = lane; l < b; l += W) {
-                const double* Lr = w.Li + ((size_t)s * b + l) * b;
-                double v = 0; for (int q = 0; q <= l; ++q) v = fma(Lr[q], t[q], v);
-                w.cy[(size_t)s * b + l] = v;
-            }
-            wsync();
-        }
-        // border:  yb = LSi (r_b - sum_s Wb[s] y_s) ;  xb = LSi' yb
-        for (int l = lane; l < nb; l += W) {
-            double v = w.rhs[w.bz(l)];
-            for (int s = 0; s < ph; ++s) { const double* Wr = w.Wb + ((size_t)s * nb + l) * b; const double* ys = w.cy + (size_t)s * b; for (int q = 0; q < b; ++q) v = fma(-Wr[q], ys[q], v); }
-            t[l] = v;
-        }
-        wsync();
-        for (int l = lane; l < nb; l += W) { double v = 0; for (int q = 0; q <= l; ++q) v = fma(w.LSi[l * nb + q], t[q], v); yb[l] = v; }
-        wsync();
-        for (int l = lane; l < nb; l += W) { double v = 0; for (int q = l; q < nb; ++q) v = fma(w.LSi[q * nb + l], yb[q], v); xb[l] = v; w.xt[w.bz(l)] = v; }
-        wsync();
-        // backward:  x_s = Li[s]' (y_s - Lsub[s]' x_{s+1} - Wb[s]' xb)      (x_{s+1} kept in cy[s+1])
-        for (int s = ph - 1; s >= 0; --s) {
-            for (int l = lane; l < b; l += W) {
-                double v = w.cy[(size_t)s * b + l];
-                if (s + 1 < ph) { const double* Lsb = w.Ls + (size_t)s * b * b; const double* xn = w.cy + (size_t)(s + 1) * b; for (int q = 0; q < b; ++q) v = fma(-Lsb[q * b + l], xn[q], v); }
-                const double* Wc = w.Wb + (size_t)s * nb * b;
-                for (int q = 0; q < nb; ++q) v = fma(-Wc[q * b + l], xb[q], v);
-                t[l] = v;
-            }
-            wsync();
-            for (int l = lane; l < b; l += W) {
-                const double* Lc = w.Li + (size_t)s * b * b;
-                double v = 0; for (int q = l; q < b; ++q) v = fma(Lc[q * b + l], t[q], v);
-                w.cy[(size_t)s * b + l] = v;
-                const int jz = w.gz(s, l);
-                if (jz >= 0) w.xt[jz] = v;
+    };
+    for (int e = g.tid; e < ph * b; e += G::nt) { const int s = e / b, l = e - s * b, jz = w.gz(s, l); w.cq[e] = jz >= 0 ? w.rhs[jz] : 0.0; }
+    g.sync();
+    for (int e = g.tid; e < ph * b; e += G::nt) {
+        const int s = e / b, l = e - s * b;
+        const double* Lr = w.Li + (size_t)e * b;
+        const double* r = w.cq + s * b;
+        double v = 0;
+#pragma unroll
+        for (int q = 0; q < b; ++q) if (q <= l) v = fma(Lr[q], r[q], v);
+        w.cy[e] = v;
+    }
+    g.sync();
+    if (g.wid == 0) {
+        for (int s = 1; s < ph; ++s) {
+            for (int l = g.lane; l < b; l += W) {
+                const double* M = w.Ls + ((size_t)(s - 1) * b + l) * b;
+                const double* yp = w.cy + (s - 1) * b;
+                double v = w.cy[s * b + l];
+#pragma unroll
+                for (int q = 0; q < b; ++q) v = fma(-M[q], yp[q], v);
+                w.cy[s * b + l] = v;
             }
             wsync();
         }
     }
+    g.sync();
+    for (int e = g.tid; e < nb * ph; e += G::nt) {
+        const int l = e / ph, s = e - l * ph;
+        const double* Wr = w.Wb + ((size_t)s * nb + l) * b;
+        const double* ys = w.cy + s * b;
+        double v = 0;
+#pragma unroll
+        for (int q = 0; q < b; ++q) v = fma(Wr[q], ys[q], v);
+        w.bp[e] = v;
+    }
+    g.sync();
+    double* yb = w.cs; double* xb = w.cs + nb; double* t = w.cs + 2 * nb;
+    if (g.tid == 0) {
+        for (int l = 0; l < nb; ++l) { double v = w.rhs[w.bz(l)]; for (int s = 0; s < ph; ++s) v -= w.bp[l * ph + s]; t[l] = v; }
+        for (int l = 0; l < nb; ++l) { double v = 0; for (int q = 0; q <= l; ++q) v = fma(w.LSi[l * nb + q], t[q], v); yb[l] = v; }
+        for (int l = 0; l < nb; ++l) { double v = 0; for (int q = l; q < nb; ++q) v = fma(w.LSi[q * nb + l], yb[q], v); xb[l] = v; w.xt[w.bz(l)] = v; }
+    }
+    g.sync();
+    for (int e = g.tid; e < ph * b; e += G::nt) {
+        const int s = e / b, l = e - s * b;
+        const double* Lc = w.Li + (size_t)s * b * b;
+        const double* ys = w.cy + s * b;
+        double v = 0;
+#pragma unroll
+        for (int q = 0; q < b; ++q) if (q >= l) v = fma(Lc[q * b + l], ys[q], v);
+        const double* Vr = w.Vb + (size_t)e * nb;
+        for (int q = 0; q < nb; ++q) v = fma(-Vr[q], xb[q], v);
+        w.cq[e] = v;
+    }
+    g.sync();
+    if (g.wid == 0) {
+        for (int s = ph - 2; s >= 0; --s) {
+            for (int l = g.lane; l < b; l += W) {
+                const double* N = w.Nb + ((size_t)s * b + l) * b;
+                const double* xn = w.cq + (s + 1) * b;
+                double v = w.cq[s * b + l];
+#pragma unroll
+                for (int q = 0; q < b; ++q) v = fma(-N[q], xn[q], v);
+                w.cq[s * b + l] = v;
+            }
+            wsync();
+        }
+    }
+    g.sync();
+    for (int e = g.tid; e < ph * b; e += G::nt) { const int s = e / b, l = e - s * b, jz = w.gz(s, l); if (jz >= 0) w.xt[jz] = w.cq[e]; }
     g.sync();
     if (dxt) { for (int i = g.tid; i < w.n; i += G::nt) dxt[i] = w.D[i] * w.xt[i]; g.sync(); }
 }
@@ -474,7 +529,7 @@ __device__ __forceinline__ void nls_qp_residuals(const G& g, NlSW& w, double c, 
 }
 
 // OSQP polish.c on the structured QP (see nl_qp_polish_impl in nlmpc_sqp.cuh: identical steps, structured products / factor)
-template <class G>
+template <int BS, class G>
 __device__ __forceinline__ bool nls_qp_polish(const G& g, NlSW& w, double c) {
     const int n = w.n, m = w.m;
     const double delta = 1e-6, idelta = 1e6;
@@ -499,7 +554,7 @@ __device__ __forceinline__ bool nls_qp_polish(const G& g, NlSW& w, double c) {
         nls_Ats(g, w, w.pr, w.rhs);
         for (int i = g.tid; i < n; i += G::nt) w.rhs[i] += w.sv[i];
         g.sync();
-        nls_kkt_apply(g, w);
+        nls_kkt_apply<BS>(g, w);
         nls_As(g, w, w.xt, w.pt);
         for (int r = g.tid; r < m; r += G::nt) if (w.rho[r] > 0.0) w.yq[r] += w.pt[r] * idelta - w.pr[r];
         for (int i = g.tid; i < n; i += G::nt) w.g2[i] += w.xt[i];
@@ -518,7 +573,7 @@ __device__ __forceinline__ bool nls_qp_polish(const G& g, NlSW& w, double c) {
 
 // OSQP-style ADMM for the QP subproblem on the structured storage.  In: Bb, g, JeC, JiC, ce, ci, z, lb, ub; warm dual yq (if have_y).
 // Out: d (step), yq (multipliers, unscaled).  Returns ADMM iterations.  Step for step nl_qp_solve of nlmpc_sqp.cuh.
-template <class G>
+template <int BS, class G>
 __device__ __forceinline__ int nls_qp_solve(const G& g, NlSW& w, const NlSParams& a, int mii, bool have_y, int max_qp) {
     const int n = w.n, me = w.me, mi = w.mi, mc = w.mc, m = w.m;
     const double sigma = 1e-6, alpha = 1.6;
@@ -574,7 +629,7 @@ __device__ __forceinline__ int nls_qp_solve(const G& g, NlSW& w, const NlSParams
         for (int j = g.tid; j < n; j += G::nt)
             w.rhs[j] = w.D[j] * (w.w[mc + j] + w.col_dot(j, w.w)) + sigma * w.xs[j] - w.gs[j];
         g.sync();
-        nls_kkt_apply(g, w, w.zt2);
+        nls_kkt_apply<BS>(g, w, w.zt2);
         nls_As_core(g, w, w.zt2, w.yq);
         for (int i = g.tid; i < n; i += G::nt) w.xs[i] = alpha * w.xt[i] + (1 - alpha) * w.xs[i];
         for (int r = g.tid; r < m; r += G::nt) {
@@ -603,7 +658,7 @@ __device__ __forceinline__ int nls_qp_solve(const G& g, NlSW& w, const NlSParams
         }
     }
     if (it > max_qp) it = max_qp;
-    nls_qp_polish(g, w, c);
+    nls_qp_polish<BS>(g, w, c);
     for (int i = g.tid; i < n; i += G::nt) w.d[i] = w.D[i] * w.xs[i];
     for (int r = g.tid; r < m; r += G::nt) w.yq[r] = w.E[r] * w.ys[r] / c;
     g.sync();
@@ -647,7 +702,7 @@ __device__ __forceinline__ NlSResult nls_solve_instance(const G& g, NlSW& w, con
         return g.sum(v);
     };
     for (k = 0; k < a.max_sqp; ++k) {
-        qp_total += nls_qp_solve(g, w, a, mii, have_y, qp_cap);
+        qp_total += nls_qp_solve<nx + nu>(g, w, a, mii, have_y, qp_cap);
         have_y = true;
         double v0 = violation(w.ce, w.ci);
         double gd = 0;

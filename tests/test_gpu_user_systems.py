@@ -61,7 +61,7 @@ def test_user_vanderpol_is_the_builtin():
     ra = L.nlmpc_solve(sid, 10, 5, z0, x0, np.array([0.1]), lb, ub)
     rb = L.nlmpc_solve(L.SYS_VANDERPOL, 10, 5, z0, x0, np.array([0.1]), lb, ub)
     assert (ra["status"] == 0).all()
-    assert np.abs(ra["z"] - rb["z"]).max() < 1e-6 and np.abs(ra["cost"] - rb["cost"]).max() < 1e-9
+    assert np.abs(ra["z"] - rb["z"]).max() < 1e-5 and np.abs(ra["cost"] - rb["cost"]).max() < 1e-8      # two compilations (nvcc / NVRTC) of one source: finite-difference noise
 
 
 def test_user_pendulum_eval_with_equality_constraints():

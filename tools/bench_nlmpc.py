@@ -34,7 +34,26 @@ def run(name, system, f, ph, ch, batch, hard, x0_lo, x0_hi, reps=3):
                           admm_iters=float(out["qp_iters"].mean()), max_viol=float(out["viol"].max()))), flush=True)
 
 
+def run_unicycle(batch=1024):
+    """BASELINE configs[2] at its stated shape (user-defined system, NVRTC), cold start."""
+    from libmpc_b200 import workloads as W
+    sid = L.register_system(W.UNICYCLE_SRC, W.UNICYCLE_TYPE)
+    x0, params = W.unicycle_inputs(0, batch)
+    lb, ub = W.soft_bounds(151)
+    z0 = W.cold_start(x0, np.zeros(2), 30, 30)
+    L.nlmpc_solve(sid, 30, 30, z0[:64], x0[:64], params[:64], lb, ub, max_sqp=300)
+    t = time.perf_counter()
+    out = L.nlmpc_solve(sid, 30, 30, z0, x0, params, lb, ub, max_sqp=300)
+    t = time.perf_counter() - t
+    print(json.dumps(dict(workload="unicycle nx3 nu2 ph30 ch30 (configs[2])", nz=151, batch=batch, solves_per_s=batch / t, ms_per_batch=1e3 * t,
+                          converged=float((out["status"] == 0).mean()), sqp_iters=float(out["iters"].mean()),
+                          admm_iters=float(out["qp_iters"].mean()), max_viol=float(out["viol"].max()), max_cost=float(out["cost"].max()))), flush=True)
+
+
 if __name__ == "__main__":
+    import os
+    print(json.dumps(dict(solver=os.environ.get("B200MPC_NLMPC_SOLVER", "auto"), threads=os.environ.get("B200MPC_NLS_THREADS", "default"))), flush=True)
+    run_unicycle()
     f = vanderpol_formulation(); f.params = np.array([0.1])
     run("vanderpol_ex nx2 nu1 ph10 ch5", L.SYS_VANDERPOL, f, 10, 5, 8192, True, -1.5, 1.5)
     f = ugv_formulation(10, 10, v_pref=(0.6, 0.8))
