@@ -301,6 +301,12 @@ static int nl_solve_impl(int system, int ph, int ch, int batch, const b200mpc_nl
     if ((rc = out(iters, (size_t)batch * 4, (void**)&a.iters))) return rc;
     if ((rc = out(qp_iters, (size_t)batch * 4, (void**)&a.qp_iters))) return rc;
     if ((rc = stage_scaling(scaling, nx, nu, &a.sx, &a.su, stream, tofree))) return rc;      // freed after the final synchronise
+    {   // work counter of the stage-structured kernel (controllers are drawn dynamically)
+        void* cnt = nullptr;
+        CK(cudaMallocAsync(&cnt, sizeof(int), stream)); tofree.push_back(cnt);
+        CK(cudaMemsetAsync(cnt, 0, sizeof(int), stream));
+        a.counter = (int*)cnt;
+    }
     if (dsx) a.sx = dsx;
     if (dsu) a.su = dsu;
     switch (system) {

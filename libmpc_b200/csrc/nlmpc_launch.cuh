@@ -57,7 +57,7 @@ int nl_launch_structured_t(NlSolveArgs& a, size_t smem, int sms, cudaStream_t st
     if (occ < 1) occ = 1;
     int grid = a.batch < sms * occ ? a.batch : sms * occ;
     a.mat_ws = nullptr;
-    kern<<<grid, NT, smem, stream>>>(a);
+    kern<<<grid, NT, smem, stream>>>(a);          // a.counter: allocated and zeroed by the caller (b200mpc_nlmpc.cu)
     CK(cudaGetLastError());
     return B200MPC_OK;
 }
@@ -70,7 +70,7 @@ int nl_solve_t(NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree) 
     CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     {
         constexpr int K = NlIneqPerStage<S>::value > 0 ? NlIneqPerStage<S>::value : 1;
-        const size_t ssm = NlSW::doubles(a.ph, a.ch, S::nx, S::nu, K) * sizeof(double);
+        const size_t ssm = nls_doubles(a.ph, a.ch, S::nx, S::nu, K) * sizeof(double);
         int nt = 64;
         const int choice = nl_structured_choice(nls_supported<S>(a.ph, a.ch), ssm, maxsm, &nt);
         if (choice < 0) return fail(B200MPC_EINVAL, "the stage-structured NLMPC solver does not apply to this system / horizon");

@@ -35,6 +35,7 @@ struct NlSolveArgs {
     int* iters;             // SQP iterations
     int* qp_iters;          // total ADMM iterations
     double* mat_ws;         // MODE 1/2 kernels: per-CTA matrix workspace [grid][NlWs::gmem_doubles]
+    int* counter;           // structured kernel: next controller to draw (zeroed by the launcher); null = static round robin
 };
 
 __device__ __forceinline__ double nl_wsum(double v) {
@@ -609,18 +610,29 @@ template <class S, int NT>
 __global__ void __launch_bounds__(NT) nlmpc_structured_kernel(const NlSolveArgs a) {
     extern __shared__ __align__(16) double nls_smem2[];
     constexpr int nx = S::nx, nu = S::nu, K = NlIneqPerStage<S>::value > 0 ? NlIneqPerStage<S>::value : 1;
-    NlSW w;
-    w.carve(nls_smem2, a.ph, a.ch, nx, nu, K);
+    NlSW<nx, nu, K> w;
+    w.carve(nls_smem2, a.ph, a.ch);
     const NlGrp<NT> g{(int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), w.red};
     NlSParams sp;
     sp.max_sqp = a.max_sqp; sp.max_qp = a.max_qp; sp.tol = a.tol; sp.ftol = a.ftol; sp.qp_eps = a.qp_eps; sp.rho0 = a.rho0;
     sp.lb = a.lb; sp.ub = a.ub; sp.sx = a.sx; sp.su = a.su;
     const int n = w.n;
-    for (int inst = blockIdx.x; inst < a.batch; inst += gridDim.x) {
+    __shared__ int next_inst;
+    // controllers are drawn from a global counter: solve times spread over 15x (iteration counts), a static split would leave
+    // the slowest CTA with several long ones
+    for (int inst = blockIdx.x;; ) {
+        if (a.counter) {
+            if (threadIdx.x == 0) next_inst = atomicAdd(a.counter, 1);
+            __syncthreads();
+            inst = next_inst;
+            __syncthreads();
+        }
+        if (inst >= a.batch) break;
         NlSResult r = nls_solve_instance<S>(g, w, sp, a.z0 + (size_t)inst * n, a.x0 + (size_t)inst * nx, a.params + (size_t)inst * a.param_stride,
                                             a.z_out + (size_t)inst * n);
         if (g.tid == 0) { a.cost[inst] = r.cost; a.viol[inst] = r.viol; a.status[inst] = r.status; a.iters[inst] = r.iters; a.qp_iters[inst] = r.qp_iters; }
         g.sync();
+        if (!a.counter) inst += gridDim.x;
     }
 }
 

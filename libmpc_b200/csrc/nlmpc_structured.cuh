@@ -36,10 +36,24 @@ struct NlSParams {
 };
 struct NlSResult { double cost, viol; int status, iters, qp_iters; };
 
-// Per-controller workspace (all shared memory) + the index algebra of the stage partition.
+// Shared-memory footprint of one controller, in doubles.
+__host__ __device__ inline size_t nls_doubles(int ph, int ch, int nx, int nu, int K) {
+    const int b = nx + nu, nb = nu + 1, n = ph * nx + ch * nu + 1, me = ph * nx, mi = (ph + 1) * K, m = me + mi + n;
+    size_t v = 13 * (size_t)n + 10 * (size_t)m + 2 * (size_t)(me + mi) + (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 16;
+    size_t mats = (size_t)me * (2 * nx + nu) + (size_t)mi * (nx + nu + 1) + (size_t)ph * b * b + 2 + 2 * (size_t)ph * b * b +
+                  (size_t)ph * nb * b + (size_t)nb * nb + (size_t)ph * b + 4 * (size_t)(ph + 1) + 2 * (size_t)nb + 8 +
+                  (size_t)ph * b * b + (size_t)ph * b * nb + (size_t)ph * b + (size_t)nb * ph;
+    return (v + mats + 1) & ~(size_t)1;
+}
+
+// Per-controller workspace (all shared memory) + the index algebra of the stage partition.  nx, nu and K (inequality rows per
+// stage, ineq_per_stage) are compile-time: every inner loop has a constant trip count and the index divisions strength-reduce.
+template <int NX, int NU, int KK>
 struct NlSW {
-    int ph, ch, nx, nu, K;                   // K = inequality rows per stage (ineq_per_stage)
-    int b, nb, we, wi, n, me, mi, mc, m;
+    static constexpr int nx = NX, nu = NU, K = KK;
+    static constexpr int b = NX + NU, nb = NU + 1, we = 2 * NX + NU, wi = NX + NU + 1;
+    int ph, ch;
+    int n, me, mi, mc, m;
     // vectors
     double *z, *g, *g2, *d, *xs, *xt, *D, *gs, *rhs, *tmp, *glo, *sv, *zt2;     // n
     double *E, *ls, *us, *zs, *ys, *rho, *yq, *w, *pr, *pt;                     // m
@@ -54,17 +68,8 @@ struct NlSW {
                                              // factorisation Ls[s-1] holds M_s = Li_s Lsub_{s-1} (Lsub itself is no longer needed)
     double *cy, *cq, *bp, *cs;               // chain vectors ph x b (y, then x), ph x b (gathered rhs / q), border partials nb x ph,
                                              // per-stage scalars 4 x (ph + 1)
-    __host__ __device__ static size_t doubles(int ph, int ch, int nx, int nu, int K) {
-        const int b = nx + nu, nb = nu + 1, n = ph * nx + ch * nu + 1, me = ph * nx, mi = (ph + 1) * K, m = me + mi + n;
-        size_t v = 13 * (size_t)n + 10 * (size_t)m + 2 * (size_t)(me + mi) + (size_t)(me + mi) + (size_t)(ph + 1) * (nx + nu) + 16;
-        size_t mats = (size_t)me * (2 * nx + nu) + (size_t)mi * (nx + nu + 1) + (size_t)ph * b * b + 2 + 2 * (size_t)ph * b * b +
-                      (size_t)ph * nb * b + (size_t)nb * nb + (size_t)ph * b + 4 * (size_t)(ph + 1) + 2 * (size_t)nb + 8 +
-                      (size_t)ph * b * b + (size_t)ph * b * nb + (size_t)ph * b + (size_t)nb * ph;
-        return (v + mats + 1) & ~(size_t)1;
-    }
-    __device__ void carve(double* p, int ph_, int ch_, int nx_, int nu_, int K_) {
-        ph = ph_; ch = ch_; nx = nx_; nu = nu_; K = K_;
-        b = nx + nu; nb = nu + 1; we = 2 * nx + nu; wi = nx + nu + 1;
+    __device__ void carve(double* p, int ph_, int ch_) {
+        ph = ph_; ch = ch_;
         n = ph * nx + ch * nu + 1; me = ph * nx; mi = (ph + 1) * K; mc = me + mi; m = mc + n;
         double** nv[] = {&z, &g, &g2, &d, &xs, &xt, &D, &gs, &rhs, &tmp, &glo, &sv, &zt2};
         for (auto q : nv) { *q = p; p += n; }
@@ -203,30 +208,30 @@ struct NlSW {
 };
 
 // out_r = E_r (A dx)_r for all m rows (dx = D .* x already formed)
-template <class G>
-__device__ __forceinline__ void nls_As_core(const G& g, NlSW& w, const double* dx, double* out) {
+template <class G, class WS>
+__device__ __forceinline__ void nls_As_core(const G& g, WS& w, const double* dx, double* out) {
     for (int r = g.tid; r < w.me; r += G::nt) out[r] = w.E[r] * w.je_row_dot(r, dx);
     for (int r = g.tid; r < w.mi; r += G::nt) out[w.me + r] = w.E[w.me + r] * w.ji_row_dot(r, dx);
     for (int j = g.tid; j < w.n; j += G::nt) out[w.mc + j] = w.E[w.mc + j] * dx[j];
     g.sync();
 }
-template <class G>
-__device__ __forceinline__ void nls_As(const G& g, NlSW& w, const double* x, double* out) {
+template <class G, class WS>
+__device__ __forceinline__ void nls_As(const G& g, WS& w, const double* x, double* out) {
     for (int i = g.tid; i < w.n; i += G::nt) w.tmp[i] = w.D[i] * x[i];
     g.sync();
     nls_As_core(g, w, w.tmp, out);
 }
 // out_j = D_j (A' (E .* v))_j
-template <class G>
-__device__ __forceinline__ void nls_Ats(const G& g, NlSW& w, const double* v, double* out) {
+template <class G, class WS>
+__device__ __forceinline__ void nls_Ats(const G& g, WS& w, const double* v, double* out) {
     for (int r = g.tid; r < w.m; r += G::nt) w.w[r] = w.E[r] * v[r];
     g.sync();
     for (int j = g.tid; j < w.n; j += G::nt) out[j] = w.D[j] * (w.w[w.mc + j] + w.col_dot(j, w.w));
     g.sync();
 }
 // out = c D B D x
-template <class G>
-__device__ __forceinline__ void nls_Ps(const G& g, NlSW& w, double c, const double* x, double* out) {
+template <class G, class WS>
+__device__ __forceinline__ void nls_Ps(const G& g, WS& w, double c, const double* x, double* out) {
     for (int i = g.tid; i < w.n; i += G::nt) w.tmp[i] = w.D[i] * x[i];
     g.sync();
     for (int i = g.tid; i < w.n; i += G::nt) out[i] = c * w.D[i] * w.b_row_dot(i, w.tmp);
@@ -236,9 +241,10 @@ __device__ __forceinline__ void nls_Ps(const G& g, NlSW& w, double c, const doub
 // ---- H = c D B D + sigma I + (E A D)' diag(rho) (E A D), bordered block tridiagonal; factorisation ------------------------------
 // Blocks are assembled straight into the factor storage (Li <- diagonal blocks, Ls[s] <- H[g_{s+1}, g_s], Wb[s] <- H[border, g_s]')
 // and factorised in place by the group's first warp.  Dead slots (U slots of groups >= ch-1) are unit rows / columns.
-template <class G>
-__device__ __forceinline__ bool nls_factor(const G& g, NlSW& w, double c, double sigma) {
-    const int ph = w.ph, b = w.b, nb = w.nb, nx = w.nx, K = w.K, me = w.me, mc = w.mc;
+template <class G, class WS>
+__device__ __forceinline__ bool nls_factor(const G& g, WS& w, double c, double sigma) {
+    constexpr int b = WS::b, nb = WS::nb, nx = WS::nx, K = WS::K;
+    const int ph = w.ph, me = w.me, mc = w.mc;
     for (int r = g.tid; r < mc; r += G::nt) w.w[r] = w.rho[r] * w.E[r] * w.E[r];
     g.sync();
     // entry (ja, jb) of D (c B + A' W A) D from the candidate rows [e0,e1) of J_eq and [i0,i1) of J_in
@@ -432,10 +438,10 @@ __device__ __forceinline__ bool nls_factor(const G& g, NlSW& w, double c, double
 //   border    y_b = LSi (r_b - sum_s Wb_s y_s),  x_b = LSi' y_b
 //   backward  x_s = (Li_s' y_s - V_s x_b) - N_s x_{s+1}   (the bracket in parallel; one mat-vec per stage on the chain)
 // The two recurrences run on the group's first warp, lane = row, one warp barrier per stage; everything else is group-parallel.
-template <int BS, class G>
-__device__ __forceinline__ void nls_kkt_apply(const G& g, NlSW& w, double* dxt = nullptr) {
-    const int ph = w.ph, nb = w.nb;
-    constexpr int b = BS;
+template <int BS, class G, class WS>
+__device__ __forceinline__ void nls_kkt_apply(const G& g, WS& w, double* dxt = nullptr) {
+    const int ph = w.ph;
+    constexpr int b = BS, nb = WS::nb;
     constexpr int W = G::nt < 32 ? G::nt : 32;
     auto wsync = [&]() {
 #ifndef B200_HOST_EMU
@@ -517,8 +523,8 @@ __device__ __forceinline__ void nls_kkt_apply(const G& g, NlSW& w, double* dxt =
 }
 
 // max bound violation of A x and max |P x + q + A' y| in the scaled problem (uses pt, rhs, zt2)
-template <class G>
-__device__ __forceinline__ void nls_qp_residuals(const G& g, NlSW& w, double c, const double* x, const double* y, double& pri, double& dua) {
+template <class G, class WS>
+__device__ __forceinline__ void nls_qp_residuals(const G& g, WS& w, double c, const double* x, const double* y, double& pri, double& dua) {
     nls_As(g, w, x, w.pt);
     double p = 0, d = 0;
     for (int r = g.tid; r < w.m; r += G::nt) p = fmax(p, fmax(fmax(w.ls[r] - w.pt[r], w.pt[r] - w.us[r]), 0.0));
@@ -529,8 +535,8 @@ __device__ __forceinline__ void nls_qp_residuals(const G& g, NlSW& w, double c, 
 }
 
 // OSQP polish.c on the structured QP (see nl_qp_polish_impl in nlmpc_sqp.cuh: identical steps, structured products / factor)
-template <int BS, class G>
-__device__ __forceinline__ bool nls_qp_polish(const G& g, NlSW& w, double c) {
+template <int BS, class G, class WS>
+__device__ __forceinline__ bool nls_qp_polish(const G& g, WS& w, double c) {
     const int n = w.n, m = w.m;
     const double delta = 1e-6, idelta = 1e6;
     double pri_a, dua_a;
@@ -573,8 +579,8 @@ __device__ __forceinline__ bool nls_qp_polish(const G& g, NlSW& w, double c) {
 
 // OSQP-style ADMM for the QP subproblem on the structured storage.  In: Bb, g, JeC, JiC, ce, ci, z, lb, ub; warm dual yq (if have_y).
 // Out: d (step), yq (multipliers, unscaled).  Returns ADMM iterations.  Step for step nl_qp_solve of nlmpc_sqp.cuh.
-template <int BS, class G>
-__device__ __forceinline__ int nls_qp_solve(const G& g, NlSW& w, const NlSParams& a, int mii, bool have_y, int max_qp) {
+template <int BS, class G, class WS>
+__device__ __forceinline__ int nls_qp_solve(const G& g, WS& w, const NlSParams& a, int mii, bool have_y, int max_qp) {
     const int n = w.n, me = w.me, mi = w.mi, mc = w.mc, m = w.m;
     const double sigma = 1e-6, alpha = 1.6;
     for (int i = g.tid; i < n; i += G::nt) { w.D[i] = 1.0; w.gs[i] = w.g[i]; }
@@ -667,13 +673,14 @@ __device__ __forceinline__ int nls_qp_solve(const G& g, NlSW& w, const NlSParams
 
 // The whole NLOptimizer::run core (NLOptimizer.hpp:519) for ONE controller on the structured storage.  z0: initial decision
 // vector; z_out [n].  The SQP loop is nlmpc_solve_kernel's (nlmpc_sqp.cuh) with the block-diagonal BFGS update.
-template <class S, class G>
-__device__ __forceinline__ NlSResult nls_solve_instance(const G& g, NlSW& w, const NlSParams& a, const double* z0, const double* x0,
+template <class S, class G, class WS>
+__device__ __forceinline__ NlSResult nls_solve_instance(const G& g, WS& w, const NlSParams& a, const double* z0, const double* x0,
                                                         const double* p, double* z_out) {
     constexpr int nx = S::nx, nu = S::nu;
-    const int ph = w.ph, ch = w.ch, n = w.n, me = w.me, mi = w.mi, mc = w.mc, b = w.b;
+    constexpr int b = WS::b;
+    const int ph = w.ph, ch = w.ch, n = w.n, me = w.me, mi = w.mi, mc = w.mc;
     const int mii = mi;                                   // no user equality constraints on this path
-    const NlCompactMap map{ph, ch, nx, nu, w.K};
+    const NlCompactMap map{ph, ch, nx, nu, WS::K};
     for (int i = g.tid; i < n; i += G::nt) w.z[i] = fmin(fmax(z0[i], a.lb[i]), a.ub[i]);
     auto reset_B = [&]() {
         for (int e = g.tid; e < ph * b * b; e += G::nt) { int l = (e / b) % b, k = e % b; w.Bb[e] = (l == k) ? 1.0 : 0.0; }

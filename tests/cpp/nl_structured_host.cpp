@@ -18,9 +18,9 @@ static int run(int ph, int ch, const double* z0, const double* x0, const double*
                int max_qp, double* z, double* out) {
     if (!nls_supported<S>(ph, ch)) return -2;
     constexpr int K = NlIneqPerStage<S>::value;
-    std::vector<double> mem(NlSW::doubles(ph, ch, S::nx, S::nu, K) + 64, 0.0);
-    NlSW w;
-    w.carve(mem.data(), ph, ch, S::nx, S::nu, K);
+    std::vector<double> mem(nls_doubles(ph, ch, S::nx, S::nu, K) + 64, 0.0);
+    NlSW<S::nx, S::nu, K> w;
+    w.carve(mem.data(), ph, ch);
     NlSParams a{max_sqp, max_qp, 1e-7, 1e-12, 1e-5, 0.1, lb, ub, nullptr, nullptr};
     NlGrpHost g;
     NlSResult r = nls_solve_instance<S>(g, w, a, z0, x0, params, z);
