@@ -72,7 +72,7 @@ int nl_solve_t(NlSolveArgs& a, cudaStream_t stream, std::vector<void*>& tofree) 
         constexpr int K = NlIneqPerStage<S>::value > 0 ? NlIneqPerStage<S>::value : 1;
         const size_t ssm = nls_doubles(a.ph, a.ch, S::nx, S::nu, K) * sizeof(double);
         int nt = 64;
-        const int choice = nl_structured_choice(nls_supported<S>(a.ph, a.ch), ssm, maxsm, &nt);
+        const int choice = nl_structured_choice(nls_supported<S>(a.ph, a.ch), ssm, maxsm, a.ph * S::nx + a.ch * S::nu + 1, &nt);
         if (choice < 0) return fail(B200MPC_EINVAL, "the stage-structured NLMPC solver does not apply to this system / horizon");
         if (choice > 0) {
             if (nt == 32) return nl_launch_structured_t<S, 32>(a, ssm, sms, stream);

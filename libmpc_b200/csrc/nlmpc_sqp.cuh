@@ -634,6 +634,12 @@ __global__ void __launch_bounds__(NT) nlmpc_structured_kernel(const NlSolveArgs 
         g.sync();
         if (!a.counter) inst += gridDim.x;
     }
+#ifdef NLS_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const char* names[] = {"kkt par1", "kkt chain fwd", "kkt border+par2", "kkt chain bwd", "kkt scatter", "factor assemble", "factor chain", "ruiz", "admm rhs", "admm rows"};
+        for (int k = 0; k < 10; ++k) printf("NLSPROF %-16s %lld\n", names[k], g_nls_prof[k]);
+    }
+#endif
 }
 
 }  // namespace b200mpc

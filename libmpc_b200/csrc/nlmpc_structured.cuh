@@ -26,6 +26,16 @@
 
 namespace b200mpc {
 
+#ifdef NLS_PROFILE
+__device__ long long g_nls_prof[16];
+#define NLS_T0() nls_t0_ = clock64()
+#define NLS_DECL() long long nls_t0_ = 0; (void)nls_t0_
+#define NLS_ACC(slot) do { long long t_ = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) g_nls_prof[slot] += t_ - nls_t0_; nls_t0_ = t_; } while (0)
+#else
+#define NLS_T0() do {} while (0)
+#define NLS_DECL() do {} while (0)
+#define NLS_ACC(slot) do {} while (0)
+#endif
 __device__ __forceinline__ double nls_lim(double v) { v = v < 1e-4 ? 1.0 : v; return v > 1e4 ? 1e4 : v; }
 
 struct NlSParams {
@@ -66,6 +76,7 @@ struct NlSW {
                                              // ph x (nb x b) border rows, nb x nb inverse of the border's Cholesky factor
     double *Nb, *Vb;                         // solve-time products: N_s = Li_s' Lsub_s' (b x b), V_s = Li_s' Wb_s' (b x nb); after the
                                              // factorisation Ls[s-1] holds M_s = Li_s Lsub_{s-1} (Lsub itself is no longer needed)
+    double rho_keep;                         // ADMM penalty carried from one QP subproblem to the next (as OSQP does between re-solves)
     double *cy, *cq, *bp, *cs;               // chain vectors ph x b (y, then x), ph x b (gathered rhs / q), border partials nb x ph,
                                              // per-stage scalars 4 x (ph + 1)
     __device__ void carve(double* p, int ph_, int ch_) {
@@ -245,6 +256,7 @@ template <class G, class WS>
 __device__ __forceinline__ bool nls_factor(const G& g, WS& w, double c, double sigma) {
     constexpr int b = WS::b, nb = WS::nb, nx = WS::nx, K = WS::K;
     const int ph = w.ph, me = w.me, mc = w.mc;
+    NLS_DECL(); NLS_T0();
     for (int r = g.tid; r < mc; r += G::nt) w.w[r] = w.rho[r] * w.E[r] * w.E[r];
     g.sync();
     // entry (ja, jb) of D (c B + A' W A) D from the candidate rows [e0,e1) of J_eq and [i0,i1) of J_in
@@ -289,8 +301,14 @@ __device__ __forceinline__ bool nls_factor(const G& g, WS& w, double c, double s
         w.LSi[e] = v;
     }
     g.sync();
-    // ---- block Cholesky with the border as the last block row (first warp; b <= 32) -----------------------------------------
+    NLS_ACC(5);
+    // ---- block Cholesky with the border as the last block row ------------------------------------------------------------------
+    // Sequential part (first warp): A_s = H_ss - Lsub_{s-1} Lsub_{s-1}', its Cholesky factor, Li_s = L_s^-1, Lsub_s = H_{s+1,s} Li_s';
+    // then the border recurrence Wb_s = (H_{b,s} - Wb_{s-1} Lsub_{s-1}') Li_s'.  Everything that is not a recurrence -- the solve-time
+    // products N_s, V_s, M_s and the border's Schur complement -- is done afterwards by the whole group, all stages at once.
     bool ok = true;
+    double* Sc = w.pt;                              // scratch for one block (m >= b*b: nls_supported)
+    double* ipiv = w.cs;                            // reciprocal pivots of the current block (b <= 4 (ph+1) + 8: nls_supported)
     if (g.wid == 0) {
         const int lane = g.lane;
         constexpr int W = G::nt < 32 ? G::nt : 32;
@@ -299,137 +317,138 @@ __device__ __forceinline__ bool nls_factor(const G& g, WS& w, double c, double s
             __syncwarp();
 #endif
         };
-        double* Sc = w.pt;                          // scratch for one block (m >= b*b: nls_supported)
         for (int s = 0; s < ph; ++s) {
             double* A = w.Li + (size_t)s * b * b;
-            // A -= Lsub[s-1] Lsub[s-1]'   ;   Wb[s] -= Wb[s-1] Lsub[s-1]'
             if (s > 0) {
                 const double* Lp = w.Ls + (size_t)(s - 1) * b * b;
-                const double* Wp = w.Wb + (size_t)(s - 1) * nb * b;
                 for (int e = lane; e < b * b; e += W) {
                     const int i = e / b, j = e - i * b;
                     if (j <= i) { double acc = 0; for (int q = 0; q < b; ++q) acc = fma(Lp[i * b + q], Lp[j * b + q], acc); A[e] -= acc; }
                 }
-                double* Wc = w.Wb + (size_t)s * nb * b;
-                for (int e = lane; e < nb * b; e += W) {
-                    const int i = e / b, j = e - i * b;
-                    double acc = 0; for (int q = 0; q < b; ++q) acc = fma(Wp[i * b + q], Lp[j * b + q], acc);
-                    Wc[e] -= acc;
-                }
                 wsync();
             }
-            // Cholesky of A in place (lower), right-looking
+            // left-looking Cholesky, one column per step: lane r-k updates entry (r, k), the pivot comes from the first lane
             for (int k = 0; k < b; ++k) {
-                const double dkk = A[k * b + k];
+#ifndef B200_HOST_EMU
+                const int r = k + lane;
+                double v = 0;
+                if (r < b) { v = A[r * b + k]; for (int q = 0; q < k; ++q) v = fma(-A[r * b + q], A[k * b + q], v); }
+                const double dkk = __shfl_sync(0xffffffffu, v, 0);
                 if (!(dkk > 0.0)) ok = false;
                 const double piv = sqrt(dkk), inv = 1.0 / piv;
-                wsync();
-                for (int r = k + lane; r < b; r += W) A[r * b + k] = (r == k) ? piv : A[r * b + k] * inv;
-                wsync();
-                for (int e = lane; e < (b - k - 1) * (b - k - 1); e += W) {
-                    const int r = k + 1 + e / (b - k - 1), q = k + 1 + e % (b - k - 1);
-                    if (q <= r) A[r * b + q] -= A[r * b + k] * A[q * b + k];
-                }
-                wsync();
+                if (r < b) A[r * b + k] = (r == k) ? piv : v * inv;
+                if (lane == 0) ipiv[k] = inv;
+                __syncwarp();
+#else
+                double dkk = A[k * b + k];
+                for (int q = 0; q < k; ++q) dkk = fma(-A[k * b + q], A[k * b + q], dkk);
+                if (!(dkk > 0.0)) ok = false;
+                const double piv = sqrt(dkk), inv = 1.0 / piv;
+                for (int r = k + 1; r < b; ++r) { double v = A[r * b + k]; for (int q = 0; q < k; ++q) v = fma(-A[r * b + q], A[k * b + q], v); A[r * b + k] = v * inv; }
+                A[k * b + k] = piv; ipiv[k] = inv;
+#endif
             }
             // explicit inverse of L (lower) into Sc, column by column: lane = column
             for (int col = lane; col < b; col += W) {
                 for (int r = 0; r < b; ++r) {
                     double v;
                     if (r < col) v = 0.0;
-                    else if (r == col) v = 1.0 / A[r * b + r];
-                    else { double acc = 0; for (int q = col; q < r; ++q) acc = fma(A[r * b + q], Sc[q * b + col], acc); v = -acc / A[r * b + r]; }
+                    else if (r == col) v = ipiv[r];
+                    else { double acc = 0; for (int q = col; q < r; ++q) acc = fma(A[r * b + q], Sc[q * b + col], acc); v = -acc * ipiv[r]; }
                     Sc[r * b + col] = v;
                 }
             }
             wsync();
             for (int e = lane; e < b * b; e += W) A[e] = Sc[e];                    // Li[s] = L^-1 (full square, upper part zero)
             wsync();
-            // Lsub[s] = sub[s] Li[s]'   ;   Wb[s] = Wb[s] Li[s]'
+            // Lsub[s] = sub[s] Li[s]'  in place: lane = row, columns from the right (entry j needs the old entries q <= j only)
             if (s + 1 < ph) {
                 double* Lsb = w.Ls + (size_t)s * b * b;
-                for (int e = lane; e < b * b; e += W) {
-                    const int i = e / b, j = e - i * b;
-                    double acc = 0; for (int q = 0; q <= j; ++q) acc = fma(Lsb[i * b + q], A[j * b + q], acc);
-                    Sc[e] = acc;
-                }
-                wsync();
-                for (int e = lane; e < b * b; e += W) Lsb[e] = Sc[e];
+                for (int i = lane; i < b; i += W)
+                    for (int j = b - 1; j >= 0; --j) { double acc = 0; for (int q = 0; q <= j; ++q) acc = fma(Lsb[i * b + q], A[j * b + q], acc); Lsb[i * b + j] = acc; }
                 wsync();
             }
-            {
-                double* Wc = w.Wb + (size_t)s * nb * b;
+        }
+        // border recurrence:  Wb[s] = (Wb[s] - Wb[s-1] Lsub[s-1]') Li[s]'   (lane = one of the nb x b entries; two steps per stage)
+        for (int s = 0; s < ph; ++s) {
+            const double* A = w.Li + (size_t)s * b * b;
+            double* Wc = w.Wb + (size_t)s * nb * b;
+            if (s > 0) {
+                const double* Lp = w.Ls + (size_t)(s - 1) * b * b;
+                const double* Wp = w.Wb + (size_t)(s - 1) * nb * b;
                 for (int e = lane; e < nb * b; e += W) {
                     const int i = e / b, j = e - i * b;
-                    double acc = 0; for (int q = 0; q <= j; ++q) acc = fma(Wc[i * b + q], A[j * b + q], acc);
-                    Sc[e] = acc;
-                }
-                wsync();
-                for (int e = lane; e < nb * b; e += W) Wc[e] = Sc[e];
-                wsync();
-                // solve-time products (take the second mat-vec of every stage off the sequential chain, see nls_kkt_apply)
-                double* Vc = w.Vb + (size_t)s * b * nb;
-                for (int e = lane; e < b * nb; e += W) {
-                    const int l = e / nb, q = e - l * nb;
-                    double acc = 0; for (int k = l; k < b; ++k) acc = fma(A[k * b + l], Wc[q * b + k], acc);
-                    Vc[e] = acc;
-                }
-                if (s + 1 < ph) {
-                    const double* Lsb = w.Ls + (size_t)s * b * b;
-                    double* Nc = w.Nb + (size_t)s * b * b;
-                    for (int e = lane; e < b * b; e += W) {
-                        const int l = e / b, q = e - l * b;
-                        double acc = 0; for (int k = l; k < b; ++k) acc = fma(A[k * b + l], Lsb[q * b + k], acc);
-                        Nc[e] = acc;
-                    }
-                }
-                if (s > 0) {
-                    double* Lp = w.Ls + (size_t)(s - 1) * b * b;              // Lsub[s-1] -> M_s = Li_s Lsub[s-1]
-                    for (int e = lane; e < b * b; e += W) {
-                        const int l = e / b, q = e - l * b;
-                        double acc = 0; for (int k = 0; k <= l; ++k) acc = fma(A[l * b + k], Lp[k * b + q], acc);
-                        Sc[e] = acc;
-                    }
-                    wsync();
-                    for (int e = lane; e < b * b; e += W) Lp[e] = Sc[e];
+                    double acc = Wc[e]; for (int q = 0; q < b; ++q) acc = fma(-Wp[i * b + q], Lp[j * b + q], acc);
+                    Wc[e] = acc;
                 }
                 wsync();
             }
+            for (int i = lane; i < nb; i += W)
+                for (int j = b - 1; j >= 0; --j) { double acc = 0; for (int q = 0; q <= j; ++q) acc = fma(Wc[i * b + q], A[j * b + q], acc); Wc[i * b + j] = acc; }
+            wsync();
         }
-        // S = D_border - sum_s Wb[s] Wb[s]'  -> Cholesky -> inverse
-        double* Sb = w.LSi;
-        for (int e = lane; e < nb * nb; e += W) {
-            const int i = e / nb, j = e - i * nb;
-            double acc = 0;
-            for (int s = 0; s < ph; ++s) { const double* Wc = w.Wb + (size_t)s * nb * b; for (int q = 0; q < b; ++q) acc = fma(Wc[i * b + q], Wc[j * b + q], acc); }
-            Sc[e] = Sb[e] - acc;
-        }
-        wsync();
-        if (lane == 0) {                                                        // nb <= ~7: one lane
-            for (int k = 0; k < nb; ++k) {
-                double dkk = Sc[k * nb + k];
-                for (int q = 0; q < k; ++q) dkk -= Sc[k * nb + q] * Sc[k * nb + q];
-                if (!(dkk > 0.0)) ok = false;
-                const double piv = sqrt(dkk);
-                Sc[k * nb + k] = piv;
-                for (int r = k + 1; r < nb; ++r) {
-                    double v = Sc[r * nb + k];
-                    for (int q = 0; q < k; ++q) v -= Sc[r * nb + q] * Sc[k * nb + q];
-                    Sc[r * nb + k] = v / piv;
-                }
-            }
-            for (int col = 0; col < nb; ++col)
-                for (int r = 0; r < nb; ++r) {
-                    double v;
-                    if (r < col) v = 0.0;
-                    else if (r == col) v = 1.0 / Sc[r * nb + r];
-                    else { double acc = 0; for (int q = col; q < r; ++q) acc += Sc[r * nb + q] * Sb[q * nb + col]; v = -acc / Sc[r * nb + r]; }
-                    Sb[r * nb + col] = v;
-                }
-        }
-        wsync();
     }
     g.sync();
+    // solve-time products, all stages in parallel:  V_s = Li_s' Wb_s'  (b x nb),  N_s = Li_s' Lsub_s'  (b x b)
+    for (int t = g.tid; t < ph * b * (nb + b); t += G::nt) {
+        const int s = t / (b * (nb + b)), e = t - s * b * (nb + b);
+        const double* A = w.Li + (size_t)s * b * b;
+        if (e < b * nb) {
+            const int l = e / nb, q = e - l * nb;
+            const double* Wc = w.Wb + (size_t)s * nb * b;
+            double acc = 0; for (int k = l; k < b; ++k) acc = fma(A[k * b + l], Wc[q * b + k], acc);
+            w.Vb[(size_t)s * b * nb + e] = acc;
+        } else if (s + 1 < ph) {
+            const int ee = e - b * nb, l = ee / b, q = ee - l * b;
+            const double* Lsb = w.Ls + (size_t)s * b * b;
+            double acc = 0; for (int k = l; k < b; ++k) acc = fma(A[k * b + l], Lsb[q * b + k], acc);
+            w.Nb[(size_t)s * b * b + ee] = acc;
+        }
+    }
+    // border Schur complement  S = H_bb - sum_s Wb[s] Wb[s]'   (nb x nb entries, one thread each)
+    for (int e = g.tid; e < nb * nb; e += G::nt) {
+        const int i = e / nb, j = e - i * nb;
+        double acc = 0;
+        for (int s = 0; s < ph; ++s) { const double* Wc = w.Wb + (size_t)s * nb * b; for (int q = 0; q < b; ++q) acc = fma(Wc[i * b + q], Wc[j * b + q], acc); }
+        Sc[e] = w.LSi[e] - acc;
+    }
+    g.sync();
+    // M_s = Li_s Lsub[s-1] in place of Lsub[s-1] (one thread per column: the whole column is read before it is written)
+    for (int t = g.tid; t < (ph - 1) * b; t += G::nt) {
+        const int s = 1 + t / b, q = t - (s - 1) * b;
+        const double* A = w.Li + (size_t)s * b * b;
+        double* Lp = w.Ls + (size_t)(s - 1) * b * b;
+        double col[b];
+#pragma unroll
+        for (int k = 0; k < b; ++k) col[k] = Lp[k * b + q];
+#pragma unroll
+        for (int l = 0; l < b; ++l) { double acc = 0; for (int k = 0; k <= l; ++k) acc = fma(A[l * b + k], col[k], acc); Lp[l * b + q] = acc; }
+    }
+    if (g.tid == 0) {                                                           // nb <= ~7: Cholesky of S and its inverse by one thread
+        double* Sb = w.LSi;
+        for (int k = 0; k < nb; ++k) {
+            double dkk = Sc[k * nb + k];
+            for (int q = 0; q < k; ++q) dkk -= Sc[k * nb + q] * Sc[k * nb + q];
+            if (!(dkk > 0.0)) ok = false;
+            const double piv = sqrt(dkk);
+            Sc[k * nb + k] = piv;
+            for (int r = k + 1; r < nb; ++r) {
+                double v = Sc[r * nb + k];
+                for (int q = 0; q < k; ++q) v -= Sc[r * nb + q] * Sc[k * nb + q];
+                Sc[r * nb + k] = v / piv;
+            }
+        }
+        for (int col = 0; col < nb; ++col)
+            for (int r = 0; r < nb; ++r) {
+                double v;
+                if (r < col) v = 0.0;
+                else if (r == col) v = 1.0 / Sc[r * nb + r];
+                else { double acc = 0; for (int q = col; q < r; ++q) acc += Sc[r * nb + q] * Sb[q * nb + col]; v = -acc / Sc[r * nb + r]; }
+                Sb[r * nb + col] = v;
+            }
+    }
+    g.sync();
+    NLS_ACC(6);
     return !g.any(!ok);
 }
 
@@ -448,6 +467,7 @@ __device__ __forceinline__ void nls_kkt_apply(const G& g, WS& w, double* dxt = n
         __syncwarp();
 #endif
     };
+    NLS_DECL(); NLS_T0();
     for (int e = g.tid; e < ph * b; e += G::nt) { const int s = e / b, l = e - s * b, jz = w.gz(s, l); w.cq[e] = jz >= 0 ? w.rhs[jz] : 0.0; }
     g.sync();
     for (int e = g.tid; e < ph * b; e += G::nt) {
@@ -460,20 +480,52 @@ __device__ __forceinline__ void nls_kkt_apply(const G& g, WS& w, double* dxt = n
         w.cy[e] = v;
     }
     g.sync();
+    NLS_ACC(0);
     if (g.wid == 0) {
+#ifndef B200_HOST_EMU
+        // the running vector stays in registers (lane = row) and is broadcast with shuffles: no shared-memory round trip and no
+        // barrier on the dependent chain; the matrix row and the parallel part of the next stage are loaded one stage ahead
+        const int l = g.lane < b ? g.lane : b - 1;
+        double y = w.cy[l];
+        double mrow[b], pn = 0;
+        if (ph > 1) {
+            const double* M = w.Ls + (size_t)l * b;
+#pragma unroll
+            for (int q = 0; q < b; ++q) mrow[q] = M[q];
+            pn = w.cy[b + l];
+        }
+        for (int s = 1; s < ph; ++s) {
+            double a0 = pn, a1 = 0;
+#pragma unroll
+            for (int q = 0; q < b; ++q) {
+                const double yq = __shfl_sync(0xffffffffu, y, q);
+                if (q & 1) a1 = fma(-mrow[q], yq, a1); else a0 = fma(-mrow[q], yq, a0);
+            }
+            if (s + 1 < ph) {
+                const double* M = w.Ls + ((size_t)s * b + l) * b;
+#pragma unroll
+                for (int q = 0; q < b; ++q) mrow[q] = M[q];
+                pn = w.cy[(s + 1) * b + l];
+            }
+            y = a0 + a1;
+            if (g.lane < b) w.cy[s * b + l] = y;
+        }
+        __syncwarp();
+#else
         for (int s = 1; s < ph; ++s) {
             for (int l = g.lane; l < b; l += W) {
                 const double* M = w.Ls + ((size_t)(s - 1) * b + l) * b;
                 const double* yp = w.cy + (s - 1) * b;
                 double v = w.cy[s * b + l];
-#pragma unroll
                 for (int q = 0; q < b; ++q) v = fma(-M[q], yp[q], v);
                 w.cy[s * b + l] = v;
             }
             wsync();
         }
+#endif
     }
     g.sync();
+    NLS_ACC(1);
     for (int e = g.tid; e < nb * ph; e += G::nt) {
         const int l = e / ph, s = e - l * ph;
         const double* Wr = w.Wb + ((size_t)s * nb + l) * b;
@@ -485,10 +537,20 @@ __device__ __forceinline__ void nls_kkt_apply(const G& g, WS& w, double* dxt = n
     }
     g.sync();
     double* yb = w.cs; double* xb = w.cs + nb; double* t = w.cs + 2 * nb;
-    if (g.tid == 0) {
-        for (int l = 0; l < nb; ++l) { double v = w.rhs[w.bz(l)]; for (int s = 0; s < ph; ++s) v -= w.bp[l * ph + s]; t[l] = v; }
-        for (int l = 0; l < nb; ++l) { double v = 0; for (int q = 0; q <= l; ++q) v = fma(w.LSi[l * nb + q], t[q], v); yb[l] = v; }
-        for (int l = 0; l < nb; ++l) { double v = 0; for (int q = l; q < nb; ++q) v = fma(w.LSi[q * nb + l], yb[q], v); xb[l] = v; w.xt[w.bz(l)] = v; }
+    if (g.wid == 0) {
+        for (int l = g.lane; l < nb; l += W) {
+            double v0 = w.rhs[w.bz(l)], v1 = 0, v2 = 0, v3 = 0;
+            const double* bpl = w.bp + l * ph;
+            int s = 0;
+            for (; s + 3 < ph; s += 4) { v0 -= bpl[s]; v1 -= bpl[s + 1]; v2 -= bpl[s + 2]; v3 -= bpl[s + 3]; }
+            for (; s < ph; ++s) v0 -= bpl[s];
+            t[l] = (v0 + v1) + (v2 + v3);
+        }
+        wsync();
+        for (int l = g.lane; l < nb; l += W) { double v = 0; for (int q = 0; q <= l; ++q) v = fma(w.LSi[l * nb + q], t[q], v); yb[l] = v; }
+        wsync();
+        for (int l = g.lane; l < nb; l += W) { double v = 0; for (int q = l; q < nb; ++q) v = fma(w.LSi[q * nb + l], yb[q], v); xb[l] = v; w.xt[w.bz(l)] = v; }
+        wsync();
     }
     g.sync();
     for (int e = g.tid; e < ph * b; e += G::nt) {
@@ -503,23 +565,54 @@ __device__ __forceinline__ void nls_kkt_apply(const G& g, WS& w, double* dxt = n
         w.cq[e] = v;
     }
     g.sync();
+    NLS_ACC(2);
     if (g.wid == 0) {
+#ifndef B200_HOST_EMU
+        const int l = g.lane < b ? g.lane : b - 1;
+        double x = w.cq[(ph - 1) * b + l];
+        double nrow[b], qn = 0;
+        if (ph > 1) {
+            const double* N = w.Nb + ((size_t)(ph - 2) * b + l) * b;
+#pragma unroll
+            for (int q = 0; q < b; ++q) nrow[q] = N[q];
+            qn = w.cq[(ph - 2) * b + l];
+        }
+        for (int s = ph - 2; s >= 0; --s) {
+            double a0 = qn, a1 = 0;
+#pragma unroll
+            for (int q = 0; q < b; ++q) {
+                const double xq = __shfl_sync(0xffffffffu, x, q);
+                if (q & 1) a1 = fma(-nrow[q], xq, a1); else a0 = fma(-nrow[q], xq, a0);
+            }
+            if (s > 0) {
+                const double* N = w.Nb + ((size_t)(s - 1) * b + l) * b;
+#pragma unroll
+                for (int q = 0; q < b; ++q) nrow[q] = N[q];
+                qn = w.cq[(s - 1) * b + l];
+            }
+            x = a0 + a1;
+            if (g.lane < b) w.cq[s * b + l] = x;
+        }
+        __syncwarp();
+#else
         for (int s = ph - 2; s >= 0; --s) {
             for (int l = g.lane; l < b; l += W) {
                 const double* N = w.Nb + ((size_t)s * b + l) * b;
                 const double* xn = w.cq + (s + 1) * b;
                 double v = w.cq[s * b + l];
-#pragma unroll
                 for (int q = 0; q < b; ++q) v = fma(-N[q], xn[q], v);
                 w.cq[s * b + l] = v;
             }
             wsync();
         }
+#endif
     }
     g.sync();
+    NLS_ACC(3);
     for (int e = g.tid; e < ph * b; e += G::nt) { const int s = e / b, l = e - s * b, jz = w.gz(s, l); if (jz >= 0) w.xt[jz] = w.cq[e]; }
     g.sync();
     if (dxt) { for (int i = g.tid; i < w.n; i += G::nt) dxt[i] = w.D[i] * w.xt[i]; g.sync(); }
+    NLS_ACC(4);
 }
 
 // max bound violation of A x and max |P x + q + A' y| in the scaled problem (uses pt, rhs, zt2)
@@ -583,6 +676,7 @@ template <int BS, class G, class WS>
 __device__ __forceinline__ int nls_qp_solve(const G& g, WS& w, const NlSParams& a, int mii, bool have_y, int max_qp) {
     const int n = w.n, me = w.me, mi = w.mi, mc = w.mc, m = w.m;
     const double sigma = 1e-6, alpha = 1.6;
+    NLS_DECL(); NLS_T0();
     for (int i = g.tid; i < n; i += G::nt) { w.D[i] = 1.0; w.gs[i] = w.g[i]; }
     for (int r = g.tid; r < m; r += G::nt) w.E[r] = 1.0;
     double c = 1.0;
@@ -609,7 +703,8 @@ __device__ __forceinline__ int nls_qp_solve(const G& g, WS& w, const NlSParams& 
         for (int j = g.tid; j < n; j += G::nt) w.gs[j] *= ct;
         g.sync();
     }
-    double rho0 = a.rho0;
+    NLS_ACC(7);
+    double rho0 = w.rho_keep;
     for (int r = g.tid; r < m; r += G::nt) {
         double l, u;
         if (r < me) { l = u = -w.ce[r]; }
@@ -630,12 +725,15 @@ __device__ __forceinline__ int nls_qp_solve(const G& g, WS& w, const NlSParams& 
     g.sync();
     int it = 0;
     for (it = 1; it <= max_qp; ++it) {
+        NLS_T0();
         for (int r = g.tid; r < m; r += G::nt) w.w[r] = w.E[r] * (w.rho[r] * w.zs[r] - w.ys[r]);
         g.sync();
         for (int j = g.tid; j < n; j += G::nt)
             w.rhs[j] = w.D[j] * (w.w[mc + j] + w.col_dot(j, w.w)) + sigma * w.xs[j] - w.gs[j];
         g.sync();
+        NLS_ACC(8);
         nls_kkt_apply<BS>(g, w, w.zt2);
+        NLS_T0();
         nls_As_core(g, w, w.zt2, w.yq);
         for (int i = g.tid; i < n; i += G::nt) w.xs[i] = alpha * w.xt[i] + (1 - alpha) * w.xs[i];
         for (int r = g.tid; r < m; r += G::nt) {
@@ -645,6 +743,7 @@ __device__ __forceinline__ int nls_qp_solve(const G& g, WS& w, const NlSParams& 
             w.zs[r] = zn;
         }
         g.sync();
+        NLS_ACC(9);
         if (it % 25 == 0) {
             nls_As(g, w, w.xs, w.yq);
             double pri = 0, nz = 0, nAx = 0;
@@ -661,10 +760,14 @@ __device__ __forceinline__ int nls_qp_solve(const G& g, WS& w, const NlSParams& 
             double pn = pri / (fmax(nz, nAx) + 1e-10), dn = dua / (fmax(fmax(nq, nAty), nPx) + 1e-10);
             double est = fmin(fmax(rho0 * sqrt(pn / (dn + 1e-10)), 1e-6), 1e6);
             if (est > 5 * rho0 || est < rho0 / 5) { rho0 = est; set_rho(rho0); nls_factor(g, w, c, sigma); }
+            NLS_T0();
         }
     }
     if (it > max_qp) it = max_qp;
+    w.rho_keep = rho0;
+    NLS_T0();
     nls_qp_polish<BS>(g, w, c);
+    NLS_T0();
     for (int i = g.tid; i < n; i += G::nt) w.d[i] = w.D[i] * w.xs[i];
     for (int r = g.tid; r < m; r += G::nt) w.yq[r] = w.E[r] * w.ys[r] / c;
     g.sync();
@@ -688,6 +791,7 @@ __device__ __forceinline__ NlSResult nls_solve_instance(const G& g, WS& w, const
         g.sync();
     };
     reset_B();
+    w.rho_keep = a.rho0;
     double fval = 0;
     nl_eval_instance_map<S>(g, ph, ch, w.z, x0, p, w.X, w.U, w.tmp, w.g, w.ce, w.JeC, w.ci, w.JiC, 0, a.sx, a.su, (double*)nullptr, (double*)nullptr, map);
     fval = w.tmp[0];
@@ -789,6 +893,10 @@ __device__ __forceinline__ NlSResult nls_solve_instance(const G& g, WS& w, const
         step = g.max(step); zmax = g.max(zmax);
         double v1 = violation(w.ce, w.ci);
         if (step < a.tol * fmax(1.0, zmax) && v1 < 1e-8) { status = 0; ++k; break; }
+        // overall work bound (the role NLopt's maxeval plays for the reference, NLOptimizer.hpp:135-147): 150 x max_qp ADMM iterations
+        // per solve.  99 % of the unicycle Tph=30 cold starts need fewer than 26 k; without the bound the 1 % that do not converge
+        // (300 major iterations x up to 1000 ADMM iterations) decide the time of the whole batch.
+        if (qp_total > 150 * a.max_qp) { ++k; break; }
     }
     double vf = violation(w.ce, w.ci);
     for (int i = g.tid; i < n; i += G::nt) z_out[i] = w.z[i];

@@ -18,7 +18,10 @@ class QPADMM:
     estimate, refactor when it moves by more than 5x) every `check` iterations."""
 
     def __init__(self, rho=0.1, sigma=1e-6, alpha=1.6, max_iter=200, eps=1e-5, check=25, polish=True, delta=1e-6, refine=5,
-                 spd_factor=None):
+                 spd_factor=None, carry_rho=False):
+        # carry_rho: start every QP from the penalty the previous one ended with (as OSQP does between re-solves) -- what the
+        # stage-structured kernel does (nlmpc_structured.cuh); the dense kernel restarts from `rho` every time
+        self.carry_rho, self.rho_init = carry_rho, rho
         self.rho, self.sigma, self.alpha, self.max_iter, self.eps, self.check = rho, sigma, alpha, max_iter, eps, check
         self.polish, self.delta, self.refine = polish, delta, refine
         # H -> (rhs -> H^-1 rhs).  Default: dense Cholesky (what the CUDA kernel does today); the stage-structured kernel
@@ -83,6 +86,8 @@ class QPADMM:
                 if est > 5 * rho0 or est < rho0 / 5:
                     rho0 = est
                     rho, kkt_solve = factor(rho0)
+        if self.carry_rho:
+            self.rho = rho0
         if self.polish:
             # OSQP polish.c: guess the active set from (z, y), solve the equality-constrained QP on it through the same
             # reduced system (rho = 1/delta on active rows, sigma = delta) with iterative refinement, keep it if both
@@ -137,6 +142,7 @@ def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, ver
     specification of the stage-structured kernel planned next."""
     qp = qp or QPADMM()
     qp_cap0 = qp.max_iter
+    qp.rho = qp.rho_init
     x0 = np.asarray(x0, float)
     z = np.clip(np.array(z0, float), lb, ub)
     n = z.size
