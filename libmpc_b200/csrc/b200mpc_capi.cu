@@ -105,6 +105,16 @@ static int upload(b200mpc_lmpc* h, DevBuf& b, const double* src, int per_instanc
     return B200MPC_OK;
 }
 
+// Entry points run on the handle's device and put the caller's current device back when they return.
+struct DeviceScope {
+    int prev = -1; bool switched = false; cudaError_t err = cudaSuccess;
+    explicit DeviceScope(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = (err == cudaSuccess); }
+    }
+    ~DeviceScope() { if (switched) cudaSetDevice(prev); }
+};
+
 template <class T>
 static int dalloc(T** p, size_t n) {
     CK(cudaMalloc(p, (n ? n : 1) * sizeof(T)));
@@ -112,17 +122,8 @@ static int dalloc(T** p, size_t n) {
     return B200MPC_OK;
 }
 
-extern "C" int b200mpc_lmpc_create(const b200mpc_lmpc_dims* dims, int batch, int device, b200mpc_lmpc_t* out) {
-    if (!dims || !out || batch <= 0) return fail(B200MPC_EINVAL, "bad arguments");
-    if (dims->nx < 0 || dims->nu < 0 || dims->ndu < 0 || dims->ny < 0 || dims->ph < 1 || dims->ch < 1 || dims->ch > dims->ph ||
-        dims->nx + dims->nu <= 0)
-        return fail(B200MPC_EINVAL, "bad dimensions");
-    int ndev = b200mpc_device_count();
-    if (ndev <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
-    if (device < 0 || device >= ndev) return fail(B200MPC_EINVAL, "bad device index");
-    CK(cudaSetDevice(device));
-    b200mpc_lmpc* h = new (std::nothrow) b200mpc_lmpc();
-    if (!h) return fail(B200MPC_EINVAL, "out of host memory");
+// device state of a new handle (any failure: the caller destroys the partially built handle, nothing leaks)
+static int create_alloc(b200mpc_lmpc* h, const b200mpc_lmpc_dims* dims, int batch, int device) {
     h->d.nx = dims->nx; h->d.nu = dims->nu; h->d.ndu = dims->ndu; h->d.ny = dims->ny; h->d.ph = dims->ph; h->d.ch = dims->ch;
     h->d.derive();
     h->batch = batch; h->device = device;
@@ -160,15 +161,34 @@ extern "C" int b200mpc_lmpc_create(const b200mpc_lmpc_dims* dims, int batch, int
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
-    *out = h;
     return b200mpc_lmpc_set_params(h, &dp);
+}
+
+
+extern "C" int b200mpc_lmpc_create(const b200mpc_lmpc_dims* dims, int batch, int device, b200mpc_lmpc_t* out) {
+    if (!dims || !out || batch <= 0) return fail(B200MPC_EINVAL, "bad arguments");
+    if (dims->nx < 0 || dims->nu < 0 || dims->ndu < 0 || dims->ny < 0 || dims->ph < 1 || dims->ch < 1 || dims->ch > dims->ph ||
+        dims->nx + dims->nu <= 0)
+        return fail(B200MPC_EINVAL, "bad dimensions");
+    int ndev = b200mpc_device_count();
+    if (ndev <= 0) return fail(B200MPC_ENOGPU, "no CUDA device: b200mpc has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(B200MPC_EINVAL, "bad device index");
+    DeviceScope device_scope_(device);
+    if (device_scope_.err != cudaSuccess) return fail(B200MPC_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(device_scope_.err));
+    b200mpc_lmpc* h = new (std::nothrow) b200mpc_lmpc();
+    if (!h) return fail(B200MPC_EINVAL, "out of host memory");
+    h->device = device;
+    const int rc = create_alloc(h, dims, batch, device);
+    if (rc != B200MPC_OK) { b200mpc_lmpc_destroy(h); return rc; }
+    *out = h;
+    return B200MPC_OK;
 }
 
 static void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; }
 
 extern "C" int b200mpc_lmpc_destroy(b200mpc_lmpc_t h) {
     if (!h) return B200MPC_OK;
-    cudaSetDevice(h->device);
+    DeviceScope device_scope_(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->A, &h->B, &h->C, &h->Bd, &h->Dd, &h->OW, &h->UW, &h->DUW, &h->XMin, &h->XMax, &h->YMin, &h->YMax,
                       &h->UMin, &h->UMax, &h->SMin, &h->SMax, &h->SX, &h->SU, &h->yRef, &h->uRef, &h->duRef, &h->uMeas};
@@ -200,7 +220,10 @@ extern "C" int b200mpc_lmpc_set_params(b200mpc_lmpc_t h, const b200mpc_lmpc_para
     return B200MPC_OK;
 }
 
-#define HCHECK() do { if (!h) return fail(B200MPC_EINVAL, "null handle"); CK(cudaSetDevice(h->device)); } while (0)
+#define HCHECK()                                                    \
+    if (!h) return fail(B200MPC_EINVAL, "null handle");             \
+    DeviceScope device_scope_(h->device);                           \
+    if (device_scope_.err != cudaSuccess) return fail(B200MPC_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(device_scope_.err))
 
 extern "C" int b200mpc_lmpc_set_model(b200mpc_lmpc_t h, const double* A, const double* B, const double* C, int pi, int dev) {
     HCHECK();
