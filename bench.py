@@ -139,12 +139,26 @@ def nlmpc_cpu_baseline(name, cores):
                       "-- the reference's finite-difference objective / constraints restated", "converged": conv}
 
 
-def nlmpc_flops(nx, nu, ph, nz, me, mi, sqp_it, qp_it):
-    """SURVEY 8d NLMPC: sqp_iters x [model evaluations + QP]; the QP here is a dense reduced-KKT ADMM: per SQP iteration one H
-    build + Cholesky (nz^3/3 + nz^2 (me+mi)) and per ADMM iteration two triangular solves + two A products."""
-    per_sqp = nz ** 3 / 3.0 + nz * nz * (me + mi) + (ph * (nx + nu) + 3) * 2 * ph * (nx + nu) * 10
-    per_qp = 2 * nz * nz + 4 * nz * (me + mi)
-    return 2.0 * (sqp_it * per_sqp + qp_it * per_qp)
+def nlmpc_flops(nx, nu, ph, ch, K, sqp_it, qp_it):
+    """Algorithmic FP64 flops of one solve by the STAGE-STRUCTURED kernel (libmpc_b200/csrc/nlmpc_structured.cuh), from its own
+    iteration counters: b = nx+nu (stage block), nb = nu+1 (border), compact Jacobians of 2nx+nu / nx+nu+1 entries per row.
+      per SQP iteration: finite-difference evaluation (one model / cost / constraint pass per perturbed variable, ~10 flops
+        per touched entry) + ~2 factorisations (QP set-up and polish; adaptive-rho refactorisations are not counted) of
+        ph [(14/3) b^3 + 2 nb b^2] multiply-adds (Cholesky, explicit inverse, sub-diagonal, Schur, the two solve-time products, border)
+        + the reduced-KKT assembly J' R J on the compact rows;
+      per ADMM iteration: the bordered block-tridiagonal solve ph (3 b^2 + 2 b nb) multiply-adds, A x and A' y on the compact rows,
+        ~10 flops per variable / row for the relaxation, projection and dual update.
+    The dense kernel's O(nz^3) count is NOT used: it would overstate what this kernel executes."""
+    b, nb = nx + nu, nu + 1
+    me, mi = ph * nx, (ph + 1) * K
+    we, wi = 2 * nx + nu, nx + nu + 1
+    n = ph * nx + ch * nu + 1
+    m = me + mi + n
+    fd = (ph * (nx + nu) + 3) * 2 * ph * (nx + nu) * 10
+    fac = 2 * (ph * ((14.0 / 3.0) * b ** 3 + 2 * nb * b * b) + me * we * we + mi * wi * wi)     # multiply-adds
+    per_sqp = fd + 2.0 * fac
+    per_qp = 2.0 * (ph * (3 * b * b + 2 * b * nb) + 2 * (me * we + mi * wi + n)) + 10.0 * (n + m)
+    return sqp_it * per_sqp + qp_it * per_qp
 
 
 def bench_nlmpc(L, torch, rank, world, steps, fp64_peak, with_cpu):
@@ -162,14 +176,14 @@ def bench_nlmpc(L, torch, rank, world, steps, fp64_peak, with_cpu):
             x0, params = W.unicycle_inputs(first, B)
             lb, ub = W.soft_bounds(ph * nx + ch * nu + 1)
             kw = dict(max_sqp=300)
-            mi = 62
+            K = 2
         else:
             sid = L.SYS_OSCNET4
             ph, ch, nx, nu = 15, 8, 8, 4
             x0, params = W.oscnet4_inputs(first, B)
             lb, ub = W.hard_bounds(ph * nx + ch * nu + 1)
             kw = {}
-            mi = 64
+            K = 4
         nz = ph * nx + ch * nu + 1
         z0 = W.cold_start(x0, np.zeros(nu), ph, ch)
         L.nlmpc_solve(sid, ph, ch, z0[:8], x0[:8], params if params.ndim == 1 else params[:8], lb, ub, **kw)      # compile / warm up
@@ -185,13 +199,15 @@ def bench_nlmpc(L, torch, rank, world, steps, fp64_peak, with_cpu):
             tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
-        flops = float(sum(nlmpc_flops(nx, nu, ph, nz, ph * nx, mi, int(a), int(b)) for a, b in zip(r["iters"], r["qp_iters"])))
+        flops = float(sum(nlmpc_flops(nx, nu, ph, ch, K, int(a), int(b)) for a, b in zip(r["iters"], r["qp_iters"])))
         tfl = flops * world / (ms * 1e-3) / 1e12
         out[name] = {"workload": desc, "value": world * B / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms, "batch_per_gpu": B,
                      "e2e": "host buffers in, results out, inside the timed call",
                      "converged": int((r["status"] == 0).sum()), "sqp_iterations_mean": float(r["iters"].mean()),
                      "qp_iterations_mean": float(r["qp_iters"].mean()), "viol_max": float(r["viol"].max()),
-                     "roofline": {"bound": "fp64", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak}}
+                     "roofline": {"bound": "fp64", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak,
+                                  "flops_per_solve_mean": flops / B,
+                                  "note": "algorithmic flops of the stage-structured kernel (bench.py nlmpc_flops) from its own SQP / ADMM counters"}}
         if with_cpu and rank == 0:
             try:
                 out[name]["cpu_baseline"] = nlmpc_cpu_baseline(name, os.cpu_count() or 1)
