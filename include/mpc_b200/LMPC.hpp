@@ -288,6 +288,9 @@ public:
         return q;
     }
     b200mpc_lmpc_t handle() { return h_; }
+    /// Multi-GPU exchange step (no counterpart in the single-controller reference): all-gather of the command blocks
+    /// of every rank into cmd_all_dev[nranks * batch * nu] (device memory), enqueued on the handle's stream behind the solve.
+    bool allgatherCommands(b200mpc_comm_t comm, double* cmd_all_dev) { return b200mpc_lmpc_allgather_cmd(h_, comm, cmd_all_dev) == B200MPC_OK; }
 
 private:
     int n() const { return (ph_ + 1) * (nx_ + nu_) + ph_ * nu_; }
