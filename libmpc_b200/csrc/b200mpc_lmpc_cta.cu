@@ -22,7 +22,6 @@ int cta_configure(const Dm& d, bool quad, int device, int num_sms, int batch, in
     cfg->L = L;
     cfg->threads = req_threads == 384 ? 384 : 256;
     cfg->quad = quad ? 1 : 0;
-    cfg->pipelined = getenv("B200MPC_CTA_PIPE") ? atoi(getenv("B200MPC_CTA_PIPE")) : 0;
     cfg->smem_bytes = (size_t)L.total * sizeof(double);
     cfg->grid = batch < num_sms ? batch : num_sms;       // one CTA per SM: the whole SM works on one controller
     return B200MPC_OK;

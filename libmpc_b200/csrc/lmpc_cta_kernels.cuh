@@ -23,8 +23,9 @@
 //   * The factorisation of a stage is a register-resident LDL' by ONE warp (lane r = row r of the pivot block, lane q = column
 //     q of the accumulated inverse; the pivot column is the only thing that goes through shared memory), followed by
 //     stage-parallel dot products for Lc_i, the Schur complement of stage i+1 and W_i.
-//   * The ADMM iteration is warp-specialised: warp 0 runs the two serial recurrences, the other warps run per-stage jobs
-//     behind it, ordered by shared-memory progress flags (pipelined_iteration).
+//   * The ADMM iteration is bulk-synchronous: stage-parallel phases by all warps, the two serial recurrences by warp 0 with the
+//     carried vector in registers (shuffle broadcast) and the K rows loaded one stage ahead.  (A warp-specialised pipeline ordered
+//     by shared-memory progress flags was measured 2x slower -- profiles/r02_engine_probe.jsonl -- and removed.)
 //   * A x / A' y / P x never touch a matrix: rows and columns are evaluated from A, B, C, the weights and the scalar row.
 //
 // Used for batch sizes from 1 (a single mpc::LMPC<> object: the whole SM works on it) to any; the warp-per-controller engine
@@ -74,7 +75,7 @@ inline CtaLayout cta_layout(const DM& d, int fac_shared, int generic_scratch) {
     L.oRED = take(16 * 16);
     L.oLCS = take(d.ne * L.LD);
     L.oTB = take(d.ne * L.LD);
-    L.oFLAG = take((6 * (d.ph + 2) + 1) / 2);        // int32 progress flags of the pipelined sweep
+    L.oFLAG = o;
     L.lda = d.b | 1;
     L.n_aug = d.b * (d.b + 1) / 2;
     L.n_ent = L.n_aug + d.b * (d.b - 1) / 2;
@@ -164,8 +165,7 @@ struct CtaSolver {
     double c;
     double rsel[3], rinv[3];
     double time_limit; long long t_start;
-    int pipelined;       // ADMM iteration schedule: 1 warp-specialised pipeline, 0 bulk-synchronous phases
-    long long pw[8];     // profiling aid: [0] chain fwd, [1] chain bwd, [2] this warp's flag waits, [3] fwd jobs, [4] bwd jobs, [5] sweep total
+    long long pw[8];     // profiling aid (warp 0): cycles in [0] the forward recurrence, [1] the backward recurrence, all KKT solves of a run
 
     __device__ CtaSolver(const DM& d_, const Params& p_, const Prob& pr_, const CtaLayout& L_) : d(d_), p(p_), pr(pr_), L(L_) {}
 
@@ -506,7 +506,7 @@ struct CtaSolver {
         }
         __syncthreads();
         bool ok = true;
-        double* COL = CSM(RED);                      // 64 doubles of warp-0 scratch: the pivot column and the row scales
+        double* COL = CSM(RED);                      // 128 doubles of warp-0 scratch: three pivot-column buffers and the row scales
         for (int i = 0; i <= d.ph; ++i) {
             const int bi = d.bcount(i);
             double* F = fac(i);
@@ -525,32 +525,43 @@ struct CtaSolver {
                         if (r < bi && q <= r) { v = F[r * LD + q]; if (i > 0 && r < d.ne) v += TB[r * LD + q]; }
                         a[q] = v; m[q] = (q == r) ? 1.0 : 0.0;           // m[x]: entry (row x, column = lane)
                     });
+                    // Look-ahead: column k+1 is updated and published FIRST in step k, so its trip through shared memory and the
+                    // reciprocal of the next pivot overlap the rest of the trailing update (three column buffers: the one written in
+                    // step k is read in step k+1 and overwritten in step k+3, with a warp barrier in between).
+                    COL[lane] = a[0];
+                    __syncwarp();
                     cta_static_for<0, B>([&](auto kc) {
                         constexpr int k = decltype(kc)::value;
                         if (k < bi) {
-                            COL[lane] = a[k];
-                            __syncwarp();
-                            const double dk = COL[k];
+                            const double* cur = COL + 32 * (k % 3);
+                            const double dk = cur[k];
                             if (!(dk > 0.0)) ok = false;
                             const double rd = 1.0 / dk;
                             if (r == k) dsave = dk;
                             const double l = (r > k && r < bi) ? a[k] * rd : 0.0;
                             const double mk = (r <= k) ? m[k] * rd : 0.0;
-                            cta_static_for<k + 1, B>([&](auto qc) {
+                            if constexpr (k + 1 < B) {
+                                const double cq = cur[k + 1];
+                                a[k + 1] = (k + 1 <= r) ? fma(-l, cq, a[k + 1]) : a[k + 1];
+                                m[k + 1] = fma(-cq, mk, m[k + 1]);
+                                COL[32 * ((k + 1) % 3) + lane] = a[k + 1];
+                                __syncwarp();
+                            }
+                            cta_static_for<k + 2, B>([&](auto qc) {
                                 constexpr int q = decltype(qc)::value;
-                                const double cq = COL[q];
+                                const double cq = cur[q];
                                 a[q] = (q <= r) ? fma(-l, cq, a[q]) : a[q];
                                 m[q] = fma(-cq, mk, m[q]);
                             });
-                            __syncwarp();
                         }
                     });
+                    __syncwarp();
                     // row scales 1/sqrt(d_r), then L^-1(x, q) = m_q[x] rs_x : lane q writes column q (zeros where L^-1 has none)
-                    COL[32 + lane] = rsqrt(dsave);
+                    COL[96 + lane] = rsqrt(dsave);
                     __syncwarp();
                     cta_static_for<0, B>([&](auto xc) {
                         constexpr int x = decltype(xc)::value;
-                        if (lane < B) F[x * LD + lane] = (x >= lane && x < bi && lane < bi) ? m[x] * COL[32 + x] : 0.0;
+                        if (lane < B) F[x * LD + lane] = (x >= lane && x < bi && lane < bi) ? m[x] * COL[96 + x] : 0.0;
                     });
                 }
                 __syncthreads();
@@ -620,32 +631,45 @@ struct CtaSolver {
         return !__syncthreads_or(ok ? 0 : 1);
     }
 
+    // ---- the two stage recurrences of the KKT solve (one warp) -----------------------------------------------------------------
+    //   forward   c_{i+1} = g_i - K_i c_i      (K_i = W_i[:, :ne];  g in GT, c in CAR)
+    //   backward  xe_i = s_i[:ne] - K_i' xe_{i+1}   (s in R, xe in XE)
+    // The carried vector goes through shared memory (store, warp barrier, broadcast loads: 34 cycles).  Keeping it in registers with
+    // shuffle broadcast and the K rows loaded one stage ahead was measured no faster (~440 vs ~410 cycles per step: a step is
+    // bound by its ~100 instructions on one warp, 32 SHFL.32 cost more issue slots than 8 LDS.128; tools/ulat.cu has the latencies).
+    __device__ __forceinline__ void chain_forward() {
+        double* CAR = CSM(CAR); const double* GT = CSM(GT);
+        const int LD = fLD();
+        for (int r = lane; r < d.ne; r += 32) CAR[r] = 0.0;
+        __syncwarp();
+        for (int i = 0; i < d.ph; ++i) {
+            for (int r = lane; r < d.ne; r += 32) CAR[(i + 1) * d.ne + r] = GT[i * d.ne + r] - cta_dot<SNE, 0>(fac(i) + fWm() + r * LD, 1, CAR + i * d.ne, d.ne);
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ void chain_backward() {
+        double* XE = CSM(XE); const double* R = CSM(R);
+        const int LD = fLD();
+        for (int r = lane; r < d.ne; r += 32) XE[d.ph * d.ne + r] = R[d.ph * d.b + r];
+        __syncwarp();
+        for (int i = d.ph - 1; i >= 0; --i) {
+            for (int cc = lane; cc < d.ne; cc += 32) XE[i * d.ne + cc] = R[i * d.b + cc] - cta_dot<SNE, 1>(fac(i) + fWm() + cc, LD, XE + (i + 1) * d.ne, d.ne);
+            __syncwarp();
+        }
+    }
+
     // ---- reduced KKT solve, bulk-synchronous (polish): in R = right-hand side, out T = solution (scaled), R = D .* solution ----
     template <class Epi>
     __device__ __forceinline__ void kkt_solve(Epi epilogue) {
-        double* R = CSM(R); double* T = CSM(T); double* GT = CSM(GT); double* CAR = CSM(CAR); double* XE = CSM(XE); const double* D = CSM(D);
+        double* R = CSM(R); double* T = CSM(T); double* XE = CSM(XE); const double* D = CSM(D);
         const int LD = fLD();
         for (int j = warp; j <= d.ph; j += NW) stage_p3(j);
         __syncthreads();
-        if (warp == 0) {
-            for (int r = lane; r < d.ne; r += 32) CAR[r] = 0.0;
-            __syncwarp();
-            for (int i = 0; i < d.ph; ++i) {
-                for (int r = lane; r < d.ne; r += 32) CAR[(i + 1) * d.ne + r] = GT[i * d.ne + r] - cta_dot<SNE, 0>(fac(i) + fWm() + r * LD, 1, CAR + i * d.ne, d.ne);
-                __syncwarp();
-            }
-        }
+        if (warp == 0) { const long long q0 = clock64(); chain_forward(); pw[0] += clock64() - q0; }
         __syncthreads();
         for (int j = warp; j <= d.ph; j += NW) stage_fwd(j);
         __syncthreads();
-        if (warp == 0) {
-            for (int r = lane; r < d.ne; r += 32) XE[d.ph * d.ne + r] = R[d.ph * d.b + r];
-            __syncwarp();
-            for (int i = d.ph - 1; i >= 0; --i) {
-                for (int cc = lane; cc < d.ne; cc += 32) XE[i * d.ne + cc] = R[i * d.b + cc] - cta_dot<SNE, 1>(fac(i) + fWm() + cc, LD, XE + (i + 1) * d.ne, d.ne);
-                __syncwarp();
-            }
-        }
+        if (warp == 0) { const long long q0 = clock64(); chain_backward(); pw[1] += clock64() - q0; }
         __syncthreads();
         for (int kg = tid; kg < d.n; kg += NT) {
             const int i = kg / d.b, k = kg - i * d.b;
@@ -659,41 +683,7 @@ struct CtaSolver {
         __syncthreads();
     }
 
-    // ================= per-stage jobs (one warp each) and the pipelined ADMM sweep ===============================================
-    // The serial recurrences of the KKT solve take ~40 dependent ne x ne mat-vecs per iteration; a bulk-synchronous schedule
-    // leaves all but one warp idle meanwhile.  Here warp 0 runs ONLY the two recurrences and the other warps run per-stage
-    // jobs behind it, ordered by shared-memory progress flags (value = sweep number, monotone, never reset):
-    //   fwd sweep:  chain  c_{i+1} = g_i - K_i c_i            | job F_i: t_i = rhat_i - L_i^-1[:, :ne] c_i, s_i = L_i^-T t_i
-    //   bwd sweep:  chain  xe_i = s_i[:ne] - K_i' xe_{i+1}     | job B_i: x_i, u_i = D x_i, x-update; rows of stage i (z~, relax,
-    //               projection, dual update, next row weights); right-hand side and rhat / g of stage i+1 for the NEXT iteration
-    // Dependencies: F_i <- c_i;  chain(bwd, i) <- s_i;  B_i <- xe_i, u_{i+1} (B_{i+1}), rows_{i+1} (B_{i+1}): acyclic, every job
-    // waits only on jobs that precede it in its own warp's order or on the chain.
-    __device__ __forceinline__ volatile int* flagp(int which, int i) const { return reinterpret_cast<volatile int*>(smem + L.oFLAG) + which * (d.ph + 2) + i; }
-    enum { FG = 0, FC = 1, FS = 2, FX = 3, FU = 4, FV = 5 };
-    __device__ __forceinline__ void wait_flag(int which, int i, int stamp) const {
-#ifdef B200_CTA_PROF
-        const long long q0 = clock64();
-#endif
-        if (lane == 0) { volatile int* f = flagp(which, i); while (*f < stamp) { } }
-        __syncwarp();
-        asm volatile("" ::: "memory");
-#ifdef B200_CTA_PROF
-        const_cast<CtaSolver*>(this)->pw[2] += clock64() - q0;
-#endif
-    }
-    // Data and flag are both shared memory written by the same warp in program order (the data by warp-wide stores BEFORE the
-    // flag store); the shared-memory pipeline of an SM keeps a warp's accesses in order and has no per-thread cache, so a warp
-    // that observes the flag observes the data (a membar.cta per post was measured and changes nothing but the cost).
-    __device__ __forceinline__ void post_flag(int which, int i, int stamp) const {
-        __syncwarp();
-        asm volatile("" ::: "memory");
-        if (lane == 0) *flagp(which, i) = stamp;
-    }
-    __device__ void init_flags() {
-        int* f = reinterpret_cast<int*>(smem + L.oFLAG);
-        for (int e = tid; e < 6 * (d.ph + 2); e += NT) f[e] = 0;
-        __syncthreads();
-    }
+    // ================= per-stage jobs (one warp each) =========================================================================
     // rhat_j = L_j^-1 r_j -> T,  g_j = W_j r_j -> GT  (one warp; r_j in R)
     __device__ __forceinline__ void stage_p3(int j) {
         const int nt = d.b + (j < d.ph ? d.ne : 0), LD = fLD();
@@ -721,23 +711,6 @@ struct CtaSolver {
         __syncwarp();
         for (int k = lane; k < d.b; k += 32) R[k] = cta_dot<SB, 1>(F + k, LD, T, d.b);
     }
-    // x_i = [xe_i ; s_i[ne:] - W_i[:, ne:]' xe_{i+1}],  u_i = D x_i -> R,  x-update (update_x of osqp.c)
-    __device__ __forceinline__ void stage_x(int i, bool store_delta) {
-        const int bi = d.bcount(i), LD = fLD();
-        const double alpha = p.alpha;
-        double* va = gws + L.gVA;
-        for (int k = lane; k < bi; k += 32) {
-            const int kg = i * d.b + k;
-            double xt;
-            if (k < d.ne) xt = CSM(XE)[i * d.ne + k];
-            else xt = CSM(R)[kg] - cta_dot<SNE, 1>(fac(i) + fWm() + k, LD, CSM(XE) + (i + 1) * d.ne, d.ne);
-            CSM(R)[kg] = CSM(D)[kg] * xt;
-            const double xo = CSM(X)[kg];
-            const double xnw = alpha * xt + (1.0 - alpha) * xo;
-            CSM(X)[kg] = xnw;
-            if (store_delta) va[kg] = xnw - xo;
-        }
-    }
     // z~ = A x~ of one row, relaxation, projection, dual update, row weight of the next right-hand side
     __device__ __forceinline__ void row_update(int g, int i, int r, bool store_delta) {
         const int ty = rtp()[g];
@@ -753,134 +726,7 @@ struct CtaSolver {
         CSM(V)[g] = e * (rho_of(ty) * zn - yn);
         if (store_delta) (gws + L.gRA)[g] = dy;
     }
-    __device__ __forceinline__ void stage_rows(int i, bool store_delta) {
-        const int rs = d.rcount(i), ro = d.roff(i);
-        // dot-product rows first (eq, out, sc), then the single-entry rows, so that a warp round has uniform work
-        const int nd = (i < d.ph ? d.ne : 0) + d.ny + 1;
-        for (int t = lane; t < rs; t += 32) {
-            int r;
-            if (i < d.ph) r = t < d.ne ? d.oEQ + t : (t < nd ? d.oOUT + (t - d.ne) : (t < nd + d.ne ? d.oBOX + (t - nd) : d.oDU + (t - nd - d.ne)));
-            else r = t < d.ny + 1 ? d.oOUT + t : d.oBOX + (t - d.ny - 1);
-            row_update(ro + r, i, r, store_delta);
-        }
-        if (i == 0) for (int r = lane; r < d.ne; r += 32) row_update(r, -1, r, store_delta);
-    }
-    // the two recurrences (warp 0).  Static dimensions: the K rows / columns of the next stage are prefetched into registers
-    // while the current stage's flag is awaited, so only the broadcast of the carried vector sits between two steps.
-    __device__ __forceinline__ void chain_sweeps(int S) {
-        const int LD = fLD();
-        const long long qc0 = clock64();
-        double* CAR = CSM(CAR); double* XE = CSM(XE); const double* GT = CSM(GT); const double* R = CSM(R);
-        if constexpr (SNE > 0) {
-            constexpr int NE = SNE;
-            const int r = lane < NE ? lane : NE - 1;
-            double kr[NE], kn[NE];
-            auto ld_row = [&](double (&dst)[NE], int st) {
-                const double2* w2 = reinterpret_cast<const double2*>(fac(st) + fWm() + r * LD);
-                cta_static_for<0, NE / 2>([&](auto jc) { constexpr int j = decltype(jc)::value; const double2 v = w2[j]; dst[2 * j] = v.x; dst[2 * j + 1] = v.y; });
-            };
-            auto ld_col = [&](double (&dst)[NE], int st) {
-                const double* w = fac(st) + fWm() + r;
-                cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; dst[q] = w[q * LD]; });
-            };
-            auto dotk = [&](const double (&kk)[NE], const double* x) {
-                const double2* x2 = reinterpret_cast<const double2*>(x);
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                cta_static_for<0, NE / 2>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    const double2 xv = x2[j];
-                    if constexpr (j & 1) { a2 = fma(kk[2 * j], xv.x, a2); a3 = fma(kk[2 * j + 1], xv.y, a3); } else { a0 = fma(kk[2 * j], xv.x, a0); a1 = fma(kk[2 * j + 1], xv.y, a1); }
-                });
-                return (a0 + a1) + (a2 + a3);
-            };
-            if (lane < NE) CAR[lane] = 0.0;
-            ld_row(kr, 0);
-            for (int i = 0; i < d.ph; ++i) {
-                ld_row(kn, i + 1 < d.ph ? i + 1 : i);
-                wait_flag(FG, i, S);
-                const double g = GT[i * NE + r];
-                const double v = g - dotk(kr, CAR + i * NE);
-                if (lane < NE) CAR[(i + 1) * NE + lane] = v;
-                post_flag(FC, i + 1, S);
-                cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; kr[q] = kn[q]; });
-            }
-            pw[0] += clock64() - qc0;
-            // backward: lane = column c of K_i
-            if (d.ph >= 1) ld_col(kr, d.ph - 1);
-            wait_flag(FS, d.ph, S);
-            if (lane < NE) XE[d.ph * NE + lane] = R[d.ph * d.b + lane];
-            post_flag(FX, d.ph, S);
-            for (int i = d.ph - 1; i >= 0; --i) {
-                ld_col(kn, i > 0 ? i - 1 : 0);
-                wait_flag(FS, i, S);
-                const double sv_ = R[i * d.b + r];
-                const double v = sv_ - dotk(kr, XE + (i + 1) * NE);
-                if (lane < NE) XE[i * NE + lane] = v;
-                post_flag(FX, i, S);
-                cta_static_for<0, NE>([&](auto qc) { constexpr int q = decltype(qc)::value; kr[q] = kn[q]; });
-            }
-            pw[1] += clock64() - qc0;
-        } else {
-            for (int r = lane; r < d.ne; r += 32) CAR[r] = 0.0;
-            __syncwarp();
-            for (int i = 0; i < d.ph; ++i) {
-                wait_flag(FG, i, S);
-                for (int r = lane; r < d.ne; r += 32) CAR[(i + 1) * d.ne + r] = GT[i * d.ne + r] - cta_dot<0, 0>(fac(i) + fWm() + r * LD, 1, CAR + i * d.ne, d.ne);
-                post_flag(FC, i + 1, S);
-            }
-            wait_flag(FS, d.ph, S);
-            for (int r = lane; r < d.ne; r += 32) XE[d.ph * d.ne + r] = R[d.ph * d.b + r];
-            post_flag(FX, d.ph, S);
-            for (int i = d.ph - 1; i >= 0; --i) {
-                wait_flag(FS, i, S);
-                for (int cc = lane; cc < d.ne; cc += 32) XE[i * d.ne + cc] = R[i * d.b + cc] - cta_dot<0, 1>(fac(i) + fWm() + cc, LD, XE + (i + 1) * d.ne, d.ne);
-                post_flag(FX, i, S);
-            }
-        }
-    }
-    // One ADMM iteration.  Needs T = rhat, GT = g of this iteration (flags FG >= S) on entry; leaves them for iteration S + 1.
-    __device__ __forceinline__ void pipelined_iteration(int S, bool store_delta) {
-        constexpr int NH = NW - 1;
-        const long long q0 = clock64();
-        if (warp == 0) chain_sweeps(S);
-        else {
-            const int h = warp - 1;
-            for (int i = h; i <= d.ph; i += NH) {
-                wait_flag(FG, i, S);
-                if (i > 0) wait_flag(FC, i, S);
-                stage_fwd(i);
-                post_flag(FS, i, S);
-            }
-            pw[3] += clock64() - q0;
-            int itop = h + ((d.ph - h) / NH) * NH;
-            if (h > d.ph) itop = -1;
-            for (int i = itop; i >= 0; i -= NH) {
-                wait_flag(FX, i, S);
-                stage_x(i, store_delta);
-                post_flag(FU, i, S);
-                if (i < d.ph) wait_flag(FU, i + 1, S);
-                stage_rows(i, store_delta);
-                post_flag(FV, i, S);
-                if (i < d.ph) {
-                    wait_flag(FV, i + 1, S);
-                    stage_rhs(i + 1);
-                    __syncwarp();
-                    stage_p3(i + 1);
-                    post_flag(FG, i + 1, S + 1);
-                }
-                if (i == 0) {
-                    stage_rhs(0);
-                    __syncwarp();
-                    stage_p3(0);
-                    post_flag(FG, 0, S + 1);
-                }
-            }
-            pw[4] += clock64() - q0;
-        }
-        __syncthreads();
-        pw[5] += clock64() - q0;
-    }
-    // The same iteration, bulk-synchronous: every phase by all warps, the recurrences by warp 0 between barriers.
+    // One ADMM iteration, bulk-synchronous: every phase by all warps, the recurrences by warp 0 between barriers.
     __device__ __forceinline__ void bulk_iteration(bool store_delta) {
         for (int j = warp; j <= d.ph; j += NW) stage_rhs(j);
         __syncthreads();
@@ -895,16 +741,6 @@ struct CtaSolver {
         for (int t = tid; t < d.m; t += NT) { int i, r; const int g = row_task(t, i, r); row_update(g, i, r, store_delta); }
         __syncthreads();
     }
-    // bulk right-hand side + rhat / g of every stage (first iteration, and after a refactorisation); marks them ready for sweep S
-    __device__ void prologue(int S) {
-        for (int j = warp; j <= d.ph; j += NW) stage_rhs(j);
-        __syncthreads();
-        for (int j = warp; j <= d.ph; j += NW) stage_p3(j);
-        __syncthreads();
-        for (int i = tid; i <= d.ph; i += NT) *flagp(FG, i) = S;
-        __syncthreads();
-    }
-
     // ---- update_info (auxil.c): residuals and the norms of the termination test / rho estimate ---------------------------------
     // XSRC 0: x = X (ADMM iterate), 1: x = px (polish iterate, global).  ZY 0: (z, y) = (Z, Y); 1: polish pair
     // z = clip(Ax + pnu), y = Ax + pnu - z (project_normalcone).  Leaves rc = E y (global scratch: V, the row weights of the next right-hand side, must survive); clobbers R, YV.
@@ -1064,13 +900,10 @@ struct CtaSolver {
             __syncthreads();
         }
         refresh_V();
-        init_flags();
         InfoNorms I; I.pri = I.dua = 0; I.xPx = I.qx = 0;
         bool can_check = false, done = false;
         const double sigma = p.sigma;
         const int8_t* rt = rtp();
-        int sweep = 1;                 // sweep number = value the progress flags are compared with
-        bool need_prologue = true;     // rhat / g of every stage must be (re)built in bulk: first iteration, new factor
         int it = 1;
         for (; it <= p.max_iter; ++it) {
             if (time_limit > 0.0) {       // osqp.c: run time (set-up included) against settings->time_limit at the top of every iteration
@@ -1087,11 +920,7 @@ struct CtaSolver {
             can_check = p.check_termination && (it % p.check_termination == 0);
             const bool can_adapt = p.adaptive_rho && p.adaptive_rho_interval && (it % p.adaptive_rho_interval == 0);
             const bool store_delta = can_check || it == p.max_iter;
-            if (pipelined) {
-                if (need_prologue) { prologue(sweep); need_prologue = false; }
-                pipelined_iteration(sweep, store_delta);
-                ++sweep;
-            } else bulk_iteration(store_delta);
+            bulk_iteration(store_delta);
             PROF(2);
             if (can_check || can_adapt) {
                 I = info_pass<0, 0>();
@@ -1107,7 +936,6 @@ struct CtaSolver {
                         rho = est; set_rho(rho);
                         factorize(sigma);
                         refresh_V();           // new rho (and the factorisation used V as scratch)
-                        need_prologue = true;
                         PROF(1);
                         ++rho_updates;
                     }
@@ -1242,13 +1070,12 @@ template <class DM, int NT, bool FSH>
 __global__ void __launch_bounds__(NT, 1) lmpc_cta_kernel(const __grid_constant__ DM d, const __grid_constant__ Params p,
                                                          const __grid_constant__ Prob pr, const __grid_constant__ Out o,
                                                          const __grid_constant__ CtaLayout L, int batch, double* gscratch, int* counter,
-                                                         int model_shared, const int* order, double time_limit, int pipelined) {
+                                                         int model_shared, const int* order, double time_limit) {
     __shared__ int s_next;
     CtaSolver<DM, NT, FSH> S(d, p, pr, L);
     S.tid = threadIdx.x; S.lane = threadIdx.x & 31; S.warp = threadIdx.x >> 5;
     S.gws = gscratch + (size_t)blockIdx.x * L.gtotal;
     S.time_limit = time_limit;
-    S.pipelined = (pipelined && NT >= 64) ? 1 : 0;
     S.inst = 0;
     S.build_table();
     if (model_shared) S.load_model();

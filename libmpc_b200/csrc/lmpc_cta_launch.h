@@ -8,7 +8,7 @@ namespace b200mpc {
 
 struct CtaLaunchCfg {
     CtaLayout L;
-    int threads = 0, grid = 0, quad = 0, pipelined = 0;
+    int threads = 0, grid = 0, quad = 0;
     size_t smem_bytes = 0;
 };
 

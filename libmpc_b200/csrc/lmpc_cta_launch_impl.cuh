@@ -9,7 +9,7 @@ static int cta_launch_k(const CtaLaunchCfg& cfg, const DM& dm, const Params& p, 
                         int* counter, int model_shared, const int* order, double time_limit, cudaStream_t stream) {
     auto kern = lmpc_cta_kernel<DM, NT, FSH>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes));
-    kern<<<cfg.grid, NT, cfg.smem_bytes, stream>>>(dm, p, pr, o, cfg.L, batch, scratch, counter, model_shared, order, time_limit, cfg.pipelined);
+    kern<<<cfg.grid, NT, cfg.smem_bytes, stream>>>(dm, p, pr, o, cfg.L, batch, scratch, counter, model_shared, order, time_limit);
     CK(cudaGetLastError());
     return B200MPC_OK;
 }

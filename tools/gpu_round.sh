@@ -10,6 +10,13 @@ if want tests; then
   timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
   tail -3 gpurun_out/pytest_gpu.log
 fi
+if want lmpc_tests; then
+  timeout 900 python -m pytest tests/test_gpu_lmpc.py tests/test_gpu_lmpc_properties.py tests/test_gpu_golden.py tests/test_gpu_closed_loop.py -x -q > gpurun_out/pytest_lmpc.log 2>&1; echo "pytest lmpc rc=$?"
+  tail -5 gpurun_out/pytest_lmpc.log
+fi
+if want quick; then
+  timeout 300 python tools/bshort.py default > gpurun_out/bshort.txt 2>&1; cat gpurun_out/bshort.txt
+fi
 if want bench; then
   timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
   cut -c1-600 gpurun_out/bench.json
@@ -31,6 +38,13 @@ if want probe2; then
   ( CTA_THREADS=384 timeout 300 python tools/engine_probe.py 148; B200MPC_CTA_PIPE=1 timeout 300 python tools/engine_probe.py 148; \
     B200MPC_CTA_PIPE=1 CTA_THREADS=384 timeout 300 python tools/engine_probe.py 148 ) > gpurun_out/engine_probe2.jsonl 2>&1; echo "probe2 rc=$?"
   cut -c1-1500 gpurun_out/engine_probe2.jsonl
+fi
+if want sweep; then
+  # BASELINE configs[4]: horizon sweep at the stated global batch (here on however many GPUs the call has; 1 GPU = one shard of 65536)
+  for PH in 10 20 50 100; do
+    timeout 600 python bench.py --global-batch 65536 --ph $PH --steps 3 --warmup 3 --no-nlmpc --no-cpu-baseline >> gpurun_out/horizon_sweep.jsonl 2>> gpurun_out/sweep.err
+  done
+  echo "sweep rc=$?"; cut -c1-200 gpurun_out/horizon_sweep.jsonl
 fi
 if want ncu_lmpc; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:lmpc_solve_kernel -s 2 -c 1 -o gpurun_out/lmpc_full -f \
