@@ -419,9 +419,10 @@ static int configure_launch(b200mpc_lmpc* h) {
     const bool quad = !h->force_generic && is_quad(h->d);
     const bool mshared = !h->A.per_instance && !h->B.per_instance && !h->C.per_instance && !h->SX.per_instance && !h->SU.per_instance;
     // automatic choice: the CTA engine runs one controller per SM at a time (best latency, no HBM streaming); the warp engine
-    // keeps ~12 controllers per SM in flight and wins on throughput once the batch is several times the SM count
+    // keeps 12 controllers per SM in flight and wins on throughput once the batch exceeds its resident slots (measured on the
+    // quadrotor, profiles/r02_engine_crossover.jsonl: batch 1184: 17.8 vs 25.2 ms, 1776: 26.1 vs 25.4 ms, 4096: 59 vs 39 ms)
     static const int kAutoMax = getenv("B200MPC_ENGINE2_MAX_BATCH") ? atoi(getenv("B200MPC_ENGINE2_MAX_BATCH")) : 0;
-    const int auto_max = kAutoMax > 0 ? kAutoMax : 4 * h->num_sms;
+    const int auto_max = kAutoMax > 0 ? kAutoMax : 11 * h->num_sms;
     if (h->engine_req == 2 || (h->engine_req == 0 && h->batch <= auto_max)) {
         CtaLaunchCfg cfg;
         int rc = cta_configure(h->d, quad, h->device, h->num_sms, h->batch, h->req_cta_threads, &cfg);
