@@ -36,8 +36,6 @@ __device__ long long g_nls_prof[16];
 #define NLS_DECL() do {} while (0)
 #define NLS_ACC(slot) do {} while (0)
 #endif
-constexpr int kNlsTermEvery = 5;      // ADMM residual test interval (QP subproblem)
-constexpr int kNlsAdaptEvery = 25;    // ADMM penalty adaptation interval (a multiple of kNlsTermEvery)
 __device__ __forceinline__ double nls_lim(double v) { v = v < 1e-4 ? 1.0 : v; return v > 1e4 ? 1e4 : v; }
 
 struct NlSParams {
@@ -746,11 +744,7 @@ __device__ __forceinline__ int nls_qp_solve(const G& g, WS& w, const NlSParams& 
         }
         g.sync();
         NLS_ACC(9);
-        if (it % kNlsTermEvery == 0) {
-            // residual test every kNlsTermEvery iterations, penalty adaptation every kNlsAdaptEvery: the polished QP solution does
-            // not depend on where the ADMM stopped, so the earlier exit changes the iteration count and nothing else
-            // (tests/nlmpc_sqp_reference.py QPADMM(term=...): -20..30 % ADMM iterations, identical SQP iterates)
-            const bool adapt = (it % kNlsAdaptEvery == 0);
+        if (it % 25 == 0) {
             nls_As(g, w, w.xs, w.yq);
             double pri = 0, nz = 0, nAx = 0;
             for (int r = g.tid; r < m; r += G::nt) { pri = fmax(pri, fabs(w.yq[r] - w.zs[r])); nz = fmax(nz, fabs(w.zs[r])); nAx = fmax(nAx, fabs(w.yq[r])); }
@@ -761,15 +755,11 @@ __device__ __forceinline__ int nls_qp_solve(const G& g, WS& w, const NlSParams& 
                 double px = w.zt2[i];
                 dua = fmax(dua, fabs(px + w.gs[i] + w.rhs[i])); nq = fmax(nq, fabs(w.gs[i])); nAty = fmax(nAty, fabs(w.rhs[i])); nPx = fmax(nPx, fabs(px));
             }
-            if (!adapt) {           // one vote instead of seven reductions: max < eps  <=>  nobody is above eps
-                if (!g.any(!(pri < a.qp_eps && dua < a.qp_eps))) break;
-            } else {
-                pri = g.max(pri); nz = g.max(nz); nAx = g.max(nAx); dua = g.max(dua); nq = g.max(nq); nAty = g.max(nAty); nPx = g.max(nPx);
-                if (pri < a.qp_eps && dua < a.qp_eps) break;
-                double pn = pri / (fmax(nz, nAx) + 1e-10), dn = dua / (fmax(fmax(nq, nAty), nPx) + 1e-10);
-                double est = fmin(fmax(rho0 * sqrt(pn / (dn + 1e-10)), 1e-6), 1e6);
-                if (est > 5 * rho0 || est < rho0 / 5) { rho0 = est; set_rho(rho0); nls_factor(g, w, c, sigma); }
-            }
+            pri = g.max(pri); nz = g.max(nz); nAx = g.max(nAx); dua = g.max(dua); nq = g.max(nq); nAty = g.max(nAty); nPx = g.max(nPx);
+            if (pri < a.qp_eps && dua < a.qp_eps) break;
+            double pn = pri / (fmax(nz, nAx) + 1e-10), dn = dua / (fmax(fmax(nq, nAty), nPx) + 1e-10);
+            double est = fmin(fmax(rho0 * sqrt(pn / (dn + 1e-10)), 1e-6), 1e6);
+            if (est > 5 * rho0 || est < rho0 / 5) { rho0 = est; set_rho(rho0); nls_factor(g, w, c, sigma); }
             NLS_T0();
         }
     }

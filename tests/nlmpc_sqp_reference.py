@@ -15,16 +15,14 @@ import numpy as np
 
 class QPADMM:
     """Dense OSQP-style ADMM: Jacobi equilibration, rho_eq = 1e3 rho, alpha = 1.6, residual test + adaptive rho (OSQP's
-    estimate, refactor when it moves by more than 5x) every `check` iterations; `term` (default = `check`): the residual test
-    alone at a shorter interval (the stage-structured kernel tests every 10 iterations and adapts every 25)."""
+    estimate, refactor when it moves by more than 5x) every `check` iterations."""
 
     def __init__(self, rho=0.1, sigma=1e-6, alpha=1.6, max_iter=200, eps=1e-5, check=25, polish=True, delta=1e-6, refine=5,
-                 spd_factor=None, carry_rho=False, term=None):
+                 spd_factor=None, carry_rho=False):
         # carry_rho: start every QP from the penalty the previous one ended with (as OSQP does between re-solves) -- what the
         # stage-structured kernel does (nlmpc_structured.cuh); the dense kernel restarts from `rho` every time
         self.carry_rho, self.rho_init = carry_rho, rho
         self.rho, self.sigma, self.alpha, self.max_iter, self.eps, self.check = rho, sigma, alpha, max_iter, eps, check
-        self.term = term or check
         self.polish, self.delta, self.refine = polish, delta, refine
         # H -> (rhs -> H^-1 rhs).  Default: dense Cholesky (what the CUDA kernel does today); the stage-structured kernel
         # plugs in the bordered block-tridiagonal factorisation of tests/nlmpc_structured_kkt_reference.py.
@@ -74,7 +72,7 @@ class QPADMM:
             zn = np.clip(zr + ys / rho, ls, us)
             ys = ys + rho * (zr - zn)
             xs, zs = xn, zn
-            if it % self.check == 0 or it % self.term == 0:
+            if it % self.check == 0:
                 Ax = As @ xs
                 Px = Bs @ xs
                 Aty = As.T @ ys
@@ -82,8 +80,6 @@ class QPADMM:
                 dua = np.abs(Px + gs + Aty).max()
                 if pri < self.eps and dua < self.eps:
                     break
-                if it % self.check != 0:
-                    continue
                 pn = pri / (max(np.abs(zs).max(initial=0.0), np.abs(Ax).max(initial=0.0)) + 1e-10)
                 dn = dua / (max(np.abs(gs).max(), np.abs(Aty).max(), np.abs(Px).max()) + 1e-10)
                 est = min(max(rho0 * np.sqrt(pn / (dn + 1e-10)), 1e-6), 1e6)

@@ -66,7 +66,7 @@ def test_host_emulated_kernel_matches_specification_and_slsqp(name, sid, f, para
         lb[-1] = 0.0
     z0 = S.initial_guess(f, x0, np.zeros(f.nu), lb=lb, ub=ub)
     out = host_solve(sid, f.ph, f.ch, z0, x0, params, lb, ub)
-    spec = sqp_solve(f, x0, z0, lb, ub, bfgs_groups=stage_groups(f), qp=QPADMM(carry_rho=True, term=5))
+    spec = sqp_solve(f, x0, z0, lb, ub, bfgs_groups=stage_groups(f), qp=QPADMM(carry_rho=True))
     ref = S.solve(f, x0, z0, lb, ub)
     assert out["status"] == 0 and out["viol"] < 1e-8
     # same algorithm in two languages: the iterates differ by finite-difference noise only
