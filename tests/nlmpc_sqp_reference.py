@@ -139,7 +139,7 @@ def stage_groups(f):
 def sqp_solve(f, x0, z0, lb, ub, max_sqp=100, tol=1e-7, ftol=1e-12, qp=None, verbose=False, bfgs_groups=None):
     """bfgs_groups=None: the dense damped BFGS the CUDA kernel implements.  bfgs_groups=stage_groups(f): the same update applied
     block by block (B stays block diagonal, so the QP's reduced KKT matrix is block tridiagonal over the stages) -- the
-    specification of the stage-structured kernel planned next."""
+    specification of the stage-structured kernel (libmpc_b200/csrc/nlmpc_structured.cuh)."""
     qp = qp or QPADMM()
     qp_cap0 = qp.max_iter
     qp.rho = qp.rho_init
