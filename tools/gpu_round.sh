@@ -14,6 +14,10 @@ if want lmpc_tests; then
   timeout 900 python -m pytest tests/test_gpu_lmpc.py tests/test_gpu_lmpc_properties.py tests/test_gpu_golden.py tests/test_gpu_closed_loop.py -x -q > gpurun_out/pytest_lmpc.log 2>&1; echo "pytest lmpc rc=$?"
   tail -5 gpurun_out/pytest_lmpc.log
 fi
+if want nlmpc_tests; then
+  timeout 1500 python -m pytest tests/test_gpu_nlmpc.py tests/test_gpu_nlmpc_solve.py tests/test_gpu_nlmpc_structured.py tests/test_gpu_nlmpc_closed_loop.py tests/test_gpu_baseline_configs.py tests/test_gpu_user_systems.py tests/test_gpu_golden.py -x -q > gpurun_out/pytest_nlmpc.log 2>&1; echo "pytest nlmpc rc=$?"
+  tail -5 gpurun_out/pytest_nlmpc.log
+fi
 if want quick; then
   timeout 300 python tools/bshort.py default > gpurun_out/bshort.txt 2>&1; cat gpurun_out/bshort.txt
 fi
