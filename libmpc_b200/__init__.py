@@ -468,7 +468,9 @@ class LMPC:
         return dict(warp_slots=a.value, workspace_bytes_per_slot=b.value, launches=c.value)
 
     def profile(self, fetch=False):
-        """Enable (first call) or fetch the per-instance phase cycle counters [batch, 8]."""
+        """Enable (first call) or fetch the per-instance cycle counters [batch, 16]: columns 0..7 the phases [setup, factorize, admm sweeps, info,
+        polish prep, polish factor, polish solve, unpack], 8..15 engine-specific sub-phase counters (engine 2: 8 / 9 = cycles in the
+        forward / backward recurrence of all KKT solves)."""
         if not fetch:
             _check(self.lib.b200mpc_lmpc_profile(self._h, None))
             return None
