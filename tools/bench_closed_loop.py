@@ -8,13 +8,13 @@ import numpy as np
 
 sys.path.insert(0, ".")
 import libmpc_b200 as L
-from bench import build_controller, synth_inputs
+from libmpc_b200 import workloads as W
 
 PH, B, K = 20, 4096, 8
 for warm in (False, True):
-    f, c = build_controller(L, PH, B, 250)
+    c = W.build_quadrotor_controller(L, PH, B, 250)
     c.setOptimizerParameters(L.LParameters(maximum_iteration=250, enable_warm_start=warm))
-    x0, r = synth_inputs(0, B)
+    x0, r = W.quadrotor_inputs(0, B)
     yref = np.zeros((B, 12, PH)); yref[:, 2, :] = r[:, None]
     c.setReferences(yref, np.zeros((4, PH)), np.zeros((4, PH)))
     c.closed_loop(x0, np.zeros((B, 4)), 2)                       # warm-up

@@ -3,7 +3,7 @@ import json, subprocess, sys, threading, time
 import numpy as np
 sys.path.insert(0, ".")
 import libmpc_b200 as L
-from bench import build_controller, synth_inputs
+from libmpc_b200 import workloads as W
 PH, MAXIT = 20, 250
 samples = []
 stop = False
@@ -13,12 +13,12 @@ def sampler():
         samples.append((time.perf_counter(), o))
         time.sleep(0.05)
 for B in [int(v) for v in sys.argv[1:]] or [1776, 3552, 4096, 32768]:
-    f, c = build_controller(L, PH, B, MAXIT)
+    c = W.build_quadrotor_controller(L, PH, B, MAXIT)
     import os
     if os.environ.get('GENERIC'): c.set_launch(-int(os.environ['GENERIC']), 0)
     if os.environ.get('NOHIST'): c.set_history_order(False)
     if os.environ.get('WPC'): c.set_launch(int(os.environ['WPC']), int(os.environ.get('CPS', 0)))
-    x0, r = synth_inputs(0, B)
+    x0, r = W.quadrotor_inputs(0, B)
     yref = np.zeros((B, 12, PH)); yref[:, 2, :] = r[:, None]
     c.setReferences(yref, np.zeros((4, PH)), np.zeros((4, PH)))
     u0 = np.zeros((B, 4))

@@ -8,14 +8,14 @@ import numpy as np
 
 sys.path.insert(0, ".")
 import libmpc_b200 as L
-from bench import build_controller, synth_inputs
+from libmpc_b200 import workloads as W
 
 PH, MAXIT = 20, 250
 names = ["setup", "factorize", "admm sweeps", "info/termination", "polish prep", "polish factor", "polish solve", "unpack"]
 batches = [int(v) for v in sys.argv[1:]] or [2048, 4096, 8192, 16384, 32768]
 for B in batches:
-    f, c = build_controller(L, PH, B, MAXIT)
-    x0, r = synth_inputs(0, B)
+    c = W.build_quadrotor_controller(L, PH, B, MAXIT)
+    x0, r = W.quadrotor_inputs(0, B)
     yref = np.zeros((B, 12, PH)); yref[:, 2, :] = r[:, None]
     c.setReferences(yref, np.zeros((4, PH)), np.zeros((4, PH)))
     u0 = np.zeros((B, 4))
