@@ -642,9 +642,27 @@ struct CtaSolver {
         const int LD = fLD();
         for (int r = lane; r < d.ne; r += 32) CAR[r] = 0.0;
         __syncwarp();
-        for (int i = 0; i < d.ph; ++i) {
-            for (int r = lane; r < d.ne; r += 32) CAR[(i + 1) * d.ne + r] = GT[i * d.ne + r] - cta_dot<SNE, 0>(fac(i) + fWm() + r * LD, 1, CAR + i * d.ne, d.ne);
-            __syncwarp();
+        if constexpr (SNE == 16) {
+            // two lanes per row: lane = (half, row) computes half of the dot product, one shuffle adds the halves -- the step is bound
+            // by the instructions one warp issues, and this halves them
+            constexpr int NE = SNE, H = SNE / 2;
+            const int r = lane & (NE - 1), hf = (lane >> 4) & 1;      // NE == 16: lanes 0..15 first half, 16..31 second half
+            for (int i = 0; i < d.ph; ++i) {
+                const double2* a2 = reinterpret_cast<const double2*>(fac(i) + fWm() + r * LD + hf * H);
+                const double2* x2 = reinterpret_cast<const double2*>(CAR + i * NE + hf * H);
+                double s0 = 0, s1 = 0;
+#pragma unroll
+                for (int j = 0; j < H / 2; ++j) { const double2 av = a2[j], xv = x2[j]; s0 = fma(av.x, xv.x, s0); s1 = fma(av.y, xv.y, s1); }
+                double sv_ = s0 + s1;
+                sv_ += __shfl_xor_sync(0xffffffffu, sv_, 16);
+                if (lane < NE) CAR[(i + 1) * NE + lane] = GT[i * NE + lane] - sv_;
+                __syncwarp();
+            }
+        } else {
+            for (int i = 0; i < d.ph; ++i) {
+                for (int r = lane; r < d.ne; r += 32) CAR[(i + 1) * d.ne + r] = GT[i * d.ne + r] - cta_dot<SNE, 0>(fac(i) + fWm() + r * LD, 1, CAR + i * d.ne, d.ne);
+                __syncwarp();
+            }
         }
     }
     __device__ __forceinline__ void chain_backward() {
@@ -652,9 +670,25 @@ struct CtaSolver {
         const int LD = fLD();
         for (int r = lane; r < d.ne; r += 32) XE[d.ph * d.ne + r] = R[d.ph * d.b + r];
         __syncwarp();
-        for (int i = d.ph - 1; i >= 0; --i) {
-            for (int cc = lane; cc < d.ne; cc += 32) XE[i * d.ne + cc] = R[i * d.b + cc] - cta_dot<SNE, 1>(fac(i) + fWm() + cc, LD, XE + (i + 1) * d.ne, d.ne);
-            __syncwarp();
+        if constexpr (SNE == 16) {
+            constexpr int NE = SNE, H = SNE / 2;
+            const int cc = lane & (NE - 1), hf = (lane >> 4) & 1;
+            for (int i = d.ph - 1; i >= 0; --i) {
+                const double* a = fac(i) + fWm() + cc + hf * H * LD;
+                const double2* x2 = reinterpret_cast<const double2*>(XE + (i + 1) * NE + hf * H);
+                double s0 = 0, s1 = 0;
+#pragma unroll
+                for (int j = 0; j < H / 2; ++j) { const double2 xv = x2[j]; s0 = fma(a[(2 * j) * LD], xv.x, s0); s1 = fma(a[(2 * j + 1) * LD], xv.y, s1); }
+                double sv_ = s0 + s1;
+                sv_ += __shfl_xor_sync(0xffffffffu, sv_, 16);
+                if (lane < NE) XE[i * NE + lane] = R[i * d.b + lane] - sv_;
+                __syncwarp();
+            }
+        } else {
+            for (int i = d.ph - 1; i >= 0; --i) {
+                for (int cc = lane; cc < d.ne; cc += 32) XE[i * d.ne + cc] = R[i * d.b + cc] - cta_dot<SNE, 1>(fac(i) + fWm() + cc, LD, XE + (i + 1) * d.ne, d.ne);
+                __syncwarp();
+            }
         }
     }
 
