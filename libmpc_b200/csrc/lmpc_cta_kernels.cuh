@@ -647,15 +647,28 @@ struct CtaSolver {
             // by the instructions one warp issues, and this halves them
             constexpr int NE = SNE, H = SNE / 2;
             const int r = lane & (NE - 1), hf = (lane >> 4) & 1;      // NE == 16: lanes 0..15 first half, 16..31 second half
+            // the half row of K_{i+1} and g_{i+1} are loaded before the barrier of step i: only the carried vector is waited for
+            double2 ak[H / 2];
+            double gk = GT[r];
+            {
+                const double2* a2 = reinterpret_cast<const double2*>(fac(0) + fWm() + r * LD + hf * H);
+#pragma unroll
+                for (int j = 0; j < H / 2; ++j) ak[j] = a2[j];
+            }
             for (int i = 0; i < d.ph; ++i) {
-                const double2* a2 = reinterpret_cast<const double2*>(fac(i) + fWm() + r * LD + hf * H);
                 const double2* x2 = reinterpret_cast<const double2*>(CAR + i * NE + hf * H);
                 double s0 = 0, s1 = 0;
 #pragma unroll
-                for (int j = 0; j < H / 2; ++j) { const double2 av = a2[j], xv = x2[j]; s0 = fma(av.x, xv.x, s0); s1 = fma(av.y, xv.y, s1); }
+                for (int j = 0; j < H / 2; ++j) { const double2 xv = x2[j]; s0 = fma(ak[j].x, xv.x, s0); s1 = fma(ak[j].y, xv.y, s1); }
+                const int st = i + 1 < d.ph ? i + 1 : i;
+                const double2* a2 = reinterpret_cast<const double2*>(fac(st) + fWm() + r * LD + hf * H);
+#pragma unroll
+                for (int j = 0; j < H / 2; ++j) ak[j] = a2[j];
+                const double gn = GT[st * NE + r];
                 double sv_ = s0 + s1;
                 sv_ += __shfl_xor_sync(0xffffffffu, sv_, 16);
-                if (lane < NE) CAR[(i + 1) * NE + lane] = GT[i * NE + lane] - sv_;
+                if (lane < NE) CAR[(i + 1) * NE + lane] = gk - sv_;
+                gk = gn;
                 __syncwarp();
             }
         } else {
