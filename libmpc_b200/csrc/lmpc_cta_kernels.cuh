@@ -710,7 +710,16 @@ struct CtaSolver {
     __device__ __forceinline__ void kkt_solve(Epi epilogue) {
         double* R = CSM(R); double* T = CSM(T); double* XE = CSM(XE); const double* D = CSM(D);
         const int LD = fLD();
-        for (int j = warp; j <= d.ph; j += NW) stage_p3(j);
+        {   // rhat_j = L_j^-1 r_j -> T,  g_j = W_j r_j -> GT as ONE flat task list over the rows of all stages (the records of
+            // consecutive stages are contiguous: row t of the list starts at fac(0) + t * LD) -- a warp per stage would run a second,
+            // almost empty round for rows 32..35 of every stage
+            const int nrow = d.b + d.ne, ntask = (d.ph + 1) * nrow - d.ne;      // the last stage has no W rows
+            for (int t = tid; t < ntask; t += NT) {
+                const int j = t / nrow, rr = t - j * nrow;
+                const double v = cta_dot<SB, 0>(fac(0) + (size_t)t * LD, 1, R + j * d.b, d.b);
+                if (rr < d.b) T[j * d.b + rr] = v; else CSM(GT)[j * d.ne + (rr - d.b)] = v;
+            }
+        }
         __syncthreads();
         if (warp == 0) { const long long q0 = clock64(); chain_forward(); pw[0] += clock64() - q0; }
         __syncthreads();
