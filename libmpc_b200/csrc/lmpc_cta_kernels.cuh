@@ -723,7 +723,17 @@ struct CtaSolver {
         __syncthreads();
         if (warp == 0) { const long long q0 = clock64(); chain_forward(); pw[0] += clock64() - q0; }
         __syncthreads();
-        for (int j = warp; j <= d.ph; j += NW) stage_fwd(j);
+        // t_i = rhat_i - L_i^-1[:, :ne] c_i, then s_i = L_i^-T t_i: both flat over the variable index (two rounds instead of three
+        // stage rounds at 20 of 32 lanes), one block barrier in between
+        for (int kg = tid; kg < L.nP; kg += NT) {
+            const int i = kg / d.b, r = kg - i * d.b;
+            if (i > 0) T[kg] -= cta_dot<SNE, 0>(fac(i) + r * LD, 1, CSM(CAR) + i * d.ne, d.ne);
+        }
+        __syncthreads();
+        for (int kg = tid; kg < L.nP; kg += NT) {
+            const int i = kg / d.b, k = kg - i * d.b;
+            R[kg] = cta_dot<SB, 1>(fac(i) + k, LD, T + i * d.b, d.b);
+        }
         __syncthreads();
         if (warp == 0) { const long long q0 = clock64(); chain_backward(); pw[1] += clock64() - q0; }
         __syncthreads();
@@ -784,7 +794,13 @@ struct CtaSolver {
     }
     // One ADMM iteration, bulk-synchronous: every phase by all warps, the recurrences by warp 0 between barriers.
     __device__ __forceinline__ void bulk_iteration(bool store_delta) {
-        for (int j = warp; j <= d.ph; j += NW) stage_rhs(j);
+        {   // right-hand side of every stage, flat over the (padded) variable index
+            const double sigma = p.sigma;
+            for (int kg = tid; kg < L.nP; kg += NT) {
+                const int j = kg / d.b, k = kg - j * d.b;
+                CSM(R)[kg] = k < d.bcount(j) ? sigma * CSM(X)[kg] - CSM(Q)[kg] + CSM(D)[kg] * col_atv(j, k, CSM(V)) : 0.0;
+            }
+        }
         __syncthreads();
         const double alpha = p.alpha;
         double* va = gws + L.gVA;
