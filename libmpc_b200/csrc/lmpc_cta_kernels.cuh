@@ -23,9 +23,11 @@
 //   * The factorisation of a stage is a register-resident LDL' by ONE warp (lane r = row r of the pivot block, lane q = column
 //     q of the accumulated inverse; the pivot column is the only thing that goes through shared memory), followed by
 //     stage-parallel dot products for Lc_i, the Schur complement of stage i+1 and W_i.
-//   * The ADMM iteration is bulk-synchronous: stage-parallel phases by all warps, the two serial recurrences by warp 0 with the
-//     carried vector in registers (shuffle broadcast) and the K rows loaded one stage ahead.  (A warp-specialised pipeline ordered
-//     by shared-memory progress flags was measured 2x slower -- profiles/r02_engine_probe.jsonl -- and removed.)
+//   * The ADMM iteration is bulk-synchronous: the stage-parallel phases (right-hand side, L^-1 r / W r, forward substitution,
+//     L^-T products, x update, row updates) are flat task lists over ALL stages spread over all threads; the two serial
+//     recurrences run on warp 0 with two lanes per row (half a dot product each, one shuffle), the carried vector exchanged
+//     through shared memory and the next stage's K half-row loaded before the step's barrier.  (A warp-specialised pipeline
+//     ordered by shared-memory progress flags was measured 2x slower -- profiles/r02_engine_probe.jsonl -- and removed.)
 //   * A x / A' y / P x never touch a matrix: rows and columns are evaluated from A, B, C, the weights and the scalar row.
 //
 // Used for batch sizes from 1 (a single mpc::LMPC<> object: the whole SM works on it) to any; the warp-per-controller engine
@@ -749,34 +751,6 @@ struct CtaSolver {
         __syncthreads();
     }
 
-    // ================= per-stage jobs (one warp each) =========================================================================
-    // rhat_j = L_j^-1 r_j -> T,  g_j = W_j r_j -> GT  (one warp; r_j in R)
-    __device__ __forceinline__ void stage_p3(int j) {
-        const int nt = d.b + (j < d.ph ? d.ne : 0), LD = fLD();
-        const double* x = CSM(R) + j * d.b;
-        for (int t = lane; t < nt; t += 32) {
-            const double v = cta_dot<SB, 0>(fac(j) + t * LD, 1, x, d.b);      // rows 0..b-1: L^-1, rows b..b+ne-1: W
-            if (t < d.b) CSM(T)[j * d.b + t] = v; else CSM(GT)[j * d.ne + (t - d.b)] = v;
-        }
-    }
-    __device__ __forceinline__ void stage_rhs(int j) {
-        const double sigma = p.sigma;
-        for (int k = lane; k < d.b; k += 32) {
-            const int kg = j * d.b + k;
-            CSM(R)[kg] = k < d.bcount(j) ? sigma * CSM(X)[kg] - CSM(Q)[kg] + CSM(D)[kg] * col_atv(j, k, CSM(V)) : 0.0;
-        }
-    }
-    // job F_i
-    __device__ __forceinline__ void stage_fwd(int i) {
-        double* T = CSM(T) + i * d.b; double* R = CSM(R) + i * d.b; const double* F = fac(i);
-        const int LD = fLD();
-        if (i > 0) {
-            const double* cp = CSM(CAR) + i * d.ne;
-            for (int r = lane; r < d.b; r += 32) T[r] -= cta_dot<SNE, 0>(F + r * LD, 1, cp, d.ne);
-        }
-        __syncwarp();
-        for (int k = lane; k < d.b; k += 32) R[k] = cta_dot<SB, 1>(F + k, LD, T, d.b);
-    }
     // z~ = A x~ of one row, relaxation, projection, dual update, row weight of the next right-hand side
     __device__ __forceinline__ void row_update(int g, int i, int r, bool store_delta) {
         const int ty = rtp()[g];
